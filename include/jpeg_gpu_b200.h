@@ -1,0 +1,179 @@
+/* jpeg_gpu_b200.h — C ABI of the B200 JPEG block-decode back end.
+ *
+ * The library replaces the GPU half of negge/jpeg_gpu — the fragment-shader
+ * passes res/{horz,vert,horz_quant_yuv,horz_quant_grey,unyuv,ungrey,rgb}.fs.glsl
+ * driven from src/jpeg_gpu.c:1320-1363 — with one fused sm_100a CUDA kernel:
+ *
+ *     quantised int16 coefficient planes (JPEG_DECODE_QUANT layout,
+ *     src/xjpeg.c:550-563, src/image.c:66-95)  +  DQT tables (natural order)
+ *         -> dequantise -> 8x8 inverse DCT (bit-exact with src/dct.c)
+ *         -> +128 / clamp (Y, Cb, Cr planes, bit-exact with src/xjpeg.c:565-584)
+ *         -> nearest-neighbour chroma upsample -> YCbCr->RGB (res/yuv.fs.glsl)
+ *         -> interleaved RGB8 in the layout of image.pixels (src/image.h:50)
+ *
+ * Two surfaces are exported:
+ *
+ *  (1) the reference's own plugin boundary: CUDA_DECODE_CTX_VTBL is a third
+ *      `jpeg_decode_ctx_vtbl` (src/jpeg_wrap.h:45-54) with the same five slots,
+ *      call protocol, ownership and EXIT_SUCCESS/EXIT_FAILURE + stderr error
+ *      convention as LIBJPEG_DECODE_CTX_VTBL / XJPEG_DECODE_CTX_VTBL
+ *      (src/jpeg_wrap.c:246-252,352-358);
+ *  (2) a batch API over device-resident (or host) buffers, which the vtable
+ *      path is a one-image wrapper around.
+ *
+ * Everything is plain C: pointers, sizes, ints.  Functions returning int
+ * return 0 (EXIT_SUCCESS) or 1 (EXIT_FAILURE); jgpu_last_error() holds the
+ * message of the last failure on the calling thread.  No call aborts.
+ * A jgpu_ctx / jgpu_plan must be used by one host thread at a time.
+ */
+#ifndef JPEG_GPU_B200_H
+#define JPEG_GPU_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+#include "jgpu_ref_abi.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define JGPU_VERSION 100
+
+/* ------------------------------------------------------------------------
+ * (1) decoder-plugin boundary
+ * --------------------------------------------------------------------- */
+
+/* Third backend.  decode_image(dec, img, out):
+ *   PACK / QUANT / DCT  forwarded to the CPU front end (no GPU work);
+ *   YUV   front end -> QUANT planes -> GPU -> img->plane[i].data
+ *         (bit-exact with XJPEG_DECODE_CTX_VTBL's YUV output);
+ *   RGB   front end -> QUANT planes -> GPU -> img->pixels, width*height*3
+ *         bytes R,G,B (width*height bytes for 1-component files, the
+ *         convention of the libjpeg backend, src/jpeg_wrap.c:215-220).
+ * Replaces: the per-frame GL sequence src/jpeg_gpu.c:1320-1363. */
+extern const jpeg_decode_ctx_vtbl CUDA_DECODE_CTX_VTBL;
+
+/* Our own CPU entropy front end (baseline sequential Huffman, DRI/RSTn).  It
+ * supports PACK/QUANT/DCT and produces buffers identical to
+ * XJPEG_DECODE_CTX_VTBL's (src/xjpeg.c:449-632); YUV/RGB return
+ * EXIT_FAILURE exactly like the xjpeg backend does for RGB
+ * (src/jpeg_wrap.c:335-339).  It is the default producer behind
+ * CUDA_DECODE_CTX_VTBL when the library is used outside the reference tree. */
+extern const jpeg_decode_ctx_vtbl JFRONT_DECODE_CTX_VTBL;
+
+/* Inside the reference tree: make CUDA_DECODE_CTX_VTBL pull its coefficient
+ * planes from the reference's own reader, e.g.
+ *     cuda_decode_set_frontend(&XJPEG_DECODE_CTX_VTBL);
+ * NULL restores JFRONT_DECODE_CTX_VTBL.  Affects contexts allocated later. */
+void cuda_decode_set_frontend(const jpeg_decode_ctx_vtbl *frontend);
+/* CUDA device ordinal used by contexts allocated later (default 0, or
+ * $JGPU_DEVICE). */
+void cuda_decode_set_device(int device);
+
+/* Output-surface helpers with the semantics of the reference's
+ * image_init / image_zero / image_clear (src/image.c:24-123) and
+ * jpeg_info_init / jpeg_info_clear (src/jpeg_info.c:31-61), for callers that
+ * do not link the reference objects.  Buffers are 16-byte aligned. */
+int jgpu_image_init(image *img, jpeg_header *header);
+void jgpu_image_zero(image *img);
+void jgpu_image_clear(image *img);
+int jgpu_info_init(jpeg_info *info, const char *name);
+void jgpu_info_clear(jpeg_info *info);
+
+/* ------------------------------------------------------------------------
+ * (2) batch API
+ * --------------------------------------------------------------------- */
+
+typedef struct jgpu_ctx jgpu_ctx;
+typedef struct jgpu_plan jgpu_plan;
+
+/* One image of a batch.  Geometry is derived exactly as the reference does
+ * (nhmb/nvmb src/xjpeg.c:403-407, hblocks/vblocks src/jpeg_wrap.c:305-306,
+ * plane size / xdec / ydec / cstride / coefficient offsets src/image.c:38-95).
+ * Requires hsamp[0] == max(hsamp) (the reference's coefficient layout is only
+ * self-consistent in that case, src/xjpeg.c:558-560). */
+typedef struct jgpu_image_desc {
+  int32_t width, height;      /* visible size, 1..65535 */
+  int32_t ncomps;             /* 1 or 3 */
+  int32_t hsamp[3], vsamp[3]; /* 1, 2 or 4 */
+  int32_t tq[3];              /* DQT slot 0..3 of each component */
+  int32_t qtab_set;           /* index of this image's 4x64 table set */
+  int32_t reserved;
+  int64_t coef_off;           /* first int16 of this image in the coef buffer
+                                 (multiple of 8); layout = image.coef */
+  int64_t rgb_off;            /* first byte of this image in the rgb buffer */
+  int64_t yuv_off;            /* first byte of the padded Y|Cb|Cr planes in the
+                                 yuv buffer, or -1 */
+} jgpu_image_desc;
+
+/* What the reference's image_init would allocate for this image. */
+typedef struct jgpu_plane_layout {
+  int32_t hblocks, vblocks;   /* coded blocks */
+  int32_t width, height;      /* padded plane size */
+  int32_t xdec, ydec, cstride, reserved;
+  int64_t coef_off;           /* plane.coef - image.coef, in int16 */
+  int64_t data_off;           /* offset in a packed Y|Cb|Cr buffer, bytes */
+} jgpu_plane_layout;
+
+typedef struct jgpu_layout {
+  int32_t nhmb, nvmb, hmax, vmax;
+  int64_t coef_len;           /* int16 elements incl. the reference's padding */
+  int64_t coded_blocks;       /* sum hblocks*vblocks */
+  int64_t data_len;           /* bytes of the three padded planes */
+  int64_t rgb_len;            /* width*height*(ncomps==1 ? 1 : 3) */
+  jgpu_plane_layout plane[3];
+} jgpu_layout;
+
+/* Host-only; needs no GPU. */
+int jgpu_layout_query(const jgpu_image_desc *desc, jgpu_layout *out);
+
+const char *jgpu_last_error(void);
+int jgpu_device_count(void);
+
+jgpu_ctx *jgpu_create(int device);
+void jgpu_destroy(jgpu_ctx *ctx);
+
+#define JGPU_OUT_RGB 1u          /* write interleaved RGB8 / grey8 */
+#define JGPU_OUT_YUV 2u          /* write the padded u8 Y|Cb|Cr planes */
+#define JGPU_FORCE_GENERIC 4u    /* use the two-kernel generic path (tests) */
+
+/* A plan holds the device-side work lists for one batch shape; running it
+ * launches kernels only (no allocation, no host<->device copies). */
+jgpu_plan *jgpu_plan_create(jgpu_ctx *ctx, const jgpu_image_desc *descs, int n,
+                            unsigned flags);
+void jgpu_plan_destroy(jgpu_plan *plan);
+/* Kernels one jgpu_plan_run launches. */
+int jgpu_plan_launches(const jgpu_plan *plan);
+/* Total algorithmic bytes (128 B per coded block + output bytes) of one run. */
+int64_t jgpu_plan_bytes(const jgpu_plan *plan);
+
+/* All pointers are DEVICE pointers; d_qtabs is n_sets x 4 x 64 uint16 in
+ * natural order (jpeg_quant.tbl); stream is a cudaStream_t (NULL = default).
+ * Asynchronous: returns after enqueueing. */
+int jgpu_plan_run(jgpu_plan *plan, const int16_t *d_coef,
+                  const uint16_t *d_qtabs, int n_sets, uint8_t *d_rgb,
+                  uint8_t *d_yuv, void *stream);
+
+/* HOST buffers in, HOST buffers out: pinned staging, chunked H2D / kernel /
+ * D2H overlapped on internal streams; synchronous.  h_rgb / h_yuv may be NULL
+ * according to flags. */
+int jgpu_decode_batch_host(jgpu_ctx *ctx, const jgpu_image_desc *descs, int n,
+                           unsigned flags, const int16_t *h_coef,
+                           const uint16_t *h_qtabs, int n_sets, uint8_t *h_rgb,
+                           uint8_t *h_yuv);
+
+/* One image on the reference's own structs: img->coef holds QUANT planes
+ * (from any backend that honours src/xjpeg.c:550-563), header holds the
+ * tables.  out = JPEG_DECODE_YUV fills img->plane[i].data, JPEG_DECODE_RGB
+ * fills img->pixels.  Synchronous. */
+int jgpu_decode_image(jgpu_ctx *ctx, const jpeg_header *header, image *img,
+                      jpeg_decode_out out);
+
+/* Page-locked host memory for the batch entry points. */
+void *jgpu_host_alloc(size_t bytes);
+void jgpu_host_free(void *p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JPEG_GPU_B200_H */

@@ -1,0 +1,196 @@
+"""Batch API: device-resident (torch tensors) and host-buffer decoding.
+
+Thin wrappers over jgpu_plan_* / jgpu_decode_batch_host
+(include/jpeg_gpu_b200.h).  PyTorch is used only for device memory and
+streams; all work happens in the C/CUDA library.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _capi
+
+SUBSAMPLINGS = {
+    "gray": ((1,), (1,)),
+    "444": ((1, 1, 1), (1, 1, 1)),
+    "422": ((2, 1, 1), (1, 1, 1)),
+    "420": ((2, 1, 1), (2, 1, 1)),
+    "440": ((1, 1, 1), (2, 1, 1)),
+    "411": ((4, 1, 1), (1, 1, 1)),
+}
+
+
+@dataclass
+class PlaneLayout:
+    hblocks: int
+    vblocks: int
+    width: int
+    height: int
+    xdec: int
+    ydec: int
+    cstride: int
+    coef_off: int
+    data_off: int
+
+
+@dataclass
+class Layout:
+    nhmb: int
+    nvmb: int
+    hmax: int
+    vmax: int
+    coef_len: int
+    coded_blocks: int
+    data_len: int
+    rgb_len: int
+    planes: List[PlaneLayout]
+
+
+@dataclass
+class ImageDesc:
+    """One image of a batch (jgpu_image_desc)."""
+    width: int
+    height: int
+    hsamp: Sequence[int]
+    vsamp: Sequence[int]
+    tq: Sequence[int] = (0, 1, 1)
+    qtab_set: int = 0
+    coef_off: int = 0
+    rgb_off: int = 0
+    yuv_off: int = -1
+    layout: Optional[Layout] = field(default=None, compare=False)
+
+    def to_c(self) -> _capi.jgpu_image_desc:
+        d = _capi.jgpu_image_desc()
+        d.width, d.height, d.ncomps = self.width, self.height, len(self.hsamp)
+        for i in range(len(self.hsamp)):
+            d.hsamp[i], d.vsamp[i], d.tq[i] = self.hsamp[i], self.vsamp[i], self.tq[i]
+        d.qtab_set, d.coef_off, d.rgb_off, d.yuv_off = self.qtab_set, self.coef_off, self.rgb_off, self.yuv_off
+        return d
+
+    def query_layout(self) -> Layout:
+        """jgpu_layout_query: host-only, needs no GPU."""
+        if self.layout is None:
+            out = _capi.jgpu_layout()
+            d = self.to_c()
+            if _capi.lib().jgpu_layout_query(C.byref(d), C.byref(out)) != 0:
+                raise ValueError(_capi.last_error())
+            planes = [PlaneLayout(p.hblocks, p.vblocks, p.width, p.height, p.xdec, p.ydec, p.cstride,
+                                  p.coef_off, p.data_off) for p in out.plane[:len(self.hsamp)]]
+            self.layout = Layout(out.nhmb, out.nvmb, out.hmax, out.vmax, out.coef_len, out.coded_blocks,
+                                 out.data_len, out.rgb_len, planes)
+        return self.layout
+
+
+def pack_batch(descs: List[ImageDesc], want_yuv: bool = False, align: int = 256):
+    """Assigns back-to-back coef / rgb / yuv offsets.  Returns the buffer sizes
+    (coef in int16 elements, rgb and yuv in bytes)."""
+    coef = rgb = yuv = 0
+    for d in descs:
+        lay = d.query_layout()
+        d.coef_off, d.rgb_off = coef, rgb
+        coef += -(-lay.coef_len // 8) * 8
+        rgb += -(-lay.rgb_len // align) * align
+        if want_yuv:
+            d.yuv_off = yuv
+            yuv += -(-lay.data_len // align) * align
+        else:
+            d.yuv_off = -1
+    return coef, rgb, yuv
+
+
+def _desc_array(descs: List[ImageDesc]):
+    arr = (_capi.jgpu_image_desc * len(descs))()
+    for i, d in enumerate(descs):
+        arr[i] = d.to_c()
+    return arr
+
+
+class Context:
+    """jgpu_ctx: one per device per host thread."""
+
+    def __init__(self, device: int = 0):
+        self._h = _capi.lib().jgpu_create(device)
+        if not self._h:
+            raise RuntimeError(f"jgpu_create({device}) failed: {_capi.last_error()}")
+        self.device = device
+
+    def close(self):
+        if self._h:
+            _capi.lib().jgpu_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- device-resident ----------------------------------------------------------
+    def plan(self, descs: List[ImageDesc], rgb: bool = True, yuv: bool = False, force_generic: bool = False):
+        return Plan(self, descs, rgb, yuv, force_generic)
+
+    # -- host buffers ---------------------------------------------------------------
+    def decode_batch_host(self, descs: List[ImageDesc], coef: np.ndarray, qtabs: np.ndarray,
+                          rgb: Optional[np.ndarray] = None, yuv: Optional[np.ndarray] = None,
+                          force_generic: bool = False) -> None:
+        """coef int16, qtabs uint16 (n_sets,4,64), rgb/yuv uint8: numpy arrays or
+        anything exposing .ctypes / data_ptr (e.g. pinned torch tensors)."""
+        flags = (_capi.JGPU_OUT_RGB if rgb is not None else 0) | (_capi.JGPU_OUT_YUV if yuv is not None else 0)
+        if force_generic:
+            flags |= _capi.JGPU_FORCE_GENERIC
+        n_sets = int(np.prod(qtabs.shape)) // 256
+        rc = _capi.lib().jgpu_decode_batch_host(self._h, _desc_array(descs), len(descs), flags, _addr(coef),
+                                                _addr(qtabs), n_sets, _addr(rgb), _addr(yuv))
+        if rc != 0:
+            raise RuntimeError(f"jgpu_decode_batch_host failed: {_capi.last_error()}")
+
+
+def _addr(a):
+    if a is None:
+        return None
+    if hasattr(a, "data_ptr"):
+        return C.c_void_p(a.data_ptr())
+    return C.c_void_p(a.ctypes.data)
+
+
+class Plan:
+    """jgpu_plan: device work lists for one batch shape; run() only launches."""
+
+    def __init__(self, ctx: Context, descs: List[ImageDesc], rgb=True, yuv=False, force_generic=False):
+        self.ctx = ctx
+        self.descs = descs
+        self.flags = (_capi.JGPU_OUT_RGB if rgb else 0) | (_capi.JGPU_OUT_YUV if yuv else 0) | \
+                     (_capi.JGPU_FORCE_GENERIC if force_generic else 0)
+        self._h = _capi.lib().jgpu_plan_create(ctx._h, _desc_array(descs), len(descs), self.flags)
+        if not self._h:
+            raise RuntimeError(f"jgpu_plan_create failed: {_capi.last_error()}")
+        self.launches = _capi.lib().jgpu_plan_launches(self._h)
+        self.bytes = _capi.lib().jgpu_plan_bytes(self._h)
+
+    def run(self, coef, qtabs, rgb=None, yuv=None, stream: Optional[int] = None) -> None:
+        """coef/qtabs/rgb/yuv: CUDA torch tensors (int16 / uint16-as-int16 / uint8).
+        stream: raw cudaStream_t; default = torch's current stream."""
+        if stream is None:
+            import torch
+            stream = torch.cuda.current_stream(coef.device).cuda_stream
+        n_sets = qtabs.numel() // 256
+        rc = _capi.lib().jgpu_plan_run(self._h, _addr(coef), _addr(qtabs), n_sets, _addr(rgb), _addr(yuv),
+                                       C.c_void_p(stream))
+        if rc != 0:
+            raise RuntimeError(f"jgpu_plan_run failed: {_capi.last_error()}")
+
+    def close(self):
+        if self._h:
+            _capi.lib().jgpu_plan_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

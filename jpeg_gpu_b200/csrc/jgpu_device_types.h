@@ -1,0 +1,75 @@
+/* Device-side work descriptors shared by the kernels and the runtime that
+ * builds them.  Plain PODs; built on the host by jgpu_plan_create and read by
+ * the kernels from global memory. */
+#ifndef JGPU_DEVICE_TYPES_H
+#define JGPU_DEVICE_TYPES_H
+
+#include <stdint.h>
+
+namespace jgpu {
+
+/* ---- generic path -------------------------------------------------------- */
+
+/* One colour plane of one image: a run of nblocks coefficient blocks in raster
+ * order (the reference layout is block-linear inside a plane, src/xjpeg.c:
+ * 558-562) and the padded u8 plane they decode into. */
+struct PlaneSeg {
+  int64_t coef_off;   /* first int16 of the plane in the coef buffer */
+  int64_t out_off;    /* first byte of the plane in the planes buffer */
+  int32_t hblocks;    /* blocks per block row */
+  int32_t nblocks;    /* hblocks*vblocks */
+  int32_t pitch;      /* plane row stride in bytes = hblocks*8 */
+  int32_t qidx;       /* 64-entry table index: qtab_set*4 + tq */
+};
+
+/* One CTA of k_coef_to_planes: `first` is the first block PAIR it owns. */
+struct PairWork {
+  int32_t seg;
+  int32_t first;
+};
+
+/* One image for k_planes_to_rgb. */
+struct ColourImage {
+  int64_t plane_off[3]; /* byte offsets of Y, Cb, Cr in the planes buffer */
+  int64_t rgb_off;      /* byte offset of the output in the rgb buffer */
+  int32_t width, height;
+  int32_t pitch[3];
+  int32_t xdec[3], ydec[3];
+  int32_t ncomps;
+  int32_t groups_per_row; /* ceil(width/4) */
+  int32_t reserved;
+};
+
+/* One CTA of k_planes_to_rgb: `first` is the first 4-pixel group it owns. */
+struct ColourWork {
+  int32_t img;
+  int32_t first;
+};
+
+/* ---- fused path ---------------------------------------------------------- */
+
+/* Subsampling classes the fused kernel specialises on. */
+enum FusedMode : int32_t {
+  kModeGray = 0, /* 1 component                         MCU  8x8,  1 block  */
+  kMode444 = 1,  /* 1x1,1x1,1x1                         MCU  8x8,  3 blocks */
+  kMode422 = 2,  /* 2x1,1x1,1x1                         MCU 16x8,  4 blocks */
+  kMode420 = 3,  /* 2x2,1x1,1x1                         MCU 16x16, 6 blocks */
+};
+
+/* One image for the fused kernel. */
+struct FusedImage {
+  int64_t coef_off[3]; /* first int16 of each plane */
+  int64_t rgb_off;
+  int64_t yuv_off[3];  /* byte offsets of the padded planes, or -1 */
+  int32_t width, height;
+  int32_t hblocks[3];  /* blocks per block row, per plane */
+  int32_t nhmb, nvmb;
+  int32_t qidx[3];
+  int32_t mode;
+  int32_t tiles_per_row; /* ceil(nhmb / MCUs per tile) */
+  int32_t first_tile;    /* index of this image's first tile in the batch */
+  int32_t reserved;
+};
+
+}  // namespace jgpu
+#endif

@@ -1,0 +1,46 @@
+/* Launch entry points of jgpu_kernels.cu, called by jgpu_runtime.cu. */
+#ifndef JGPU_LAUNCH_H
+#define JGPU_LAUNCH_H
+
+#include <cuda_runtime.h>
+#include "jgpu_device_types.h"
+#include "jpeg_gpu_b200.h"
+
+namespace jgpu {
+
+constexpr int kPairThreads = 128;   /* block pairs per CTA, generic IDCT kernel */
+constexpr int kColourThreads = 256; /* 4-pixel groups per CTA, colour kernel   */
+
+cudaError_t launch_coef_to_planes(const PlaneSeg *segs, const PairWork *work,
+                                  int ncta, const int16_t *coef,
+                                  const uint16_t *qtabs, uint8_t *planes,
+                                  cudaStream_t stream);
+
+cudaError_t launch_planes_to_rgb(const ColourImage *imgs, const ColourWork *work,
+                                 int ncta, const uint8_t *planes, uint8_t *rgb,
+                                 cudaStream_t stream);
+
+/* ---- fused path (jgpu_fused.cu) ------------------------------------------ */
+
+struct FusedPlan {
+  void *d_images = nullptr;   /* FusedImage[n] */
+  void *d_tiles = nullptr;    /* per-tile work items */
+  int n_images = 0;
+  int n_tiles = 0;
+  int sm_count = 0;
+  unsigned flags = 0;
+  int *img_first_tile = nullptr; /* host, n+1 entries */
+};
+
+/* false while the fused kernel is not built into the library */
+bool fused_available();
+cudaError_t fused_configure(int device);
+int fused_plan_build(FusedPlan &fp, const jgpu_image_desc *descs, const jgpu_layout *layouts,
+                     const int *modes, int n, unsigned flags, int sm_count);
+void fused_plan_release(FusedPlan &fp);
+cudaError_t fused_plan_launch(const FusedPlan &fp, int i0, int i1, const int16_t *coef,
+                              const uint16_t *qtabs, uint8_t *rgb, uint8_t *yuv,
+                              cudaStream_t stream);
+
+}  // namespace jgpu
+#endif

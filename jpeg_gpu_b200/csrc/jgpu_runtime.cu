@@ -1,0 +1,608 @@
+/* jgpu_runtime.cu — contexts, plans and the batch entry points of the C ABI
+ * (include/jpeg_gpu_b200.h).  Host code only; the kernels live in
+ * jgpu_kernels.cu / jgpu_fused.cu. */
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <algorithm>
+#include <new>
+#include <vector>
+
+#include "jgpu_internal.h"
+#include "jgpu_launch.h"
+
+using namespace jgpu;
+
+#define CU_TRY(expr)                                                          \
+  do {                                                                        \
+    cudaError_t e_ = (expr);                                                  \
+    if (e_ != cudaSuccess) {                                                  \
+      return jgpu_fail("CUDA error %s at %s:%d (%s)", cudaGetErrorName(e_),   \
+                       __FILE__, __LINE__, cudaGetErrorString(e_));           \
+    }                                                                         \
+  } while (0)
+
+namespace {
+
+constexpr int kHostStreams = 3;
+
+/* A grow-only device or pinned-host buffer. */
+struct Buffer {
+  void *ptr = nullptr;
+  size_t cap = 0;
+  bool pinned_host = false;
+  int reserve(size_t bytes) {
+    if (bytes <= cap) return 0;
+    release();
+    cudaError_t e = pinned_host ? cudaHostAlloc(&ptr, bytes, cudaHostAllocDefault)
+                                : cudaMalloc(&ptr, bytes);
+    if (e != cudaSuccess) {
+      ptr = nullptr;
+      return jgpu_fail("could not allocate %zu bytes of %s memory (%s)", bytes,
+                       pinned_host ? "pinned host" : "device", cudaGetErrorString(e));
+    }
+    cap = bytes;
+    return 0;
+  }
+  void release() {
+    if (ptr) {
+      if (pinned_host) cudaFreeHost(ptr); else cudaFree(ptr);
+    }
+    ptr = nullptr;
+    cap = 0;
+  }
+};
+
+template <typename T>
+int upload(Buffer &buf, const std::vector<T> &v) {
+  size_t bytes = std::max<size_t>(v.size() * sizeof(T), 16);
+  if (buf.reserve(bytes)) return 1;
+  if (!v.empty()) {
+    cudaError_t e = cudaMemcpy(buf.ptr, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return jgpu_fail("descriptor upload failed (%s)", cudaGetErrorString(e));
+  }
+  return 0;
+}
+
+}  // namespace
+
+struct jgpu_ctx {
+  int device = 0;
+  int sm_count = 0;
+  cudaStream_t streams[kHostStreams] = {};
+  cudaEvent_t events[kHostStreams] = {};
+  /* device mirrors used by the host-buffer entry points (grow-only) */
+  Buffer d_coef, d_qtabs, d_rgb, d_yuv;
+  /* pinned bounce buffers for pageable host memory */
+  Buffer h_in[kHostStreams], h_out[kHostStreams];
+  /* last plan built by jgpu_decode_batch_host, reused while descs match */
+  jgpu_plan *cached_plan = nullptr;
+  std::vector<jgpu_image_desc> cached_descs;
+  unsigned cached_flags = 0;
+};
+
+struct jgpu_plan {
+  jgpu_ctx *ctx = nullptr;
+  unsigned flags = 0;
+  int n = 0;
+  std::vector<jgpu_image_desc> descs;
+  std::vector<jgpu_layout> layouts;
+  int64_t bytes = 0;
+  int64_t scratch_len = 0;          /* planes scratch when the caller has no yuv */
+  std::vector<int64_t> scratch_off; /* per image offset into the scratch */
+  bool use_scratch = false;
+  /* generic path */
+  Buffer d_segs, d_pair_work, d_cimgs, d_colour_work, d_scratch;
+  std::vector<int> img_first_pair_cta, img_first_colour_cta; /* size n+1 */
+  /* fused path */
+  bool fused = false;
+  FusedPlan fp;
+};
+
+/* -------------------------------------------------------------------------- */
+
+extern "C" int jgpu_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+extern "C" jgpu_ctx *jgpu_create(int device) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0) {
+    jgpu_fail("no CUDA device available (%s)", cudaGetErrorString(e));
+    cudaGetLastError();
+    return nullptr;
+  }
+  if (device < 0 || device >= n) {
+    jgpu_fail("CUDA device %d out of range (have %d)", device, n);
+    return nullptr;
+  }
+  cudaDeviceProp prop;
+  if ((e = cudaSetDevice(device)) != cudaSuccess ||
+      (e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) {
+    jgpu_fail("cudaSetDevice(%d) failed (%s)", device, cudaGetErrorString(e));
+    return nullptr;
+  }
+  if (prop.major != 10) {
+    jgpu_fail("device %d is sm_%d%d; this library contains sm_100a code only",
+              device, prop.major, prop.minor);
+    return nullptr;
+  }
+  jgpu_ctx *ctx = new (std::nothrow) jgpu_ctx();
+  if (!ctx) {
+    jgpu_fail("out of host memory");
+    return nullptr;
+  }
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  for (int i = 0; i < kHostStreams; i++) {
+    ctx->h_in[i].pinned_host = ctx->h_out[i].pinned_host = true;
+    if (cudaStreamCreateWithFlags(&ctx->streams[i], cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->events[i], cudaEventDisableTiming) != cudaSuccess) {
+      jgpu_fail("could not create CUDA streams");
+      jgpu_destroy(ctx);
+      return nullptr;
+    }
+  }
+  if (fused_configure(device) != cudaSuccess) {
+    jgpu_fail("could not configure the fused kernel (%s)", cudaGetErrorString(cudaGetLastError()));
+    jgpu_destroy(ctx);
+    return nullptr;
+  }
+  return ctx;
+}
+
+extern "C" void jgpu_destroy(jgpu_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->cached_plan) jgpu_plan_destroy(ctx->cached_plan);
+  for (int i = 0; i < kHostStreams; i++) {
+    if (ctx->streams[i]) cudaStreamDestroy(ctx->streams[i]);
+    if (ctx->events[i]) cudaEventDestroy(ctx->events[i]);
+    ctx->h_in[i].release();
+    ctx->h_out[i].release();
+  }
+  ctx->d_coef.release();
+  ctx->d_qtabs.release();
+  ctx->d_rgb.release();
+  ctx->d_yuv.release();
+  delete ctx;
+}
+
+extern "C" void *jgpu_host_alloc(size_t bytes) {
+  void *p = nullptr;
+  cudaError_t e = cudaHostAlloc(&p, bytes ? bytes : 16, cudaHostAllocDefault);
+  if (e != cudaSuccess) {
+    jgpu_fail("cudaHostAlloc(%zu) failed (%s)", bytes, cudaGetErrorString(e));
+    return nullptr;
+  }
+  return p;
+}
+
+extern "C" void jgpu_host_free(void *p) {
+  if (p) cudaFreeHost(p);
+}
+
+/* -------------------------------------------------------------------------- */
+/* plans                                                                      */
+
+static bool fused_eligible(const jgpu_image_desc &d, const jgpu_layout &lay, unsigned flags,
+                           int *mode) {
+  (void)lay;
+  if (d.ncomps == 1) {
+    *mode = kModeGray;
+  } else {
+    if (d.hsamp[1] != 1 || d.vsamp[1] != 1 || d.hsamp[2] != 1 || d.vsamp[2] != 1) return false;
+    if (d.hsamp[0] == 1 && d.vsamp[0] == 1) *mode = kMode444;
+    else if (d.hsamp[0] == 2 && d.vsamp[0] == 1) *mode = kMode422;
+    else if (d.hsamp[0] == 2 && d.vsamp[0] == 2) *mode = kMode420;
+    else return false;
+  }
+  if (!(flags & JGPU_OUT_RGB)) return false;
+  return true;
+}
+
+extern "C" jgpu_plan *jgpu_plan_create(jgpu_ctx *ctx, const jgpu_image_desc *descs, int n,
+                                       unsigned flags) {
+  if (!ctx || !descs || n <= 0) {
+    jgpu_fail("jgpu_plan_create: bad arguments");
+    return nullptr;
+  }
+  if (!(flags & (JGPU_OUT_RGB | JGPU_OUT_YUV))) {
+    jgpu_fail("jgpu_plan_create: flags select no output");
+    return nullptr;
+  }
+  if (cudaSetDevice(ctx->device) != cudaSuccess) {
+    jgpu_fail("cudaSetDevice(%d) failed", ctx->device);
+    return nullptr;
+  }
+  jgpu_plan *plan = new (std::nothrow) jgpu_plan();
+  if (!plan) {
+    jgpu_fail("out of host memory");
+    return nullptr;
+  }
+  plan->ctx = ctx;
+  plan->flags = flags;
+  plan->n = n;
+  plan->descs.assign(descs, descs + n);
+  plan->layouts.resize(n);
+  bool all_fused = fused_available() && !(flags & JGPU_FORCE_GENERIC);
+  std::vector<int> modes(n, 0);
+  for (int i = 0; i < n; i++) {
+    const jgpu_image_desc &d = descs[i];
+    if (jgpu_layout_query(&d, &plan->layouts[i])) goto fail;
+    if (d.coef_off < 0 || (d.coef_off & 7)) {
+      jgpu_fail("image %d: coef_off must be a non-negative multiple of 8 int16", i);
+      goto fail;
+    }
+    if ((flags & JGPU_OUT_RGB) && d.rgb_off < 0) {
+      jgpu_fail("image %d: rgb_off must be non-negative", i);
+      goto fail;
+    }
+    if ((flags & JGPU_OUT_YUV) && (d.yuv_off < 0 || (d.yuv_off & 15))) {
+      jgpu_fail("image %d: yuv_off must be a non-negative multiple of 16", i);
+      goto fail;
+    }
+    if (d.qtab_set < 0) {
+      jgpu_fail("image %d: negative qtab_set", i);
+      goto fail;
+    }
+    plan->bytes += 128 * plan->layouts[i].coded_blocks;
+    if (flags & JGPU_OUT_RGB) plan->bytes += plan->layouts[i].rgb_len;
+    if (flags & JGPU_OUT_YUV) plan->bytes += plan->layouts[i].data_len;
+    if (!fused_eligible(d, plan->layouts[i], flags, &modes[i])) all_fused = false;
+  }
+  plan->fused = all_fused;
+
+  if (plan->fused) {
+    if (fused_plan_build(plan->fp, plan->descs.data(), plan->layouts.data(), modes.data(), n,
+                         flags, ctx->sm_count)) {
+      goto fail;
+    }
+    return plan;
+  }
+
+  {
+    /* generic path: planes kernel + colour kernel */
+    std::vector<PlaneSeg> segs;
+    std::vector<PairWork> pair_work;
+    std::vector<ColourImage> cimgs;
+    std::vector<ColourWork> colour_work;
+    plan->use_scratch = !(flags & JGPU_OUT_YUV);
+    plan->scratch_off.assign(n, 0);
+    plan->img_first_pair_cta.assign(n + 1, 0);
+    plan->img_first_colour_cta.assign(n + 1, 0);
+    for (int i = 0; i < n; i++) {
+      const jgpu_image_desc &d = descs[i];
+      const jgpu_layout &lay = plan->layouts[i];
+      int64_t planes_base = d.yuv_off;
+      if (plan->use_scratch) {
+        plan->scratch_off[i] = plan->scratch_len;
+        planes_base = plan->scratch_len;
+        plan->scratch_len += (lay.data_len + 15) & ~(int64_t)15;
+      }
+      plan->img_first_pair_cta[i] = (int)pair_work.size();
+      plan->img_first_colour_cta[i] = (int)colour_work.size();
+      ColourImage ci;
+      memset(&ci, 0, sizeof(ci));
+      for (int p = 0; p < d.ncomps; p++) {
+        const jgpu_plane_layout &pl = lay.plane[p];
+        PlaneSeg s;
+        s.coef_off = d.coef_off + pl.coef_off;
+        s.out_off = planes_base + pl.data_off;
+        s.hblocks = pl.hblocks;
+        s.nblocks = pl.hblocks * pl.vblocks;
+        s.pitch = pl.width;
+        s.qidx = d.qtab_set * 4 + d.tq[p];
+        int npairs = (s.nblocks + 1) / 2;
+        for (int first = 0; first < npairs; first += kPairThreads) {
+          PairWork w = {(int32_t)segs.size(), first};
+          pair_work.push_back(w);
+        }
+        segs.push_back(s);
+        ci.plane_off[p] = s.out_off;
+        ci.pitch[p] = pl.width;
+        ci.xdec[p] = pl.xdec;
+        ci.ydec[p] = pl.ydec;
+      }
+      if (flags & JGPU_OUT_RGB) {
+        ci.rgb_off = d.rgb_off;
+        ci.width = d.width;
+        ci.height = d.height;
+        ci.ncomps = d.ncomps;
+        ci.groups_per_row = (d.width + 3) / 4;
+        int64_t items = (int64_t)ci.groups_per_row * d.height;
+        for (int64_t first = 0; first < items; first += kColourThreads) {
+          ColourWork w = {(int32_t)cimgs.size(), (int32_t)first};
+          colour_work.push_back(w);
+        }
+        cimgs.push_back(ci);
+      }
+    }
+    plan->img_first_pair_cta[n] = (int)pair_work.size();
+    plan->img_first_colour_cta[n] = (int)colour_work.size();
+    if (upload(plan->d_segs, segs) || upload(plan->d_pair_work, pair_work) ||
+        upload(plan->d_cimgs, cimgs) || upload(plan->d_colour_work, colour_work)) {
+      goto fail;
+    }
+    if (plan->use_scratch && plan->d_scratch.reserve((size_t)plan->scratch_len + 16)) goto fail;
+  }
+  return plan;
+
+fail:
+  jgpu_plan_destroy(plan);
+  return nullptr;
+}
+
+extern "C" void jgpu_plan_destroy(jgpu_plan *plan) {
+  if (!plan) return;
+  if (plan->ctx) cudaSetDevice(plan->ctx->device);
+  plan->d_segs.release();
+  plan->d_pair_work.release();
+  plan->d_cimgs.release();
+  plan->d_colour_work.release();
+  plan->d_scratch.release();
+  fused_plan_release(plan->fp);
+  delete plan;
+}
+
+extern "C" int jgpu_plan_launches(const jgpu_plan *plan) {
+  if (!plan) return 0;
+  if (plan->fused) return 1;
+  return (plan->flags & JGPU_OUT_RGB) ? 2 : 1;
+}
+
+extern "C" int64_t jgpu_plan_bytes(const jgpu_plan *plan) { return plan ? plan->bytes : 0; }
+
+/* Runs images [i0, i1) of the plan. */
+static int plan_run_range(jgpu_plan *plan, int i0, int i1, const int16_t *d_coef,
+                          const uint16_t *d_qtabs, uint8_t *d_rgb, uint8_t *d_yuv,
+                          cudaStream_t stream) {
+  if (i0 >= i1) return 0;
+  if (plan->fused) {
+    CU_TRY(fused_plan_launch(plan->fp, i0, i1, d_coef, d_qtabs, d_rgb, d_yuv, stream));
+    return 0;
+  }
+  uint8_t *planes = plan->use_scratch ? (uint8_t *)plan->d_scratch.ptr : d_yuv;
+  int c0 = plan->img_first_pair_cta[i0], c1 = plan->img_first_pair_cta[i1];
+  CU_TRY(launch_coef_to_planes((const PlaneSeg *)plan->d_segs.ptr,
+                               (const PairWork *)plan->d_pair_work.ptr + c0, c1 - c0, d_coef,
+                               d_qtabs, planes, stream));
+  if (plan->flags & JGPU_OUT_RGB) {
+    c0 = plan->img_first_colour_cta[i0];
+    c1 = plan->img_first_colour_cta[i1];
+    CU_TRY(launch_planes_to_rgb((const ColourImage *)plan->d_cimgs.ptr,
+                                (const ColourWork *)plan->d_colour_work.ptr + c0, c1 - c0,
+                                planes, d_rgb, stream));
+  }
+  return 0;
+}
+
+extern "C" int jgpu_plan_run(jgpu_plan *plan, const int16_t *d_coef, const uint16_t *d_qtabs,
+                             int n_sets, uint8_t *d_rgb, uint8_t *d_yuv, void *stream) {
+  if (!plan || !d_coef || !d_qtabs) return jgpu_fail("jgpu_plan_run: NULL argument");
+  if ((plan->flags & JGPU_OUT_RGB) && !d_rgb) return jgpu_fail("jgpu_plan_run: d_rgb is NULL");
+  if ((plan->flags & JGPU_OUT_YUV) && !d_yuv) return jgpu_fail("jgpu_plan_run: d_yuv is NULL");
+  for (int i = 0; i < plan->n; i++) {
+    if (plan->descs[i].qtab_set >= n_sets) {
+      return jgpu_fail("image %d uses table set %d but only %d were passed", i,
+                       plan->descs[i].qtab_set, n_sets);
+    }
+  }
+  CU_TRY(cudaSetDevice(plan->ctx->device));
+  return plan_run_range(plan, 0, plan->n, d_coef, d_qtabs, d_rgb, d_yuv, (cudaStream_t)stream);
+}
+
+/* -------------------------------------------------------------------------- */
+/* host-buffer entry point                                                    */
+
+static bool is_pinned(const void *p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost;
+}
+
+static bool same_descs(const std::vector<jgpu_image_desc> &a, const jgpu_image_desc *b, int n) {
+  return (int)a.size() == n && memcmp(a.data(), b, sizeof(jgpu_image_desc) * n) == 0;
+}
+
+extern "C" int jgpu_decode_batch_host(jgpu_ctx *ctx, const jgpu_image_desc *descs, int n,
+                                      unsigned flags, const int16_t *h_coef,
+                                      const uint16_t *h_qtabs, int n_sets, uint8_t *h_rgb,
+                                      uint8_t *h_yuv) {
+  if (!ctx || !descs || n <= 0 || !h_coef || !h_qtabs || n_sets <= 0) {
+    return jgpu_fail("jgpu_decode_batch_host: bad arguments");
+  }
+  if ((flags & JGPU_OUT_RGB) && !h_rgb) return jgpu_fail("jgpu_decode_batch_host: h_rgb is NULL");
+  if ((flags & JGPU_OUT_YUV) && !h_yuv) return jgpu_fail("jgpu_decode_batch_host: h_yuv is NULL");
+  CU_TRY(cudaSetDevice(ctx->device));
+
+  if (!ctx->cached_plan || ctx->cached_flags != flags || !same_descs(ctx->cached_descs, descs, n)) {
+    if (ctx->cached_plan) jgpu_plan_destroy(ctx->cached_plan);
+    ctx->cached_plan = jgpu_plan_create(ctx, descs, n, flags);
+    if (!ctx->cached_plan) return EXIT_FAILURE;
+    ctx->cached_descs.assign(descs, descs + n);
+    ctx->cached_flags = flags;
+  }
+  jgpu_plan *plan = ctx->cached_plan;
+  for (int i = 0; i < n; i++) {
+    if (descs[i].qtab_set >= n_sets) {
+      return jgpu_fail("image %d uses table set %d but only %d were passed", i, descs[i].qtab_set,
+                       n_sets);
+    }
+  }
+
+  /* device mirrors with the same offsets as the host buffers */
+  int64_t coef_end = 0, rgb_end = 0, yuv_end = 0;
+  for (int i = 0; i < n; i++) {
+    const jgpu_layout &lay = plan->layouts[i];
+    coef_end = std::max(coef_end, descs[i].coef_off + lay.coef_len);
+    if (flags & JGPU_OUT_RGB) rgb_end = std::max(rgb_end, descs[i].rgb_off + lay.rgb_len);
+    if (flags & JGPU_OUT_YUV) yuv_end = std::max(yuv_end, descs[i].yuv_off + lay.data_len);
+  }
+  if (ctx->d_coef.reserve((size_t)coef_end * 2 + 256) ||
+      ctx->d_qtabs.reserve((size_t)n_sets * 4 * 64 * 2) ||
+      ((flags & JGPU_OUT_RGB) && ctx->d_rgb.reserve((size_t)rgb_end + 256)) ||
+      ((flags & JGPU_OUT_YUV) && ctx->d_yuv.reserve((size_t)yuv_end + 256))) {
+    return EXIT_FAILURE;
+  }
+  int16_t *d_coef = (int16_t *)ctx->d_coef.ptr;
+  uint16_t *d_qtabs = (uint16_t *)ctx->d_qtabs.ptr;
+  uint8_t *d_rgb = (uint8_t *)ctx->d_rgb.ptr;
+  uint8_t *d_yuv = (uint8_t *)ctx->d_yuv.ptr;
+
+  const bool in_pinned = is_pinned(h_coef);
+  const bool rgb_pinned = !(flags & JGPU_OUT_RGB) || is_pinned(h_rgb);
+  const bool yuv_pinned = !(flags & JGPU_OUT_YUV) || is_pinned(h_yuv);
+
+  CU_TRY(cudaMemcpyAsync(d_qtabs, h_qtabs, (size_t)n_sets * 4 * 64 * 2, cudaMemcpyHostToDevice,
+                         ctx->streams[0]));
+  CU_TRY(cudaEventRecord(ctx->events[0], ctx->streams[0]));
+  for (int s = 1; s < kHostStreams; s++) CU_TRY(cudaStreamWaitEvent(ctx->streams[s], ctx->events[0], 0));
+
+  /* chunk the batch so that copies of chunk k+1 overlap the kernel and the
+   * read-back of chunk k; ~48 MB of coefficients per chunk */
+  const int64_t chunk_bytes = 48ll << 20;
+  int i0 = 0, chunk = 0;
+  struct Pending { int i0, i1; };
+  std::vector<Pending> pending_out[kHostStreams];
+  while (i0 < n) {
+    int i1 = i0;
+    int64_t acc = 0;
+    while (i1 < n && (i1 == i0 || acc + plan->layouts[i1].coef_len * 2 <= chunk_bytes)) {
+      acc += plan->layouts[i1].coef_len * 2;
+      i1++;
+    }
+    const int s = chunk % kHostStreams;
+    cudaStream_t st = ctx->streams[s];
+    /* H2D */
+    if (in_pinned) {
+      for (int i = i0; i < i1; i++) {
+        CU_TRY(cudaMemcpyAsync(d_coef + descs[i].coef_off, h_coef + descs[i].coef_off,
+                               (size_t)plan->layouts[i].coef_len * 2, cudaMemcpyHostToDevice, st));
+      }
+    } else {
+      /* pageable source: bounce through this stream's pinned buffer */
+      CU_TRY(cudaStreamSynchronize(st));
+      if (ctx->h_in[s].reserve((size_t)acc)) return EXIT_FAILURE;
+      size_t off = 0;
+      for (int i = i0; i < i1; i++) {
+        size_t bytes = (size_t)plan->layouts[i].coef_len * 2;
+        memcpy((char *)ctx->h_in[s].ptr + off, h_coef + descs[i].coef_off, bytes);
+        CU_TRY(cudaMemcpyAsync(d_coef + descs[i].coef_off, (char *)ctx->h_in[s].ptr + off, bytes,
+                               cudaMemcpyHostToDevice, st));
+        off += bytes;
+      }
+    }
+    /* kernels */
+    if (plan_run_range(plan, i0, i1, d_coef, d_qtabs, d_rgb, d_yuv, st)) return EXIT_FAILURE;
+    /* D2H */
+    if (rgb_pinned && yuv_pinned) {
+      for (int i = i0; i < i1; i++) {
+        if (flags & JGPU_OUT_RGB) {
+          CU_TRY(cudaMemcpyAsync(h_rgb + descs[i].rgb_off, d_rgb + descs[i].rgb_off,
+                                 (size_t)plan->layouts[i].rgb_len, cudaMemcpyDeviceToHost, st));
+        }
+        if (flags & JGPU_OUT_YUV) {
+          CU_TRY(cudaMemcpyAsync(h_yuv + descs[i].yuv_off, d_yuv + descs[i].yuv_off,
+                                 (size_t)plan->layouts[i].data_len, cudaMemcpyDeviceToHost, st));
+        }
+      }
+    } else {
+      /* pageable destination: stage per chunk, drain synchronously */
+      size_t need = 0;
+      for (int i = i0; i < i1; i++) {
+        if (flags & JGPU_OUT_RGB) need += (size_t)plan->layouts[i].rgb_len;
+        if (flags & JGPU_OUT_YUV) need += (size_t)plan->layouts[i].data_len;
+      }
+      if (ctx->h_out[s].reserve(need)) return EXIT_FAILURE;
+      size_t off = 0;
+      for (int i = i0; i < i1; i++) {
+        if (flags & JGPU_OUT_RGB) {
+          CU_TRY(cudaMemcpyAsync((char *)ctx->h_out[s].ptr + off, d_rgb + descs[i].rgb_off,
+                                 (size_t)plan->layouts[i].rgb_len, cudaMemcpyDeviceToHost, st));
+          off += (size_t)plan->layouts[i].rgb_len;
+        }
+        if (flags & JGPU_OUT_YUV) {
+          CU_TRY(cudaMemcpyAsync((char *)ctx->h_out[s].ptr + off, d_yuv + descs[i].yuv_off,
+                                 (size_t)plan->layouts[i].data_len, cudaMemcpyDeviceToHost, st));
+          off += (size_t)plan->layouts[i].data_len;
+        }
+      }
+      CU_TRY(cudaStreamSynchronize(st));
+      off = 0;
+      for (int i = i0; i < i1; i++) {
+        if (flags & JGPU_OUT_RGB) {
+          memcpy(h_rgb + descs[i].rgb_off, (char *)ctx->h_out[s].ptr + off,
+                 (size_t)plan->layouts[i].rgb_len);
+          off += (size_t)plan->layouts[i].rgb_len;
+        }
+        if (flags & JGPU_OUT_YUV) {
+          memcpy(h_yuv + descs[i].yuv_off, (char *)ctx->h_out[s].ptr + off,
+                 (size_t)plan->layouts[i].data_len);
+          off += (size_t)plan->layouts[i].data_len;
+        }
+      }
+    }
+    i0 = i1;
+    chunk++;
+  }
+  for (int s = 0; s < kHostStreams; s++) CU_TRY(cudaStreamSynchronize(ctx->streams[s]));
+  return EXIT_SUCCESS;
+}
+
+/* -------------------------------------------------------------------------- */
+/* one image on the reference's structs                                       */
+
+extern "C" int jgpu_decode_image(jgpu_ctx *ctx, const jpeg_header *header, image *img,
+                                 jpeg_decode_out out) {
+  if (!ctx || !header || !img) return jgpu_fail("jgpu_decode_image: NULL argument");
+  if (out != JPEG_DECODE_YUV && out != JPEG_DECODE_RGB) {
+    return jgpu_fail("jgpu_decode_image: output must be yuv or rgb");
+  }
+  jgpu_image_desc d;
+  jgpu_layout lay;
+  if (jgpu_desc_from_header(header, &d) || jgpu_layout_query(&d, &lay)) return EXIT_FAILURE;
+  if (img->nplanes != d.ncomps || img->width != d.width || img->height != d.height ||
+      !img->coef) {
+    return jgpu_fail("jgpu_decode_image: image surface does not match the header");
+  }
+  for (int p = 0; p < d.ncomps; p++) {
+    const image_plane *pl = &img->plane[p];
+    if (pl->width != lay.plane[p].width || pl->height != lay.plane[p].height ||
+        pl->coef - img->coef != lay.plane[p].coef_off) {
+      return jgpu_fail("jgpu_decode_image: plane %d layout differs from image_init's", p);
+    }
+  }
+  uint16_t qt[NQUANT_MAX * 64];
+  for (int t = 0; t < NQUANT_MAX; t++) memcpy(qt + 64 * t, header->quant[t].tbl, 128);
+  d.coef_off = 0;
+  d.qtab_set = 0;
+  if (out == JPEG_DECODE_RGB) {
+    d.rgb_off = 0;
+    d.yuv_off = -1;
+    return jgpu_decode_batch_host(ctx, &d, 1, JGPU_OUT_RGB, img->coef, qt, 1, img->pixels, nullptr);
+  }
+  /* YUV: planes are separate allocations on the image surface */
+  d.yuv_off = 0;
+  Buffer &stage = ctx->h_out[kHostStreams - 1];
+  if (stage.reserve((size_t)lay.data_len)) return EXIT_FAILURE;
+  if (jgpu_decode_batch_host(ctx, &d, 1, JGPU_OUT_YUV, img->coef, qt, 1, nullptr,
+                             (uint8_t *)stage.ptr)) {
+    return EXIT_FAILURE;
+  }
+  for (int p = 0; p < d.ncomps; p++) {
+    memcpy(img->plane[p].data, (uint8_t *)stage.ptr + lay.plane[p].data_off,
+           (size_t)lay.plane[p].width * lay.plane[p].height);
+  }
+  return EXIT_SUCCESS;
+}
