@@ -1,0 +1,91 @@
+"""GPU parity: the CUDA path against the CPU oracle, bit for bit.
+
+Y/Cb/Cr planes must equal what the reference's xjpeg + glj_real_idct8x8 produce
+(src/xjpeg.c:565-584, src/dct.c:100-121); RGB must equal the colour oracle
+(oracle/oracle_pipeline.c, from res/yuv.fs.glsl:11-23).  Tolerance: none.
+"""
+import numpy as np
+import pytest
+
+import jpeg_gpu_b200 as J
+from jpeg_gpu_b200 import synth
+from util import compare_batch, gpu_batch, make_batch, oracle_batch
+
+pytestmark = pytest.mark.gpu
+
+SIZES = [(8, 8), (16, 16), (70, 50), (64, 48), (129, 65), (512, 512), (1000, 563)]
+KINDS = ["natural", "dense", "dc", "zero", "impulse"]
+
+
+@pytest.mark.parametrize("force_generic", [True, False])
+@pytest.mark.parametrize("ss", ["gray", "444", "422", "420", "440", "411"])
+def test_parity_by_subsampling(gpu_ctx, checker, ss, force_generic):
+    shapes = [(w, h, ss) for (w, h) in SIZES]
+    descs, coef_len, rgb_len, yuv_len = make_batch(shapes)
+    q = synth.quality_tables(85)
+    coef = synth.batch_coefficients(descs, coef_len, q, kinds=KINDS)
+    exp_rgb, exp_yuv = oracle_batch(checker, descs, coef, q, rgb_len, yuv_len)
+    got_rgb, got_yuv = gpu_batch(gpu_ctx, descs, coef, q, rgb_len, yuv_len, force_generic)
+    compare_batch(descs, got_rgb, got_yuv, exp_rgb, exp_yuv)
+
+
+@pytest.mark.parametrize("force_generic", [True, False])
+def test_parity_mixed_batch_two_table_sets(gpu_ctx, checker, force_generic):
+    shapes = [(512, 512, "gray"), (1920, 1080, "420"), (70, 50, "444"), (640, 360, "422"), (33, 17, "420"),
+              (256, 256, "411"), (48, 80, "440"), (1000, 563, "420")]
+    descs, coef_len, rgb_len, yuv_len = make_batch(shapes, n_sets=2)
+    q = np.stack([synth.quality_tables(85), synth.quality_tables(40)])
+    coef = synth.batch_coefficients(descs, coef_len, q, kinds=KINDS)
+    exp_rgb, exp_yuv = oracle_batch(checker, descs, coef, q, rgb_len, yuv_len)
+    got_rgb, got_yuv = gpu_batch(gpu_ctx, descs, coef, q, rgb_len, yuv_len, force_generic)
+    compare_batch(descs, got_rgb, got_yuv, exp_rgb, exp_yuv)
+
+
+@pytest.mark.parametrize("force_generic", [True, False])
+def test_rgb_only_and_yuv_only(gpu_ctx, checker, force_generic):
+    shapes = [(320, 240, "420"), (100, 100, "444"), (64, 64, "gray")]
+    q = synth.quality_tables(85)
+    descs, coef_len, rgb_len, yuv_len = make_batch(shapes, want_yuv=True)
+    coef = synth.batch_coefficients(descs, coef_len, q)
+    exp_rgb, exp_yuv = oracle_batch(checker, descs, coef, q, rgb_len, yuv_len)
+    got_rgb, got_yuv = gpu_batch(gpu_ctx, descs, coef, q, rgb_len, yuv_len, force_generic, want_rgb=False)
+    assert got_rgb is None
+    compare_batch(descs, None, got_yuv, exp_rgb, exp_yuv)
+    descs2, coef_len2, rgb_len2, _ = make_batch(shapes, want_yuv=False)
+    got_rgb, got_yuv = gpu_batch(gpu_ctx, descs2, coef, q, rgb_len2, 0, force_generic)
+    assert got_yuv is None
+    compare_batch(descs2, got_rgb, None, exp_rgb, None)
+
+
+def test_dequantisation_wraps_like_a_short(gpu_ctx, checker):
+    """src/xjpeg.c:501-503,524-527 store the int product into a short.  Inputs
+    whose IDCT output stays inside int16 after the wrap must still match."""
+    shapes = [(64, 64, "420"), (40, 24, "444")]
+    descs, coef_len, rgb_len, yuv_len = make_batch(shapes)
+    q = synth.quality_tables(85)
+    rng = np.random.default_rng(7)
+    coef = synth.batch_coefficients(descs, coef_len, q, kinds=["zero"])
+    # sparse large coefficients: products exceed 32767 and wrap, outputs stay bounded
+    idx = rng.choice(coef_len, size=coef_len // 40, replace=False)
+    coef[idx] = rng.integers(-32768, 32768, size=idx.size).astype(np.int16)
+    exp_rgb, exp_yuv = oracle_batch(checker, descs, coef, q, rgb_len, yuv_len)
+    for fg in (True, False):
+        got_rgb, got_yuv = gpu_batch(gpu_ctx, descs, coef, q, rgb_len, yuv_len, fg)
+        compare_batch(descs, got_rgb, got_yuv, exp_rgb, exp_yuv)
+
+
+def test_host_batch_api(gpu_ctx, checker):
+    shapes = [(1920, 1080, "420"), (512, 512, "gray"), (70, 50, "422")]
+    descs, coef_len, rgb_len, yuv_len = make_batch(shapes)
+    q = synth.quality_tables(85)
+    coef = synth.batch_coefficients(descs, coef_len, q)
+    exp_rgb, exp_yuv = oracle_batch(checker, descs, coef, q, rgb_len, yuv_len)
+    rgb = np.zeros(rgb_len, dtype=np.uint8)
+    yuv = np.zeros(yuv_len, dtype=np.uint8)
+    gpu_ctx.decode_batch_host(descs, coef, q, rgb, yuv)       # pageable buffers
+    compare_batch(descs, rgb, yuv, exp_rgb, exp_yuv)
+    import torch
+    p_coef = torch.from_numpy(coef).pin_memory()
+    p_rgb = torch.zeros(rgb_len, dtype=torch.uint8).pin_memory()
+    gpu_ctx.decode_batch_host(descs, p_coef, q, p_rgb, None)  # pinned buffers
+    compare_batch(descs, p_rgb.numpy(), None, exp_rgb, None)
