@@ -1,0 +1,294 @@
+#!/usr/bin/env python
+"""bench.py — coefficient -> RGB block decode throughput on B200.
+
+Metric (BASELINE.json): Mpixels/s decoded (coeff -> RGB); HBM GB/s vs roofline.
+Workload at every N: BASELINE config 3 — 3840x2160 4:2:0, batch 256 synthetic
+coefficient sets PER GPU (weak scaling), inputs resident in HBM for `value`,
+host buffers with H2D/D2H inside the timed region for `e2e`.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (width, height, subsampling, images per GPU)
+    "4k420_b256": (3840, 2160, "420", 256),
+    "4k422_b128": (3840, 2160, "422", 128),
+    "1080p420_b1": (1920, 1080, "420", 1),
+    "4k420_b16": (3840, 2160, "420", 16),
+}
+METRIC = "Mpixels/s decoded (coeff->RGB)"
+UNIT = "Mpixels/s"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, copy read+write)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi style clock / throttle-reason samples during the timed region (NVML)."""
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self._nv = None
+
+    def _run(self):
+        nv = self._nv
+        names = {
+            nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+            nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+            nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+            nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+            nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake",
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.05)
+
+    def __enter__(self):
+        if self._nv is not None:
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def build_batch(workload: str):
+    import jpeg_gpu_b200 as J
+    w, h, ss, n = WORKLOADS[workload]
+    hs, vs = J.SUBSAMPLINGS[ss]
+    descs = [J.ImageDesc(w, h, hs, vs, tq=(0, 1, 1)[:len(hs)]) for _ in range(n)]
+    coef_len, rgb_len, _ = J.pack_batch(descs)
+    return descs, coef_len, rgb_len
+
+
+def cpu_reference_run(workload: str, sample_images: int, repeats: int, threads: int):
+    """Times the reference's CPU implementation of the path (oracle/_ref when it
+    was compiled, else our C port) on `sample_images` images of the workload."""
+    import jpeg_gpu_b200 as J
+    import oracle
+    from jpeg_gpu_b200 import synth
+    lib = oracle.best()
+    w, h, ss, n = WORKLOADS[workload]
+    hs, vs = J.SUBSAMPLINGS[ss]
+    k = max(1, min(sample_images, n))
+    descs = [J.ImageDesc(w, h, hs, vs, tq=(0, 1, 1)[:len(hs)]) for _ in range(k)]
+    coef_len, rgb_len, _ = J.pack_batch(descs)
+    q = synth.quality_tables(85)
+    # distinct coefficients for 2 images, tiled: the CPU cost does not depend on the values' identity
+    base = min(k, 2)
+    coef = np.zeros(coef_len, dtype=np.int16)
+    for i, d in enumerate(descs):
+        if i < base:
+            c = synth.image_coefficients(d, q, synth.SEED_BASE + i)
+        else:
+            c = coef[descs[i % base].coef_off:descs[i % base].coef_off + d.query_layout().coef_len]
+        coef[d.coef_off:d.coef_off + c.size] = c
+    rows = []
+    for d in descs:
+        g = oracle.geometry(d.width, d.height, d.hsamp, d.vsamp)
+        rows.append(oracle.make_desc(g, d.tq, d.coef_off, d.rgb_off, 0))
+    rows = np.stack(rows)
+    qq = q.reshape(1, 4, 64)
+    times = []
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        lib.decode_batch(rows, coef, qq, rgb_len, 0, threads)
+        times.append(time.perf_counter() - t0)
+    mpx = k * w * h / 1e6
+    return lib.kind, mpx, times
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="4k420_b256", choices=sorted(WORKLOADS))
+    ap.add_argument("--e2e-steps", type=int, default=None, help="steps of the host-buffer leg (default: min(steps, 5))")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--force-generic", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    w, h, ss, n_img = WORKLOADS[args.workload]
+    threads = os.cpu_count() or 1
+
+    # ---------------------------------------------------------------- reference arm
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        sample = 16
+        kind, mpx, times = cpu_reference_run(args.workload, sample, args.warmup + args.steps, threads)
+        timed = times[args.warmup:]
+        total = sum(timed)
+        value = mpx * len(timed) / total
+        line = {
+            "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(timed),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": f"{w}x{h} {ss} coeff->RGB, CPU path of the reference "
+                                   f"(xjpeg dequant + glj_real_idct8x8 + clamp, yuv.fs.glsl colour), "
+                                   f"each step = {sample} images of the batch-{n_img} workload"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind,
+                             "sample": f"{sample} images per step x {len(timed)} steps, {threads} threads"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+        }
+        print(json.dumps(line))
+        return 0
+
+    # ---------------------------------------------------------------- our arm
+    import torch
+    import jpeg_gpu_b200 as J
+    from jpeg_gpu_b200 import shard, synth
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a CUDA device; there is no CPU fallback")
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    descs, coef_len, rgb_len = build_batch(args.workload)
+    # quantisation tables: rank 0's copy is THE copy (one broadcast)
+    q = shard.broadcast_tables(synth.quality_tables(85), device=dev)
+    d_q = torch.from_numpy(q.astype(np.int16).reshape(-1)).to(dev)
+    # per-rank batch: image seeds continue across ranks
+    d_coef = synth.torch_batch_coefficients(descs, coef_len, q, dev, first_index=rank * n_img)
+    d_rgb = torch.zeros(rgb_len, dtype=torch.uint8, device=dev)
+    ctx = J.Context(local_rank)
+    plan = ctx.plan(descs, rgb=True, yuv=False, force_generic=args.force_generic)
+    px_per_step = n_img * w * h
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        plan.run(d_coef, d_q, d_rgb)
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clk:
+        ev0.record()
+        for _ in range(args.steps):
+            plan.run(d_coef, d_q, d_rgb)
+        ev1.record()
+        barrier()
+    ms = ev0.elapsed_time(ev1)
+    ms = shard.max_over_ranks(ms, dev)
+    ms_per_step = ms / args.steps
+    value = world * px_per_step / 1e6 / (ms_per_step / 1e3)
+
+    # roofline of the dominant kernel: algorithmic bytes / device time of the step
+    peak, peak_src = peaks()
+    achieved = plan.bytes / (ms_per_step * 1e-3) / 1e9
+    coef_bytes = sum(128 * d.query_layout().coded_blocks for d in descs)
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src,
+                "read_only_frac": coef_bytes / (ms_per_step * 1e-3) / 1e9 / peak,
+                "algorithmic_bytes_per_launch": plan.bytes}
+
+    # end-to-end: host buffers through the C ABI, copies inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        e2e_steps = args.e2e_steps or min(args.steps, 5)
+        h_coef = torch.empty(coef_len, dtype=torch.int16).pin_memory()
+        h_coef.copy_(d_coef.cpu())
+        h_rgb = torch.zeros(rgb_len, dtype=torch.uint8).pin_memory()
+        ctx.decode_batch_host(descs, h_coef, q, h_rgb, None, force_generic=args.force_generic)  # warm-up
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            ctx.decode_batch_host(descs, h_coef, q, h_rgb, None, force_generic=args.force_generic)
+        barrier()
+        dt = shard.max_over_ranks(time.perf_counter() - t0, dev)
+        assert torch.equal(h_rgb[:4096], d_rgb[:4096].cpu()), "host path and device path disagree"
+        e2e = {"value": world * px_per_step * e2e_steps / 1e6 / dt, "unit": UNIT,
+               "h2d_bytes_per_step": int(coef_bytes + q.nbytes), "d2h_bytes_per_step": int(rgb_len),
+               "steps": e2e_steps, "ms_per_step": 1e3 * dt / e2e_steps}
+        del h_coef, h_rgb
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        kind, mpx, times = cpu_reference_run(args.workload, 16, 4, threads)
+        best = min(times[1:])
+        cpu = {"value": mpx / best, "unit": UNIT, "cores": threads, "kind": kind,
+               "sample": f"16 of the {n_img} images, best of 3 after 1 warm-up, {threads} threads"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{w}x{h} {ss}, batch {n_img} per GPU, synthetic coefficient planes (SURVEY 8d)",
+                       "l2": "inputs larger than L2 (%.2f GB coef + %.2f GB rgb per GPU)" % (coef_len * 2 / 1e9, rgb_len / 1e9),
+                       "path": "generic" if args.force_generic else "fused", "parallelism": f"images sharded x{world}"},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": args.steps * plan.launches, "clocks": clk.summary(),
+        }
+        print(json.dumps(line))
+    plan.close()
+    ctx.close()
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -48,27 +48,32 @@ struct ColourWork {
 
 /* ---- fused path ---------------------------------------------------------- */
 
-/* Subsampling classes the fused kernel specialises on. */
+/* Sampling classes the fused kernel is instantiated for (chroma 1x1). */
 enum FusedMode : int32_t {
-  kModeGray = 0, /* 1 component                         MCU  8x8,  1 block  */
-  kMode444 = 1,  /* 1x1,1x1,1x1                         MCU  8x8,  3 blocks */
-  kMode422 = 2,  /* 2x1,1x1,1x1                         MCU 16x8,  4 blocks */
-  kMode420 = 3,  /* 2x2,1x1,1x1                         MCU 16x16, 6 blocks */
+  kModeGray = 0, /* 1 component                 MCU  8x8,  1 block  */
+  kMode444 = 1,  /* luma 1x1                    MCU  8x8,  3 blocks */
+  kMode422 = 2,  /* luma 2x1                    MCU 16x8,  4 blocks */
+  kMode420 = 3,  /* luma 2x2                    MCU 16x16, 6 blocks */
+  kMode440 = 4,  /* luma 1x2                    MCU  8x16, 4 blocks */
+  kNumFusedModes = 5
 };
 
-/* One image for the fused kernel. */
+/* One image for the fused kernel.  block0[] are GLOBAL block indices: the
+ * coefficient buffer viewed as rows of 64 int16 (128 bytes). */
 struct FusedImage {
-  int64_t coef_off[3]; /* first int16 of each plane */
   int64_t rgb_off;
-  int64_t yuv_off[3];  /* byte offsets of the padded planes, or -1 */
+  int32_t block0[3];
+  int32_t hblocks[3];
   int32_t width, height;
-  int32_t hblocks[3];  /* blocks per block row, per plane */
-  int32_t nhmb, nvmb;
-  int32_t qidx[3];
-  int32_t mode;
-  int32_t tiles_per_row; /* ceil(nhmb / MCUs per tile) */
-  int32_t first_tile;    /* index of this image's first tile in the batch */
+  int32_t qidx[3];     /* 64-entry table index: qtab_set*4 + tq */
   int32_t reserved;
+};
+
+/* One tile: a run of MCUs in one MCU row of one image. */
+struct TileRef {
+  int32_t img;
+  int16_t mrow; /* MCU row */
+  int16_t mx0;  /* first MCU (units of the mode's tile width, see jgpu_fused.cu) */
 };
 
 }  // namespace jgpu

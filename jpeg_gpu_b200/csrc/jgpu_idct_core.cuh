@@ -181,5 +181,27 @@ JGPU_DEV void column_pass(pair32 (&m)[8][8]) {
   }
 }
 
+/* Same column pass, two columns at a time, handing each finished column pair
+ * (8 rows x 2 adjacent columns) to `sink(j, left, right)`, j = 0..3.  Lets a
+ * consumer narrow the samples as they are produced instead of keeping all 64
+ * un-floored pairs live. */
+template <typename Sink>
+JGPU_DEV void column_pass_by_pairs(pair32 (&m)[8][8], Sink &&sink) {
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    pair32 u[8], v[8];
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+      u[r] = m[r][2 * j];
+      v[r] = m[r][2 * j + 1];
+    }
+    u[0] = p_add_half(u[0]);
+    v[0] = p_add_half(v[0]);
+    inv_pass8(u);
+    inv_pass8(v);
+    sink(j, u, v);
+  }
+}
+
 }  // namespace jgpu
 #endif

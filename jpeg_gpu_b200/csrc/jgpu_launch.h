@@ -23,24 +23,19 @@ cudaError_t launch_planes_to_rgb(const ColourImage *imgs, const ColourWork *work
 /* ---- fused path (jgpu_fused.cu) ------------------------------------------ */
 
 struct FusedPlan {
-  void *d_images = nullptr;   /* FusedImage[n] */
-  void *d_tiles = nullptr;    /* per-tile work items */
-  int n_images = 0;
-  int n_tiles = 0;
-  int sm_count = 0;
-  unsigned flags = 0;
-  int *img_first_tile = nullptr; /* host, n+1 entries */
+  void *impl = nullptr; /* FusedPlanImpl, jgpu_fused.cu */
 };
 
-/* false while the fused kernel is not built into the library */
 bool fused_available();
 cudaError_t fused_configure(int device);
+/* modes[i] is the FusedMode of image i.  Returns 0 or 1 (jgpu_fail). */
 int fused_plan_build(FusedPlan &fp, const jgpu_image_desc *descs, const jgpu_layout *layouts,
                      const int *modes, int n, unsigned flags, int sm_count);
 void fused_plan_release(FusedPlan &fp);
-cudaError_t fused_plan_launch(const FusedPlan &fp, int i0, int i1, const int16_t *coef,
-                              const uint16_t *qtabs, uint8_t *rgb, uint8_t *yuv,
-                              cudaStream_t stream);
+int fused_plan_launches(const FusedPlan &fp);
+/* Enqueues images [i0, i1).  Returns 0 or 1 (jgpu_fail). */
+int fused_plan_launch(FusedPlan &fp, int i0, int i1, const int16_t *coef, const uint16_t *qtabs,
+                      int n_sets, uint8_t *rgb, cudaStream_t stream);
 
 }  // namespace jgpu
 #endif

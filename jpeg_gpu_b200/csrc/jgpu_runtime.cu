@@ -202,9 +202,12 @@ static bool fused_eligible(const jgpu_image_desc &d, const jgpu_layout &lay, uns
     if (d.hsamp[0] == 1 && d.vsamp[0] == 1) *mode = kMode444;
     else if (d.hsamp[0] == 2 && d.vsamp[0] == 1) *mode = kMode422;
     else if (d.hsamp[0] == 2 && d.vsamp[0] == 2) *mode = kMode420;
+    else if (d.hsamp[0] == 1 && d.vsamp[0] == 2) *mode = kMode440;
     else return false;
   }
-  if (!(flags & JGPU_OUT_RGB)) return false;
+  /* the fused kernel writes RGB only and addresses coefficients by 128-byte row */
+  if ((flags & (JGPU_OUT_RGB | JGPU_OUT_YUV)) != JGPU_OUT_RGB) return false;
+  if (d.coef_off & 63) return false;
   return true;
 }
 
@@ -354,7 +357,7 @@ extern "C" void jgpu_plan_destroy(jgpu_plan *plan) {
 
 extern "C" int jgpu_plan_launches(const jgpu_plan *plan) {
   if (!plan) return 0;
-  if (plan->fused) return 1;
+  if (plan->fused) return fused_plan_launches(plan->fp);
   return (plan->flags & JGPU_OUT_RGB) ? 2 : 1;
 }
 
@@ -362,12 +365,11 @@ extern "C" int64_t jgpu_plan_bytes(const jgpu_plan *plan) { return plan ? plan->
 
 /* Runs images [i0, i1) of the plan. */
 static int plan_run_range(jgpu_plan *plan, int i0, int i1, const int16_t *d_coef,
-                          const uint16_t *d_qtabs, uint8_t *d_rgb, uint8_t *d_yuv,
+                          const uint16_t *d_qtabs, int n_sets, uint8_t *d_rgb, uint8_t *d_yuv,
                           cudaStream_t stream) {
   if (i0 >= i1) return 0;
   if (plan->fused) {
-    CU_TRY(fused_plan_launch(plan->fp, i0, i1, d_coef, d_qtabs, d_rgb, d_yuv, stream));
-    return 0;
+    return fused_plan_launch(plan->fp, i0, i1, d_coef, d_qtabs, n_sets, d_rgb, stream);
   }
   uint8_t *planes = plan->use_scratch ? (uint8_t *)plan->d_scratch.ptr : d_yuv;
   int c0 = plan->img_first_pair_cta[i0], c1 = plan->img_first_pair_cta[i1];
@@ -396,7 +398,7 @@ extern "C" int jgpu_plan_run(jgpu_plan *plan, const int16_t *d_coef, const uint1
     }
   }
   CU_TRY(cudaSetDevice(plan->ctx->device));
-  return plan_run_range(plan, 0, plan->n, d_coef, d_qtabs, d_rgb, d_yuv, (cudaStream_t)stream);
+  return plan_run_range(plan, 0, plan->n, d_coef, d_qtabs, n_sets, d_rgb, d_yuv, (cudaStream_t)stream);
 }
 
 /* -------------------------------------------------------------------------- */
@@ -504,7 +506,7 @@ extern "C" int jgpu_decode_batch_host(jgpu_ctx *ctx, const jgpu_image_desc *desc
       }
     }
     /* kernels */
-    if (plan_run_range(plan, i0, i1, d_coef, d_qtabs, d_rgb, d_yuv, st)) return EXIT_FAILURE;
+    if (plan_run_range(plan, i0, i1, d_coef, d_qtabs, n_sets, d_rgb, d_yuv, st)) return EXIT_FAILURE;
     /* D2H */
     if (rgb_pinned && yuv_pinned) {
       for (int i = i0; i < i1; i++) {

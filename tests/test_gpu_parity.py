@@ -17,11 +17,17 @@ SIZES = [(8, 8), (16, 16), (70, 50), (64, 48), (129, 65), (512, 512), (1000, 563
 KINDS = ["natural", "dense", "dc", "zero", "impulse"]
 
 
-@pytest.mark.parametrize("force_generic", [True, False])
+# (force_generic, want_yuv): RGB-only plans take the fused kernel for gray/444/422/420/440,
+# plans that also want the planes (or 411, or force_generic) take the two-kernel generic path
+PATHS = [(False, False), (False, True), (True, False), (True, True)]
+PATH_IDS = ["fused-rgb", "auto-rgb+yuv", "generic-rgb", "generic-rgb+yuv"]
+
+
+@pytest.mark.parametrize("force_generic,want_yuv", PATHS, ids=PATH_IDS)
 @pytest.mark.parametrize("ss", ["gray", "444", "422", "420", "440", "411"])
-def test_parity_by_subsampling(gpu_ctx, checker, ss, force_generic):
+def test_parity_by_subsampling(gpu_ctx, checker, ss, force_generic, want_yuv):
     shapes = [(w, h, ss) for (w, h) in SIZES]
-    descs, coef_len, rgb_len, yuv_len = make_batch(shapes)
+    descs, coef_len, rgb_len, yuv_len = make_batch(shapes, want_yuv=want_yuv)
     q = synth.quality_tables(85)
     coef = synth.batch_coefficients(descs, coef_len, q, kinds=KINDS)
     exp_rgb, exp_yuv = oracle_batch(checker, descs, coef, q, rgb_len, yuv_len)
@@ -29,16 +35,28 @@ def test_parity_by_subsampling(gpu_ctx, checker, ss, force_generic):
     compare_batch(descs, got_rgb, got_yuv, exp_rgb, exp_yuv)
 
 
-@pytest.mark.parametrize("force_generic", [True, False])
-def test_parity_mixed_batch_two_table_sets(gpu_ctx, checker, force_generic):
+@pytest.mark.parametrize("force_generic,want_yuv", PATHS, ids=PATH_IDS)
+def test_parity_mixed_batch_two_table_sets(gpu_ctx, checker, force_generic, want_yuv):
     shapes = [(512, 512, "gray"), (1920, 1080, "420"), (70, 50, "444"), (640, 360, "422"), (33, 17, "420"),
-              (256, 256, "411"), (48, 80, "440"), (1000, 563, "420")]
-    descs, coef_len, rgb_len, yuv_len = make_batch(shapes, n_sets=2)
+              (256, 256, "411"), (48, 80, "440"), (1000, 563, "420"), (2048, 16, "420"), (16, 2048, "422"),
+              (1600, 1200, "444"), (1537, 9, "gray"), (3840, 2160, "420")]
+    descs, coef_len, rgb_len, yuv_len = make_batch(shapes, want_yuv=want_yuv, n_sets=2)
     q = np.stack([synth.quality_tables(85), synth.quality_tables(40)])
     coef = synth.batch_coefficients(descs, coef_len, q, kinds=KINDS)
     exp_rgb, exp_yuv = oracle_batch(checker, descs, coef, q, rgb_len, yuv_len)
     got_rgb, got_yuv = gpu_batch(gpu_ctx, descs, coef, q, rgb_len, yuv_len, force_generic)
     compare_batch(descs, got_rgb, got_yuv, exp_rgb, exp_yuv)
+
+
+def test_fused_many_tiles_per_cta(gpu_ctx, checker):
+    """More tiles than resident CTAs, so the persistent loop and the smem ring wrap."""
+    shapes = [(3840, 2160, "420")] * 3 + [(3840, 2160, "422")] * 2 + [(1920, 1080, "444")] * 2 + [(4096, 1024, "gray")]
+    descs, coef_len, rgb_len, _ = make_batch(shapes, want_yuv=False)
+    q = synth.quality_tables(85)
+    coef = synth.batch_coefficients(descs, coef_len, q, kinds=["natural", "dense"])
+    exp_rgb, _ = oracle_batch(checker, descs, coef, q, rgb_len, 0, nthreads=16)
+    got_rgb, _ = gpu_batch(gpu_ctx, descs, coef, q, rgb_len, 0)
+    compare_batch(descs, got_rgb, None, exp_rgb, None)
 
 
 @pytest.mark.parametrize("force_generic", [True, False])
@@ -62,6 +80,7 @@ def test_dequantisation_wraps_like_a_short(gpu_ctx, checker):
     whose IDCT output stays inside int16 after the wrap must still match."""
     shapes = [(64, 64, "420"), (40, 24, "444")]
     descs, coef_len, rgb_len, yuv_len = make_batch(shapes)
+    descs_rgb, _, rgb_len2, _ = make_batch(shapes, want_yuv=False)
     q = synth.quality_tables(85)
     rng = np.random.default_rng(7)
     coef = synth.batch_coefficients(descs, coef_len, q, kinds=["zero"])
@@ -72,6 +91,9 @@ def test_dequantisation_wraps_like_a_short(gpu_ctx, checker):
     for fg in (True, False):
         got_rgb, got_yuv = gpu_batch(gpu_ctx, descs, coef, q, rgb_len, yuv_len, fg)
         compare_batch(descs, got_rgb, got_yuv, exp_rgb, exp_yuv)
+    got_rgb, _ = gpu_batch(gpu_ctx, descs_rgb, coef, q, rgb_len2, 0)   # fused kernel
+    assert rgb_len2 == rgb_len
+    compare_batch(descs_rgb, got_rgb, None, exp_rgb, None)
 
 
 def test_host_batch_api(gpu_ctx, checker):
