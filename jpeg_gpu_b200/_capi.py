@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libjpeg_gpu_b200.so")
+# JGPU_LIB_PATH selects a tuning variant built by csrc/Makefile (VARIANT=...); default is the product build
+LIB_PATH = os.environ.get("JGPU_LIB_PATH") or os.path.join(HERE, "libjpeg_gpu_b200.so")
 
 NCOMPS_MAX = 3
 NQUANT_MAX = 4

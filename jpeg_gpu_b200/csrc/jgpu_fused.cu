@@ -44,41 +44,68 @@
 
 namespace jgpu {
 
+/* Build-time tuning knobs (A/B-tested on the GPU, see profiles/). */
+#ifndef JGPU_FUSED_G
+#define JGPU_FUSED_G 1          /* 32-pair column groups per tile */
+#endif
+#ifndef JGPU_FUSED_STAGES
+#define JGPU_FUSED_STAGES 1     /* smem stages per CTA */
+#endif
+#ifndef JGPU_FUSED_MINCTAS
+#define JGPU_FUSED_MINCTAS 0    /* 0: size registers for 12 warps per SM */
+#endif
+
 constexpr int kBoxRows = 32;                 /* blocks per TMA box */
 constexpr int kBoxBytes = kBoxRows * 128;    /* 4 KB */
-constexpr int kStageTail = 1024;             /* tables + header, keeps boxes 1 KB aligned */
+constexpr int kStageTail = 1024;             /* the three tables; keeps boxes 1 KB aligned */
 constexpr int kQtabBytes = 64 * 4;           /* one table as int32 */
+constexpr int kMaxYBoxPairs = 6;             /* luma warps per CTA, upper bound */
+constexpr int kMaxCBoxes = 4;                /* chroma warps per CTA, upper bound */
 
-struct __align__(16) StageHeader {
+/* What the producer thread prepares for one tile: where its boxes start in the
+ * coefficient buffer and where its pixels go.  Two of these live in shared
+ * memory (tile parity), so the next tile can be described while the current
+ * one is still being read. */
+struct __align__(16) TileDesc {
   long long rgb_base;   /* byte offset in the rgb buffer of the tile's top-left pixel */
   int32_t width_left;   /* visible pixels from the tile's left edge to the image's right edge */
   int32_t rows_left;    /* visible rows from the tile's top row to the image's bottom */
   int32_t pitch;        /* bytes per output row */
   int32_t flags;        /* bit 0: output rows are 16-byte aligned */
-  int32_t pad[2];
+  int32_t qidx[3];      /* table indices */
+  int32_t pad0;
+  int32_t yfirst[kMaxYBoxPairs];  /* first block (global index) of each luma warp's 64-block run */
+  int32_t cfirst[2][kMaxCBoxes];  /* first Cb / Cr block of each chroma warp's 32-block run */
+  int32_t pad1[4];
 };
+static_assert(sizeof(TileDesc) % 16 == 0, "TileDesc is read with 128-bit loads");
 
-template <int HS, int VS, bool GRAY>
+/* HS, VS: luma sampling factors (chroma is 1x1); G: 32-pair column groups per tile. */
+template <int HS, int VS, bool GRAY, int G>
 struct Cfg {
-  static constexpr int kYWarps = GRAY ? 3 : VS;
-  static constexpr int kCWarps = GRAY ? 0 : 2 / HS;
+  static constexpr int kYWarps = (GRAY ? 3 : VS) * G;
+  static constexpr int kCWarps = GRAY ? 0 : (2 / HS) * G;
   static constexpr int kWarps = kYWarps + kCWarps;
   static constexpr int kThreads = 32 * kWarps;
-  /* MCUs per tile */
-  static constexpr int kTileMcus = GRAY ? 192 : (HS == 2 ? 32 : 64);
   static constexpr int kMcuW = GRAY ? 8 : 8 * HS;
   static constexpr int kMcuH = GRAY ? 8 : 8 * VS;
+  /* MCUs per tile: every luma warp covers 64 blocks of one block row */
+  static constexpr int kTileMcus = GRAY ? 64 * kYWarps : 64 * G / HS;
+  static constexpr int kTilePx = kTileMcus * kMcuW;
   static constexpr int kBoxes = 2 * kYWarps + 2 * kCWarps;
   static constexpr int kStageBytes = kBoxes * kBoxBytes + kStageTail;
   static constexpr int kTables = GRAY ? 1 : 3;
-  /* exchange buffer: colour offsets of one chroma block, 8 rows */
-  static constexpr int kExRow = HS == 2 ? 96 : 48;        /* bytes per chroma row */
-  static constexpr int kExTask = 8 * kExRow + 16;          /* padded: odd multiple of 16 */
-  static constexpr int kExRegion1 = 32 * kExTask + 64;     /* HS==1: odd MCUs live here */
-  static constexpr int kExBytes = GRAY ? 0 : (HS == 2 ? 32 * kExTask : 2 * 32 * kExTask + 64 + 64);
+  /* exchange buffer: colour offsets of one chroma block (8 rows).
+   * HS==2: per sample (rc|gc<<16, bc) = 8 bytes, 64 bytes per row.
+   * HS==1: per horizontal sample pair (R2, G2, B2) s16x2 words = 12 bytes, 48 per row. */
+  static constexpr int kExRow = HS == 2 ? 64 : 48;
+  static constexpr int kExTask = 8 * kExRow + 16;            /* odd multiple of 16 bytes */
+  static constexpr int kExRegion1 = 32 * G * kExTask + 64;   /* HS==1: odd MCUs live here */
+  static constexpr int kExBytes = GRAY ? 0 : (HS == 2 ? 32 * G * kExTask : 2 * 32 * G * kExTask + 128);
   static constexpr int kChannels = GRAY ? 1 : 3;
-  /* resident CTAs per SM the register budget is sized for (smem allows no more) */
-  static constexpr int kMinCtas = kThreads <= 64 ? 4 : (kThreads <= 96 ? 3 : 2);
+  /* resident CTAs per SM the register allocation is sized for */
+  static constexpr int kMinCtas = JGPU_FUSED_MINCTAS > 0 ? JGPU_FUSED_MINCTAS : 384 / kThreads;
+  static_assert(kYWarps <= kMaxYBoxPairs && kCWarps <= kMaxCBoxes, "TileDesc too small");
 };
 
 /* ---- PTX wrappers ---------------------------------------------------------- */
@@ -152,6 +179,14 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
                "r"(v.z), "r"(v.w)
                : "memory");
 }
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint2 lds64(uint32_t addr) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+  return v;
+}
 __device__ __forceinline__ void stg128_stream(uint8_t *p, uint4 v) {
   asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y),
                "r"(v.z), "r"(v.w)
@@ -219,168 +254,219 @@ __device__ __forceinline__ void rgb4(uint32_t ya, uint32_t yb, uint32_t ra, uint
   w2 = __byte_perm(u, Bb, 0x6324);                  /* B2 R3 G3 B3 */
 }
 
-/* Stores `nbytes` (<= 48) of one output row segment. */
-__device__ __forceinline__ void store_row(uint8_t *dst, const uint32_t (&w)[12], int nbytes,
-                                          bool fast) {
-  if (fast && nbytes == 48) {
-    stg128_stream(dst, make_uint4(w[0], w[1], w[2], w[3]));
-    stg128_stream(dst + 16, make_uint4(w[4], w[5], w[6], w[7]));
-    stg128_stream(dst + 32, make_uint4(w[8], w[9], w[10], w[11]));
-  } else {
-#pragma unroll
-    for (int i = 0; i < 12; i++) {
-#pragma unroll
-      for (int b = 0; b < 4; b++) {
-        if (4 * i + b < nbytes) dst[4 * i + b] = (uint8_t)(w[i] >> (8 * b));
-      }
-    }
-  }
+/* Cold path: a row segment that is cropped or not 16-byte aligned. */
+__device__ __noinline__ void store_row_slow(uint8_t *dst, uint4 a, uint4 b, uint4 c, int nbytes) {
+  const uint32_t w[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+  for (int i = 0; i < nbytes; i++) dst[i] = (uint8_t)(w[i >> 2] >> (8 * (i & 3)));
 }
 
 /* ---- the kernel ------------------------------------------------------------ */
 
-/* What every role needs to know about the launch; lives in registers. */
-struct TileLoop {
-  uint32_t smem0;      /* shared-space address of stage 0 (1 KB aligned) */
-  uint8_t *smem_gen;   /* the same location as a generic pointer */
-  uint32_t ex0;        /* exchange buffer */
-  uint32_t bar0;       /* mbarriers, one per stage */
-  int n_tiles;
-};
+template <int HS, int VS, bool GRAY, int G, int STAGES>
+__global__ void __launch_bounds__(Cfg<HS, VS, GRAY, G>::kThreads, Cfg<HS, VS, GRAY, G>::kMinCtas)
+k_fused(const __grid_constant__ CUtensorMap tm_rows,   /* (64, rows)            */
+        const __grid_constant__ CUtensorMap tm_pairs,  /* (64, parity, pairs)   */
+        const FusedImage *__restrict__ images, const TileRef *__restrict__ tiles, int n_tiles,
+        const int32_t *__restrict__ qint, uint8_t *__restrict__ rgb) {
+  using C = Cfg<HS, VS, GRAY, G>;
+  constexpr int kDescSlots = STAGES + 1;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  /* dynamic smem is only guaranteed 16-byte aligned: round up to 1 KB for the swizzle */
+  const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t *const smem_gen = smem_raw + (smem0 - smem_u32(smem_raw));
+  const uint32_t ex0 = smem0 + STAGES * C::kStageBytes;
+  const uint32_t desc0 = ex0 + ((C::kExBytes + 15) & ~15);
+  const uint32_t bar0 = desc0 + kDescSlots * (uint32_t)sizeof(TileDesc);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-/* Tile header of stage `s`, as the producer wrote it. */
-struct TileView {
-  long long rgb_base;
-  int width_left, rows_left, pitch;
-  bool fast;
-};
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; s++) mbar_init(bar0 + 8 * s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
 
-template <typename C>
-__device__ __forceinline__ TileView read_header(const TileLoop &L, int s) {
-  const uint32_t a = L.smem0 + s * C::kStageBytes + C::kBoxes * kBoxBytes + 3 * kQtabBytes;
-  const uint4 h0 = lds128(a), h1 = lds128(a + 16);
-  TileView v;
-  v.rgb_base = (long long)(((unsigned long long)h0.y << 32) | h0.x);
-  v.width_left = (int)h0.z;
-  v.rows_left = (int)h0.w;
-  v.pitch = (int)h1.x;
-  v.fast = (h1.y & 1u) != 0;
-  return v;
-}
-
-/* C warps: Cb/Cr block pair -> colour offsets in the exchange buffer. */
-template <int HS, int VS, bool GRAY, int STAGES>
-__device__ __forceinline__ void chroma_role(const TileLoop &L, int cw, int lane) {
-  using C = Cfg<HS, VS, GRAY>;
-  int it = 0;
-  for (int tile = blockIdx.x; tile < L.n_tiles; tile += gridDim.x, it++) {
-    const int s = it % STAGES;
-    mbar_wait(L.bar0 + 8 * s, (uint32_t)(it / STAGES) & 1u);
-    const TileView tv = read_header<C>(L, s);
-    const uint8_t *stp = L.smem_gen + s * C::kStageBytes;
-    const int *qtp = reinterpret_cast<const int *>(stp + C::kBoxes * kBoxBytes);
-    const int mcu = 32 * cw + lane;
-    const bool active = (HS == 2 ? 16 : 8) * mcu < tv.width_left;
-    pair32 m[8][8];
-    if (active) {
-      pair_row_pass(m, stp + (2 * C::kYWarps + cw) * kBoxBytes,
-                    stp + (2 * C::kYWarps + C::kCWarps + cw) * kBoxBytes, lane, qtp + 64, qtp + 128);
-    }
-    named_sync(1, C::kThreads);   /* stage s consumed */
-    if (active) {
-      column_pass(m);
-      const uint32_t base = HS == 2 ? L.ex0 + lane * C::kExTask
-                                    : L.ex0 + (mcu & 1) * C::kExRegion1 + (mcu >> 1) * C::kExTask;
+  /* ---- producer (thread 0): describe a tile, later start its loads -------- */
+  auto prepare = [&](int t, int slot) {
+    const TileRef tr = tiles[t];
+    const FusedImage im = images[tr.img];
+    const int x0 = tr.mx0 * C::kMcuW, y0 = tr.mrow * C::kMcuH;
+    TileDesc d;
+    d.pitch = im.width * C::kChannels;
+    d.rgb_base = im.rgb_off + ((long long)y0 * im.width + x0) * C::kChannels;
+    d.width_left = im.width - x0;
+    d.rows_left = im.height - y0;
+    d.flags = (((reinterpret_cast<uintptr_t>(rgb) + (uintptr_t)d.rgb_base) & 15) == 0 &&
+               (d.pitch & 15) == 0) ? 1 : 0;
+    d.pad0 = 0;
 #pragma unroll
-      for (int k = 0; k < 8; k++) {
-        uint32_t rb[8], gb[8], bb[8];
+    for (int c = 0; c < 3; c++) d.qidx[c] = im.qidx[c];
 #pragma unroll
-        for (int c = 0; c < 8; c++) chroma_offsets_bits(m[k][c], rb[c], gb[c], bb[c]);
-        if (HS == 2) {
-          /* each chroma sample serves a horizontal pixel pair: replicate */
-#pragma unroll
-          for (int v = 0; v < 6; v++) {
-            uint32_t w[4];
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-              const int word = 4 * v + i, c = word / 3, ch = word % 3;
-              const uint32_t src = ch == 0 ? rb[c] : (ch == 1 ? gb[c] : bb[c]);
-              w[i] = __byte_perm(src, src, 0x1010);
-            }
-            sts128(base + k * 96 + 16 * v, make_uint4(w[0], w[1], w[2], w[3]));
-          }
+    for (int w = 0; w < kMaxYBoxPairs; w++) {
+      int first = 0;
+      if (w < C::kYWarps) {
+        if (GRAY) {
+          first = im.block0[0] + tr.mrow * im.hblocks[0] + tr.mx0 + 64 * w;
         } else {
-#pragma unroll
-          for (int v = 0; v < 3; v++) {
-            uint32_t w[4];
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-              const int word = 4 * v + i, j = word / 3, ch = word % 3;
-              const uint32_t s0 = ch == 0 ? rb[2 * j] : (ch == 1 ? gb[2 * j] : bb[2 * j]);
-              const uint32_t s1 = ch == 0 ? rb[2 * j + 1] : (ch == 1 ? gb[2 * j + 1] : bb[2 * j + 1]);
-              w[i] = __byte_perm(s0, s1, 0x5410);
-            }
-            sts128(base + k * 48 + 16 * v, make_uint4(w[0], w[1], w[2], w[3]));
-          }
+          first = im.block0[0] + (tr.mrow * VS + w / G) * im.hblocks[0] + tr.mx0 * HS + 64 * (w % G);
         }
       }
+      d.yfirst[w] = first;
     }
-    named_arrive(2, C::kThreads);   /* offsets of this tile are in the exchange buffer */
-  }
-}
+#pragma unroll
+    for (int cw = 0; cw < kMaxCBoxes; cw++) {
+      const bool on = cw < C::kCWarps;
+      d.cfirst[0][cw] = on ? im.block0[1] + tr.mrow * im.hblocks[1] + tr.mx0 + 32 * cw : 0;
+      d.cfirst[1][cw] = on ? im.block0[2] + tr.mrow * im.hblocks[2] + tr.mx0 + 32 * cw : 0;
+    }
+    d.pad1[0] = d.pad1[1] = d.pad1[2] = d.pad1[3] = 0;
+    *reinterpret_cast<TileDesc *>(smem_gen + (desc0 - smem0) + slot * sizeof(TileDesc)) = d;
+  };
+  auto fire = [&](int slot, int s) {
+    const TileDesc *d = reinterpret_cast<const TileDesc *>(smem_gen + (desc0 - smem0) + slot * sizeof(TileDesc));
+    const uint32_t st = smem0 + s * C::kStageBytes;
+    const uint32_t bar = bar0 + 8 * s;
+    mbar_expect_tx(bar, C::kBoxes * kBoxBytes + C::kTables * kQtabBytes);
+    /* luma: the 32 even-position and the 32 odd-position blocks of each warp's 64-block run */
+#pragma unroll
+    for (int w = 0; w < C::kYWarps; w++) {
+      const int first = d->yfirst[w];
+      tma_load_3d(st + (2 * w) * kBoxBytes, &tm_pairs, 0, first & 1, first >> 1, bar);
+      tma_load_3d(st + (2 * w + 1) * kBoxBytes, &tm_pairs, 0, (first + 1) & 1, (first + 1) >> 1, bar);
+    }
+#pragma unroll
+    for (int cw = 0; cw < C::kCWarps; cw++) {
+      tma_load_2d(st + (2 * C::kYWarps + cw) * kBoxBytes, &tm_rows, 0, d->cfirst[0][cw], bar);
+      tma_load_2d(st + (2 * C::kYWarps + C::kCWarps + cw) * kBoxBytes, &tm_rows, 0, d->cfirst[1][cw], bar);
+    }
+#pragma unroll
+    for (int c = 0; c < C::kTables; c++) {
+      bulk_load(st + C::kBoxes * kBoxBytes + c * kQtabBytes, qint + (size_t)d->qidx[c] * 64,
+                kQtabBytes, bar);
+    }
+  };
 
-/* Y warps: luma block pair -> 16 x 8 pixels of RGB (or grey). */
-template <int HS, int VS, bool GRAY, int STAGES, typename Issue>
-__device__ __forceinline__ void luma_role(const TileLoop &L, int wy, int lane, uint8_t *rgb,
-                                          Issue &&issue) {
-  using C = Cfg<HS, VS, GRAY>;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; s++) {
+      const int t = blockIdx.x + s * gridDim.x;
+      if (t < n_tiles) {
+        prepare(t, s);
+        fire(s, s);
+      }
+    }
+  }
+
+  /* ---- role of this warp: which boxes, which tables, which pixels --------- */
+  const bool is_c = warp >= C::kYWarps;
+  const int cw = warp - C::kYWarps;                       /* chroma warp index */
+  const int box_a = is_c ? 2 * C::kYWarps + cw : 2 * warp;
+  const int box_b = is_c ? 2 * C::kYWarps + C::kCWarps + cw : 2 * warp + 1;
+  const int qa_off = is_c ? 64 : 0, qb_off = is_c ? 128 : 0;
+  /* pixel position of this thread's pair inside the tile */
+  int px_x, px_y;
+  if (is_c) {
+    px_x = (HS == 2 ? 16 : 8) * (32 * cw + lane);
+    px_y = 0;
+  } else if (GRAY) {
+    px_x = 16 * (32 * warp + lane);
+    px_y = 0;
+  } else {
+    px_x = 16 * (32 * (warp % G) + lane);
+    px_y = 8 * (warp / G);
+  }
+  /* exchange-buffer slot this thread writes (C) or reads (Y) */
+  uint32_t ex_a = 0;
+  if (!GRAY) {
+    if (HS == 2) {
+      ex_a = ex0 + (uint32_t)(is_c ? 32 * cw + lane : 32 * (warp % G) + lane) * C::kExTask;
+    } else if (is_c) {
+      const int mcu = 32 * cw + lane;
+      ex_a = ex0 + (mcu & 1) * C::kExRegion1 + (mcu >> 1) * C::kExTask;
+    } else {
+      ex_a = ex0 + (uint32_t)(32 * (warp % G) + lane) * C::kExTask;
+    }
+  }
+
   int it = 0;
-  for (int tile = blockIdx.x; tile < L.n_tiles; tile += gridDim.x, it++) {
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
     const int s = it % STAGES;
-    mbar_wait(L.bar0 + 8 * s, (uint32_t)(it / STAGES) & 1u);
-    const TileView tv = read_header<C>(L, s);
-    const uint8_t *stp = L.smem_gen + s * C::kStageBytes;
+    /* describe the tile STAGES ahead while registers are still free */
+    const int nt = tile + STAGES * gridDim.x;
+    if (threadIdx.x == 0 && nt < n_tiles) prepare(nt, (it + STAGES) % kDescSlots);
+
+    mbar_wait(bar0 + 8 * s, (uint32_t)(it / STAGES) & 1u);
+    const uint32_t da = desc0 + (it % kDescSlots) * (uint32_t)sizeof(TileDesc);
+    bool active;
+    {
+      const uint4 h0 = lds128(da);
+      active = px_x < (int)h0.z && px_y < (int)h0.w;
+    }
+    const uint8_t *stp = smem_gen + s * C::kStageBytes;
     const int *qtp = reinterpret_cast<const int *>(stp + C::kBoxes * kBoxBytes);
-    const int px_x = GRAY ? 512 * wy + 16 * lane : 16 * lane;
-    const int px_y = GRAY ? 0 : 8 * wy;
-    const bool active = px_x < tv.width_left && px_y < tv.rows_left;
 
     uint32_t ya[8][4], yb[8][4];
     {
       pair32 m[8][8];
       if (active) {
-        pair_row_pass(m, stp + (2 * wy) * kBoxBytes, stp + (2 * wy + 1) * kBoxBytes, lane, qtp, qtp);
+        pair_row_pass(m, stp + box_a * kBoxBytes, stp + box_b * kBoxBytes, lane, qtp + qa_off,
+                      qtp + qb_off);
       }
-      named_sync(1, C::kThreads);   /* every warp has consumed stage s */
+      named_sync(1, C::kThreads);   /* every warp has consumed stage s: refill it */
+      if (threadIdx.x == 0 && nt < n_tiles) fire((it + STAGES) % kDescSlots, s);
       if (active) {
-        /* (short)floor + 128, clamp, two columns at a time as the column pass
-         * produces them: ya[k][j] / yb[k][j] = pixels 2j, 2j+1 of row k of
-         * block A / block B as s16x2 */
         const pair32 magic = p_make_bits(kMagicBits, kMagicBits);
         column_pass_by_pairs(m, [&](int j, pair32 (&u)[8], pair32 (&v)[8]) {
+          if (!is_c) {
+            /* luma: (short)floor + 128, clamp; ya[k][j] / yb[k][j] = pixels 2j, 2j+1 of row k
+             * of block A / block B as s16x2 */
 #pragma unroll
-          for (int k = 0; k < 8; k++) {
-            uint32_t ulo, uhi, vlo, vhi;
-            p_split_bits(p_add_rm(u[k], magic), ulo, uhi);
-            p_split_bits(p_add_rm(v[k], magic), vlo, vhi);
-            ya[k][j] = clamp_pair_u8(ulo, vlo);
-            yb[k][j] = clamp_pair_u8(uhi, vhi);
+            for (int k = 0; k < 8; k++) {
+              uint32_t ulo, uhi, vlo, vhi;
+              p_split_bits(p_add_rm(u[k], magic), ulo, uhi);
+              p_split_bits(p_add_rm(v[k], magic), vlo, vhi);
+              ya[k][j] = clamp_pair_u8(ulo, vlo);
+              yb[k][j] = clamp_pair_u8(uhi, vhi);
+            }
+          } else if (!GRAY) {
+            /* chroma: integer colour offsets of columns 2j, 2j+1 -> exchange buffer */
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+              uint32_t r0, g0, b0, r1, g1, b1;
+              chroma_offsets_bits(u[k], r0, g0, b0);
+              chroma_offsets_bits(v[k], r1, g1, b1);
+              if (HS == 2) {
+                /* per sample: (rc | gc<<16), (bc | junk<<16) */
+                sts128(ex_a + k * C::kExRow + 16 * j,
+                       make_uint4(__byte_perm(r0, g0, 0x5410), b0, __byte_perm(r1, g1, 0x5410), b1));
+              } else {
+                /* per sample pair: R, G, B offsets as s16x2 */
+                sts32(ex_a + k * C::kExRow + 12 * j, __byte_perm(r0, r1, 0x5410));
+                sts32(ex_a + k * C::kExRow + 12 * j + 4, __byte_perm(g0, g1, 0x5410));
+                sts32(ex_a + k * C::kExRow + 12 * j + 8, __byte_perm(b0, b1, 0x5410));
+              }
+            }
           }
         });
       }
     }
-    /* refill stage s with the tile STAGES ahead (after the column pass: the 64
-     * sample pairs are dead by now, so the producer's state costs no registers) */
-    if (threadIdx.x == 0) {
-      const int nt = tile + STAGES * gridDim.x;
-      if (nt < L.n_tiles) issue(nt, s);
+    if (GRAY) {
+      if (!active) continue;
+    } else if (is_c) {
+      named_arrive(2, C::kThreads);   /* this tile's offsets are in the exchange buffer */
+      continue;
+    } else {
+      named_sync(2, C::kThreads);
+      if (!active) continue;
     }
-    if (!GRAY) named_sync(2, C::kThreads);   /* colour offsets of this tile are ready */
-    if (!active) continue;
 
-    uint8_t *out = rgb + tv.rgb_base + (long long)px_y * tv.pitch + (long long)px_x * C::kChannels;
-    const int vis_px = min(16, tv.width_left - px_x);
-    const int vis_rows = min(8, tv.rows_left - px_y);
+    /* ---- luma threads: add the colour offsets, pack, store ------------------ */
+    const uint4 h0 = lds128(da);
+    const uint2 h1 = lds64(da + 16);
+    const long long rgb_base = (long long)(((unsigned long long)h0.y << 32) | h0.x);
+    const int pitch = (int)h1.x;
+    const bool fast = (h1.y & 1u) != 0;
+    const int vis_px = min(16, (int)h0.z - px_x);
+    const int vis_rows = min(8, (int)h0.w - px_y);
+    uint8_t *out = rgb + rgb_base + (long long)px_y * pitch + (long long)px_x * C::kChannels;
     if (GRAY) {
 #pragma unroll
       for (int k = 0; k < 8; k++) {
@@ -390,16 +476,9 @@ __device__ __forceinline__ void luma_role(const TileLoop &L, int wy, int lane, u
           v.y = __byte_perm(ya[k][2], ya[k][3], 0x6420);
           v.z = __byte_perm(yb[k][0], yb[k][1], 0x6420);
           v.w = __byte_perm(yb[k][2], yb[k][3], 0x6420);
-          uint8_t *dst = out + (long long)k * tv.pitch;
-          if (tv.fast && vis_px == 16) {
-            stg128_stream(dst, v);
-          } else {
-            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-            for (int i = 0; i < 16; i++) {
-              if (i < vis_px) dst[i] = (uint8_t)(w[i >> 2] >> (8 * (i & 3)));
-            }
-          }
+          uint8_t *dst = out + (long long)k * pitch;
+          if (fast && vis_px == 16) stg128_stream(dst, v);
+          else store_row_slow(dst, v, v, v, vis_px);
         }
       }
     } else {
@@ -407,14 +486,30 @@ __device__ __forceinline__ void luma_role(const TileLoop &L, int wy, int lane, u
 #pragma unroll
       for (int k = 0; k < 8; k++) {
         if (k % VS == 0) {        /* VS pixel rows share one chroma row */
-          const int crow = (8 * wy + k) / VS;
-          const uint32_t a = L.ex0 + lane * C::kExTask + crow * C::kExRow;
-          const uint32_t b = HS == 2 ? a + 48 : a + C::kExRegion1;
+          const int crow = (px_y + k) / VS;
+          const uint32_t a = ex_a + crow * C::kExRow;
+          if (HS == 2) {
+            /* 8 chroma samples x (rc|gc, bc): replicate each for its pixel pair */
 #pragma unroll
-          for (int v = 0; v < 3; v++) {
-            const uint4 t0 = lds128(a + 16 * v), t1 = lds128(b + 16 * v);
-            ca[4 * v] = t0.x; ca[4 * v + 1] = t0.y; ca[4 * v + 2] = t0.z; ca[4 * v + 3] = t0.w;
-            cb[4 * v] = t1.x; cb[4 * v + 1] = t1.y; cb[4 * v + 2] = t1.z; cb[4 * v + 3] = t1.w;
+            for (int v = 0; v < 4; v++) {
+              const uint4 t = lds128(a + 16 * v);
+              uint32_t *dst = v < 2 ? ca : cb;
+              const int o = 6 * (v & 1);
+              dst[o + 0] = __byte_perm(t.x, t.x, 0x1010);
+              dst[o + 1] = __byte_perm(t.x, t.x, 0x3232);
+              dst[o + 2] = __byte_perm(t.y, t.y, 0x1010);
+              dst[o + 3] = __byte_perm(t.z, t.z, 0x1010);
+              dst[o + 4] = __byte_perm(t.z, t.z, 0x3232);
+              dst[o + 5] = __byte_perm(t.w, t.w, 0x1010);
+            }
+          } else {
+            const uint32_t b = a + C::kExRegion1;
+#pragma unroll
+            for (int v = 0; v < 3; v++) {
+              const uint4 t0 = lds128(a + 16 * v), t1 = lds128(b + 16 * v);
+              ca[4 * v] = t0.x; ca[4 * v + 1] = t0.y; ca[4 * v + 2] = t0.z; ca[4 * v + 3] = t0.w;
+              cb[4 * v] = t1.x; cb[4 * v + 1] = t1.y; cb[4 * v + 2] = t1.z; cb[4 * v + 3] = t1.w;
+            }
           }
         }
         if (k < vis_rows) {
@@ -423,91 +518,20 @@ __device__ __forceinline__ void luma_role(const TileLoop &L, int wy, int lane, u
           rgb4(ya[k][2], ya[k][3], ca[6], ca[7], ca[8], ca[9], ca[10], ca[11], w[3], w[4], w[5]);
           rgb4(yb[k][0], yb[k][1], cb[0], cb[1], cb[2], cb[3], cb[4], cb[5], w[6], w[7], w[8]);
           rgb4(yb[k][2], yb[k][3], cb[6], cb[7], cb[8], cb[9], cb[10], cb[11], w[9], w[10], w[11]);
-          store_row(out + (long long)k * tv.pitch, w, 3 * vis_px, tv.fast);
+          uint8_t *dst = out + (long long)k * pitch;
+          const uint4 q0 = make_uint4(w[0], w[1], w[2], w[3]);
+          const uint4 q1 = make_uint4(w[4], w[5], w[6], w[7]);
+          const uint4 q2 = make_uint4(w[8], w[9], w[10], w[11]);
+          if (fast && vis_px == 16) {
+            stg128_stream(dst, q0);
+            stg128_stream(dst + 16, q1);
+            stg128_stream(dst + 32, q2);
+          } else {
+            store_row_slow(dst, q0, q1, q2, 3 * vis_px);
+          }
         }
       }
     }
-  }
-}
-
-template <int HS, int VS, bool GRAY, int STAGES>
-__global__ void __launch_bounds__(Cfg<HS, VS, GRAY>::kThreads, Cfg<HS, VS, GRAY>::kMinCtas)
-k_fused(const __grid_constant__ CUtensorMap tm_rows,   /* (64, rows)            */
-        const __grid_constant__ CUtensorMap tm_pairs,  /* (64, parity, pairs)   */
-        const FusedImage *__restrict__ images, const TileRef *__restrict__ tiles, int n_tiles,
-        const int32_t *__restrict__ qint, uint8_t *__restrict__ rgb) {
-  using C = Cfg<HS, VS, GRAY>;
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  TileLoop L;
-  /* dynamic smem is only guaranteed 16-byte aligned: round up to 1 KB for the swizzle */
-  L.smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  L.smem_gen = smem_raw + (L.smem0 - smem_u32(smem_raw));
-  L.ex0 = L.smem0 + STAGES * C::kStageBytes;
-  L.bar0 = L.ex0 + ((C::kExBytes + 15) & ~15);
-  L.n_tiles = n_tiles;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; s++) mbar_init(L.bar0 + 8 * s, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-
-  /* Producer side (thread 0 only): describe tile `t` in stage `s` and start its loads. */
-  auto issue = [&](int t, int s) {
-    const TileRef tr = tiles[t];
-    const FusedImage im = images[tr.img];
-    const uint32_t st = L.smem0 + s * C::kStageBytes;
-    const uint32_t bar = L.bar0 + 8 * s;
-    const int x0 = tr.mx0 * C::kMcuW, y0 = tr.mrow * C::kMcuH;
-    StageHeader h;
-    h.pitch = im.width * C::kChannels;
-    h.rgb_base = im.rgb_off + ((long long)y0 * im.width + x0) * C::kChannels;
-    h.width_left = im.width - x0;
-    h.rows_left = im.height - y0;
-    h.flags = (((reinterpret_cast<uintptr_t>(rgb) + (uintptr_t)h.rgb_base) & 15) == 0 &&
-               (h.pitch & 15) == 0) ? 1 : 0;
-    h.pad[0] = h.pad[1] = 0;
-    *reinterpret_cast<StageHeader *>(L.smem_gen + s * C::kStageBytes + C::kBoxes * kBoxBytes +
-                                     3 * kQtabBytes) = h;
-    mbar_expect_tx(bar, C::kBoxes * kBoxBytes + C::kTables * kQtabBytes);
-    /* luma boxes: even blocks then odd blocks of each Y warp's 64-block run */
-#pragma unroll
-    for (int wy = 0; wy < C::kYWarps; wy++) {
-      int first;
-      if (GRAY) {
-        first = im.block0[0] + tr.mrow * im.hblocks[0] + tr.mx0 + 64 * wy;
-      } else {
-        first = im.block0[0] + (tr.mrow * VS + wy) * im.hblocks[0] + tr.mx0 * HS;
-      }
-      tma_load_3d(st + (2 * wy) * kBoxBytes, &tm_pairs, 0, first & 1, first >> 1, bar);
-      tma_load_3d(st + (2 * wy + 1) * kBoxBytes, &tm_pairs, 0, (first + 1) & 1, (first + 1) >> 1, bar);
-    }
-#pragma unroll
-    for (int cw = 0; cw < C::kCWarps; cw++) {
-      const int fb = im.block0[1] + tr.mrow * im.hblocks[1] + tr.mx0 + 32 * cw;
-      const int fr = im.block0[2] + tr.mrow * im.hblocks[2] + tr.mx0 + 32 * cw;
-      tma_load_2d(st + (2 * C::kYWarps + cw) * kBoxBytes, &tm_rows, 0, fb, bar);
-      tma_load_2d(st + (2 * C::kYWarps + C::kCWarps + cw) * kBoxBytes, &tm_rows, 0, fr, bar);
-    }
-#pragma unroll
-    for (int c = 0; c < C::kTables; c++) {
-      bulk_load(st + C::kBoxes * kBoxBytes + c * kQtabBytes, qint + (size_t)im.qidx[c] * 64,
-                kQtabBytes, bar);
-    }
-  };
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; s++) {
-      const int t = blockIdx.x + s * gridDim.x;
-      if (t < n_tiles) issue(t, s);
-    }
-  }
-
-  if (warp < C::kYWarps) {
-    luma_role<HS, VS, GRAY, STAGES>(L, warp, lane, rgb, issue);
-  } else {
-    chroma_role<HS, VS, GRAY, STAGES>(L, warp - C::kYWarps, lane);
   }
 }
 
@@ -539,18 +563,22 @@ EncodeTiledFn encode_fn() {
   return fn;
 }
 
-constexpr int kDefaultStages = 2;
+/* Tile shape knobs (measured on B200, see profiles/): one 32-pair column group per
+ * tile and a single smem stage per CTA; four 3-warp CTAs per SM overlap each
+ * other's loads. */
+constexpr int kG = JGPU_FUSED_G;
+constexpr int kDefaultStages = JGPU_FUSED_STAGES;
 
 template <int HS, int VS, bool GRAY>
 size_t smem_bytes() {
-  using C = Cfg<HS, VS, GRAY>;
-  return 1024 + kDefaultStages * C::kStageBytes + ((C::kExBytes + 15) & ~15) + 8 * kDefaultStages + 16;
+  using C = Cfg<HS, VS, GRAY, kG>;
+  return 1024 + kDefaultStages * C::kStageBytes + ((C::kExBytes + 15) & ~15) +
+         (kDefaultStages + 1) * sizeof(TileDesc) + 8 * kDefaultStages + 16;
 }
 
 struct ModeInfo {
   int tile_mcus, mcu_w, mcu_h, threads;
   size_t smem;
-  const void *func;
   int ctas_per_sm;
 };
 
@@ -559,15 +587,14 @@ bool g_configured = false;
 
 template <int HS, int VS, bool GRAY>
 cudaError_t configure_mode(int mode) {
-  using C = Cfg<HS, VS, GRAY>;
-  auto *f = &k_fused<HS, VS, GRAY, kDefaultStages>;
+  using C = Cfg<HS, VS, GRAY, kG>;
+  auto *f = &k_fused<HS, VS, GRAY, kG, kDefaultStages>;
   ModeInfo &mi = g_modes[mode];
   mi.tile_mcus = C::kTileMcus;
   mi.mcu_w = C::kMcuW;
   mi.mcu_h = C::kMcuH;
   mi.threads = C::kThreads;
   mi.smem = smem_bytes<HS, VS, GRAY>();
-  mi.func = reinterpret_cast<const void *>(f);
   cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mi.smem);
   if (e != cudaSuccess) return e;
   int n = 0;
@@ -581,8 +608,8 @@ template <int HS, int VS, bool GRAY>
 cudaError_t launch_mode(int grid, size_t smem, cudaStream_t stream, const CUtensorMap &tm_rows,
                         const CUtensorMap &tm_pairs, const FusedImage *images, const TileRef *tiles,
                         int n_tiles, const int32_t *qint, uint8_t *rgb) {
-  using C = Cfg<HS, VS, GRAY>;
-  k_fused<HS, VS, GRAY, kDefaultStages><<<grid, C::kThreads, smem, stream>>>(
+  using C = Cfg<HS, VS, GRAY, kG>;
+  k_fused<HS, VS, GRAY, kG, kDefaultStages><<<grid, C::kThreads, smem, stream>>>(
       tm_rows, tm_pairs, images, tiles, n_tiles, qint, rgb);
   return cudaGetLastError();
 }
