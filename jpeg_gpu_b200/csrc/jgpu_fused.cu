@@ -95,10 +95,9 @@ struct Cfg {
   static constexpr int kBoxes = 2 * kYWarps + 2 * kCWarps;
   static constexpr int kStageBytes = kBoxes * kBoxBytes + kStageTail;
   static constexpr int kTables = GRAY ? 1 : 3;
-  /* exchange buffer: colour offsets of one chroma block (8 rows).
-   * HS==2: per sample (rc|gc<<16, bc) = 8 bytes, 64 bytes per row.
-   * HS==1: per horizontal sample pair (R2, G2, B2) s16x2 words = 12 bytes, 48 per row. */
-  static constexpr int kExRow = HS == 2 ? 64 : 48;
+  /* exchange buffer: the clamped chroma samples of one MCU's Cb/Cr block pair, 8 rows x 8
+   * samples, each sample one s16x2 word (Cb-128 | Cr-128 << 16): 32 bytes per row. */
+  static constexpr int kExRow = 32;
   static constexpr int kExTask = 8 * kExRow + 16;            /* odd multiple of 16 bytes */
   static constexpr int kExRegion1 = 32 * G * kExTask + 64;   /* HS==1: odd MCUs live here */
   static constexpr int kExBytes = GRAY ? 0 : (HS == 2 ? 32 * G * kExTask : 2 * 32 * G * kExTask + 128);
@@ -182,6 +181,9 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
 __device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) {
   asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
+__device__ __forceinline__ void sts64(uint32_t addr, uint2 v) {
+  asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(v.x), "r"(v.y) : "memory");
+}
 __device__ __forceinline__ uint2 lds64(uint32_t addr) {
   uint2 v;
   asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
@@ -213,17 +215,23 @@ __device__ __forceinline__ void pair_row_pass(pair32 (&m)[8][8], const uint8_t *
   }
 }
 
-/* Chroma sample pair (Cb in .lo, Cr in .hi, un-floored) -> the raw bits of
- * RN(offset + 1.5*2^23) for R, G, B (low 16 bits = the integer offset).
- * Arithmetic is colour_offsets() of jgpu_kernels.cuh, i.e. the oracle's. */
-__device__ __forceinline__ void chroma_offsets_bits(pair32 v, uint32_t &rb, uint32_t &gb,
-                                                    uint32_t &bb) {
+/* Chroma sample pair (Cb in .lo, Cr in .hi, un-floored) -> one s16x2 word
+ * (Cb-128 | Cr-128 << 16) of the CLAMPED samples: (short)floor as in src/dct.c:118, then
+ * clamp(v+128, 0, 255) - 128 == clamp(v, -128, 127) (src/xjpeg.c:578). */
+__device__ __forceinline__ uint32_t chroma_clamped(pair32 v) {
   const pair32 magic = p_make_bits(kMagicBits, kMagicBits);
   uint32_t cbits, rbits;
   p_split_bits(p_add_rm(v, magic), cbits, rbits);
-  uint32_t s = __byte_perm(cbits, rbits, 0x5410);   /* (short)floor of Cb | Cr */
-  s = __viaddmin_s16x2(s, 0u, 0x007f007fu);         /* clamp(v+128,0,255)-128 == clamp(v,-128,127) */
-  s = __viaddmax_s16x2(s, 0u, 0xff80ff80u);
+  uint32_t s = __byte_perm(cbits, rbits, 0x5410);
+  s = __viaddmin_s16x2(s, 0u, 0x007f007fu);
+  return __viaddmax_s16x2(s, 0u, 0xff80ff80u);
+}
+
+/* Clamped chroma word -> raw bits of RN(offset + 1.5*2^23) for R, G, B (low 16 bits = the
+ * integer colour offset).  Arithmetic is colour_offsets() of jgpu_kernels.cuh, i.e. the
+ * oracle's jgo_colour_offsets. */
+__device__ __forceinline__ void chroma_offsets_bits(uint32_t s, uint32_t &rb, uint32_t &gb,
+                                                    uint32_t &bb) {
   const float cbf = (float)(short)(s & 0xffffu);
   const float crf = (float)((int)s >> 16);
   const float fm = __uint_as_float(kMagicBits);
@@ -427,22 +435,10 @@ k_fused(const __grid_constant__ CUtensorMap tm_rows,   /* (64, rows)            
               yb[k][j] = clamp_pair_u8(uhi, vhi);
             }
           } else if (!GRAY) {
-            /* chroma: integer colour offsets of columns 2j, 2j+1 -> exchange buffer */
+            /* chroma: clamped samples of columns 2j, 2j+1 -> exchange buffer */
 #pragma unroll
             for (int k = 0; k < 8; k++) {
-              uint32_t r0, g0, b0, r1, g1, b1;
-              chroma_offsets_bits(u[k], r0, g0, b0);
-              chroma_offsets_bits(v[k], r1, g1, b1);
-              if (HS == 2) {
-                /* per sample: (rc | gc<<16), (bc | junk<<16) */
-                sts128(ex_a + k * C::kExRow + 16 * j,
-                       make_uint4(__byte_perm(r0, g0, 0x5410), b0, __byte_perm(r1, g1, 0x5410), b1));
-              } else {
-                /* per sample pair: R, G, B offsets as s16x2 */
-                sts32(ex_a + k * C::kExRow + 12 * j, __byte_perm(r0, r1, 0x5410));
-                sts32(ex_a + k * C::kExRow + 12 * j + 4, __byte_perm(g0, g1, 0x5410));
-                sts32(ex_a + k * C::kExRow + 12 * j + 8, __byte_perm(b0, b1, 0x5410));
-              }
+              sts64(ex_a + k * C::kExRow + 8 * j, make_uint2(chroma_clamped(u[k]), chroma_clamped(v[k])));
             }
           }
         });
@@ -489,26 +485,39 @@ k_fused(const __grid_constant__ CUtensorMap tm_rows,   /* (64, rows)            
           const int crow = (px_y + k) / VS;
           const uint32_t a = ex_a + crow * C::kExRow;
           if (HS == 2) {
-            /* 8 chroma samples x (rc|gc, bc): replicate each for its pixel pair */
+            /* 8 chroma samples, each serving one horizontal pixel pair of this row (and of
+             * the next one when VS == 2): offsets, replicated into both halves */
 #pragma unroll
-            for (int v = 0; v < 4; v++) {
+            for (int v = 0; v < 2; v++) {
               const uint4 t = lds128(a + 16 * v);
-              uint32_t *dst = v < 2 ? ca : cb;
-              const int o = 6 * (v & 1);
-              dst[o + 0] = __byte_perm(t.x, t.x, 0x1010);
-              dst[o + 1] = __byte_perm(t.x, t.x, 0x3232);
-              dst[o + 2] = __byte_perm(t.y, t.y, 0x1010);
-              dst[o + 3] = __byte_perm(t.z, t.z, 0x1010);
-              dst[o + 4] = __byte_perm(t.z, t.z, 0x3232);
-              dst[o + 5] = __byte_perm(t.w, t.w, 0x1010);
+              const uint32_t cs[4] = {t.x, t.y, t.z, t.w};
+              uint32_t *dst = v == 0 ? ca : cb;
+#pragma unroll
+              for (int i = 0; i < 4; i++) {
+                uint32_t r, g, b;
+                chroma_offsets_bits(cs[i], r, g, b);
+                dst[3 * i + 0] = __byte_perm(r, r, 0x1010);
+                dst[3 * i + 1] = __byte_perm(g, g, 0x1010);
+                dst[3 * i + 2] = __byte_perm(b, b, 0x1010);
+              }
             }
           } else {
-            const uint32_t b = a + C::kExRegion1;
+            /* block A = even MCU, block B = odd MCU: 8 samples each, paired horizontally */
 #pragma unroll
-            for (int v = 0; v < 3; v++) {
-              const uint4 t0 = lds128(a + 16 * v), t1 = lds128(b + 16 * v);
-              ca[4 * v] = t0.x; ca[4 * v + 1] = t0.y; ca[4 * v + 2] = t0.z; ca[4 * v + 3] = t0.w;
-              cb[4 * v] = t1.x; cb[4 * v + 1] = t1.y; cb[4 * v + 2] = t1.z; cb[4 * v + 3] = t1.w;
+            for (int blk = 0; blk < 2; blk++) {
+              const uint32_t base = blk == 0 ? a : a + C::kExRegion1;
+              const uint4 t0 = lds128(base), t1 = lds128(base + 16);
+              const uint32_t cs[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+              uint32_t *dst = blk == 0 ? ca : cb;
+#pragma unroll
+              for (int i = 0; i < 4; i++) {
+                uint32_t r0, g0, b0, r1, g1, b1;
+                chroma_offsets_bits(cs[2 * i], r0, g0, b0);
+                chroma_offsets_bits(cs[2 * i + 1], r1, g1, b1);
+                dst[3 * i + 0] = __byte_perm(r0, r1, 0x5410);
+                dst[3 * i + 1] = __byte_perm(g0, g1, 0x5410);
+                dst[3 * i + 2] = __byte_perm(b0, b1, 0x5410);
+              }
             }
           }
         }
