@@ -101,6 +101,10 @@ struct Cfg {
   static constexpr int kExTask = 8 * kExRow + 16;            /* odd multiple of 16 bytes */
   static constexpr int kExRegion1 = 32 * G * kExTask + 64;   /* HS==1: odd MCUs live here */
   static constexpr int kExBytes = GRAY ? 0 : (HS == 2 ? 32 * G * kExTask : 2 * 32 * G * kExTask + 128);
+  /* luma staging: each luma thread parks its 16x8 clamped samples (s16x2 words) here between
+   * the column pass and the colour loop: 8 rows x 32 bytes, padded */
+  static constexpr int kYsTask = 8 * 32 + 16;
+  static constexpr int kYsBytes = 32 * kYWarps * kYsTask;
   static constexpr int kChannels = GRAY ? 1 : 3;
   /* resident CTAs per SM the register allocation is sized for */
   static constexpr int kMinCtas = JGPU_FUSED_MINCTAS > 0 ? JGPU_FUSED_MINCTAS : 384 / kThreads;
@@ -283,7 +287,8 @@ k_fused(const __grid_constant__ CUtensorMap tm_rows,   /* (64, rows)            
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t *const smem_gen = smem_raw + (smem0 - smem_u32(smem_raw));
   const uint32_t ex0 = smem0 + STAGES * C::kStageBytes;
-  const uint32_t desc0 = ex0 + ((C::kExBytes + 15) & ~15);
+  const uint32_t ys0 = ex0 + ((C::kExBytes + 15) & ~15);
+  const uint32_t desc0 = ys0 + C::kYsBytes;
   const uint32_t bar0 = desc0 + kDescSlots * (uint32_t)sizeof(TileDesc);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -394,6 +399,8 @@ k_fused(const __grid_constant__ CUtensorMap tm_rows,   /* (64, rows)            
     }
   }
 
+  const uint32_t ys_a = ys0 + (uint32_t)(is_c ? 0 : 32 * warp + lane) * C::kYsTask;
+
   int it = 0;
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
     const int s = it % STAGES;
@@ -411,7 +418,6 @@ k_fused(const __grid_constant__ CUtensorMap tm_rows,   /* (64, rows)            
     const uint8_t *stp = smem_gen + s * C::kStageBytes;
     const int *qtp = reinterpret_cast<const int *>(stp + C::kBoxes * kBoxBytes);
 
-    uint32_t ya[8][4], yb[8][4];
     {
       pair32 m[8][8];
       if (active) {
@@ -424,15 +430,14 @@ k_fused(const __grid_constant__ CUtensorMap tm_rows,   /* (64, rows)            
         const pair32 magic = p_make_bits(kMagicBits, kMagicBits);
         column_pass_by_pairs(m, [&](int j, pair32 (&u)[8], pair32 (&v)[8]) {
           if (!is_c) {
-            /* luma: (short)floor + 128, clamp; ya[k][j] / yb[k][j] = pixels 2j, 2j+1 of row k
-             * of block A / block B as s16x2 */
+            /* luma: (short)floor + 128, clamp; pixels 2j, 2j+1 of row k of block A and of
+             * block B as two s16x2 words, parked in this thread's staging rows */
 #pragma unroll
             for (int k = 0; k < 8; k++) {
               uint32_t ulo, uhi, vlo, vhi;
               p_split_bits(p_add_rm(u[k], magic), ulo, uhi);
               p_split_bits(p_add_rm(v[k], magic), vlo, vhi);
-              ya[k][j] = clamp_pair_u8(ulo, vlo);
-              yb[k][j] = clamp_pair_u8(uhi, vhi);
+              sts64(ys_a + 32 * k + 8 * j, make_uint2(clamp_pair_u8(ulo, vlo), clamp_pair_u8(uhi, vhi)));
             }
           } else if (!GRAY) {
             /* chroma: clamped samples of columns 2j, 2j+1 -> exchange buffer */
@@ -459,84 +464,87 @@ k_fused(const __grid_constant__ CUtensorMap tm_rows,   /* (64, rows)            
     const uint2 h1 = lds64(da + 16);
     const long long rgb_base = (long long)(((unsigned long long)h0.y << 32) | h0.x);
     const int pitch = (int)h1.x;
-    const bool fast = (h1.y & 1u) != 0;
+    const bool fast = (h1.y & 1u) != 0 && (int)h0.z - px_x >= 16;
     const int vis_px = min(16, (int)h0.z - px_x);
     const int vis_rows = min(8, (int)h0.w - px_y);
-    uint8_t *out = rgb + rgb_base + (long long)px_y * pitch + (long long)px_x * C::kChannels;
+    uint8_t *dst = rgb + rgb_base + (long long)px_y * pitch + (long long)px_x * C::kChannels;
     if (GRAY) {
-#pragma unroll
-      for (int k = 0; k < 8; k++) {
-        if (k < vis_rows) {
-          uint4 v;
-          v.x = __byte_perm(ya[k][0], ya[k][1], 0x6420);
-          v.y = __byte_perm(ya[k][2], ya[k][3], 0x6420);
-          v.z = __byte_perm(yb[k][0], yb[k][1], 0x6420);
-          v.w = __byte_perm(yb[k][2], yb[k][3], 0x6420);
-          uint8_t *dst = out + (long long)k * pitch;
-          if (fast && vis_px == 16) stg128_stream(dst, v);
-          else store_row_slow(dst, v, v, v, vis_px);
-        }
+#pragma unroll 1
+      for (int k = 0; k < vis_rows; k++, dst += pitch) {
+        /* staging row: (a0 b0 a1 b1 | a2 b2 a3 b3), a = block A pairs, b = block B pairs */
+        const uint4 t0 = lds128(ys_a + 32 * k), t1 = lds128(ys_a + 32 * k + 16);
+        uint4 v;
+        v.x = __byte_perm(t0.x, t0.z, 0x6420);
+        v.y = __byte_perm(t1.x, t1.z, 0x6420);
+        v.z = __byte_perm(t0.y, t0.w, 0x6420);
+        v.w = __byte_perm(t1.y, t1.w, 0x6420);
+        if (fast) stg128_stream(dst, v);
+        else store_row_slow(dst, v, v, v, vis_px);
       }
     } else {
-      uint32_t ca[12], cb[12];   /* offsets for block A / block B: 4 pixel pairs x (R,G,B) */
+      /* one iteration per chroma row = VS pixel rows */
+#pragma unroll 1
+      for (int cr = 0; cr < 8 / VS; cr++) {
+        if (cr * VS >= vis_rows) break;
+        uint32_t ca[12], cb[12];   /* offsets for block A / block B: 4 pixel pairs x (R,G,B) */
+        const uint32_t a = ex_a + (px_y / VS + cr) * C::kExRow;
+        if (HS == 2) {
+          /* 8 chroma samples, each serving one horizontal pixel pair of VS rows: offsets,
+           * replicated into both halves of an s16x2 word */
 #pragma unroll
-      for (int k = 0; k < 8; k++) {
-        if (k % VS == 0) {        /* VS pixel rows share one chroma row */
-          const int crow = (px_y + k) / VS;
-          const uint32_t a = ex_a + crow * C::kExRow;
-          if (HS == 2) {
-            /* 8 chroma samples, each serving one horizontal pixel pair of this row (and of
-             * the next one when VS == 2): offsets, replicated into both halves */
+          for (int v = 0; v < 2; v++) {
+            const uint4 t = lds128(a + 16 * v);
+            const uint32_t cs[4] = {t.x, t.y, t.z, t.w};
+            uint32_t *o = v == 0 ? ca : cb;
 #pragma unroll
-            for (int v = 0; v < 2; v++) {
-              const uint4 t = lds128(a + 16 * v);
-              const uint32_t cs[4] = {t.x, t.y, t.z, t.w};
-              uint32_t *dst = v == 0 ? ca : cb;
-#pragma unroll
-              for (int i = 0; i < 4; i++) {
-                uint32_t r, g, b;
-                chroma_offsets_bits(cs[i], r, g, b);
-                dst[3 * i + 0] = __byte_perm(r, r, 0x1010);
-                dst[3 * i + 1] = __byte_perm(g, g, 0x1010);
-                dst[3 * i + 2] = __byte_perm(b, b, 0x1010);
-              }
+            for (int i = 0; i < 4; i++) {
+              uint32_t r, g, b;
+              chroma_offsets_bits(cs[i], r, g, b);
+              o[3 * i + 0] = __byte_perm(r, r, 0x1010);
+              o[3 * i + 1] = __byte_perm(g, g, 0x1010);
+              o[3 * i + 2] = __byte_perm(b, b, 0x1010);
             }
-          } else {
-            /* block A = even MCU, block B = odd MCU: 8 samples each, paired horizontally */
+          }
+        } else {
+          /* block A = even MCU, block B = odd MCU: 8 samples each, paired horizontally */
 #pragma unroll
-            for (int blk = 0; blk < 2; blk++) {
-              const uint32_t base = blk == 0 ? a : a + C::kExRegion1;
-              const uint4 t0 = lds128(base), t1 = lds128(base + 16);
-              const uint32_t cs[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
-              uint32_t *dst = blk == 0 ? ca : cb;
+          for (int blk = 0; blk < 2; blk++) {
+            const uint32_t base = blk == 0 ? a : a + C::kExRegion1;
+            const uint4 t0 = lds128(base), t1 = lds128(base + 16);
+            const uint32_t cs[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+            uint32_t *o = blk == 0 ? ca : cb;
 #pragma unroll
-              for (int i = 0; i < 4; i++) {
-                uint32_t r0, g0, b0, r1, g1, b1;
-                chroma_offsets_bits(cs[2 * i], r0, g0, b0);
-                chroma_offsets_bits(cs[2 * i + 1], r1, g1, b1);
-                dst[3 * i + 0] = __byte_perm(r0, r1, 0x5410);
-                dst[3 * i + 1] = __byte_perm(g0, g1, 0x5410);
-                dst[3 * i + 2] = __byte_perm(b0, b1, 0x5410);
-              }
+            for (int i = 0; i < 4; i++) {
+              uint32_t r0, g0, b0, r1, g1, b1;
+              chroma_offsets_bits(cs[2 * i], r0, g0, b0);
+              chroma_offsets_bits(cs[2 * i + 1], r1, g1, b1);
+              o[3 * i + 0] = __byte_perm(r0, r1, 0x5410);
+              o[3 * i + 1] = __byte_perm(g0, g1, 0x5410);
+              o[3 * i + 2] = __byte_perm(b0, b1, 0x5410);
             }
           }
         }
-        if (k < vis_rows) {
-          uint32_t w[12];
-          rgb4(ya[k][0], ya[k][1], ca[0], ca[1], ca[2], ca[3], ca[4], ca[5], w[0], w[1], w[2]);
-          rgb4(ya[k][2], ya[k][3], ca[6], ca[7], ca[8], ca[9], ca[10], ca[11], w[3], w[4], w[5]);
-          rgb4(yb[k][0], yb[k][1], cb[0], cb[1], cb[2], cb[3], cb[4], cb[5], w[6], w[7], w[8]);
-          rgb4(yb[k][2], yb[k][3], cb[6], cb[7], cb[8], cb[9], cb[10], cb[11], w[9], w[10], w[11]);
-          uint8_t *dst = out + (long long)k * pitch;
-          const uint4 q0 = make_uint4(w[0], w[1], w[2], w[3]);
-          const uint4 q1 = make_uint4(w[4], w[5], w[6], w[7]);
-          const uint4 q2 = make_uint4(w[8], w[9], w[10], w[11]);
-          if (fast && vis_px == 16) {
-            stg128_stream(dst, q0);
-            stg128_stream(dst + 16, q1);
-            stg128_stream(dst + 32, q2);
-          } else {
-            store_row_slow(dst, q0, q1, q2, 3 * vis_px);
+#pragma unroll
+        for (int sub = 0; sub < VS; sub++) {
+          const int k = cr * VS + sub;
+          if (k < vis_rows) {
+            const uint4 t0 = lds128(ys_a + 32 * k), t1 = lds128(ys_a + 32 * k + 16);
+            uint32_t w[12];
+            rgb4(t0.x, t0.z, ca[0], ca[1], ca[2], ca[3], ca[4], ca[5], w[0], w[1], w[2]);
+            rgb4(t1.x, t1.z, ca[6], ca[7], ca[8], ca[9], ca[10], ca[11], w[3], w[4], w[5]);
+            rgb4(t0.y, t0.w, cb[0], cb[1], cb[2], cb[3], cb[4], cb[5], w[6], w[7], w[8]);
+            rgb4(t1.y, t1.w, cb[6], cb[7], cb[8], cb[9], cb[10], cb[11], w[9], w[10], w[11]);
+            const uint4 q0 = make_uint4(w[0], w[1], w[2], w[3]);
+            const uint4 q1 = make_uint4(w[4], w[5], w[6], w[7]);
+            const uint4 q2 = make_uint4(w[8], w[9], w[10], w[11]);
+            if (fast) {
+              stg128_stream(dst, q0);
+              stg128_stream(dst + 16, q1);
+              stg128_stream(dst + 32, q2);
+            } else {
+              store_row_slow(dst, q0, q1, q2, 3 * vis_px);
+            }
+            dst += pitch;
           }
         }
       }
@@ -581,7 +589,7 @@ constexpr int kDefaultStages = JGPU_FUSED_STAGES;
 template <int HS, int VS, bool GRAY>
 size_t smem_bytes() {
   using C = Cfg<HS, VS, GRAY, kG>;
-  return 1024 + kDefaultStages * C::kStageBytes + ((C::kExBytes + 15) & ~15) +
+  return 1024 + kDefaultStages * C::kStageBytes + ((C::kExBytes + 15) & ~15) + C::kYsBytes +
          (kDefaultStages + 1) * sizeof(TileDesc) + 8 * kDefaultStages + 16;
 }
 
