@@ -13,26 +13,33 @@
  *   thread = one PAIR of 8x8 blocks, 64 sample pairs in registers through both
  *            IDCT passes (jgpu_idct_core.cuh); the pair is two horizontally
  *            adjacent luma blocks, or the Cb and the Cr block of one MCU.
- *   warp   = 32 pairs of one block row: "Y warps" (one per luma block row of
- *            the MCU row) and "C warps" (chroma).
+ *   warp   = 32 pairs of one block row: "luma warps" (one per luma block row
+ *            of the MCU row) and "chroma warps".
  *
  * Data movement
- *   HBM -> smem: TMA tensor loads (cp.async.bulk.tensor) issued by one thread,
- *     completion on an mbarrier, kStages-deep ring.  The coefficient buffer is
- *     described ONCE as rows of 128 bytes (one block per row); a box is 32 rows
- *     = 32 blocks, written with the 128-byte swizzle so that lane L reading
- *     16-byte chunk r of row L is bank-conflict free.  Luma uses a 3-D view
- *     (64, parity, pair) of the same memory so that one box gathers the 32
- *     even (or the 32 odd) blocks of 64 consecutive blocks: lane L then owns
+ *   HBM -> smem: TMA tensor loads (cp.async.bulk.tensor).  The coefficient
+ *     buffer is described ONCE as rows of 128 bytes (one block per row); a box
+ *     is 32 rows = 32 blocks, written with the 128-byte swizzle so that lane L
+ *     reading 16-byte chunk r of row L is bank-conflict free.  Luma uses a 3-D
+ *     view (64, parity, pair) of the same memory so that one box gathers the
+ *     32 even (or the 32 odd) blocks of 64 consecutive blocks: lane L then owns
  *     blocks 2L and 2L+1, i.e. 16 adjacent output pixels.
- *   C warps -> Y warps: per chroma sample the three integer colour offsets,
- *     already laid out as the s16x2 operands the Y threads need, through a
- *     padded shared-memory exchange buffer and one named barrier.
- *   regs -> HBM: each Y thread holds 16 adjacent pixels of a row = 48 bytes =
+ *     Every WARP owns its two boxes, its quantisation tables and its mbarrier:
+ *     as soon as a warp has pulled its coefficients into registers (row pass)
+ *     its lane 0 starts the loads of the warp's next tile, which land while the
+ *     warp runs the column pass and the colour loop.  There is no CTA-wide
+ *     barrier on the load path.
+ *   tile descriptors: built on the host per plan (128 bytes per tile), fetched
+ *     two tiles ahead into a 4-slot smem ring with cp.async.bulk.
+ *   chroma warps -> luma warps: the clamped Cb/Cr samples (2 bytes per sample)
+ *     through a double-buffered exchange area and named barriers, so chroma
+ *     may run up to two tiles ahead of luma.
+ *   regs -> HBM: each luma thread holds 16 adjacent pixels of a row = 48 bytes =
  *     three 128-bit stores; a warp covers 1536 contiguous bytes per row.
  */
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <stddef.h>
 #include <stdio.h>
 #include <string.h>
 #include <algorithm>
@@ -48,37 +55,34 @@ namespace jgpu {
 #ifndef JGPU_FUSED_G
 #define JGPU_FUSED_G 1          /* 32-pair column groups per tile */
 #endif
-#ifndef JGPU_FUSED_STAGES
-#define JGPU_FUSED_STAGES 1     /* smem stages per CTA */
-#endif
 #ifndef JGPU_FUSED_MINCTAS
 #define JGPU_FUSED_MINCTAS 0    /* 0: size registers for 12 warps per SM */
 #endif
 
 constexpr int kBoxRows = 32;                 /* blocks per TMA box */
 constexpr int kBoxBytes = kBoxRows * 128;    /* 4 KB */
-constexpr int kStageTail = 1024;             /* the three tables; keeps boxes 1 KB aligned */
 constexpr int kQtabBytes = 64 * 4;           /* one table as int32 */
-constexpr int kMaxYBoxPairs = 6;             /* luma warps per CTA, upper bound */
-constexpr int kMaxCBoxes = 4;                /* chroma warps per CTA, upper bound */
+constexpr int kWarpBytes = 2 * kBoxBytes + 1024; /* two boxes + up to two tables, 1 KB aligned */
+constexpr int kMaxYWarps = 6;
+constexpr int kMaxCWarps = 4;
+constexpr int kDescSlots = 4;
 
-/* What the producer thread prepares for one tile: where its boxes start in the
- * coefficient buffer and where its pixels go.  Two of these live in shared
- * memory (tile parity), so the next tile can be described while the current
- * one is still being read. */
+/* One tile, as the host describes it (fused_plan_build): where its boxes start
+ * in the coefficient buffer (global block indices: the buffer viewed as rows of
+ * 64 int16) and where its pixels go. */
 struct __align__(16) TileDesc {
   long long rgb_base;   /* byte offset in the rgb buffer of the tile's top-left pixel */
   int32_t width_left;   /* visible pixels from the tile's left edge to the image's right edge */
   int32_t rows_left;    /* visible rows from the tile's top row to the image's bottom */
   int32_t pitch;        /* bytes per output row */
-  int32_t flags;        /* bit 0: output rows are 16-byte aligned */
-  int32_t qidx[3];      /* table indices */
+  int32_t flags;        /* bit 0: output rows are 16-byte aligned (given an aligned base pointer) */
+  int32_t qidx[3];      /* 64-entry table indices: qtab_set*4 + tq */
   int32_t pad0;
-  int32_t yfirst[kMaxYBoxPairs];  /* first block (global index) of each luma warp's 64-block run */
-  int32_t cfirst[2][kMaxCBoxes];  /* first Cb / Cr block of each chroma warp's 32-block run */
-  int32_t pad1[4];
+  int32_t yfirst[kMaxYWarps];     /* first block of each luma warp's 64-block run */
+  int32_t cfirst[2][kMaxCWarps];  /* first Cb / Cr block of each chroma warp's 32-block run */
+  int32_t pad1[8];
 };
-static_assert(sizeof(TileDesc) % 16 == 0, "TileDesc is read with 128-bit loads");
+static_assert(sizeof(TileDesc) == 128, "TileDesc is copied with cp.async.bulk and read with 128-bit loads");
 
 /* HS, VS: luma sampling factors (chroma is 1x1); G: 32-pair column groups per tile. */
 template <int HS, int VS, bool GRAY, int G>
@@ -91,24 +95,26 @@ struct Cfg {
   static constexpr int kMcuH = GRAY ? 8 : 8 * VS;
   /* MCUs per tile: every luma warp covers 64 blocks of one block row */
   static constexpr int kTileMcus = GRAY ? 64 * kYWarps : 64 * G / HS;
-  static constexpr int kTilePx = kTileMcus * kMcuW;
-  static constexpr int kBoxes = 2 * kYWarps + 2 * kCWarps;
-  static constexpr int kStageBytes = kBoxes * kBoxBytes + kStageTail;
-  static constexpr int kTables = GRAY ? 1 : 3;
-  /* exchange buffer: the clamped chroma samples of one MCU's Cb/Cr block pair, 8 rows x 8
-   * samples, each sample one s16x2 word (Cb-128 | Cr-128 << 16): 32 bytes per row. */
-  static constexpr int kExRow = 32;
-  static constexpr int kExTask = 8 * kExRow + 16;            /* odd multiple of 16 bytes */
+  static constexpr int kChannels = GRAY ? 1 : 3;
+  /* exchange area: the clamped chroma samples of one MCU's Cb/Cr block pair: 8 rows x 8
+   * samples x (Cb-128, Cr-128) as two signed bytes = 16 bytes per row, padded per task */
+  static constexpr int kExTask = 8 * 16 + 16;                /* odd multiple of 16 bytes */
   static constexpr int kExRegion1 = 32 * G * kExTask + 64;   /* HS==1: odd MCUs live here */
-  static constexpr int kExBytes = GRAY ? 0 : (HS == 2 ? 32 * G * kExTask : 2 * 32 * G * kExTask + 128);
+  static constexpr int kExSlot = GRAY ? 0 : (HS == 2 ? 32 * G * kExTask : 2 * 32 * G * kExTask + 128);
   /* luma staging: each luma thread parks its 16x8 clamped samples (s16x2 words) here between
    * the column pass and the colour loop: 8 rows x 32 bytes, padded */
   static constexpr int kYsTask = 8 * 32 + 16;
   static constexpr int kYsBytes = 32 * kYWarps * kYsTask;
-  static constexpr int kChannels = GRAY ? 1 : 3;
+  /* shared-memory map (offsets from a 1 KB aligned base) */
+  static constexpr int kOffWarp = 0;
+  static constexpr int kOffEx = kWarps * kWarpBytes;
+  static constexpr int kOffYs = kOffEx + 2 * kExSlot;
+  static constexpr int kOffDesc = kOffYs + kYsBytes;
+  static constexpr int kOffBar = kOffDesc + kDescSlots * (int)sizeof(TileDesc);
+  static constexpr int kSmemBytes = kOffBar + 8 * (kWarps + kDescSlots) + 1024 /* alignment slack */;
   /* resident CTAs per SM the register allocation is sized for */
   static constexpr int kMinCtas = JGPU_FUSED_MINCTAS > 0 ? JGPU_FUSED_MINCTAS : 384 / kThreads;
-  static_assert(kYWarps <= kMaxYBoxPairs && kCWarps <= kMaxCBoxes, "TileDesc too small");
+  static_assert(kYWarps <= kMaxYWarps && kCWarps <= kMaxCWarps, "TileDesc too small");
 };
 
 /* ---- PTX wrappers ---------------------------------------------------------- */
@@ -177,21 +183,21 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
                : "r"(addr));
   return v;
 }
-__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
-  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y),
-               "r"(v.z), "r"(v.w)
-               : "memory");
+__device__ __forceinline__ uint2 lds64(uint32_t addr) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
 }
 __device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) {
   asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
 __device__ __forceinline__ void sts64(uint32_t addr, uint2 v) {
   asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(v.x), "r"(v.y) : "memory");
-}
-__device__ __forceinline__ uint2 lds64(uint32_t addr) {
-  uint2 v;
-  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
-  return v;
 }
 __device__ __forceinline__ void stg128_stream(uint8_t *p, uint4 v) {
   asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y),
@@ -231,13 +237,15 @@ __device__ __forceinline__ uint32_t chroma_clamped(pair32 v) {
   return __viaddmax_s16x2(s, 0u, 0xff80ff80u);
 }
 
-/* Clamped chroma word -> raw bits of RN(offset + 1.5*2^23) for R, G, B (low 16 bits = the
- * integer colour offset).  Arithmetic is colour_offsets() of jgpu_kernels.cuh, i.e. the
- * oracle's jgo_colour_offsets. */
-__device__ __forceinline__ void chroma_offsets_bits(uint32_t s, uint32_t &rb, uint32_t &gb,
+/* Two signed bytes (Cb-128 at byte 2*I, Cr-128 at byte 2*I+1 of w) -> raw bits of
+ * RN(offset + 1.5*2^23) for R, G, B (low 16 bits = the integer colour offset).
+ * Arithmetic is colour_offsets() of jgpu_kernels.cuh, i.e. the oracle's
+ * jgo_colour_offsets. */
+template <int I>
+__device__ __forceinline__ void chroma_offsets_bits(uint32_t w, uint32_t &rb, uint32_t &gb,
                                                     uint32_t &bb) {
-  const float cbf = (float)(short)(s & 0xffffu);
-  const float crf = (float)((int)s >> 16);
+  const float cbf = (float)(signed char)((w >> (16 * I)) & 0xffu);
+  const float crf = (float)(signed char)((w >> (16 * I + 8)) & 0xffu);
   const float fm = __uint_as_float(kMagicBits);
   const float rc = __fmul_rn(1.402f, crf);
   const float gc = __fadd_rn(__fmul_rn(-0.34414f, cbf), __fmul_rn(-0.71414f, crf));
@@ -274,106 +282,77 @@ __device__ __noinline__ void store_row_slow(uint8_t *dst, uint4 a, uint4 b, uint
 
 /* ---- the kernel ------------------------------------------------------------ */
 
-template <int HS, int VS, bool GRAY, int G, int STAGES>
+template <int HS, int VS, bool GRAY, int G>
 __global__ void __launch_bounds__(Cfg<HS, VS, GRAY, G>::kThreads, Cfg<HS, VS, GRAY, G>::kMinCtas)
 k_fused(const __grid_constant__ CUtensorMap tm_rows,   /* (64, rows)            */
         const __grid_constant__ CUtensorMap tm_pairs,  /* (64, parity, pairs)   */
-        const FusedImage *__restrict__ images, const TileRef *__restrict__ tiles, int n_tiles,
-        const int32_t *__restrict__ qint, uint8_t *__restrict__ rgb) {
+        const TileDesc *__restrict__ descs, int n_tiles, const int32_t *__restrict__ qint,
+        uint8_t *__restrict__ rgb, int rgb_aligned) {
   using C = Cfg<HS, VS, GRAY, G>;
-  constexpr int kDescSlots = STAGES + 1;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   /* dynamic smem is only guaranteed 16-byte aligned: round up to 1 KB for the swizzle */
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t *const smem_gen = smem_raw + (smem0 - smem_u32(smem_raw));
-  const uint32_t ex0 = smem0 + STAGES * C::kStageBytes;
-  const uint32_t ys0 = ex0 + ((C::kExBytes + 15) & ~15);
-  const uint32_t desc0 = ys0 + C::kYsBytes;
-  const uint32_t bar0 = desc0 + kDescSlots * (uint32_t)sizeof(TileDesc);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bar_data = smem0 + C::kOffBar + 8 * warp;           /* this warp's coefficients */
+  const uint32_t bar_desc0 = smem0 + C::kOffBar + 8 * C::kWarps;     /* + 8*slot */
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; s++) mbar_init(bar0 + 8 * s, 1);
+    for (int i = 0; i < C::kWarps + kDescSlots; i++) mbar_init(smem0 + C::kOffBar + 8 * i, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
 
-  /* ---- producer (thread 0): describe a tile, later start its loads -------- */
-  auto prepare = [&](int t, int slot) {
-    const TileRef tr = tiles[t];
-    const FusedImage im = images[tr.img];
-    const int x0 = tr.mx0 * C::kMcuW, y0 = tr.mrow * C::kMcuH;
-    TileDesc d;
-    d.pitch = im.width * C::kChannels;
-    d.rgb_base = im.rgb_off + ((long long)y0 * im.width + x0) * C::kChannels;
-    d.width_left = im.width - x0;
-    d.rows_left = im.height - y0;
-    d.flags = (((reinterpret_cast<uintptr_t>(rgb) + (uintptr_t)d.rgb_base) & 15) == 0 &&
-               (d.pitch & 15) == 0) ? 1 : 0;
-    d.pad0 = 0;
-#pragma unroll
-    for (int c = 0; c < 3; c++) d.qidx[c] = im.qidx[c];
-#pragma unroll
-    for (int w = 0; w < kMaxYBoxPairs; w++) {
-      int first = 0;
-      if (w < C::kYWarps) {
-        if (GRAY) {
-          first = im.block0[0] + tr.mrow * im.hblocks[0] + tr.mx0 + 64 * w;
-        } else {
-          first = im.block0[0] + (tr.mrow * VS + w / G) * im.hblocks[0] + tr.mx0 * HS + 64 * (w % G);
-        }
-      }
-      d.yfirst[w] = first;
-    }
-#pragma unroll
-    for (int cw = 0; cw < kMaxCBoxes; cw++) {
-      const bool on = cw < C::kCWarps;
-      d.cfirst[0][cw] = on ? im.block0[1] + tr.mrow * im.hblocks[1] + tr.mx0 + 32 * cw : 0;
-      d.cfirst[1][cw] = on ? im.block0[2] + tr.mrow * im.hblocks[2] + tr.mx0 + 32 * cw : 0;
-    }
-    d.pad1[0] = d.pad1[1] = d.pad1[2] = d.pad1[3] = 0;
-    *reinterpret_cast<TileDesc *>(smem_gen + (desc0 - smem0) + slot * sizeof(TileDesc)) = d;
+  /* CTA-local tile n is global tile blockIdx.x + n*gridDim.x; its descriptor lives in ring
+   * slot n % kDescSlots */
+  const int my_tiles = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  auto fetch_desc = [&](int n) {   /* thread 0 only */
+    const uint32_t slot = (uint32_t)n % kDescSlots;
+    mbar_expect_tx(bar_desc0 + 8 * slot, (uint32_t)sizeof(TileDesc));
+    bulk_load(smem0 + C::kOffDesc + slot * (uint32_t)sizeof(TileDesc),
+              descs + (blockIdx.x + (size_t)n * gridDim.x), (uint32_t)sizeof(TileDesc),
+              bar_desc0 + 8 * slot);
   };
-  auto fire = [&](int slot, int s) {
-    const TileDesc *d = reinterpret_cast<const TileDesc *>(smem_gen + (desc0 - smem0) + slot * sizeof(TileDesc));
-    const uint32_t st = smem0 + s * C::kStageBytes;
-    const uint32_t bar = bar0 + 8 * s;
-    mbar_expect_tx(bar, C::kBoxes * kBoxBytes + C::kTables * kQtabBytes);
-    /* luma: the 32 even-position and the 32 odd-position blocks of each warp's 64-block run */
-#pragma unroll
-    for (int w = 0; w < C::kYWarps; w++) {
-      const int first = d->yfirst[w];
-      tma_load_3d(st + (2 * w) * kBoxBytes, &tm_pairs, 0, first & 1, first >> 1, bar);
-      tma_load_3d(st + (2 * w + 1) * kBoxBytes, &tm_pairs, 0, (first + 1) & 1, (first + 1) >> 1, bar);
-    }
-#pragma unroll
-    for (int cw = 0; cw < C::kCWarps; cw++) {
-      tma_load_2d(st + (2 * C::kYWarps + cw) * kBoxBytes, &tm_rows, 0, d->cfirst[0][cw], bar);
-      tma_load_2d(st + (2 * C::kYWarps + C::kCWarps + cw) * kBoxBytes, &tm_rows, 0, d->cfirst[1][cw], bar);
-    }
-#pragma unroll
-    for (int c = 0; c < C::kTables; c++) {
-      bulk_load(st + C::kBoxes * kBoxBytes + c * kQtabBytes, qint + (size_t)d->qidx[c] * 64,
-                kQtabBytes, bar);
+  auto wait_desc = [&](int n) -> uint32_t {   /* returns the slot's shared address */
+    const uint32_t slot = (uint32_t)n % kDescSlots;
+    mbar_wait(bar_desc0 + 8 * slot, ((uint32_t)n / kDescSlots) & 1u);
+    return smem0 + C::kOffDesc + slot * (uint32_t)sizeof(TileDesc);
+  };
+
+  /* ---- role of this warp ---------------------------------------------------- */
+  const bool is_c = warp >= C::kYWarps;
+  const int cw = warp - C::kYWarps;   /* chroma warp index */
+  const uint32_t wreg = smem0 + C::kOffWarp + warp * kWarpBytes;   /* boxes A, B, then tables */
+  /* start this warp's loads for CTA-local tile n (lane 0 only) */
+  auto fire = [&](int n) {
+    const uint32_t d = wait_desc(n);
+    if (is_c) {
+      const int fb = (int)lds32(d + offsetof(TileDesc, cfirst) + 4 * cw);
+      const int fr = (int)lds32(d + offsetof(TileDesc, cfirst) + 4 * (kMaxCWarps + cw));
+      const int qb = (int)lds32(d + offsetof(TileDesc, qidx) + 4);
+      const int qr = (int)lds32(d + offsetof(TileDesc, qidx) + 8);
+      mbar_expect_tx(bar_data, 2 * kBoxBytes + 2 * kQtabBytes);
+      tma_load_2d(wreg, &tm_rows, 0, fb, bar_data);
+      tma_load_2d(wreg + kBoxBytes, &tm_rows, 0, fr, bar_data);
+      bulk_load(wreg + 2 * kBoxBytes, qint + (size_t)qb * 64, kQtabBytes, bar_data);
+      bulk_load(wreg + 2 * kBoxBytes + kQtabBytes, qint + (size_t)qr * 64, kQtabBytes, bar_data);
+    } else {
+      /* the 32 even-position and the 32 odd-position blocks of this warp's 64-block run */
+      const int first = (int)lds32(d + offsetof(TileDesc, yfirst) + 4 * warp);
+      const int qy = (int)lds32(d + offsetof(TileDesc, qidx));
+      mbar_expect_tx(bar_data, 2 * kBoxBytes + kQtabBytes);
+      tma_load_3d(wreg, &tm_pairs, 0, first & 1, first >> 1, bar_data);
+      tma_load_3d(wreg + kBoxBytes, &tm_pairs, 0, (first + 1) & 1, (first + 1) >> 1, bar_data);
+      bulk_load(wreg + 2 * kBoxBytes, qint + (size_t)qy * 64, kQtabBytes, bar_data);
     }
   };
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; s++) {
-      const int t = blockIdx.x + s * gridDim.x;
-      if (t < n_tiles) {
-        prepare(t, s);
-        fire(s, s);
-      }
-    }
+    fetch_desc(0);
+    if (my_tiles > 1) fetch_desc(1);
   }
+  if (lane == 0) fire(0);
 
-  /* ---- role of this warp: which boxes, which tables, which pixels --------- */
-  const bool is_c = warp >= C::kYWarps;
-  const int cw = warp - C::kYWarps;                       /* chroma warp index */
-  const int box_a = is_c ? 2 * C::kYWarps + cw : 2 * warp;
-  const int box_b = is_c ? 2 * C::kYWarps + C::kCWarps + cw : 2 * warp + 1;
-  const int qa_off = is_c ? 64 : 0, qb_off = is_c ? 128 : 0;
   /* pixel position of this thread's pair inside the tile */
   int px_x, px_y;
   if (is_c) {
@@ -386,46 +365,48 @@ k_fused(const __grid_constant__ CUtensorMap tm_rows,   /* (64, rows)            
     px_x = 16 * (32 * (warp % G) + lane);
     px_y = 8 * (warp / G);
   }
-  /* exchange-buffer slot this thread writes (C) or reads (Y) */
-  uint32_t ex_a = 0;
+  /* exchange-area task of this thread (chroma: the MCU it writes; luma: the MCU(s) it reads),
+   * relative to the slot base */
+  uint32_t ex_rel = 0;
   if (!GRAY) {
     if (HS == 2) {
-      ex_a = ex0 + (uint32_t)(is_c ? 32 * cw + lane : 32 * (warp % G) + lane) * C::kExTask;
+      ex_rel = (uint32_t)(is_c ? 32 * cw + lane : 32 * (warp % G) + lane) * C::kExTask;
     } else if (is_c) {
       const int mcu = 32 * cw + lane;
-      ex_a = ex0 + (mcu & 1) * C::kExRegion1 + (mcu >> 1) * C::kExTask;
+      ex_rel = (mcu & 1) * C::kExRegion1 + (mcu >> 1) * C::kExTask;
     } else {
-      ex_a = ex0 + (uint32_t)(32 * (warp % G) + lane) * C::kExTask;
+      ex_rel = (uint32_t)(32 * (warp % G) + lane) * C::kExTask;
     }
   }
+  const uint32_t ys_a = smem0 + C::kOffYs + (uint32_t)(is_c ? 0 : 32 * warp + lane) * C::kYsTask;
+  const uint8_t *const wgen = smem_gen + C::kOffWarp + warp * kWarpBytes;
+  const int *const qa = reinterpret_cast<const int *>(wgen + 2 * kBoxBytes);
+  const int *const qb = is_c ? qa + 64 : qa;
 
-  const uint32_t ys_a = ys0 + (uint32_t)(is_c ? 0 : 32 * warp + lane) * C::kYsTask;
+  for (int it = 0; it < my_tiles; it++) {
+    /* grey has no chroma hand-off that would keep its warps within a tile of each other;
+     * the descriptor ring needs that, so couple them here */
+    if (GRAY) named_sync(1, C::kThreads);
+    /* keep the descriptor ring two tiles ahead (slot of tile it-2: nobody reads it any more) */
+    if (threadIdx.x == 0 && it + 2 < my_tiles) fetch_desc(it + 2);
 
-  int it = 0;
-  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
-    const int s = it % STAGES;
-    /* describe the tile STAGES ahead while registers are still free */
-    const int nt = tile + STAGES * gridDim.x;
-    if (threadIdx.x == 0 && nt < n_tiles) prepare(nt, (it + STAGES) % kDescSlots);
-
-    mbar_wait(bar0 + 8 * s, (uint32_t)(it / STAGES) & 1u);
-    const uint32_t da = desc0 + (it % kDescSlots) * (uint32_t)sizeof(TileDesc);
+    const uint32_t da = wait_desc(it);
     bool active;
     {
       const uint4 h0 = lds128(da);
       active = px_x < (int)h0.z && px_y < (int)h0.w;
     }
-    const uint8_t *stp = smem_gen + s * C::kStageBytes;
-    const int *qtp = reinterpret_cast<const int *>(stp + C::kBoxes * kBoxBytes);
+    mbar_wait(bar_data, (uint32_t)it & 1u);
 
+    const uint32_t ex_a = smem0 + C::kOffEx + (it & 1) * C::kExSlot + ex_rel;
     {
       pair32 m[8][8];
-      if (active) {
-        pair_row_pass(m, stp + box_a * kBoxBytes, stp + box_b * kBoxBytes, lane, qtp + qa_off,
-                      qtp + qb_off);
-      }
-      named_sync(1, C::kThreads);   /* every warp has consumed stage s: refill it */
-      if (threadIdx.x == 0 && nt < n_tiles) fire((it + STAGES) % kDescSlots, s);
+      if (active) pair_row_pass(m, wgen, wgen + kBoxBytes, lane, qa, qb);
+      /* this warp's boxes are in registers: start the loads of its next tile */
+      __syncwarp();
+      if (lane == 0 && it + 1 < my_tiles) fire(it + 1);
+      /* chroma may not overwrite an exchange slot the luma warps still read (tile it-2) */
+      if (!GRAY && is_c && it >= 2) named_sync(4 + (it & 1), C::kThreads);
       if (active) {
         const pair32 magic = p_make_bits(kMagicBits, kMagicBits);
         column_pass_by_pairs(m, [&](int j, pair32 (&u)[8], pair32 (&v)[8]) {
@@ -440,10 +421,11 @@ k_fused(const __grid_constant__ CUtensorMap tm_rows,   /* (64, rows)            
               sts64(ys_a + 32 * k + 8 * j, make_uint2(clamp_pair_u8(ulo, vlo), clamp_pair_u8(uhi, vhi)));
             }
           } else if (!GRAY) {
-            /* chroma: clamped samples of columns 2j, 2j+1 -> exchange buffer */
+            /* chroma: clamped samples of columns 2j, 2j+1 as four signed bytes
+             * (Cb, Cr, Cb, Cr) -> exchange area */
 #pragma unroll
             for (int k = 0; k < 8; k++) {
-              sts64(ex_a + k * C::kExRow + 8 * j, make_uint2(chroma_clamped(u[k]), chroma_clamped(v[k])));
+              sts32(ex_a + 16 * k + 4 * j, __byte_perm(chroma_clamped(u[k]), chroma_clamped(v[k]), 0x6420));
             }
           }
         });
@@ -452,113 +434,117 @@ k_fused(const __grid_constant__ CUtensorMap tm_rows,   /* (64, rows)            
     if (GRAY) {
       if (!active) continue;
     } else if (is_c) {
-      named_arrive(2, C::kThreads);   /* this tile's offsets are in the exchange buffer */
+      named_arrive(2 + (it & 1), C::kThreads);   /* this tile's chroma is in the exchange area */
       continue;
     } else {
-      named_sync(2, C::kThreads);
-      if (!active) continue;
+      named_sync(2 + (it & 1), C::kThreads);
     }
 
     /* ---- luma threads: add the colour offsets, pack, store ------------------ */
-    const uint4 h0 = lds128(da);
-    const uint2 h1 = lds64(da + 16);
-    const long long rgb_base = (long long)(((unsigned long long)h0.y << 32) | h0.x);
-    const int pitch = (int)h1.x;
-    const bool fast = (h1.y & 1u) != 0 && (int)h0.z - px_x >= 16;
-    const int vis_px = min(16, (int)h0.z - px_x);
-    const int vis_rows = min(8, (int)h0.w - px_y);
-    uint8_t *dst = rgb + rgb_base + (long long)px_y * pitch + (long long)px_x * C::kChannels;
-    if (GRAY) {
+    if (active) {
+      const uint4 h0 = lds128(da);
+      const uint2 h1 = lds64(da + 16);
+      const long long rgb_base = (long long)(((unsigned long long)h0.y << 32) | h0.x);
+      const int pitch = (int)h1.x;
+      const int vis_px = min(16, (int)h0.z - px_x);
+      const int vis_rows = min(8, (int)h0.w - px_y);
+      const bool fast = (h1.y & (uint32_t)rgb_aligned & 1u) != 0 && vis_px == 16;
+      uint8_t *dst = rgb + rgb_base + (long long)px_y * pitch + (long long)px_x * C::kChannels;
+      if (GRAY) {
 #pragma unroll 1
-      for (int k = 0; k < vis_rows; k++, dst += pitch) {
-        /* staging row: (a0 b0 a1 b1 | a2 b2 a3 b3), a = block A pairs, b = block B pairs */
-        const uint4 t0 = lds128(ys_a + 32 * k), t1 = lds128(ys_a + 32 * k + 16);
-        uint4 v;
-        v.x = __byte_perm(t0.x, t0.z, 0x6420);
-        v.y = __byte_perm(t1.x, t1.z, 0x6420);
-        v.z = __byte_perm(t0.y, t0.w, 0x6420);
-        v.w = __byte_perm(t1.y, t1.w, 0x6420);
-        if (fast) stg128_stream(dst, v);
-        else store_row_slow(dst, v, v, v, vis_px);
-      }
-    } else {
-      /* one iteration per chroma row = VS pixel rows */
-#pragma unroll 1
-      for (int cr = 0; cr < 8 / VS; cr++) {
-        if (cr * VS >= vis_rows) break;
-        uint32_t ca[12], cb[12];   /* offsets for block A / block B: 4 pixel pairs x (R,G,B) */
-        const uint32_t a = ex_a + (px_y / VS + cr) * C::kExRow;
-        if (HS == 2) {
-          /* 8 chroma samples, each serving one horizontal pixel pair of VS rows: offsets,
-           * replicated into both halves of an s16x2 word */
-#pragma unroll
-          for (int v = 0; v < 2; v++) {
-            const uint4 t = lds128(a + 16 * v);
-            const uint32_t cs[4] = {t.x, t.y, t.z, t.w};
-            uint32_t *o = v == 0 ? ca : cb;
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-              uint32_t r, g, b;
-              chroma_offsets_bits(cs[i], r, g, b);
-              o[3 * i + 0] = __byte_perm(r, r, 0x1010);
-              o[3 * i + 1] = __byte_perm(g, g, 0x1010);
-              o[3 * i + 2] = __byte_perm(b, b, 0x1010);
-            }
-          }
-        } else {
-          /* block A = even MCU, block B = odd MCU: 8 samples each, paired horizontally */
-#pragma unroll
-          for (int blk = 0; blk < 2; blk++) {
-            const uint32_t base = blk == 0 ? a : a + C::kExRegion1;
-            const uint4 t0 = lds128(base), t1 = lds128(base + 16);
-            const uint32_t cs[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
-            uint32_t *o = blk == 0 ? ca : cb;
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-              uint32_t r0, g0, b0, r1, g1, b1;
-              chroma_offsets_bits(cs[2 * i], r0, g0, b0);
-              chroma_offsets_bits(cs[2 * i + 1], r1, g1, b1);
-              o[3 * i + 0] = __byte_perm(r0, r1, 0x5410);
-              o[3 * i + 1] = __byte_perm(g0, g1, 0x5410);
-              o[3 * i + 2] = __byte_perm(b0, b1, 0x5410);
-            }
-          }
+        for (int k = 0; k < vis_rows; k++, dst += pitch) {
+          /* staging row: (a0 b0 a1 b1 | a2 b2 a3 b3), a = block A pairs, b = block B pairs */
+          const uint4 t0 = lds128(ys_a + 32 * k), t1 = lds128(ys_a + 32 * k + 16);
+          uint4 v;
+          v.x = __byte_perm(t0.x, t0.z, 0x6420);
+          v.y = __byte_perm(t1.x, t1.z, 0x6420);
+          v.z = __byte_perm(t0.y, t0.w, 0x6420);
+          v.w = __byte_perm(t1.y, t1.w, 0x6420);
+          if (fast) stg128_stream(dst, v);
+          else store_row_slow(dst, v, v, v, vis_px);
         }
+      } else {
+        /* one iteration per chroma row = VS pixel rows */
+#pragma unroll 1
+        for (int cr = 0; cr < 8 / VS; cr++) {
+          if (cr * VS >= vis_rows) break;
+          uint32_t ca[12], cb[12];   /* offsets for block A / block B: 4 pixel pairs x (R,G,B) */
+          const uint32_t a = ex_a + (px_y / VS + cr) * 16;
+          if (HS == 2) {
+            /* 8 chroma samples, each serving one horizontal pixel pair of VS rows: offsets,
+             * replicated into both halves of an s16x2 word */
+            const uint4 t = lds128(a);
+            const uint32_t cs[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
-        for (int sub = 0; sub < VS; sub++) {
-          const int k = cr * VS + sub;
-          if (k < vis_rows) {
-            const uint4 t0 = lds128(ys_a + 32 * k), t1 = lds128(ys_a + 32 * k + 16);
-            uint32_t w[12];
-            rgb4(t0.x, t0.z, ca[0], ca[1], ca[2], ca[3], ca[4], ca[5], w[0], w[1], w[2]);
-            rgb4(t1.x, t1.z, ca[6], ca[7], ca[8], ca[9], ca[10], ca[11], w[3], w[4], w[5]);
-            rgb4(t0.y, t0.w, cb[0], cb[1], cb[2], cb[3], cb[4], cb[5], w[6], w[7], w[8]);
-            rgb4(t1.y, t1.w, cb[6], cb[7], cb[8], cb[9], cb[10], cb[11], w[9], w[10], w[11]);
-            const uint4 q0 = make_uint4(w[0], w[1], w[2], w[3]);
-            const uint4 q1 = make_uint4(w[4], w[5], w[6], w[7]);
-            const uint4 q2 = make_uint4(w[8], w[9], w[10], w[11]);
-            if (fast) {
-              stg128_stream(dst, q0);
-              stg128_stream(dst + 16, q1);
-              stg128_stream(dst + 32, q2);
-            } else {
-              store_row_slow(dst, q0, q1, q2, 3 * vis_px);
+            for (int i = 0; i < 4; i++) {
+              uint32_t *o = i < 2 ? ca : cb;
+              const int p = 6 * (i & 1);
+              uint32_t r, g, b;
+              chroma_offsets_bits<0>(cs[i], r, g, b);
+              o[p + 0] = __byte_perm(r, r, 0x1010);
+              o[p + 1] = __byte_perm(g, g, 0x1010);
+              o[p + 2] = __byte_perm(b, b, 0x1010);
+              chroma_offsets_bits<1>(cs[i], r, g, b);
+              o[p + 3] = __byte_perm(r, r, 0x1010);
+              o[p + 4] = __byte_perm(g, g, 0x1010);
+              o[p + 5] = __byte_perm(b, b, 0x1010);
             }
-            dst += pitch;
+          } else {
+            /* block A = even MCU, block B = odd MCU: 8 samples each, paired horizontally */
+#pragma unroll
+            for (int blk = 0; blk < 2; blk++) {
+              const uint4 t = lds128(blk == 0 ? a : a + C::kExRegion1);
+              const uint32_t cs[4] = {t.x, t.y, t.z, t.w};
+              uint32_t *o = blk == 0 ? ca : cb;
+#pragma unroll
+              for (int i = 0; i < 4; i++) {
+                uint32_t r0, g0, b0, r1, g1, b1;
+                chroma_offsets_bits<0>(cs[i], r0, g0, b0);
+                chroma_offsets_bits<1>(cs[i], r1, g1, b1);
+                o[3 * i + 0] = __byte_perm(r0, r1, 0x5410);
+                o[3 * i + 1] = __byte_perm(g0, g1, 0x5410);
+                o[3 * i + 2] = __byte_perm(b0, b1, 0x5410);
+              }
+            }
+          }
+#pragma unroll
+          for (int sub = 0; sub < VS; sub++) {
+            const int k = cr * VS + sub;
+            if (k < vis_rows) {
+              const uint4 t0 = lds128(ys_a + 32 * k), t1 = lds128(ys_a + 32 * k + 16);
+              uint32_t w[12];
+              rgb4(t0.x, t0.z, ca[0], ca[1], ca[2], ca[3], ca[4], ca[5], w[0], w[1], w[2]);
+              rgb4(t1.x, t1.z, ca[6], ca[7], ca[8], ca[9], ca[10], ca[11], w[3], w[4], w[5]);
+              rgb4(t0.y, t0.w, cb[0], cb[1], cb[2], cb[3], cb[4], cb[5], w[6], w[7], w[8]);
+              rgb4(t1.y, t1.w, cb[6], cb[7], cb[8], cb[9], cb[10], cb[11], w[9], w[10], w[11]);
+              const uint4 q0 = make_uint4(w[0], w[1], w[2], w[3]);
+              const uint4 q1 = make_uint4(w[4], w[5], w[6], w[7]);
+              const uint4 q2 = make_uint4(w[8], w[9], w[10], w[11]);
+              if (fast) {
+                stg128_stream(dst, q0);
+                stg128_stream(dst + 16, q1);
+                stg128_stream(dst + 32, q2);
+              } else {
+                store_row_slow(dst, q0, q1, q2, 3 * vis_px);
+              }
+              dst += pitch;
+            }
           }
         }
       }
     }
+    /* luma is done with exchange slot it&1: chroma may refill it for tile it+2 */
+    if (!GRAY && it + 2 < my_tiles) named_arrive(4 + (it & 1), C::kThreads);
   }
 }
-
-/* ---- host side ------------------------------------------------------------- */
 
 /* u16 tables -> int32 tables (one tiny launch per run) */
 __global__ void k_prep_qtabs(const uint16_t *__restrict__ q, int32_t *__restrict__ out, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = q[i];
 }
+
+/* ---- host side ------------------------------------------------------------- */
 
 namespace {
 
@@ -580,21 +566,11 @@ EncodeTiledFn encode_fn() {
   return fn;
 }
 
-/* Tile shape knobs (measured on B200, see profiles/): one 32-pair column group per
- * tile and a single smem stage per CTA; four 3-warp CTAs per SM overlap each
- * other's loads. */
 constexpr int kG = JGPU_FUSED_G;
-constexpr int kDefaultStages = JGPU_FUSED_STAGES;
-
-template <int HS, int VS, bool GRAY>
-size_t smem_bytes() {
-  using C = Cfg<HS, VS, GRAY, kG>;
-  return 1024 + kDefaultStages * C::kStageBytes + ((C::kExBytes + 15) & ~15) + C::kYsBytes +
-         (kDefaultStages + 1) * sizeof(TileDesc) + 8 * kDefaultStages + 16;
-}
 
 struct ModeInfo {
-  int tile_mcus, mcu_w, mcu_h, threads;
+  int hs, vs, gray;
+  int tile_mcus, mcu_w, mcu_h, threads, ywarps, cwarps, channels;
   size_t smem;
   int ctas_per_sm;
 };
@@ -605,13 +581,17 @@ bool g_configured = false;
 template <int HS, int VS, bool GRAY>
 cudaError_t configure_mode(int mode) {
   using C = Cfg<HS, VS, GRAY, kG>;
-  auto *f = &k_fused<HS, VS, GRAY, kG, kDefaultStages>;
+  auto *f = &k_fused<HS, VS, GRAY, kG>;
   ModeInfo &mi = g_modes[mode];
+  mi.hs = HS; mi.vs = VS; mi.gray = GRAY;
   mi.tile_mcus = C::kTileMcus;
   mi.mcu_w = C::kMcuW;
   mi.mcu_h = C::kMcuH;
   mi.threads = C::kThreads;
-  mi.smem = smem_bytes<HS, VS, GRAY>();
+  mi.ywarps = C::kYWarps;
+  mi.cwarps = C::kCWarps;
+  mi.channels = C::kChannels;
+  mi.smem = C::kSmemBytes;
   cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mi.smem);
   if (e != cudaSuccess) return e;
   int n = 0;
@@ -623,11 +603,11 @@ cudaError_t configure_mode(int mode) {
 
 template <int HS, int VS, bool GRAY>
 cudaError_t launch_mode(int grid, size_t smem, cudaStream_t stream, const CUtensorMap &tm_rows,
-                        const CUtensorMap &tm_pairs, const FusedImage *images, const TileRef *tiles,
-                        int n_tiles, const int32_t *qint, uint8_t *rgb) {
+                        const CUtensorMap &tm_pairs, const TileDesc *descs, int n_tiles,
+                        const int32_t *qint, uint8_t *rgb, int rgb_aligned) {
   using C = Cfg<HS, VS, GRAY, kG>;
-  k_fused<HS, VS, GRAY, kG, kDefaultStages><<<grid, C::kThreads, smem, stream>>>(
-      tm_rows, tm_pairs, images, tiles, n_tiles, qint, rgb);
+  k_fused<HS, VS, GRAY, kG><<<grid, C::kThreads, smem, stream>>>(tm_rows, tm_pairs, descs, n_tiles,
+                                                                 qint, rgb, rgb_aligned);
   return cudaGetLastError();
 }
 
@@ -650,8 +630,7 @@ cudaError_t fused_configure(int device) {
 struct FusedPlanImpl {
   int n = 0;
   int sm_count = 0;
-  void *d_images = nullptr;
-  void *d_tiles[kNumFusedModes] = {};
+  void *d_descs[kNumFusedModes] = {};
   int n_tiles[kNumFusedModes] = {};
   std::vector<int> first_tile[kNumFusedModes]; /* per mode, n+1 entries */
   void *d_qint = nullptr;
@@ -671,48 +650,57 @@ int fused_plan_build(FusedPlan &fp, const jgpu_image_desc *descs, const jgpu_lay
   p->n = n;
   p->sm_count = sm_count;
   (void)flags;
-  std::vector<FusedImage> images(n);
-  std::vector<TileRef> tiles[kNumFusedModes];
+  std::vector<TileDesc> tiles[kNumFusedModes];
   for (int m = 0; m < kNumFusedModes; m++) p->first_tile[m].assign(n + 1, 0);
   for (int i = 0; i < n; i++) {
     const jgpu_image_desc &d = descs[i];
     const jgpu_layout &lay = layouts[i];
-    FusedImage &im = images[i];
-    memset(&im, 0, sizeof(im));
-    im.rgb_off = d.rgb_off;
-    im.width = d.width;
-    im.height = d.height;
+    const ModeInfo &mi = g_modes[modes[i]];
+    int block0[3] = {0, 0, 0}, hblocks[3] = {0, 0, 0};
     for (int c = 0; c < d.ncomps; c++) {
-      im.block0[c] = (int32_t)((d.coef_off + lay.plane[c].coef_off) / 64);
-      im.hblocks[c] = lay.plane[c].hblocks;
-      im.qidx[c] = d.qtab_set * 4 + d.tq[c];
+      block0[c] = (int)((d.coef_off + lay.plane[c].coef_off) / 64);
+      hblocks[c] = lay.plane[c].hblocks;
     }
     p->coef_rows = std::max<long long>(p->coef_rows, (d.coef_off + lay.coef_len + 63) / 64);
-    const ModeInfo &mi = g_modes[modes[i]];
     for (int m = 0; m < kNumFusedModes; m++) p->first_tile[m][i] = (int)tiles[m].size();
-    const int nh = modes[i] == kModeGray ? lay.plane[0].hblocks : lay.nhmb;
-    const int nv = modes[i] == kModeGray ? lay.plane[0].vblocks : lay.nvmb;
+    const int nh = mi.gray ? lay.plane[0].hblocks : lay.nhmb;
+    const int nv = mi.gray ? lay.plane[0].vblocks : lay.nvmb;
     for (int r = 0; r < nv; r++) {
       for (int x = 0; x < nh; x += mi.tile_mcus) {
+        const int x0 = x * mi.mcu_w, y0 = r * mi.mcu_h;
         /* tiles wholly to the right of / below the visible image carry no pixels */
-        if (x * mi.mcu_w >= d.width || r * mi.mcu_h >= d.height) continue;
-        TileRef t = {i, (int16_t)r, (int16_t)x};
+        if (x0 >= d.width || y0 >= d.height) continue;
+        TileDesc t;
+        memset(&t, 0, sizeof(t));
+        t.pitch = d.width * mi.channels;
+        t.rgb_base = d.rgb_off + ((long long)y0 * d.width + x0) * mi.channels;
+        t.width_left = d.width - x0;
+        t.rows_left = d.height - y0;
+        t.flags = ((t.rgb_base & 15) == 0 && (t.pitch & 15) == 0) ? 1 : 0;
+        for (int c = 0; c < d.ncomps; c++) t.qidx[c] = d.qtab_set * 4 + d.tq[c];
+        for (int w = 0; w < mi.ywarps; w++) {
+          if (mi.gray) {
+            t.yfirst[w] = block0[0] + r * hblocks[0] + x + 64 * w;
+          } else {
+            t.yfirst[w] = block0[0] + (r * mi.vs + w / kG) * hblocks[0] + x * mi.hs + 64 * (w % kG);
+          }
+        }
+        for (int cw = 0; cw < mi.cwarps; cw++) {
+          t.cfirst[0][cw] = block0[1] + r * hblocks[1] + x + 32 * cw;
+          t.cfirst[1][cw] = block0[2] + r * hblocks[2] + x + 32 * cw;
+        }
         tiles[modes[i]].push_back(t);
       }
     }
   }
   for (int m = 0; m < kNumFusedModes; m++) p->first_tile[m][n] = (int)tiles[m].size();
-  if (cudaMalloc(&p->d_images, sizeof(FusedImage) * n) != cudaSuccess ||
-      cudaMemcpy(p->d_images, images.data(), sizeof(FusedImage) * n, cudaMemcpyHostToDevice) != cudaSuccess) {
-    return jgpu_fail("fused plan: image table upload failed");
-  }
   for (int m = 0; m < kNumFusedModes; m++) {
     p->n_tiles[m] = (int)tiles[m].size();
     if (tiles[m].empty()) continue;
-    if (cudaMalloc(&p->d_tiles[m], sizeof(TileRef) * tiles[m].size()) != cudaSuccess ||
-        cudaMemcpy(p->d_tiles[m], tiles[m].data(), sizeof(TileRef) * tiles[m].size(),
+    if (cudaMalloc(&p->d_descs[m], sizeof(TileDesc) * tiles[m].size()) != cudaSuccess ||
+        cudaMemcpy(p->d_descs[m], tiles[m].data(), sizeof(TileDesc) * tiles[m].size(),
                    cudaMemcpyHostToDevice) != cudaSuccess) {
-      return jgpu_fail("fused plan: tile list upload failed");
+      return jgpu_fail("fused plan: tile descriptor upload failed");
     }
   }
   return 0;
@@ -721,8 +709,7 @@ int fused_plan_build(FusedPlan &fp, const jgpu_image_desc *descs, const jgpu_lay
 void fused_plan_release(FusedPlan &fp) {
   FusedPlanImpl *p = static_cast<FusedPlanImpl *>(fp.impl);
   if (!p) return;
-  cudaFree(p->d_images);
-  for (int m = 0; m < kNumFusedModes; m++) cudaFree(p->d_tiles[m]);
+  for (int m = 0; m < kNumFusedModes; m++) cudaFree(p->d_descs[m]);
   cudaFree(p->d_qint);
   delete p;
   fp.impl = nullptr;
@@ -782,20 +769,20 @@ int fused_plan_launch(FusedPlan &fp, int i0, int i1, const int16_t *coef, const 
   k_prep_qtabs<<<(n_tables * 64 + 255) / 256, 256, 0, stream>>>(qtabs, (int32_t *)p->d_qint, n_tables * 64);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return jgpu_fail("k_prep_qtabs launch failed (%s)", cudaGetErrorString(e));
+  const int rgb_aligned = (reinterpret_cast<uintptr_t>(rgb) & 15) == 0 ? 1 : 0;
   for (int m = 0; m < kNumFusedModes; m++) {
     const int t0 = p->first_tile[m][i0], t1 = p->first_tile[m][i1];
     if (t1 <= t0) continue;
     const ModeInfo &mi = g_modes[m];
     const int grid = std::min(t1 - t0, p->sm_count * mi.ctas_per_sm);
-    const TileRef *tiles = static_cast<const TileRef *>(p->d_tiles[m]) + t0;
-    const FusedImage *images = static_cast<const FusedImage *>(p->d_images);
+    const TileDesc *descs = static_cast<const TileDesc *>(p->d_descs[m]) + t0;
     const int32_t *qint = static_cast<const int32_t *>(p->d_qint);
     switch (m) {
-      case kModeGray: e = launch_mode<1, 1, true>(grid, mi.smem, stream, p->tm_rows, p->tm_pairs, images, tiles, t1 - t0, qint, rgb); break;
-      case kMode444: e = launch_mode<1, 1, false>(grid, mi.smem, stream, p->tm_rows, p->tm_pairs, images, tiles, t1 - t0, qint, rgb); break;
-      case kMode422: e = launch_mode<2, 1, false>(grid, mi.smem, stream, p->tm_rows, p->tm_pairs, images, tiles, t1 - t0, qint, rgb); break;
-      case kMode420: e = launch_mode<2, 2, false>(grid, mi.smem, stream, p->tm_rows, p->tm_pairs, images, tiles, t1 - t0, qint, rgb); break;
-      case kMode440: e = launch_mode<1, 2, false>(grid, mi.smem, stream, p->tm_rows, p->tm_pairs, images, tiles, t1 - t0, qint, rgb); break;
+      case kModeGray: e = launch_mode<1, 1, true>(grid, mi.smem, stream, p->tm_rows, p->tm_pairs, descs, t1 - t0, qint, rgb, rgb_aligned); break;
+      case kMode444: e = launch_mode<1, 1, false>(grid, mi.smem, stream, p->tm_rows, p->tm_pairs, descs, t1 - t0, qint, rgb, rgb_aligned); break;
+      case kMode422: e = launch_mode<2, 1, false>(grid, mi.smem, stream, p->tm_rows, p->tm_pairs, descs, t1 - t0, qint, rgb, rgb_aligned); break;
+      case kMode420: e = launch_mode<2, 2, false>(grid, mi.smem, stream, p->tm_rows, p->tm_pairs, descs, t1 - t0, qint, rgb, rgb_aligned); break;
+      case kMode440: e = launch_mode<1, 2, false>(grid, mi.smem, stream, p->tm_rows, p->tm_pairs, descs, t1 - t0, qint, rgb, rgb_aligned); break;
     }
     if (e != cudaSuccess) return jgpu_fail("fused kernel launch failed (%s)", cudaGetErrorString(e));
   }
