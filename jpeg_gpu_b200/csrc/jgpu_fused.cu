@@ -53,7 +53,7 @@ namespace jgpu {
 
 /* Build-time tuning knobs (A/B-tested on the GPU, see profiles/). */
 #ifndef JGPU_FUSED_G
-#define JGPU_FUSED_G 1          /* 32-pair column groups per tile */
+#define JGPU_FUSED_G 2          /* 32-pair column groups per tile */
 #endif
 #ifndef JGPU_FUSED_MINCTAS
 #define JGPU_FUSED_MINCTAS 0    /* 0: size registers for 12 warps per SM */
@@ -61,7 +61,7 @@ namespace jgpu {
 
 constexpr int kBoxRows = 32;                 /* blocks per TMA box */
 constexpr int kBoxBytes = kBoxRows * 128;    /* 4 KB */
-constexpr int kQtabBytes = 64 * 4;           /* one table as int32 */
+constexpr int kQtabBytes = 64 * 4;           /* one packed table: 32 low-byte + 32 high-byte words */
 constexpr int kWarpBytes = 2 * kBoxBytes + 1024; /* two boxes + up to two tables, 1 KB aligned */
 constexpr int kMaxYWarps = 6;
 constexpr int kMaxCWarps = 4;
@@ -133,17 +133,17 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(bar), "r"(parity)
+      : "r"(bar), "r"(parity), "r"(100000u) /* suspend-time hint (ns): sleep, do not spin */
       : "memory");
   return ok != 0;
 }
 /* Bounded wait: a pipeline bug must trap, not hang the GPU. */
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   for (uint32_t spins = 0; !mbar_try_wait(bar, parity); spins++) {
-    if (spins > (1u << 24)) __trap();
+    if (spins > (1u << 18)) __trap();
   }
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *tm, int c0, int c1,
@@ -209,10 +209,12 @@ __device__ __forceinline__ void stg128_stream(uint8_t *p, uint4 v) {
 
 /* Row pass for one block pair out of two swizzled TMA boxes.  `row` is this
  * lane's row inside the boxes; chunk r of a 128-byte row sits at 16*(r ^ (row&7)).
- * qa / qb: the int32 quantisation tables of block A / block B (natural order). */
+ * qa / qb: the packed quantisation tables of block A / block B (k_prep_qtabs):
+ * 32 words of low bytes, then 32 words of high bytes. */
+template <bool WIDE>
 __device__ __forceinline__ void pair_row_pass(pair32 (&m)[8][8], const uint8_t *box_a,
-                                              const uint8_t *box_b, int row, const int *qa,
-                                              const int *qb) {
+                                              const uint8_t *box_b, int row, const uint4 *qa,
+                                              const uint4 *qb) {
   const uint8_t *ra = box_a + 128 * row, *rb = box_b + 128 * row;
   const int sw = row & 7;
 #pragma unroll
@@ -220,7 +222,8 @@ __device__ __forceinline__ void pair_row_pass(pair32 (&m)[8][8], const uint8_t *
     const int off = 16 * (r ^ sw);
     const uint4 a = *reinterpret_cast<const uint4 *>(ra + off);
     const uint4 b = *reinterpret_cast<const uint4 *>(rb + off);
-    load_row_pair(m[r], a, b, qa + 8 * r, qb + 8 * r, r);
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    load_row_pair_packed<WIDE>(m[r], a, b, qa[r], qb[r], WIDE ? qa[8 + r] : z, WIDE ? qb[8 + r] : z, r);
     inv_pass8(m[r]);
   }
 }
@@ -282,13 +285,17 @@ __device__ __noinline__ void store_row_slow(uint8_t *dst, uint4 a, uint4 b, uint
 
 /* ---- the kernel ------------------------------------------------------------ */
 
-template <int HS, int VS, bool GRAY, int G>
+/* WIDE: the instantiation for runs whose tables have entries above 255 (16-bit DQT).  Both
+ * instantiations are launched; k_prep_qtabs sets *wide_flag and the one that does not apply
+ * returns at once, which keeps the common kernel free of the two-step dequantisation. */
+template <int HS, int VS, bool GRAY, int G, bool WIDE>
 __global__ void __launch_bounds__(Cfg<HS, VS, GRAY, G>::kThreads, Cfg<HS, VS, GRAY, G>::kMinCtas)
 k_fused(const __grid_constant__ CUtensorMap tm_rows,   /* (64, rows)            */
         const __grid_constant__ CUtensorMap tm_pairs,  /* (64, parity, pairs)   */
-        const TileDesc *__restrict__ descs, int n_tiles, const int32_t *__restrict__ qint,
-        uint8_t *__restrict__ rgb, int rgb_aligned) {
+        const TileDesc *__restrict__ descs, int n_tiles, const uint32_t *__restrict__ qint,
+        const uint32_t *__restrict__ wide_flag, uint8_t *__restrict__ rgb, int rgb_aligned) {
   using C = Cfg<HS, VS, GRAY, G>;
+  if ((*wide_flag != 0) != WIDE) return;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   /* dynamic smem is only guaranteed 16-byte aligned: round up to 1 KB for the swizzle */
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -380,8 +387,8 @@ k_fused(const __grid_constant__ CUtensorMap tm_rows,   /* (64, rows)            
   }
   const uint32_t ys_a = smem0 + C::kOffYs + (uint32_t)(is_c ? 0 : 32 * warp + lane) * C::kYsTask;
   const uint8_t *const wgen = smem_gen + C::kOffWarp + warp * kWarpBytes;
-  const int *const qa = reinterpret_cast<const int *>(wgen + 2 * kBoxBytes);
-  const int *const qb = is_c ? qa + 64 : qa;
+  const uint4 *const qa = reinterpret_cast<const uint4 *>(wgen + 2 * kBoxBytes);
+  const uint4 *const qb = is_c ? qa + 16 : qa;   /* chroma: Cb table, then Cr table */
 
   for (int it = 0; it < my_tiles; it++) {
     /* grey has no chroma hand-off that would keep its warps within a tile of each other;
@@ -401,7 +408,7 @@ k_fused(const __grid_constant__ CUtensorMap tm_rows,   /* (64, rows)            
     const uint32_t ex_a = smem0 + C::kOffEx + (it & 1) * C::kExSlot + ex_rel;
     {
       pair32 m[8][8];
-      if (active) pair_row_pass(m, wgen, wgen + kBoxBytes, lane, qa, qb);
+      if (active) pair_row_pass<WIDE>(m, wgen, wgen + kBoxBytes, lane, qa, qb);
       /* this warp's boxes are in registers: start the loads of its next tile */
       __syncwarp();
       if (lane == 0 && it + 1 < my_tiles) fire(it + 1);
@@ -538,10 +545,18 @@ k_fused(const __grid_constant__ CUtensorMap tm_rows,   /* (64, rows)            
   }
 }
 
-/* u16 tables -> int32 tables (one tiny launch per run) */
-__global__ void k_prep_qtabs(const uint16_t *__restrict__ q, int32_t *__restrict__ out, int n) {
+/* u16 tables -> packed tables for IDP.2A (one tiny launch per run).  Per table 64 words:
+ * word r*4+i        = (q[r][2i] & 255)  | (q[r][2i+1] & 255) << 24      (low bytes)
+ * word 32 + r*4+i   = (q[r][2i] >> 8)   | (q[r][2i+1] >> 8)  << 24      (high bytes) */
+__global__ void k_prep_qtabs(const uint16_t *__restrict__ q, uint32_t *__restrict__ out, int n_words,
+                             uint32_t *__restrict__ wide_flag) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = q[i];
+  if (i >= n_words) return;
+  const int table = i >> 6, w = i & 63, hi = w >> 5, idx = (w & 31) * 2;
+  const uint32_t q0 = q[table * 64 + idx], q1 = q[table * 64 + idx + 1];
+  const uint32_t v = hi ? ((q0 >> 8) | ((q1 >> 8) << 24)) : ((q0 & 255u) | ((q1 & 255u) << 24));
+  out[i] = v;
+  if (hi && v) atomicOr(wide_flag, 1u);   /* wide_flag is zeroed by the host before this launch */
 }
 
 /* ---- host side ------------------------------------------------------------- */
@@ -581,7 +596,10 @@ bool g_configured = false;
 template <int HS, int VS, bool GRAY>
 cudaError_t configure_mode(int mode) {
   using C = Cfg<HS, VS, GRAY, kG>;
-  auto *f = &k_fused<HS, VS, GRAY, kG>;
+  auto *f = &k_fused<HS, VS, GRAY, kG, false>;
+  cudaError_t ew = cudaFuncSetAttribute(&k_fused<HS, VS, GRAY, kG, true>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmemBytes);
+  if (ew != cudaSuccess) return ew;
   ModeInfo &mi = g_modes[mode];
   mi.hs = HS; mi.vs = VS; mi.gray = GRAY;
   mi.tile_mcus = C::kTileMcus;
@@ -604,10 +622,12 @@ cudaError_t configure_mode(int mode) {
 template <int HS, int VS, bool GRAY>
 cudaError_t launch_mode(int grid, size_t smem, cudaStream_t stream, const CUtensorMap &tm_rows,
                         const CUtensorMap &tm_pairs, const TileDesc *descs, int n_tiles,
-                        const int32_t *qint, uint8_t *rgb, int rgb_aligned) {
+                        const uint32_t *qint, const uint32_t *wide_flag, uint8_t *rgb, int rgb_aligned) {
   using C = Cfg<HS, VS, GRAY, kG>;
-  k_fused<HS, VS, GRAY, kG><<<grid, C::kThreads, smem, stream>>>(tm_rows, tm_pairs, descs, n_tiles,
-                                                                 qint, rgb, rgb_aligned);
+  k_fused<HS, VS, GRAY, kG, false><<<grid, C::kThreads, smem, stream>>>(
+      tm_rows, tm_pairs, descs, n_tiles, qint, wide_flag, rgb, rgb_aligned);
+  k_fused<HS, VS, GRAY, kG, true><<<grid, C::kThreads, smem, stream>>>(
+      tm_rows, tm_pairs, descs, n_tiles, qint, wide_flag, rgb, rgb_aligned);
   return cudaGetLastError();
 }
 
@@ -718,7 +738,7 @@ void fused_plan_release(FusedPlan &fp) {
 int fused_plan_launches(const FusedPlan &fp) {
   const FusedPlanImpl *p = static_cast<const FusedPlanImpl *>(fp.impl);
   int n = 1; /* table conversion */
-  for (int m = 0; m < kNumFusedModes; m++) n += p->n_tiles[m] > 0;
+  for (int m = 0; m < kNumFusedModes; m++) n += 2 * (p->n_tiles[m] > 0); /* 8-bit and 16-bit table variants */
   return n;
 }
 
@@ -761,12 +781,15 @@ int fused_plan_launch(FusedPlan &fp, int i0, int i1, const int16_t *coef, const 
   if (n_tables > p->qint_cap) {
     cudaFree(p->d_qint);
     p->d_qint = nullptr;
-    if (cudaMalloc(&p->d_qint, (size_t)n_tables * 64 * 4) != cudaSuccess) {
+    if (cudaMalloc(&p->d_qint, (size_t)n_tables * 64 * 4 + 16) != cudaSuccess) {
       return jgpu_fail("fused path: table buffer allocation failed");
     }
     p->qint_cap = n_tables;
   }
-  k_prep_qtabs<<<(n_tables * 64 + 255) / 256, 256, 0, stream>>>(qtabs, (int32_t *)p->d_qint, n_tables * 64);
+  /* the wide flag lives right behind the tables */
+  uint32_t *wide_flag = (uint32_t *)p->d_qint + (size_t)p->qint_cap * 64;
+  if (cudaMemsetAsync(wide_flag, 0, 4, stream) != cudaSuccess) return jgpu_fail("fused path: memset failed");
+  k_prep_qtabs<<<(n_tables * 64 + 255) / 256, 256, 0, stream>>>(qtabs, (uint32_t *)p->d_qint, n_tables * 64, wide_flag);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return jgpu_fail("k_prep_qtabs launch failed (%s)", cudaGetErrorString(e));
   const int rgb_aligned = (reinterpret_cast<uintptr_t>(rgb) & 15) == 0 ? 1 : 0;
@@ -776,13 +799,13 @@ int fused_plan_launch(FusedPlan &fp, int i0, int i1, const int16_t *coef, const 
     const ModeInfo &mi = g_modes[m];
     const int grid = std::min(t1 - t0, p->sm_count * mi.ctas_per_sm);
     const TileDesc *descs = static_cast<const TileDesc *>(p->d_descs[m]) + t0;
-    const int32_t *qint = static_cast<const int32_t *>(p->d_qint);
+    const uint32_t *qint = static_cast<const uint32_t *>(p->d_qint);
     switch (m) {
-      case kModeGray: e = launch_mode<1, 1, true>(grid, mi.smem, stream, p->tm_rows, p->tm_pairs, descs, t1 - t0, qint, rgb, rgb_aligned); break;
-      case kMode444: e = launch_mode<1, 1, false>(grid, mi.smem, stream, p->tm_rows, p->tm_pairs, descs, t1 - t0, qint, rgb, rgb_aligned); break;
-      case kMode422: e = launch_mode<2, 1, false>(grid, mi.smem, stream, p->tm_rows, p->tm_pairs, descs, t1 - t0, qint, rgb, rgb_aligned); break;
-      case kMode420: e = launch_mode<2, 2, false>(grid, mi.smem, stream, p->tm_rows, p->tm_pairs, descs, t1 - t0, qint, rgb, rgb_aligned); break;
-      case kMode440: e = launch_mode<1, 2, false>(grid, mi.smem, stream, p->tm_rows, p->tm_pairs, descs, t1 - t0, qint, rgb, rgb_aligned); break;
+      case kModeGray: e = launch_mode<1, 1, true>(grid, mi.smem, stream, p->tm_rows, p->tm_pairs, descs, t1 - t0, qint, wide_flag, rgb, rgb_aligned); break;
+      case kMode444: e = launch_mode<1, 1, false>(grid, mi.smem, stream, p->tm_rows, p->tm_pairs, descs, t1 - t0, qint, wide_flag, rgb, rgb_aligned); break;
+      case kMode422: e = launch_mode<2, 1, false>(grid, mi.smem, stream, p->tm_rows, p->tm_pairs, descs, t1 - t0, qint, wide_flag, rgb, rgb_aligned); break;
+      case kMode420: e = launch_mode<2, 2, false>(grid, mi.smem, stream, p->tm_rows, p->tm_pairs, descs, t1 - t0, qint, wide_flag, rgb, rgb_aligned); break;
+      case kMode440: e = launch_mode<1, 2, false>(grid, mi.smem, stream, p->tm_rows, p->tm_pairs, descs, t1 - t0, qint, wide_flag, rgb, rgb_aligned); break;
     }
     if (e != cudaSuccess) return jgpu_fail("fused kernel launch failed (%s)", cudaGetErrorString(e));
   }

@@ -42,6 +42,49 @@ JGPU_DEV void load_row_pair(pair32 (&row)[8], uint4 a, uint4 b, const int *qa,
   }
 }
 
+/* ---- packed-table variant (fused kernel) -------------------------------------
+ * The product of one int16 coefficient with one 8-bit table entry is a single
+ * IDP.2A: dp2a treats `w` as two int16 and `q` as four bytes,
+ *     lo: w.h0*q.b0 + w.h1*q.b1        hi: w.h0*q.b2 + w.h1*q.b3
+ * so with q = (q_even, 0, 0, q_odd) the two forms pick and multiply one half
+ * each with no unpack instruction.  Table entries above 255 (16-bit DQT) are
+ * split: c*q = c*(q&255) + ((c*(q>>8)) << 8), all modulo 2^16, which is the
+ * reference's wrap into `short` anyway (src/xjpeg.c:501-503,524-527). */
+JGPU_DEV int dp2a_lo_s16_u8(uint32_t w, uint32_t q) {
+  int d;
+  asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(w), "r"(q), "r"(0));
+  return d;
+}
+JGPU_DEV int dp2a_hi_s16_u8(uint32_t w, uint32_t q) {
+  int d;
+  asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(w), "r"(q), "r"(0));
+  return d;
+}
+
+/* One coefficient row of block A and of block B (8 int16 each) with the packed
+ * table rows qa / qb (4 words each; WIDE: plus the high-byte rows qah / qbh):
+ * dequantise, convert, prescale. */
+template <bool WIDE>
+JGPU_DEV void load_row_pair_packed(pair32 (&row)[8], uint4 a, uint4 b, uint4 qa, uint4 qb,
+                                   uint4 qah, uint4 qbh, int r) {
+  const uint32_t wa[4] = {a.x, a.y, a.z, a.w}, wb[4] = {b.x, b.y, b.z, b.w};
+  const uint32_t ka[4] = {qa.x, qa.y, qa.z, qa.w}, kb[4] = {qb.x, qb.y, qb.z, qb.w};
+  const uint32_t ha[4] = {qah.x, qah.y, qah.z, qah.w}, hb[4] = {qbh.x, qbh.y, qbh.z, qbh.w};
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    int a0 = dp2a_lo_s16_u8(wa[i], ka[i]), a1 = dp2a_hi_s16_u8(wa[i], ka[i]);
+    int b0 = dp2a_lo_s16_u8(wb[i], kb[i]), b1 = dp2a_hi_s16_u8(wb[i], kb[i]);
+    if (WIDE) {
+      a0 += dp2a_lo_s16_u8(wa[i], ha[i]) << 8;
+      a1 += dp2a_hi_s16_u8(wa[i], ha[i]) << 8;
+      b0 += dp2a_lo_s16_u8(wb[i], hb[i]) << 8;
+      b1 += dp2a_hi_s16_u8(wb[i], hb[i]) << 8;
+    }
+    row[2 * i] = prescale(p_make((float)(short)a0, (float)(short)b0), r, 2 * i);
+    row[2 * i + 1] = prescale(p_make((float)(short)a1, (float)(short)b1), r, 2 * i + 1);
+  }
+}
+
 /* Two un-floored samples (same block, adjacent columns) -> two clamped u8
  * samples in the halves of a 32-bit word:
  *   floor            src/dct.c:118 ((short)floor(t): low 16 bits of the integer)

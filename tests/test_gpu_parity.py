@@ -96,6 +96,21 @@ def test_dequantisation_wraps_like_a_short(gpu_ctx, checker):
     compare_batch(descs_rgb, got_rgb, None, exp_rgb, None)
 
 
+@pytest.mark.parametrize("force_generic", [True, False])
+def test_sixteen_bit_quant_tables(gpu_ctx, checker, force_generic):
+    """xjpeg accepts Pq=1 DQT segments (src/xjpeg.c:235-241): entries above 255."""
+    shapes = [(96, 64, "420"), (64, 64, "444"), (80, 40, "422"), (64, 32, "gray")]
+    descs, coef_len, rgb_len, _ = make_batch(shapes, want_yuv=False)
+    rng = np.random.default_rng(11)
+    q = synth.quality_tables(50).astype(np.uint16)
+    q[0, 5] = 300; q[0, 63] = 1000; q[1, 1] = 256; q[1, 40] = 65535; q[1, 41] = 511
+    coef = rng.integers(-40, 41, size=coef_len).astype(np.int16)
+    coef[rng.random(coef_len) < 0.7] = 0
+    exp_rgb, _ = oracle_batch(checker, descs, coef, q, rgb_len, 0)
+    got_rgb, _ = gpu_batch(gpu_ctx, descs, coef, q, rgb_len, 0, force_generic)
+    compare_batch(descs, got_rgb, None, exp_rgb, None)
+
+
 def test_host_batch_api(gpu_ctx, checker):
     shapes = [(1920, 1080, "420"), (512, 512, "gray"), (70, 50, "422")]
     descs, coef_len, rgb_len, yuv_len = make_batch(shapes)
