@@ -360,35 +360,46 @@ k_fused(const __grid_constant__ CUtensorMap tm_rows,   /* (64, rows)            
   }
   if (lane == 0) fire(0);
 
-  /* pixel position of this thread's pair inside the tile */
-  int px_x, px_y;
-  if (is_c) {
-    px_x = (HS == 2 ? 16 : 8) * (32 * cw + lane);
-    px_y = 0;
-  } else if (GRAY) {
-    px_x = 16 * (32 * warp + lane);
-    px_y = 0;
-  } else {
-    px_x = 16 * (32 * (warp % G) + lane);
-    px_y = 8 * (warp / G);
-  }
-  /* exchange-area task of this thread (chroma: the MCU it writes; luma: the MCU(s) it reads),
-   * relative to the slot base */
-  uint32_t ex_rel = 0;
-  if (!GRAY) {
-    if (HS == 2) {
-      ex_rel = (uint32_t)(is_c ? 32 * cw + lane : 32 * (warp % G) + lane) * C::kExTask;
-    } else if (is_c) {
-      const int mcu = 32 * cw + lane;
-      ex_rel = (mcu & 1) * C::kExRegion1 + (mcu >> 1) * C::kExTask;
+  /* Per-thread geometry, derived from the thread index.  It is re-derived (from a fresh,
+   * un-CSE-able read of %tid.x) at each point of use instead of being kept in registers
+   * across the IDCT, where every register counts. */
+  struct Geo {
+    int px_x, px_y;      /* pixel position of this thread's pair inside the tile */
+    uint32_t ex_rel;     /* exchange-area task (chroma: the MCU it writes; luma: the one(s) it reads) */
+    uint32_t ys_a;       /* luma staging rows */
+  };
+  auto geo = [&]() -> Geo {
+    uint32_t tid;
+    asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
+    const int w = (int)(tid >> 5), l = (int)(tid & 31);
+    const bool c = w >= C::kYWarps;
+    const int cwi = w - C::kYWarps;
+    Geo g;
+    if (c) {
+      g.px_x = (HS == 2 ? 16 : 8) * (32 * cwi + l);
+      g.px_y = 0;
+    } else if (GRAY) {
+      g.px_x = 16 * (32 * w + l);
+      g.px_y = 0;
     } else {
-      ex_rel = (uint32_t)(32 * (warp % G) + lane) * C::kExTask;
+      g.px_x = 16 * (32 * (w % G) + l);
+      g.px_y = 8 * (w / G);
     }
-  }
-  const uint32_t ys_a = smem0 + C::kOffYs + (uint32_t)(is_c ? 0 : 32 * warp + lane) * C::kYsTask;
+    g.ex_rel = 0;
+    if (!GRAY) {
+      if (HS == 2) {
+        g.ex_rel = (uint32_t)(c ? 32 * cwi + l : 32 * (w % G) + l) * C::kExTask;
+      } else if (c) {
+        const int mcu = 32 * cwi + l;
+        g.ex_rel = (mcu & 1) * C::kExRegion1 + (mcu >> 1) * C::kExTask;
+      } else {
+        g.ex_rel = (uint32_t)(32 * (w % G) + l) * C::kExTask;
+      }
+    }
+    g.ys_a = smem0 + C::kOffYs + (uint32_t)(c ? 0 : 32 * w + l) * C::kYsTask;
+    return g;
+  };
   const uint8_t *const wgen = smem_gen + C::kOffWarp + warp * kWarpBytes;
-  const uint4 *const qa = reinterpret_cast<const uint4 *>(wgen + 2 * kBoxBytes);
-  const uint4 *const qb = is_c ? qa + 16 : qa;   /* chroma: Cb table, then Cr table */
 
   for (int it = 0; it < my_tiles; it++) {
     /* grey has no chroma hand-off that would keep its warps within a tile of each other;
@@ -400,15 +411,19 @@ k_fused(const __grid_constant__ CUtensorMap tm_rows,   /* (64, rows)            
     const uint32_t da = wait_desc(it);
     bool active;
     {
+      const Geo g = geo();
       const uint4 h0 = lds128(da);
-      active = px_x < (int)h0.z && px_y < (int)h0.w;
+      active = g.px_x < (int)h0.z && g.px_y < (int)h0.w;
     }
     mbar_wait(bar_data, (uint32_t)it & 1u);
 
-    const uint32_t ex_a = smem0 + C::kOffEx + (it & 1) * C::kExSlot + ex_rel;
     {
       pair32 m[8][8];
-      if (active) pair_row_pass<WIDE>(m, wgen, wgen + kBoxBytes, lane, qa, qb);
+      if (active) {
+        const uint4 *const qa = reinterpret_cast<const uint4 *>(wgen + 2 * kBoxBytes);
+        const uint4 *const qb = is_c ? qa + 16 : qa;   /* chroma: Cb table, then Cr table */
+        pair_row_pass<WIDE>(m, wgen, wgen + kBoxBytes, lane, qa, qb);
+      }
       /* this warp's boxes are in registers: start the loads of its next tile */
       __syncwarp();
       if (lane == 0 && it + 1 < my_tiles) fire(it + 1);
@@ -416,6 +431,9 @@ k_fused(const __grid_constant__ CUtensorMap tm_rows,   /* (64, rows)            
       if (!GRAY && is_c && it >= 2) named_sync(4 + (it & 1), C::kThreads);
       if (active) {
         const pair32 magic = p_make_bits(kMagicBits, kMagicBits);
+        const Geo g = geo();
+        const uint32_t ys_a = g.ys_a;
+        const uint32_t ex_a = smem0 + C::kOffEx + (it & 1) * C::kExSlot + g.ex_rel;
         column_pass_by_pairs(m, [&](int j, pair32 (&u)[8], pair32 (&v)[8]) {
           if (!is_c) {
             /* luma: (short)floor + 128, clamp; pixels 2j, 2j+1 of row k of block A and of
@@ -449,6 +467,10 @@ k_fused(const __grid_constant__ CUtensorMap tm_rows,   /* (64, rows)            
 
     /* ---- luma threads: add the colour offsets, pack, store ------------------ */
     if (active) {
+      const Geo g = geo();
+      const int px_x = g.px_x, px_y = g.px_y;
+      const uint32_t ys_a = g.ys_a;
+      const uint32_t ex_a = smem0 + C::kOffEx + (it & 1) * C::kExSlot + g.ex_rel;
       const uint4 h0 = lds128(da);
       const uint2 h1 = lds64(da + 16);
       const long long rgb_base = (long long)(((unsigned long long)h0.y << 32) | h0.x);
