@@ -1,0 +1,79 @@
+"""Static audit of the shipped sm_100a machine code (cuobjdump, no GPU needed).
+
+Bit-exactness with src/dct.c forbids fused multiply-adds in the IDCT.  ptxas 12.9 fuses
+`mul.rn.f32x2` + `add.rn.f32x2` into FFMA2 despite the explicit .rn, so the core issues every
+product as fma(a, b, -0.0) with -0.0 in a register loaded from __constant__ memory
+(jgpu_idct_core.cuh).  This test checks that the SASS has that shape: no packed multiply at
+all, every packed FMA adds that one register, no scalar FFMA in the kernels, and that the
+kernels really use the Blackwell features the design rests on (FADD2/FFMA2, TMA, mbarrier)."""
+import os
+import re
+import shutil
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB = os.path.join(ROOT, "jpeg_gpu_b200", "libjpeg_gpu_b200.so")
+
+
+@pytest.fixture(scope="module")
+def sass():
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not on PATH")
+    out = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True, check=True).stdout
+    funcs, name = {}, None
+    for line in out.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            name = m.group(1)
+            funcs[name] = []
+        elif name and re.match(r"\s+/\*[0-9a-f]{4,}\*/", line):
+            funcs[name].append(line)
+    return funcs
+
+
+def test_only_sm100a_code(sass):
+    out = subprocess.run(["cuobjdump", "-lelf", LIB], capture_output=True, text=True, check=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_idct_has_no_contracted_multiply_add(sass):
+    kernels = {n: body for n, body in sass.items() if "k_fused" in n or "k_coef_to_planes" in n}
+    assert len(kernels) >= 11      # generic + 5 fused modes x {8-bit, 16-bit tables}
+    for name, body in kernels.items():
+        text = "\n".join(body)
+        assert "FMUL2" not in text, name
+        ffma2 = [l for l in body if re.search(r"\bFFMA2\b", l)]
+        fadd2 = [l for l in body if re.search(r"\bFADD2\b", l)]
+        # 2 x 64 prescale products + 16 passes x 5 products = 208 packed products per block pair
+        assert len(ffma2) == 208, (name, len(ffma2))
+        assert len(fadd2) >= 16 * 29 + 8 + 64, (name, len(fadd2))
+        # the addend of every packed FMA is a register pair loaded from c_negzero2 (bank 3)
+        negzero_regs = set(re.findall(r"LDC\.64 (R\d+), c\[0x3\]", text))
+        assert negzero_regs, name
+        addends = set()
+        for l in ffma2:
+            ops = l.split("FFMA2", 1)[1].split(";")[0].split(",")
+            addends.add(ops[-1].strip().split(".")[0])
+        assert addends <= negzero_regs, (name, addends, negzero_regs)
+        assert not re.search(r"\bFFMA\b", text), name        # no scalar contraction either
+
+
+def test_colour_stage_has_no_fma(sass):
+    for name, body in sass.items():
+        if "k_planes_to_rgb" in name:
+            assert not any(re.search(r"\bFFMA\b", l) for l in body), name
+
+
+def test_fused_kernel_uses_tma_and_mbarriers(sass):
+    fused = [body for n, body in sass.items() if "k_fused" in n]
+    for body in fused:
+        text = "\n".join(body)
+        assert "UTMALDG" in text          # cp.async.bulk.tensor
+        assert "UBLKCP" in text           # cp.async.bulk (tables, tile descriptors)
+        assert "SYNCS" in text            # mbarrier arrive / try_wait
+        assert "IDP.2A" in text           # packed-table dequantisation
+        assert "VIADDMNMX" in text        # s16x2 add+clamp
+        assert "STG.E.EF.128" in text or "STG.E.128" in text or re.search(r"STG\.E\.[A-Z.]*128", text)
