@@ -78,7 +78,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._stop.wait(0.05)
+            self._stop.wait(0.005)
 
     def __enter__(self):
         if self._nv is not None:
@@ -96,6 +96,18 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
         return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def measured_traffic(workload: str):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full`
+    capture of this workload (profiles/r1_traffic.json), or None."""
+    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            t = json.load(f).get(workload)
+        if t:
+            return t["dram_bytes_read"] + t["dram_bytes_write"]
+    return None
 
 
 def build_batch(workload: str):
@@ -239,7 +251,7 @@ def main():
     achieved = plan.bytes / (ms_per_step * 1e-3) / 1e9
     coef_bytes = sum(128 * d.query_layout().coded_blocks for d in descs)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src,
+                "traffic": measured_traffic(args.workload), "peak_source": peak_src,
                 "read_only_frac": coef_bytes / (ms_per_step * 1e-3) / 1e9 / peak,
                 "algorithmic_bytes_per_launch": plan.bytes}
 
@@ -277,7 +289,8 @@ def main():
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{w}x{h} {ss}, batch {n_img} per GPU, synthetic coefficient planes (SURVEY 8d)",
                        "l2": "inputs larger than L2 (%.2f GB coef + %.2f GB rgb per GPU)" % (coef_len * 2 / 1e9, rgb_len / 1e9),
-                       "path": "generic" if args.force_generic else "fused", "parallelism": f"images sharded x{world}"},
+                       "path": "generic (2 kernels)" if args.force_generic else "fused kernel",
+                       "kernel_launches_per_step": plan.launches, "parallelism": f"images sharded x{world}"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": args.steps * plan.launches, "clocks": clk.summary(),
         }
