@@ -48,7 +48,8 @@ def test_idct_has_no_contracted_multiply_add(sass):
         ffma2 = [l for l in body if re.search(r"\bFFMA2\b", l)]
         fadd2 = [l for l in body if re.search(r"\bFADD2\b", l)]
         # 2 x 64 prescale products + 16 passes x 5 products = 208 packed products per block pair
-        assert len(ffma2) == 208, (name, len(ffma2))
+        # (the fused kernel adds 4 per exchange word for the colour offsets, 16 or 32 in all)
+        assert len(ffma2) in (208, 208 + 16, 208 + 32), (name, len(ffma2))
         assert len(fadd2) >= 16 * 29 + 8 + 64, (name, len(fadd2))
         # the addend of every packed FMA is a register pair loaded from c_negzero2 (bank 3)
         negzero_regs = set(re.findall(r"LDC\.64 (R\d+), c\[0x3\]", text))
