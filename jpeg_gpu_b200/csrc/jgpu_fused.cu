@@ -53,7 +53,7 @@ namespace jgpu {
 
 /* Build-time tuning knobs (A/B-tested on the GPU, see profiles/). */
 #ifndef JGPU_FUSED_G
-#define JGPU_FUSED_G 2          /* 32-pair column groups per tile */
+#define JGPU_FUSED_G 0          /* 32-pair column groups per tile; 0: per-mode default (mode_groups) */
 #endif
 #ifndef JGPU_STORE_POLICY
 #define JGPU_STORE_POLICY 1     /* 0: L1::no_allocate, 1: .cs (streaming; 6 % faster on B200) */
@@ -65,10 +65,18 @@ namespace jgpu {
 #define JGPU_FUSED_MINCTAS 0    /* 0: size registers for 12 warps per SM */
 #endif
 
+/* Column groups per tile, chosen per sampling mode so that a CTA has 6 warps where shared
+ * memory lets two such CTAs share an SM (12 warps, the most 168 registers per thread allow):
+ * 4:2:0 -> 4 luma + 2 chroma warps, 4:2:2 -> 3 + 3; the chroma-heavy modes stay at one group. */
+constexpr int mode_groups(int hs, int vs, bool gray) {
+  return JGPU_FUSED_G > 0 ? JGPU_FUSED_G : gray ? 1 : (hs == 2 ? (vs == 2 ? 2 : 3) : 1);
+}
+
 constexpr int kBoxRows = 32;                 /* blocks per TMA box */
 constexpr int kBoxBytes = kBoxRows * 128;    /* 4 KB */
 constexpr int kQtabBytes = 64 * 4;           /* one packed table: 32 low-byte + 32 high-byte words */
-constexpr int kWarpBytes = 2 * kBoxBytes + 1024; /* two boxes + up to two tables, 1 KB aligned */
+constexpr int kWarpBytes = 2 * kBoxBytes;        /* the two boxes of a warp, 1 KB aligned */
+constexpr int kWarpTabBytes = 2 * kQtabBytes;    /* its table(s): luma one, chroma Cb then Cr */
 constexpr int kMaxYWarps = 6;
 constexpr int kMaxCWarps = 4;
 constexpr int kDescSlots = 4;
@@ -113,11 +121,16 @@ struct Cfg {
   static constexpr int kYsBytes = 32 * kYWarps * kYsTask;
   /* shared-memory map (offsets from a 1 KB aligned base) */
   static constexpr int kOffWarp = 0;
-  static constexpr int kOffEx = kWarps * kWarpBytes;
+  static constexpr int kOffTab = kWarps * kWarpBytes;
+  static constexpr int kOffEx = kOffTab + kWarps * kWarpTabBytes;
   static constexpr int kOffYs = kOffEx + 2 * kExSlot;
-  static constexpr int kOffDesc = kOffYs + kYsBytes;
+  /* chroma threads park row 0 of their tile here between the passes (luma threads use their
+   * staging rows): 4 chunks of 16 bytes per thread, padded */
+  static constexpr int kParkTask = 64 + 16;
+  static constexpr int kOffPark = kOffYs + kYsBytes;
+  static constexpr int kOffDesc = kOffPark + 32 * kCWarps * kParkTask;
   static constexpr int kOffBar = kOffDesc + kDescSlots * (int)sizeof(TileDesc);
-  static constexpr int kSmemBytes = kOffBar + 8 * (kWarps + kDescSlots) + 1024 /* alignment slack */;
+  static constexpr int kSmemBytes = kOffBar + 8 * (kWarps + kDescSlots);
   /* resident CTAs per SM the register allocation is sized for */
   static constexpr int kMinCtas = JGPU_FUSED_MINCTAS > 0 ? JGPU_FUSED_MINCTAS : 384 / kThreads;
   static_assert(kYWarps <= kMaxYWarps && kCWarps <= kMaxCWarps, "TileDesc too small");
@@ -199,6 +212,11 @@ __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
   return v;
 }
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y),
+               "r"(v.z), "r"(v.w)
+               : "memory");
+}
 __device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) {
   asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
@@ -228,7 +246,7 @@ __device__ __forceinline__ void stg128_stream(uint8_t *p, uint4 v) {
 template <bool WIDE>
 __device__ __forceinline__ void pair_row_pass(pair32 (&m)[8][8], const uint8_t *box_a,
                                               const uint8_t *box_b, int row, const uint4 *qa,
-                                              const uint4 *qb) {
+                                              const uint4 *qb, const uint32_t (&park)[4]) {
   const uint8_t *ra = box_a + 128 * row, *rb = box_b + 128 * row;
   const int sw = row & 7;
 #pragma unroll
@@ -239,6 +257,16 @@ __device__ __forceinline__ void pair_row_pass(pair32 (&m)[8][8], const uint8_t *
     const uint4 z = make_uint4(0, 0, 0, 0);
     load_row_pair_packed<WIDE>(m[r], a, b, qa[r], qb[r], WIDE ? qa[8 + r] : z, WIDE ? qb[8 + r] : z, r);
     inv_pass8(m[r]);
+    if (r == 0) {
+      /* park row 0 in shared memory until the column pass asks for it, two pairs per chunk */
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        uint4 c;
+        p_split_bits(m[0][2 * j], c.x, c.y);
+        p_split_bits(m[0][2 * j + 1], c.z, c.w);
+        sts128(park[j], c);
+      }
+    }
   }
 }
 
@@ -324,9 +352,10 @@ k_fused(const __grid_constant__ CUtensorMap tm_rows,   /* (64, rows)            
   using C = Cfg<HS, VS, GRAY, G>;
   if ((*wide_flag != 0) != WIDE) return;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  /* dynamic smem is only guaranteed 16-byte aligned: round up to 1 KB for the swizzle */
-  const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t *const smem_gen = smem_raw + (smem0 - smem_u32(smem_raw));
+  /* the 128-byte swizzle needs the boxes 1 KB aligned; the declaration above asks for it */
+  const uint32_t smem0 = smem_u32(smem_raw);
+  uint8_t *const smem_gen = smem_raw;
+  if (smem0 & 1023u) __trap();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t bar_data = smem0 + C::kOffBar + 8 * warp;           /* this warp's coefficients */
   const uint32_t bar_desc0 = smem0 + C::kOffBar + 8 * C::kWarps;     /* + 8*slot */
@@ -356,7 +385,8 @@ k_fused(const __grid_constant__ CUtensorMap tm_rows,   /* (64, rows)            
   /* ---- role of this warp ---------------------------------------------------- */
   const bool is_c = warp >= C::kYWarps;
   const int cw = warp - C::kYWarps;   /* chroma warp index */
-  const uint32_t wreg = smem0 + C::kOffWarp + warp * kWarpBytes;   /* boxes A, B, then tables */
+  const uint32_t wreg = smem0 + C::kOffWarp + warp * kWarpBytes;   /* boxes A, B */
+  const uint32_t wtab = smem0 + C::kOffTab + warp * kWarpTabBytes;  /* this warp's table(s) */
   /* start this warp's loads for CTA-local tile n (lane 0 only) */
   auto fire = [&](int n) {
     const uint32_t d = wait_desc(n);
@@ -368,8 +398,8 @@ k_fused(const __grid_constant__ CUtensorMap tm_rows,   /* (64, rows)            
       mbar_expect_tx(bar_data, 2 * kBoxBytes + 2 * kQtabBytes);
       tma_load_2d(wreg, &tm_rows, 0, fb, bar_data);
       tma_load_2d(wreg + kBoxBytes, &tm_rows, 0, fr, bar_data);
-      bulk_load(wreg + 2 * kBoxBytes, qint + (size_t)qb * 64, kQtabBytes, bar_data);
-      bulk_load(wreg + 2 * kBoxBytes + kQtabBytes, qint + (size_t)qr * 64, kQtabBytes, bar_data);
+      bulk_load(wtab, qint + (size_t)qb * 64, kQtabBytes, bar_data);
+      bulk_load(wtab + kQtabBytes, qint + (size_t)qr * 64, kQtabBytes, bar_data);
     } else {
       /* the 32 even-position and the 32 odd-position blocks of this warp's 64-block run */
       const int first = (int)lds32(d + offsetof(TileDesc, yfirst) + 4 * warp);
@@ -377,7 +407,7 @@ k_fused(const __grid_constant__ CUtensorMap tm_rows,   /* (64, rows)            
       mbar_expect_tx(bar_data, 2 * kBoxBytes + kQtabBytes);
       tma_load_3d(wreg, &tm_pairs, 0, first & 1, first >> 1, bar_data);
       tma_load_3d(wreg + kBoxBytes, &tm_pairs, 0, (first + 1) & 1, (first + 1) >> 1, bar_data);
-      bulk_load(wreg + 2 * kBoxBytes, qint + (size_t)qy * 64, kQtabBytes, bar_data);
+      bulk_load(wtab, qint + (size_t)qy * 64, kQtabBytes, bar_data);
     }
   };
 
@@ -394,6 +424,7 @@ k_fused(const __grid_constant__ CUtensorMap tm_rows,   /* (64, rows)            
     int px_x, px_y;      /* pixel position of this thread's pair inside the tile */
     uint32_t ex_rel;     /* exchange-area task (chroma: the MCU it writes; luma: the one(s) it reads) */
     uint32_t ys_a;       /* luma staging rows */
+    uint32_t park[4];    /* where row 0 of the tile waits between the passes */
   };
   auto geo = [&]() -> Geo {
     uint32_t tid;
@@ -424,6 +455,18 @@ k_fused(const __grid_constant__ CUtensorMap tm_rows,   /* (64, rows)            
       }
     }
     g.ys_a = smem0 + C::kOffYs + (uint32_t)(c ? 0 : 32 * w + l) * C::kYsTask;
+    if (c) {
+      const uint32_t base = smem0 + C::kOffPark + (uint32_t)(32 * cwi + l) * C::kParkTask;
+#pragma unroll
+      for (int j = 0; j < 4; j++) g.park[j] = base + 16 * j;
+    } else {
+      /* inside the staging rows, at places the column pass overwrites only after it has
+       * fetched the chunk: pair j of every row k is written at the end of step j */
+      g.park[0] = g.ys_a;             /* row 0, bytes  0..15: written in steps 0,1; read in step 0 */
+      g.park[1] = g.ys_a + 32 + 16;   /* row 1, bytes 16..31: written in steps 2,3; read in step 1 */
+      g.park[2] = g.ys_a + 64 + 16;   /* row 2, bytes 16..31: written in steps 2,3; read in step 2 */
+      g.park[3] = g.ys_a + 256;       /* the padding */
+    }
     return g;
   };
   const uint8_t *const wgen = smem_gen + C::kOffWarp + warp * kWarpBytes;
@@ -447,9 +490,10 @@ k_fused(const __grid_constant__ CUtensorMap tm_rows,   /* (64, rows)            
     {
       pair32 m[8][8];
       if (active) {
-        const uint4 *const qa = reinterpret_cast<const uint4 *>(wgen + 2 * kBoxBytes);
+        const uint4 *const qa = reinterpret_cast<const uint4 *>(smem_gen + C::kOffTab + warp * kWarpTabBytes);
         const uint4 *const qb = is_c ? qa + 16 : qa;   /* chroma: Cb table, then Cr table */
-        pair_row_pass<WIDE>(m, wgen, wgen + kBoxBytes, lane, qa, qb);
+        const Geo g = geo();
+        pair_row_pass<WIDE>(m, wgen, wgen + kBoxBytes, lane, qa, qb, g.park);
       }
       /* this warp's boxes are in registers: start the loads of its next tile */
       __syncwarp();
@@ -461,7 +505,11 @@ k_fused(const __grid_constant__ CUtensorMap tm_rows,   /* (64, rows)            
         const Geo g = geo();
         const uint32_t ys_a = g.ys_a;
         const uint32_t ex_a = smem0 + C::kOffEx + (it & 1) * C::kExSlot + g.ex_rel;
-        column_pass_by_pairs(m, [&](int j, pair32 (&u)[8], pair32 (&v)[8]) {
+        column_pass_by_pairs_parked(m, [&](int j, pair32 &a, pair32 &b) {
+          const uint4 c = lds128(g.park[j]);
+          a = p_make_bits(c.x, c.y);
+          b = p_make_bits(c.z, c.w);
+        }, [&](int j, pair32 (&u)[8], pair32 (&v)[8]) {
           if (!is_c) {
             /* luma: (short)floor + 128, clamp; pixels 2j, 2j+1 of row k of block A and of
              * block B as two s16x2 words, parked in this thread's staging rows */
@@ -628,10 +676,9 @@ EncodeTiledFn encode_fn() {
   return fn;
 }
 
-constexpr int kG = JGPU_FUSED_G;
 
 struct ModeInfo {
-  int hs, vs, gray;
+  int hs, vs, gray, groups;
   int tile_mcus, mcu_w, mcu_h, threads, ywarps, cwarps, channels;
   size_t smem;
   int ctas_per_sm;
@@ -642,13 +689,13 @@ bool g_configured = false;
 
 template <int HS, int VS, bool GRAY>
 cudaError_t configure_mode(int mode) {
-  using C = Cfg<HS, VS, GRAY, kG>;
-  auto *f = &k_fused<HS, VS, GRAY, kG, false>;
-  cudaError_t ew = cudaFuncSetAttribute(&k_fused<HS, VS, GRAY, kG, true>,
+  using C = Cfg<HS, VS, GRAY, mode_groups(HS, VS, GRAY)>;
+  auto *f = &k_fused<HS, VS, GRAY, mode_groups(HS, VS, GRAY), false>;
+  cudaError_t ew = cudaFuncSetAttribute(&k_fused<HS, VS, GRAY, mode_groups(HS, VS, GRAY), true>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmemBytes);
   if (ew != cudaSuccess) return ew;
   ModeInfo &mi = g_modes[mode];
-  mi.hs = HS; mi.vs = VS; mi.gray = GRAY;
+  mi.hs = HS; mi.vs = VS; mi.gray = GRAY; mi.groups = mode_groups(HS, VS, GRAY);
   mi.tile_mcus = C::kTileMcus;
   mi.mcu_w = C::kMcuW;
   mi.mcu_h = C::kMcuH;
@@ -670,10 +717,10 @@ template <int HS, int VS, bool GRAY>
 cudaError_t launch_mode(int grid, size_t smem, cudaStream_t stream, const CUtensorMap &tm_rows,
                         const CUtensorMap &tm_pairs, const TileDesc *descs, int n_tiles,
                         const uint32_t *qint, const uint32_t *wide_flag, uint8_t *rgb, int rgb_aligned) {
-  using C = Cfg<HS, VS, GRAY, kG>;
-  k_fused<HS, VS, GRAY, kG, false><<<grid, C::kThreads, smem, stream>>>(
+  using C = Cfg<HS, VS, GRAY, mode_groups(HS, VS, GRAY)>;
+  k_fused<HS, VS, GRAY, mode_groups(HS, VS, GRAY), false><<<grid, C::kThreads, smem, stream>>>(
       tm_rows, tm_pairs, descs, n_tiles, qint, wide_flag, rgb, rgb_aligned);
-  k_fused<HS, VS, GRAY, kG, true><<<grid, C::kThreads, smem, stream>>>(
+  k_fused<HS, VS, GRAY, mode_groups(HS, VS, GRAY), true><<<grid, C::kThreads, smem, stream>>>(
       tm_rows, tm_pairs, descs, n_tiles, qint, wide_flag, rgb, rgb_aligned);
   return cudaGetLastError();
 }
@@ -749,7 +796,7 @@ int fused_plan_build(FusedPlan &fp, const jgpu_image_desc *descs, const jgpu_lay
           if (mi.gray) {
             t.yfirst[w] = block0[0] + r * hblocks[0] + x + 64 * w;
           } else {
-            t.yfirst[w] = block0[0] + (r * mi.vs + w / kG) * hblocks[0] + x * mi.hs + 64 * (w % kG);
+            t.yfirst[w] = block0[0] + (r * mi.vs + w / mi.groups) * hblocks[0] + x * mi.hs + 64 * (w % mi.groups);
           }
         }
         for (int cw = 0; cw < mi.cwarps; cw++) {

@@ -203,5 +203,28 @@ JGPU_DEV void column_pass_by_pairs(pair32 (&m)[8][8], Sink &&sink) {
   }
 }
 
+/* As column_pass_by_pairs, but row 0 of the tile is not in registers: `row0(j, a, b)` fetches
+ * m[0][2j] and m[0][2j+1] from wherever the caller parked them after the row pass (shared
+ * memory).  Parking one row keeps the live set under the register budget that 12 warps per
+ * SM allow, so nothing spills to local memory. */
+template <typename Row0, typename Sink>
+JGPU_DEV void column_pass_by_pairs_parked(pair32 (&m)[8][8], Row0 &&row0, Sink &&sink) {
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    pair32 u[8], v[8];
+    row0(j, u[0], v[0]);
+#pragma unroll
+    for (int r = 1; r < 8; r++) {
+      u[r] = m[r][2 * j];
+      v[r] = m[r][2 * j + 1];
+    }
+    u[0] = p_add_half(u[0]);
+    v[0] = p_add_half(v[0]);
+    inv_pass8(u);
+    inv_pass8(v);
+    sink(j, u, v);
+  }
+}
+
 }  // namespace jgpu
 #endif

@@ -51,14 +51,17 @@ def test_idct_has_no_contracted_multiply_add(sass):
         # (the fused kernel adds 4 per exchange word for the colour offsets, 16 or 32 in all)
         assert len(ffma2) in (208, 208 + 16, 208 + 32), (name, len(ffma2))
         assert len(fadd2) >= 16 * 29 + 8 + 64, (name, len(fadd2))
-        # the addend of every packed FMA is a register pair loaded from c_negzero2 (bank 3)
+        # the addend of every packed FMA is a register pair loaded from c_negzero2 (bank 3),
+        # or a MOV copy of such a pair (ptxas duplicates it now and then to dodge bank conflicts)
         negzero_regs = set(re.findall(r"LDC\.64 (R\d+), c\[0x3\]", text))
         assert negzero_regs, name
-        addends = set()
+        copies = {d for d, src in re.findall(r"\bMOV (R\d+), (R\d+) ;", text) if src in negzero_regs}
+        addends = []
         for l in ffma2:
             ops = l.split("FFMA2", 1)[1].split(";")[0].split(",")
-            addends.add(ops[-1].strip().split(".")[0])
-        assert addends <= negzero_regs, (name, addends, negzero_regs)
+            addends.append(ops[-1].strip().split(".")[0])
+        assert set(addends) <= negzero_regs | copies, (name, set(addends) - negzero_regs - copies)
+        assert sum(a in negzero_regs for a in addends) >= 0.9 * len(addends), name
         assert not re.search(r"\bFFMA\b", text), name        # no scalar contraction either
 
 
