@@ -55,7 +55,7 @@ def test_idct_has_no_contracted_multiply_add(sass):
         # or a MOV copy of such a pair (ptxas duplicates it now and then to dodge bank conflicts)
         negzero_regs = set(re.findall(r"LDC\.64 (R\d+), c\[0x3\]", text))
         assert negzero_regs, name
-        copies = {d for d, src in re.findall(r"\bMOV (R\d+), (R\d+) ;", text) if src in negzero_regs}
+        copies = {d for d, src in re.findall(r"\bMOV (R\d+), (R\d+)(?:\.reuse)? ;", text) if src in negzero_regs}
         addends = []
         for l in ffma2:
             ops = l.split("FFMA2", 1)[1].split(";")[0].split(",")
