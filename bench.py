@@ -255,25 +255,70 @@ def main():
                 "read_only_frac": coef_bytes / (ms_per_step * 1e-3) / 1e9 / peak,
                 "algorithmic_bytes_per_launch": plan.bytes}
 
-    # end-to-end: host buffers through the C ABI, copies inside the timed region
-    e2e = None
+    # end-to-end: host buffers through the C ABI, copies inside the timed region.
+    # `e2e`      the dense QUANT planes cross the link (north_star's input format);
+    # `e2e_pack` the reference's PACK stream crosses instead (JPEG_DECODE_PACK, what its GL path
+    #            uploads with `-o pack`) and is expanded on the device.
+    # With more than one rank the host side stages a quarter of the batch at a time (same pinned
+    # buffers re-sent), so that eight ranks do not pin 100 GB of host memory between them.
+    e2e = e2e_pack = None
     if not args.no_e2e:
+        from concurrent.futures import ThreadPoolExecutor
+        from jpeg_gpu_b200.batch import pack_from_quant
         e2e_steps = args.e2e_steps or min(args.steps, 5)
-        h_coef = torch.empty(coef_len, dtype=torch.int16).pin_memory()
-        h_coef.copy_(d_coef.cpu())
-        h_rgb = torch.zeros(rgb_len, dtype=torch.uint8).pin_memory()
-        ctx.decode_batch_host(descs, h_coef, q, h_rgb, None, force_generic=args.force_generic)  # warm-up
+        sub_n = n_img if world == 1 else max(1, n_img // 4)
+        calls = -(-n_img // sub_n)
+        sub = descs[:sub_n]
+        sub_coef_len = sub[-1].coef_off + sub[-1].query_layout().coef_len
+        sub_rgb_len = sub[-1].rgb_off + sub[-1].query_layout().rgb_len
+        sub_px = sub_n * w * h
+        sub_coef_bytes = sum(128 * d.query_layout().coded_blocks for d in sub)
+        h_coef = torch.empty(sub_coef_len, dtype=torch.int16).pin_memory()
+        h_coef.copy_(d_coef[:sub_coef_len].cpu())
+        h_rgb = torch.zeros(sub_rgb_len, dtype=torch.uint8).pin_memory()
+        ctx.decode_batch_host(sub, h_coef, q, h_rgb, None, force_generic=args.force_generic)  # warm-up
         barrier()
         t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            ctx.decode_batch_host(descs, h_coef, q, h_rgb, None, force_generic=args.force_generic)
+        for _ in range(e2e_steps * calls):
+            ctx.decode_batch_host(sub, h_coef, q, h_rgb, None, force_generic=args.force_generic)
         barrier()
         dt = shard.max_over_ranks(time.perf_counter() - t0, dev)
         assert torch.equal(h_rgb[:4096], d_rgb[:4096].cpu()), "host path and device path disagree"
-        e2e = {"value": world * px_per_step * e2e_steps / 1e6 / dt, "unit": UNIT,
-               "h2d_bytes_per_step": int(coef_bytes + q.nbytes), "d2h_bytes_per_step": int(rgb_len),
-               "steps": e2e_steps, "ms_per_step": 1e3 * dt / e2e_steps}
-        del h_coef, h_rgb
+        e2e = {"value": world * sub_px * calls * e2e_steps / 1e6 / dt, "unit": UNIT,
+               "h2d_bytes_per_step": int((sub_coef_bytes + q.nbytes) * calls), "d2h_bytes_per_step": int(sub_rgb_len * calls),
+               "steps": e2e_steps, "ms_per_step": 1e3 * dt / e2e_steps, "calls_per_step": calls,
+               "input": "dense QUANT planes (int16), pinned host memory"}
+
+        # PACK leg: pack the same planes on the host (outside the timed region: in the reference
+        # the Huffman reader writes this stream directly), then time words+index in, RGB out
+        coef_np = h_coef.numpy()
+        with ThreadPoolExecutor(max_workers=min(threads, 32)) as ex:
+            parts = list(ex.map(lambda d: pack_from_quant(d, coef_np[d.coef_off:d.coef_off + d.query_layout().coef_len]), sub))
+        pack_off = np.zeros(sub_n + 1, dtype=np.int64)
+        pack_off[1:] = np.cumsum([p.size for p, _ in parts])
+        h_pack = torch.empty(int(pack_off[-1]), dtype=torch.int16).pin_memory()
+        h_index = torch.zeros(sub_coef_len // 64, dtype=torch.int32).pin_memory()
+        for d, (p, ix), o in zip(sub, parts, pack_off[:-1]):
+            h_pack[int(o):int(o) + p.size] = torch.from_numpy(p.view(np.int16))
+            h_index[d.coef_off // 64:d.coef_off // 64 + ix.size] = torch.from_numpy(ix)
+        del parts
+        h_rgb.zero_()
+        ctx.decode_batch_host_packed(sub, h_pack, pack_off, h_index, q, h_rgb, None, force_generic=args.force_generic)
+        assert torch.equal(h_rgb[:1 << 20], d_rgb[:1 << 20].cpu()), "packed host path and device path disagree"
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps * calls):
+            ctx.decode_batch_host_packed(sub, h_pack, pack_off, h_index, q, h_rgb, None, force_generic=args.force_generic)
+        barrier()
+        dt = shard.max_over_ranks(time.perf_counter() - t0, dev)
+        e2e_pack = {"value": world * sub_px * calls * e2e_steps / 1e6 / dt, "unit": UNIT,
+                    "h2d_bytes_per_step": int((h_pack.numel() * 2 + h_index.numel() * 4 + pack_off.nbytes + q.nbytes) * calls),
+                    "d2h_bytes_per_step": int(sub_rgb_len * calls), "steps": e2e_steps,
+                    "ms_per_step": 1e3 * dt / e2e_steps, "calls_per_step": calls,
+                    "input": "PACK run/level words (uint16) + per-block index (int32), pinned host memory; "
+                             "expanded on the device by k_unpack",
+                    "bytes_per_block": (h_pack.numel() * 2 + h_index.numel() * 4) / (sub_coef_bytes / 128)}
+        del h_coef, h_rgb, h_pack, h_index
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -291,7 +336,7 @@ def main():
                        "l2": "inputs larger than L2 (%.2f GB coef + %.2f GB rgb per GPU)" % (coef_len * 2 / 1e9, rgb_len / 1e9),
                        "path": "generic (2 kernels)" if args.force_generic else "fused kernel",
                        "kernel_launches_per_step": plan.launches, "parallelism": f"images sharded x{world}"},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_pack": e2e_pack,
             "gpu_launches": args.steps * plan.launches, "clocks": clk.summary(),
         }
         print(json.dumps(line))

@@ -169,6 +169,56 @@ int jgpu_decode_batch_host(jgpu_ctx *ctx, const jgpu_image_desc *descs, int n,
 int jgpu_decode_image(jgpu_ctx *ctx, const jpeg_header *header, image *img,
                       jpeg_decode_out out);
 
+/* ------------------------------------------------------------------------
+ * (3) PACK input: the reference's zero-run packed coefficient stream
+ * --------------------------------------------------------------------- */
+
+/* JPEG_DECODE_PACK as the reference's reader writes it (src/xjpeg.c:484-496,
+ * 513-519,531-535) and its GL path consumes it (res/horz_pack_yuv.fs.glsl:
+ * 105-127, upload at src/jpeg_gpu.c:1286-1287):
+ *   pack[]   16-bit words in scan (MCU-interleaved) order; per block a DC word
+ *            `dc & 0xfff`, then one word `run << 12 | value & 0xfff` per coded AC
+ *            symbol (ZRL = 0xf000), then an end-of-block word 0 unless the block
+ *            ran to coefficient 63;
+ *   index[]  per block the position of its DC word, laid out like image.index
+ *            (src/image.c:85-95): entry k belongs to the block whose dense
+ *            coefficients start at image.coef + 64*k.
+ * A batch holds image i's words at pack[pack_off[i] .. pack_off[i+1]) (index
+ * values are relative to pack_off[i]) and its index entries at
+ * index[coef_off/64 ...]; coef_off must be a multiple of 64.  Typical blocks
+ * take ~20 bytes instead of 128, which is what the host->device link carries. */
+
+/* Worst case words one image can need: 64 per coded block. */
+int64_t jgpu_pack_bound(const jgpu_image_desc *desc);
+
+/* Host utility (tests, benches, callers that hold dense planes): QUANT planes
+ * of ONE image (coef = that image's image.coef) -> the PACK words and index the
+ * reference's reader produces for a baseline scan carrying the same
+ * coefficients.  Values are truncated to 12 bits exactly as the reference
+ * does.  index must have coef_len/64 entries (unused ones are set to 0).
+ * Returns the number of words written, or -1 (pack_cap too small / bad desc). */
+int64_t jgpu_pack_from_quant(const jgpu_image_desc *desc, const int16_t *coef,
+                             uint16_t *pack, int64_t pack_cap, int32_t *index);
+
+/* DEVICE pointers.  Expands the PACK stream of every image of the plan into
+ * dense QUANT planes at d_coef (the layout jgpu_plan_run reads), i.e. what
+ * res/horz_pack_*.fs.glsl does per fragment before its row transform.
+ * d_pack_off: n+1 int64 on the device.  Blocks whose words are cut off by
+ * pack_off[i+1] or overrun coefficient 63 are truncated, never read out of
+ * bounds.  Asynchronous. */
+int jgpu_plan_unpack(jgpu_plan *plan, const uint16_t *d_pack,
+                     const int64_t *d_pack_off, const int32_t *d_index,
+                     int16_t *d_coef, void *stream);
+
+/* HOST buffers: PACK words + index in, RGB / YUV out (jgpu_decode_batch_host
+ * with the packed stream on the link instead of the dense planes).
+ * pack_off: n+1 host int64. */
+int jgpu_decode_batch_host_packed(jgpu_ctx *ctx, const jgpu_image_desc *descs,
+                                  int n, unsigned flags, const uint16_t *h_pack,
+                                  const int64_t *pack_off, const int32_t *h_index,
+                                  const uint16_t *h_qtabs, int n_sets,
+                                  uint8_t *h_rgb, uint8_t *h_yuv);
+
 /* Page-locked host memory for the batch entry points. */
 void *jgpu_host_alloc(size_t bytes);
 void jgpu_host_free(void *p);

@@ -112,6 +112,12 @@ EXPORTS = [
     ("jgpu_decode_batch_host", C.c_int, [C.c_void_p, C.POINTER(jgpu_image_desc), C.c_int, C.c_uint, C.c_void_p,
                                          C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     ("jgpu_decode_image", C.c_int, [C.c_void_p, C.POINTER(jpeg_header), C.POINTER(image), C.c_int]),
+    ("jgpu_pack_bound", C.c_int64, [C.POINTER(jgpu_image_desc)]),
+    ("jgpu_pack_from_quant", C.c_int64, [C.POINTER(jgpu_image_desc), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    ("jgpu_plan_unpack", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("jgpu_decode_batch_host_packed", C.c_int, [C.c_void_p, C.POINTER(jgpu_image_desc), C.c_int, C.c_uint,
+                                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                                C.c_void_p, C.c_void_p]),
     ("jgpu_host_alloc", C.c_void_p, [C.c_size_t]),
     ("jgpu_host_free", None, [C.c_void_p]),
 ]

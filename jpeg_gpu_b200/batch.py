@@ -103,6 +103,38 @@ def pack_batch(descs: List[ImageDesc], want_yuv: bool = False, align: int = 256)
     return coef, rgb, yuv
 
 
+def pack_from_quant(desc: ImageDesc, coef: np.ndarray):
+    """Dense QUANT planes of one image (its image.coef) -> (pack uint16 words, index int32) as the
+    reference's reader would write them for JPEG_DECODE_PACK (jgpu_pack_from_quant; host only)."""
+    lay = desc.query_layout()
+    coef = np.ascontiguousarray(coef, dtype=np.int16)
+    assert coef.size >= lay.coef_len
+    d = desc.to_c()
+    cap = _capi.lib().jgpu_pack_bound(C.byref(d))
+    pack = np.empty(cap, dtype=np.uint16)
+    index = np.empty(lay.coef_len // 64, dtype=np.int32)
+    n = _capi.lib().jgpu_pack_from_quant(C.byref(d), _addr(coef), _addr(pack), cap, _addr(index))
+    if n < 0:
+        raise RuntimeError(f"jgpu_pack_from_quant failed: {_capi.last_error()}")
+    return pack[:n].copy(), index
+
+
+def pack_batch_streams(descs: List[ImageDesc], coef: np.ndarray):
+    """PACK form of a whole batch laid out by pack_batch(): returns (pack, pack_off int64[n+1],
+    index int32[coef_len/64]) for jgpu_plan_unpack / jgpu_decode_batch_host_packed."""
+    packs, offs = [], [0]
+    total = max(d.coef_off + d.query_layout().coef_len for d in descs)
+    index = np.zeros(-(-total // 64), dtype=np.int32)
+    for d in descs:
+        assert d.coef_off % 64 == 0, "PACK input needs coef_off to be a multiple of 64"
+        lay = d.query_layout()
+        p, ix = pack_from_quant(d, coef[d.coef_off:d.coef_off + lay.coef_len])
+        packs.append(p)
+        offs.append(offs[-1] + p.size)
+        index[d.coef_off // 64:d.coef_off // 64 + ix.size] = ix
+    return np.concatenate(packs), np.array(offs, dtype=np.int64), index
+
+
 def _desc_array(descs: List[ImageDesc]):
     arr = (_capi.jgpu_image_desc * len(descs))()
     for i, d in enumerate(descs):
@@ -150,6 +182,22 @@ class Context:
             raise RuntimeError(f"jgpu_decode_batch_host failed: {_capi.last_error()}")
 
 
+    def decode_batch_host_packed(self, descs: List[ImageDesc], pack, pack_off: np.ndarray, index,
+                                 qtabs: np.ndarray, rgb=None, yuv=None, force_generic: bool = False) -> None:
+        """PACK words (uint16) + pack_off (int64, n+1) + index (int32) in, rgb / yuv out; host buffers."""
+        flags = (_capi.JGPU_OUT_RGB if rgb is not None else 0) | (_capi.JGPU_OUT_YUV if yuv is not None else 0)
+        if force_generic:
+            flags |= _capi.JGPU_FORCE_GENERIC
+        n_sets = int(np.prod(qtabs.shape)) // 256
+        pack_off = np.ascontiguousarray(pack_off, dtype=np.int64)
+        assert pack_off.size == len(descs) + 1
+        rc = _capi.lib().jgpu_decode_batch_host_packed(self._h, _desc_array(descs), len(descs), flags, _addr(pack),
+                                                       _addr(pack_off), _addr(index), _addr(qtabs), n_sets,
+                                                       _addr(rgb), _addr(yuv))
+        if rc != 0:
+            raise RuntimeError(f"jgpu_decode_batch_host_packed failed: {_capi.last_error()}")
+
+
 def _addr(a):
     if a is None:
         return None
@@ -183,6 +231,16 @@ class Plan:
                                        C.c_void_p(stream))
         if rc != 0:
             raise RuntimeError(f"jgpu_plan_run failed: {_capi.last_error()}")
+
+    def unpack(self, pack, pack_off, index, coef, stream: Optional[int] = None) -> None:
+        """PACK words / pack_off (int64, n+1) / index (int32) -> dense planes `coef`; CUDA torch tensors."""
+        if stream is None:
+            import torch
+            stream = torch.cuda.current_stream(coef.device).cuda_stream
+        rc = _capi.lib().jgpu_plan_unpack(self._h, _addr(pack), _addr(pack_off), _addr(index), _addr(coef),
+                                          C.c_void_p(stream))
+        if rc != 0:
+            raise RuntimeError(f"jgpu_plan_unpack failed: {_capi.last_error()}")
 
     def close(self):
         if self._h:

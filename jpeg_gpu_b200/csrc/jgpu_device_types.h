@@ -46,6 +46,23 @@ struct ColourWork {
   int32_t first;
 };
 
+/* ---- PACK expansion (jgpu_unpack.cu) --------------------------------------- */
+
+/* One colour plane of one image: its blocks are consecutive 128-byte rows of the
+ * coefficient buffer starting at row block0, and index entry block0 + k belongs to
+ * block k (src/image.c:85-95 gives the index the layout of the coefficients). */
+struct UnpackSeg {
+  int64_t block0;   /* (coef_off + plane.coef_off) / 64 */
+  int32_t nblocks;  /* hblocks*vblocks */
+  int32_t img;      /* selects pack_off[img], pack_off[img+1] */
+};
+
+/* One CTA of k_unpack: blocks [first, first + 256) of a segment. */
+struct UnpackWork {
+  int32_t seg;
+  int32_t first;
+};
+
 /* ---- fused path ---------------------------------------------------------- */
 
 /* Sampling classes the fused kernel is instantiated for (chroma 1x1). */

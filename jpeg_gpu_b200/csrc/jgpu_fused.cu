@@ -45,6 +45,7 @@
 #include <algorithm>
 #include <vector>
 
+#include "jgpu_colour_fixed.h"
 #include "jgpu_internal.h"
 #include "jgpu_kernels.cuh"
 #include "jgpu_launch.h"
@@ -60,6 +61,9 @@ namespace jgpu {
 #endif
 #ifndef JGPU_COLOUR_PACKED
 #define JGPU_COLOUR_PACKED 0    /* 1: colour offsets of two samples per packed instruction (measured 2.5 % slower) */
+#endif
+#ifndef JGPU_COLOUR_INT
+#define JGPU_COLOUR_INT 1       /* 1: colour offsets in fixed point (jgpu_colour_fixed.h), no I2F / FMUL / FADD */
 #endif
 #ifndef JGPU_FUSED_MINCTAS
 #define JGPU_FUSED_MINCTAS 0    /* 0: size registers for 12 warps per SM */
@@ -287,8 +291,25 @@ __device__ __forceinline__ uint32_t chroma_clamped(pair32 v) {
  * colour offset).  Arithmetic is colour_offsets() of jgpu_kernels.cuh, i.e. the oracle's
  * jgo_colour_offsets, with the two samples riding in the two lanes of the packed binary32
  * instructions (each lane is one IEEE operation, products via fma(a, b, -0.0)). */
+/* PRMT selectors that turn two offset words into one s16x2 operand: (x, x) and (x, y).  The
+ * binary32 forms leave the offset in the low half of the word, the fixed-point form in the high. */
+constexpr uint32_t kSelRep = JGPU_COLOUR_INT ? 0x3232u : 0x1010u;
+constexpr uint32_t kSelPair = JGPU_COLOUR_INT ? 0x7632u : 0x5410u;
+
 __device__ __forceinline__ void chroma_offsets_bits2(uint32_t w, uint32_t (&r)[2], uint32_t (&g)[2],
                                                      uint32_t (&b)[2]) {
+#if JGPU_COLOUR_INT
+  /* sign-extending byte extracts (PRMT with the replicate-sign selector bit), then
+   * jgpu_colour_offsets_fixed: bit-identical to the binary32 definition for every input */
+  const int cb0 = (int)__byte_perm(w, 0u, 0x8880u), cr0 = (int)__byte_perm(w, 0u, 0x9991u);
+  const int cb1 = (int)__byte_perm(w, 0u, 0xaaa2u), cr1 = ((int)w) >> 24;
+  int r0, g0, b0, r1, g1, b1;
+  jgpu_colour_offsets_fixed(cb0, cr0, &r0, &g0, &b0);
+  jgpu_colour_offsets_fixed(cb1, cr1, &r1, &g1, &b1);
+  r[0] = (uint32_t)r0; g[0] = (uint32_t)g0; b[0] = (uint32_t)b0;
+  r[1] = (uint32_t)r1; g[1] = (uint32_t)g1; b[1] = (uint32_t)b1;
+  return;
+#endif
 #if JGPU_COLOUR_PACKED == 0
   /* scalar form of the same arithmetic (A/B reference) */
   const float fm = __uint_as_float(kMagicBits);
@@ -585,12 +606,12 @@ k_fused(const __grid_constant__ CUtensorMap tm_rows,   /* (64, rows)            
               const int p = 6 * (i & 1);
               uint32_t r[2], g[2], b[2];
               chroma_offsets_bits2(cs[i], r, g, b);
-              o[p + 0] = __byte_perm(r[0], r[0], 0x1010);
-              o[p + 1] = __byte_perm(g[0], g[0], 0x1010);
-              o[p + 2] = __byte_perm(b[0], b[0], 0x1010);
-              o[p + 3] = __byte_perm(r[1], r[1], 0x1010);
-              o[p + 4] = __byte_perm(g[1], g[1], 0x1010);
-              o[p + 5] = __byte_perm(b[1], b[1], 0x1010);
+              o[p + 0] = __byte_perm(r[0], r[0], kSelRep);
+              o[p + 1] = __byte_perm(g[0], g[0], kSelRep);
+              o[p + 2] = __byte_perm(b[0], b[0], kSelRep);
+              o[p + 3] = __byte_perm(r[1], r[1], kSelRep);
+              o[p + 4] = __byte_perm(g[1], g[1], kSelRep);
+              o[p + 5] = __byte_perm(b[1], b[1], kSelRep);
             }
           } else {
             /* block A = even MCU, block B = odd MCU: 8 samples each, paired horizontally */
@@ -603,9 +624,9 @@ k_fused(const __grid_constant__ CUtensorMap tm_rows,   /* (64, rows)            
               for (int i = 0; i < 4; i++) {
                 uint32_t r[2], g[2], b[2];
                 chroma_offsets_bits2(cs[i], r, g, b);
-                o[3 * i + 0] = __byte_perm(r[0], r[1], 0x5410);
-                o[3 * i + 1] = __byte_perm(g[0], g[1], 0x5410);
-                o[3 * i + 2] = __byte_perm(b[0], b[1], 0x5410);
+                o[3 * i + 0] = __byte_perm(r[0], r[1], kSelPair);
+                o[3 * i + 1] = __byte_perm(g[0], g[1], kSelPair);
+                o[3 * i + 2] = __byte_perm(b[0], b[1], kSelPair);
               }
             }
           }

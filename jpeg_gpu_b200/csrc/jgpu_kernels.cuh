@@ -61,6 +61,31 @@ JGPU_DEV int dp2a_hi_s16_u8(uint32_t w, uint32_t q) {
   return d;
 }
 
+/* A/B knob (measured, profiles/r1_ab_notes.md): (float)(short)a, (float)(short)b as one packed
+ * pair without the conversion unit.  I2F.S16 issues on the XU pipe (one warp instruction per 8
+ * cycles per sub-core; 32 % XU utilisation with 128 conversions per thread).  The alternative:
+ * the low 16 bits of the product, sign bit flipped, under the exponent of 2^23 are the binary32
+ * number 2^23 + 32768 + (short)a (ulp is 1 in that binade), and subtracting 2^23 + 32768 is
+ * exact: one LOP3 per value plus one packed FADD2 per pair, same binary32 result.  It removes
+ * the XU traffic but adds 64 issue slots per thread, and the kernel is issue-bound: 1.8 %
+ * SLOWER on B200 (3.100 vs 3.045 ms, 4K 4:2:0 batch 256), so the default stays I2F. */
+#ifndef JGPU_DEQ_MAGIC
+#define JGPU_DEQ_MAGIC 0
+#endif
+JGPU_DEV pair32 s16_pair_to_float(int a, int b) {
+#ifdef JGPU_CORE_HOST_EMULATION
+  const uint32_t ua = ((uint32_t)a & 0xffffu) ^ 0x4b008000u;
+  const uint32_t ub = ((uint32_t)b & 0xffffu) ^ 0x4b008000u;
+#else
+  /* (x & 0xffff) ^ k as ONE LOP3 (lut 0x6a = (a & b) ^ c); written in C, ptxas emits two */
+  uint32_t ua, ub;
+  const uint32_t k = 0x4b008000u;
+  asm("lop3.b32 %0, %1, 0xffff, %2, 0x6a;" : "=r"(ua) : "r"(a), "r"(k));
+  asm("lop3.b32 %0, %1, 0xffff, %2, 0x6a;" : "=r"(ub) : "r"(b), "r"(k));
+#endif
+  return p_sub(p_make_bits(ua, ub), p_make_bits(0x4b008000u, 0x4b008000u));
+}
+
 /* One coefficient row of block A and of block B (8 int16 each) with the packed
  * table rows qa / qb (4 words each; WIDE: plus the high-byte rows qah / qbh):
  * dequantise, convert, prescale. */
@@ -80,8 +105,13 @@ JGPU_DEV void load_row_pair_packed(pair32 (&row)[8], uint4 a, uint4 b, uint4 qa,
       b0 += dp2a_lo_s16_u8(wb[i], hb[i]) << 8;
       b1 += dp2a_hi_s16_u8(wb[i], hb[i]) << 8;
     }
+#if JGPU_DEQ_MAGIC
+    row[2 * i] = prescale(s16_pair_to_float(a0, b0), r, 2 * i);
+    row[2 * i + 1] = prescale(s16_pair_to_float(a1, b1), r, 2 * i + 1);
+#else
     row[2 * i] = prescale(p_make((float)(short)a0, (float)(short)b0), r, 2 * i);
     row[2 * i + 1] = prescale(p_make((float)(short)a1, (float)(short)b1), r, 2 * i + 1);
+#endif
   }
 }
 

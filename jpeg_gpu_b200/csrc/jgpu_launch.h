@@ -20,6 +20,14 @@ cudaError_t launch_planes_to_rgb(const ColourImage *imgs, const ColourWork *work
                                  int ncta, const uint8_t *planes, uint8_t *rgb,
                                  cudaStream_t stream);
 
+/* ---- PACK expansion (jgpu_unpack.cu) -------------------------------------- */
+
+constexpr int kUnpackThreads = 256; /* blocks per CTA */
+
+cudaError_t launch_unpack(const UnpackSeg *segs, const UnpackWork *work, int ncta,
+                          const uint16_t *pack, const int64_t *pack_off, const int32_t *index,
+                          int16_t *coef, cudaStream_t stream);
+
 /* ---- fused path (jgpu_fused.cu) ------------------------------------------ */
 
 struct FusedPlan {

@@ -74,6 +74,7 @@ struct jgpu_ctx {
   cudaEvent_t events[kHostStreams] = {};
   /* device mirrors used by the host-buffer entry points (grow-only) */
   Buffer d_coef, d_qtabs, d_rgb, d_yuv;
+  Buffer d_pack, d_index, d_pack_off; /* jgpu_decode_batch_host_packed */
   /* pinned bounce buffers for pageable host memory */
   Buffer h_in[kHostStreams], h_out[kHostStreams];
   /* last plan built by jgpu_decode_batch_host, reused while descs match */
@@ -98,6 +99,10 @@ struct jgpu_plan {
   /* fused path */
   bool fused = false;
   FusedPlan fp;
+  /* PACK expansion: built when every coef_off is a multiple of 64 */
+  bool can_unpack = false;
+  Buffer d_unpack_segs, d_unpack_work;
+  std::vector<int> img_first_unpack_cta; /* size n+1 */
 };
 
 /* -------------------------------------------------------------------------- */
@@ -172,6 +177,9 @@ extern "C" void jgpu_destroy(jgpu_ctx *ctx) {
   ctx->d_qtabs.release();
   ctx->d_rgb.release();
   ctx->d_yuv.release();
+  ctx->d_pack.release();
+  ctx->d_index.release();
+  ctx->d_pack_off.release();
   delete ctx;
 }
 
@@ -209,6 +217,36 @@ static bool fused_eligible(const jgpu_image_desc &d, const jgpu_layout &lay, uns
   if ((flags & (JGPU_OUT_RGB | JGPU_OUT_YUV)) != JGPU_OUT_RGB) return false;
   if (d.coef_off & 63) return false;
   return true;
+}
+
+/* Work lists of k_unpack: one segment per (image, plane), one CTA per 256 blocks. */
+static int build_unpack_lists(jgpu_plan *plan) {
+  plan->can_unpack = true;
+  for (int i = 0; i < plan->n; i++) {
+    if (plan->descs[i].coef_off & 63) plan->can_unpack = false;
+  }
+  if (!plan->can_unpack) return 0;
+  std::vector<UnpackSeg> segs;
+  std::vector<UnpackWork> work;
+  plan->img_first_unpack_cta.assign(plan->n + 1, 0);
+  for (int i = 0; i < plan->n; i++) {
+    const jgpu_image_desc &d = plan->descs[i];
+    const jgpu_layout &lay = plan->layouts[i];
+    plan->img_first_unpack_cta[i] = (int)work.size();
+    for (int p = 0; p < d.ncomps; p++) {
+      UnpackSeg s;
+      s.block0 = (d.coef_off + lay.plane[p].coef_off) / 64;
+      s.nblocks = lay.plane[p].hblocks * lay.plane[p].vblocks;
+      s.img = i;
+      for (int first = 0; first < s.nblocks; first += kUnpackThreads) {
+        UnpackWork w = {(int32_t)segs.size(), first};
+        work.push_back(w);
+      }
+      segs.push_back(s);
+    }
+  }
+  plan->img_first_unpack_cta[plan->n] = (int)work.size();
+  return upload(plan->d_unpack_segs, segs) || upload(plan->d_unpack_work, work);
 }
 
 extern "C" jgpu_plan *jgpu_plan_create(jgpu_ctx *ctx, const jgpu_image_desc *descs, int n,
@@ -262,6 +300,7 @@ extern "C" jgpu_plan *jgpu_plan_create(jgpu_ctx *ctx, const jgpu_image_desc *des
     if (!fused_eligible(d, plan->layouts[i], flags, &modes[i])) all_fused = false;
   }
   plan->fused = all_fused;
+  if (build_unpack_lists(plan)) goto fail;
 
   if (plan->fused) {
     if (fused_plan_build(plan->fp, plan->descs.data(), plan->layouts.data(), modes.data(), n,
@@ -351,6 +390,8 @@ extern "C" void jgpu_plan_destroy(jgpu_plan *plan) {
   plan->d_cimgs.release();
   plan->d_colour_work.release();
   plan->d_scratch.release();
+  plan->d_unpack_segs.release();
+  plan->d_unpack_work.release();
   fused_plan_release(plan->fp);
   delete plan;
 }
@@ -553,6 +594,138 @@ extern "C" int jgpu_decode_batch_host(jgpu_ctx *ctx, const jgpu_image_desc *desc
                  (size_t)plan->layouts[i].data_len);
           off += (size_t)plan->layouts[i].data_len;
         }
+      }
+    }
+    i0 = i1;
+    chunk++;
+  }
+  for (int s = 0; s < kHostStreams; s++) CU_TRY(cudaStreamSynchronize(ctx->streams[s]));
+  return EXIT_SUCCESS;
+}
+
+/* -------------------------------------------------------------------------- */
+/* PACK input                                                                 */
+
+static int plan_unpack_range(jgpu_plan *plan, int i0, int i1, const uint16_t *d_pack,
+                             const int64_t *d_pack_off, const int32_t *d_index, int16_t *d_coef,
+                             cudaStream_t stream) {
+  if (!plan->can_unpack) {
+    return jgpu_fail("PACK input needs every coef_off to be a multiple of 64 int16");
+  }
+  const int c0 = plan->img_first_unpack_cta[i0], c1 = plan->img_first_unpack_cta[i1];
+  CU_TRY(launch_unpack((const UnpackSeg *)plan->d_unpack_segs.ptr,
+                       (const UnpackWork *)plan->d_unpack_work.ptr + c0, c1 - c0, d_pack, d_pack_off,
+                       d_index, d_coef, stream));
+  return 0;
+}
+
+extern "C" int jgpu_plan_unpack(jgpu_plan *plan, const uint16_t *d_pack, const int64_t *d_pack_off,
+                                const int32_t *d_index, int16_t *d_coef, void *stream) {
+  if (!plan || !d_pack || !d_pack_off || !d_index || !d_coef) {
+    return jgpu_fail("jgpu_plan_unpack: NULL argument");
+  }
+  if (reinterpret_cast<uintptr_t>(d_coef) & 15) {
+    return jgpu_fail("jgpu_plan_unpack: d_coef must be 16-byte aligned");
+  }
+  CU_TRY(cudaSetDevice(plan->ctx->device));
+  return plan_unpack_range(plan, 0, plan->n, d_pack, d_pack_off, d_index, d_coef, (cudaStream_t)stream);
+}
+
+extern "C" int jgpu_decode_batch_host_packed(jgpu_ctx *ctx, const jgpu_image_desc *descs, int n,
+                                             unsigned flags, const uint16_t *h_pack,
+                                             const int64_t *pack_off, const int32_t *h_index,
+                                             const uint16_t *h_qtabs, int n_sets, uint8_t *h_rgb,
+                                             uint8_t *h_yuv) {
+  if (!ctx || !descs || n <= 0 || !h_pack || !pack_off || !h_index || !h_qtabs || n_sets <= 0) {
+    return jgpu_fail("jgpu_decode_batch_host_packed: bad arguments");
+  }
+  if ((flags & JGPU_OUT_RGB) && !h_rgb) return jgpu_fail("jgpu_decode_batch_host_packed: h_rgb is NULL");
+  if ((flags & JGPU_OUT_YUV) && !h_yuv) return jgpu_fail("jgpu_decode_batch_host_packed: h_yuv is NULL");
+  for (int i = 0; i < n; i++) {
+    if (pack_off[i] < 0 || pack_off[i + 1] < pack_off[i]) {
+      return jgpu_fail("jgpu_decode_batch_host_packed: pack_off must be non-decreasing");
+    }
+  }
+  CU_TRY(cudaSetDevice(ctx->device));
+  if (!ctx->cached_plan || ctx->cached_flags != flags || !same_descs(ctx->cached_descs, descs, n)) {
+    if (ctx->cached_plan) jgpu_plan_destroy(ctx->cached_plan);
+    ctx->cached_plan = jgpu_plan_create(ctx, descs, n, flags);
+    if (!ctx->cached_plan) return EXIT_FAILURE;
+    ctx->cached_descs.assign(descs, descs + n);
+    ctx->cached_flags = flags;
+  }
+  jgpu_plan *plan = ctx->cached_plan;
+  if (!plan->can_unpack) return jgpu_fail("PACK input needs every coef_off to be a multiple of 64 int16");
+  for (int i = 0; i < n; i++) {
+    if (descs[i].qtab_set >= n_sets) {
+      return jgpu_fail("image %d uses table set %d but only %d were passed", i, descs[i].qtab_set, n_sets);
+    }
+  }
+  int64_t coef_end = 0, rgb_end = 0, yuv_end = 0;
+  for (int i = 0; i < n; i++) {
+    const jgpu_layout &lay = plan->layouts[i];
+    coef_end = std::max(coef_end, descs[i].coef_off + lay.coef_len);
+    if (flags & JGPU_OUT_RGB) rgb_end = std::max(rgb_end, descs[i].rgb_off + lay.rgb_len);
+    if (flags & JGPU_OUT_YUV) yuv_end = std::max(yuv_end, descs[i].yuv_off + lay.data_len);
+  }
+  const int64_t pack_words = pack_off[n];
+  if (ctx->d_coef.reserve((size_t)coef_end * 2 + 256) ||
+      ctx->d_pack.reserve((size_t)pack_words * 2 + 256) ||
+      ctx->d_index.reserve((size_t)(coef_end / 64 + 1) * 4 + 256) ||
+      ctx->d_pack_off.reserve((size_t)(n + 1) * 8) ||
+      ctx->d_qtabs.reserve((size_t)n_sets * 4 * 64 * 2) ||
+      ((flags & JGPU_OUT_RGB) && ctx->d_rgb.reserve((size_t)rgb_end + 256)) ||
+      ((flags & JGPU_OUT_YUV) && ctx->d_yuv.reserve((size_t)yuv_end + 256))) {
+    return EXIT_FAILURE;
+  }
+  int16_t *d_coef = (int16_t *)ctx->d_coef.ptr;
+  uint16_t *d_pack = (uint16_t *)ctx->d_pack.ptr;
+  int32_t *d_index = (int32_t *)ctx->d_index.ptr;
+  int64_t *d_pack_off = (int64_t *)ctx->d_pack_off.ptr;
+  uint16_t *d_qtabs = (uint16_t *)ctx->d_qtabs.ptr;
+  uint8_t *d_rgb = (uint8_t *)ctx->d_rgb.ptr;
+  uint8_t *d_yuv = (uint8_t *)ctx->d_yuv.ptr;
+
+  /* pageable sources and destinations go through the driver's own staging here (cudaMemcpyAsync
+   * from pageable memory is synchronous with respect to the host); pinned ones overlap */
+  CU_TRY(cudaMemcpyAsync(d_qtabs, h_qtabs, (size_t)n_sets * 4 * 64 * 2, cudaMemcpyHostToDevice,
+                         ctx->streams[0]));
+  CU_TRY(cudaMemcpyAsync(d_pack_off, pack_off, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice,
+                         ctx->streams[0]));
+  CU_TRY(cudaEventRecord(ctx->events[0], ctx->streams[0]));
+  for (int s = 1; s < kHostStreams; s++) CU_TRY(cudaStreamWaitEvent(ctx->streams[s], ctx->events[0], 0));
+
+  /* chunks of ~48 MB of dense coefficients, as in jgpu_decode_batch_host, so that the read-back
+   * of chunk k overlaps the upload and kernels of chunk k+1 and the expanded planes of a chunk
+   * are still in L2 when the decode kernel reads them */
+  const int64_t chunk_bytes = 48ll << 20;
+  int i0 = 0, chunk = 0;
+  while (i0 < n) {
+    int i1 = i0;
+    int64_t acc = 0;
+    while (i1 < n && (i1 == i0 || acc + plan->layouts[i1].coef_len * 2 <= chunk_bytes)) {
+      acc += plan->layouts[i1].coef_len * 2;
+      i1++;
+    }
+    cudaStream_t st = ctx->streams[chunk % kHostStreams];
+    if (pack_off[i1] > pack_off[i0]) {
+      CU_TRY(cudaMemcpyAsync(d_pack + pack_off[i0], h_pack + pack_off[i0],
+                             (size_t)(pack_off[i1] - pack_off[i0]) * 2, cudaMemcpyHostToDevice, st));
+    }
+    for (int i = i0; i < i1; i++) {
+      CU_TRY(cudaMemcpyAsync(d_index + descs[i].coef_off / 64, h_index + descs[i].coef_off / 64,
+                             (size_t)(plan->layouts[i].coef_len / 64) * 4, cudaMemcpyHostToDevice, st));
+    }
+    if (plan_unpack_range(plan, i0, i1, d_pack, d_pack_off, d_index, d_coef, st)) return EXIT_FAILURE;
+    if (plan_run_range(plan, i0, i1, d_coef, d_qtabs, n_sets, d_rgb, d_yuv, st)) return EXIT_FAILURE;
+    for (int i = i0; i < i1; i++) {
+      if (flags & JGPU_OUT_RGB) {
+        CU_TRY(cudaMemcpyAsync(h_rgb + descs[i].rgb_off, d_rgb + descs[i].rgb_off,
+                               (size_t)plan->layouts[i].rgb_len, cudaMemcpyDeviceToHost, st));
+      }
+      if (flags & JGPU_OUT_YUV) {
+        CU_TRY(cudaMemcpyAsync(h_yuv + descs[i].yuv_off, d_yuv + descs[i].yuv_off,
+                               (size_t)plan->layouts[i].data_len, cudaMemcpyDeviceToHost, st));
       }
     }
     i0 = i1;

@@ -55,6 +55,12 @@ int jgo_yuv_to_rgb(const jgo_geom *g, const unsigned char *planes,
                    unsigned char *rgb);
 void jgo_colour_offsets(int cb, int cr, int out[3]);
 
+/* PACK format (oracle_pack.c) */
+int jgo_unpack_image(const jgo_geom *g, const unsigned short *pack, long long pack_len,
+                     const int *index, short *coef);
+long long jgo_pack_image(const jgo_geom *g, const short *coef, unsigned short *pack,
+                         long long pack_cap, int *index, int *packed);
+
 /* whole path over a batch; the CPU baseline */
 int jgo_decode_batch(int n, const long long *desc, const short *coef,
                      const unsigned short *qtabs, unsigned char *rgb,

@@ -106,6 +106,41 @@ int refshim_decode(const unsigned char *jpg, int size, int out_mode,
   return 0;
 }
 
+/* JPEG_DECODE_PACK as the reference's reader writes it (src/xjpeg.c:484-496,513-519,
+ * 531-535): copies the packed words (image.coef, img.packed of them), the whole index
+ * array (image.index, one int per allocated block) and the per-plane word counts
+ * (image_plane.packed).  total[0] = words, total[1] = index entries. */
+int refshim_decode_pack(const unsigned char *jpg, int size, short *pack,
+                        long long pack_cap, int *index, long long index_cap,
+                        int *packed, long long *total) {
+  xjpeg_decode_ctx ctx;
+  jpeg_header h;
+  image img;
+  int i;
+  long long blocks = 0, words = 0;
+  xjpeg_init(&ctx, jpg, size);
+  xjpeg_decode_header(&ctx);
+  if (ctx.error || !ctx.frame.valid) return 1;
+  fill_header(&ctx, &h);
+  if (image_init(&img, &h) != EXIT_SUCCESS) return 2;
+  image_zero(&img);
+  xjpeg_decode_image(&ctx, &img, XJPEG_DECODE_PACK);
+  if (ctx.error) { image_clear(&img); return 3; }
+  for (i = 0; i < img.nplanes; i++) {
+    image_plane *p = &img.plane[i];
+    blocks += (long long)((p->width >> 3) << p->xdec) * p->cstride;
+    packed[i] = p->packed;
+    words += p->packed;
+  }
+  if (words > pack_cap || blocks > index_cap) { image_clear(&img); return 4; }
+  memcpy(pack, img.coef, (size_t)words * sizeof(short));
+  memcpy(index, img.index, (size_t)blocks * sizeof(int));
+  total[0] = words;
+  total[1] = blocks;
+  image_clear(&img);
+  return 0;
+}
+
 /* Geometry as the reference's image_init computes it, for pinning our own
  * layout code.  out[0] = allocated blocks, then per plane (stride 8):
  * width,height,xdec,ydec,ystride,cstride,coef offset (shorts),index offset. */

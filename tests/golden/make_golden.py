@@ -13,6 +13,8 @@ and <name>.npz holding what the compiled reference produces for that file:
   dct          image.coef after xjpeg JPEG_DECODE_DCT            (src/xjpeg.c:501-503,524-527)
   yuv          the padded planes after xjpeg JPEG_DECODE_YUV     (src/xjpeg.c:565-584, src/dct.c)
   rgb          the colour oracle (oracle_pipeline.c, res/yuv.fs.glsl:11-23) applied to `yuv`
+  pack, index, packed   image.coef (the run/level words), image.index and image_plane.packed after
+               xjpeg JPEG_DECODE_PACK                            (src/xjpeg.c:484-496,513-519,531-535)
 plus blocks.npz: random int16 blocks and the reference's glj_real_idct8x8 output.
 The GPU box has no /root/reference; tests read only these files.
 """
@@ -69,12 +71,16 @@ def main():
         rgb, planes2 = ref.decode_image(g, quant, hdr["qtabs"], hdr["tq"])
         assert all(np.array_equal(a, b) for a, b in zip(planes, planes2)), name
         assert np.array_equal(rgb, oracle.np_rgb_from_planes(g, planes)), name
+        _, _, pack, index, packed = ref.ref_decode_pack(jpg)
+        # the consumer restatement (res/horz_pack_yuv.fs.glsl:105-127) must give back the QUANT planes
+        assert np.array_equal(ref.unpack_image(g, pack, index), quant), name
         np.savez_compressed(
             os.path.join(HERE, name + ".npz"),
             hdr_width=hdr["width"], hdr_height=hdr["height"], hdr_bits=hdr["bits"], hdr_ncomps=hdr["ncomps"],
             hdr_restart_interval=hdr["restart_interval"], hdr_hsamp=np.array(hdr["hsamp"]),
             hdr_vsamp=np.array(hdr["vsamp"]), hdr_tq=np.array(hdr["tq"]), hdr_qtabs=hdr["qtabs"],
-            hdr_qvalid=np.array(hdr["qvalid"]), quant=quant, dct=dct, yuv=yuv, rgb=rgb.reshape(-1))
+            hdr_qvalid=np.array(hdr["qvalid"]), quant=quant, dct=dct, yuv=yuv, rgb=rgb.reshape(-1),
+            pack=pack, index=index, packed=packed)
         print(f"{name}: {len(jpg)} B jpeg, {g.coef_len} coefs, subsamp h{hdr['hsamp']} v{hdr['vsamp']}")
     rng = np.random.default_rng(20261017)
     blocks = np.concatenate([
