@@ -320,6 +320,37 @@ def main():
                     "bytes_per_block": (h_pack.numel() * 2 + h_index.numel() * 4) / (sub_coef_bytes / 128)}
         del h_coef, h_rgb, h_pack, h_index
 
+    # JPEG files in, RGB out (jgpu_decode_jpegs): the multi-threaded entropy front end feeding the
+    # GPU.  Not BASELINE's metric (that starts at the coefficient planes) -- reported beside it
+    # because this is what a user of the reference's viewer loop actually waits for.
+    e2e_jpeg = None
+    if not args.no_e2e and rank == 0 and world == 1 and args.workload.startswith("4k"):
+        try:
+            import io
+            from PIL import Image
+            rng = np.random.default_rng(synth.SEED_BASE)
+            yy, xx = np.mgrid[0:h, 0:w]
+            base = np.stack([(xx * 5 + yy * 3) % 256, (yy * 7 + xx) % 256, (xx * 2 + yy * 9) % 256], -1)
+            pic = np.clip(base + rng.integers(-24, 25, size=base.shape), 0, 255).astype(np.uint8)
+            bio = io.BytesIO()
+            Image.fromarray(pic).save(bio, "JPEG", quality=85, subsampling={"420": 2, "422": 1}[ss],
+                                      restart_marker_blocks=w // 16)
+            files = [bio.getvalue()] * 32
+            total, _ = J.probe_jpegs(files)
+            out = torch.zeros(total, dtype=torch.uint8).pin_memory()
+            ctx.decode_jpegs(files, out, nthreads=threads)   # warm-up (plan, staging)
+            t0 = time.perf_counter()
+            for _ in range(3):
+                ctx.decode_jpegs(files, out, nthreads=threads)
+            dt = time.perf_counter() - t0
+            e2e_jpeg = {"value": 3 * len(files) * w * h / 1e6 / dt, "unit": UNIT, "files_per_step": len(files),
+                        "steps": 3, "host_threads": threads, "jpeg_bytes": len(files[0]),
+                        "input": f"{w}x{h} {ss} baseline JPEG (Pillow, q85, one restart interval per MCU row), "
+                                 "Huffman decoding on the host threads, block decode on the GPU"}
+            del out
+        except ImportError:
+            e2e_jpeg = None
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         kind, mpx, times = cpu_reference_run(args.workload, 16, 4, threads)
@@ -336,7 +367,7 @@ def main():
                        "l2": "inputs larger than L2 (%.2f GB coef + %.2f GB rgb per GPU)" % (coef_len * 2 / 1e9, rgb_len / 1e9),
                        "path": "generic (2 kernels)" if args.force_generic else "fused kernel",
                        "kernel_launches_per_step": plan.launches, "parallelism": f"images sharded x{world}"},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_pack": e2e_pack,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_pack": e2e_pack, "e2e_jpeg": e2e_jpeg,
             "gpu_launches": args.steps * plan.launches, "clocks": clk.summary(),
         }
         print(json.dumps(line))

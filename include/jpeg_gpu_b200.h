@@ -219,6 +219,44 @@ int jgpu_decode_batch_host_packed(jgpu_ctx *ctx, const jgpu_image_desc *descs,
                                   const uint16_t *h_qtabs, int n_sets,
                                   uint8_t *h_rgb, uint8_t *h_yuv);
 
+/* ------------------------------------------------------------------------
+ * (4) JPEG files in, RGB out: multi-threaded entropy front end + GPU back end
+ * --------------------------------------------------------------------- */
+
+/* The reference decodes one file per call on one thread (src/jpeg_gpu.c:1228-1237) and its
+ * Huffman reader is >99 % of the time once the back half runs on the GPU.
+ * This entry point runs JFRONT_DECODE_CTX_VTBL's scan decoder on `nthreads` host threads --
+ * one task per image, and per group of restart intervals for files that carry DRI (RSTn
+ * markers make the pieces independent, src/xjpeg.c:593-629) -- writing QUANT planes straight
+ * into pinned staging, and overlaps it with the upload, the fused kernel and the read-back of
+ * the images already finished. */
+typedef struct jgpu_jpeg {
+  const unsigned char *data;  /* a whole baseline JPEG file in memory (caller-owned) */
+  int64_t size;
+} jgpu_jpeg;
+
+typedef struct jgpu_jpeg_info {
+  int32_t status;             /* 0 = ok, 1 = rejected (see message) */
+  int32_t width, height, ncomps;
+  int32_t hsamp0, vsamp0;     /* luma sampling factors */
+  int32_t restart_interval;
+  int32_t tasks;              /* entropy-decode tasks the image was split into */
+  int64_t rgb_off, rgb_len;   /* where its pixels go in the output buffer */
+  const char *message;        /* static string, NULL when ok */
+} jgpu_jpeg_info;
+
+/* Host only.  Parses the headers, assigns rgb_off back to back (256-byte aligned) and
+ * returns the output buffer size in bytes (rejected files take no space), or -1. */
+int64_t jgpu_jpegs_probe(const jgpu_jpeg *files, int n, jgpu_jpeg_info *info);
+
+/* Decodes every accepted file into h_rgb + info[i].rgb_off (interleaved RGB8, or grey8 for
+ * 1-component files).  h_rgb may be pageable or pinned.  nthreads <= 0: all host cores.
+ * info is filled as by jgpu_jpegs_probe.  Returns EXIT_SUCCESS when every file decoded;
+ * EXIT_FAILURE otherwise (info[i].status / message say which and why; the others are still
+ * decoded). */
+int jgpu_decode_jpegs(jgpu_ctx *ctx, const jgpu_jpeg *files, int n, int nthreads,
+                      uint8_t *h_rgb, int64_t rgb_cap, jgpu_jpeg_info *info);
+
 /* Page-locked host memory for the batch entry points. */
 void *jgpu_host_alloc(size_t bytes);
 void jgpu_host_free(void *p);

@@ -12,8 +12,9 @@ C ABI, include/jpeg_gpu_b200.h).  There is no CPU fallback.
 """
 from . import _capi, shard, synth
 from ._capi import LibraryMissing
-from .batch import Context, ImageDesc, Layout, Plan, PlaneLayout, SUBSAMPLINGS, pack_batch
+from .batch import (Context, ImageDesc, JpegInfo, Layout, Plan, PlaneLayout, SUBSAMPLINGS, pack_batch,
+                    pack_batch_streams, pack_from_quant, probe_jpegs)
 from .decoder import DecodeError, Decoder, Header
 
 __all__ = ["Decoder", "DecodeError", "Header", "Context", "Plan", "ImageDesc", "Layout", "PlaneLayout",
-           "SUBSAMPLINGS", "pack_batch", "synth", "shard", "LibraryMissing", "_capi"]
+           "SUBSAMPLINGS", "pack_batch", "pack_batch_streams", "pack_from_quant", "probe_jpegs", "JpegInfo", "synth", "shard", "LibraryMissing", "_capi"]

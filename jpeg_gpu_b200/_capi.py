@@ -90,6 +90,16 @@ class jgpu_layout(C.Structure):
                 ("rgb_len", C.c_int64), ("plane", jgpu_plane_layout * 3)]
 
 
+class jgpu_jpeg(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("size", C.c_int64)]
+
+
+class jgpu_jpeg_info(C.Structure):
+    _fields_ = [("status", C.c_int32), ("width", C.c_int32), ("height", C.c_int32), ("ncomps", C.c_int32),
+                ("hsamp0", C.c_int32), ("vsamp0", C.c_int32), ("restart_interval", C.c_int32), ("tasks", C.c_int32),
+                ("rgb_off", C.c_int64), ("rgb_len", C.c_int64), ("message", C.c_char_p)]
+
+
 EXPORTS = [
     # name, restype, argtypes  (every function include/jpeg_gpu_b200.h declares)
     ("cuda_decode_set_frontend", None, [C.c_void_p]),
@@ -118,6 +128,9 @@ EXPORTS = [
     ("jgpu_decode_batch_host_packed", C.c_int, [C.c_void_p, C.POINTER(jgpu_image_desc), C.c_int, C.c_uint,
                                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                                 C.c_void_p, C.c_void_p]),
+    ("jgpu_jpegs_probe", C.c_int64, [C.POINTER(jgpu_jpeg), C.c_int, C.POINTER(jgpu_jpeg_info)]),
+    ("jgpu_decode_jpegs", C.c_int, [C.c_void_p, C.POINTER(jgpu_jpeg), C.c_int, C.c_int, C.c_void_p, C.c_int64,
+                                    C.POINTER(jgpu_jpeg_info)]),
     ("jgpu_host_alloc", C.c_void_p, [C.c_size_t]),
     ("jgpu_host_free", None, [C.c_void_p]),
 ]

@@ -135,6 +135,53 @@ def pack_batch_streams(descs: List[ImageDesc], coef: np.ndarray):
     return np.concatenate(packs), np.array(offs, dtype=np.int64), index
 
 
+@dataclass
+class JpegInfo:
+    """jgpu_jpeg_info: what jgpu_jpegs_probe / jgpu_decode_jpegs report per file."""
+    status: int
+    width: int
+    height: int
+    ncomps: int
+    hsamp0: int
+    vsamp0: int
+    restart_interval: int
+    tasks: int
+    rgb_off: int
+    rgb_len: int
+    message: Optional[str]
+
+    @property
+    def shape(self):
+        return (self.height, self.width) if self.ncomps == 1 else (self.height, self.width, 3)
+
+
+def _jpeg_array(files: Sequence[bytes]):
+    arr = (_capi.jgpu_jpeg * len(files))()
+    keep = []
+    for i, f in enumerate(files):
+        buf = (C.c_ubyte * max(len(f), 1)).from_buffer_copy(f if len(f) else b"\0")
+        keep.append(buf)
+        arr[i].data = C.addressof(buf)
+        arr[i].size = len(f)
+    return arr, keep
+
+
+def _jpeg_infos(raw) -> List[JpegInfo]:
+    return [JpegInfo(r.status, r.width, r.height, r.ncomps, r.hsamp0, r.vsamp0, r.restart_interval, r.tasks,
+                     r.rgb_off, r.rgb_len, r.message.decode() if r.message else None) for r in raw]
+
+
+def probe_jpegs(files: Sequence[bytes]):
+    """Headers only (host, no GPU): returns (output bytes needed, [JpegInfo])."""
+    arr, keep = _jpeg_array(files)
+    raw = (_capi.jgpu_jpeg_info * len(files))()
+    total = _capi.lib().jgpu_jpegs_probe(arr, len(files), raw)
+    if total < 0:
+        raise RuntimeError(f"jgpu_jpegs_probe failed: {_capi.last_error()}")
+    del keep
+    return int(total), _jpeg_infos(raw)
+
+
 def _desc_array(descs: List[ImageDesc]):
     arr = (_capi.jgpu_image_desc * len(descs))()
     for i, d in enumerate(descs):
@@ -181,6 +228,25 @@ class Context:
         if rc != 0:
             raise RuntimeError(f"jgpu_decode_batch_host failed: {_capi.last_error()}")
 
+
+    def decode_jpegs(self, files: Sequence[bytes], rgb=None, nthreads: int = 0, strict: bool = True):
+        """JPEG files in, RGB out (jgpu_decode_jpegs): multi-threaded entropy front end feeding the
+        GPU back end.  Returns (rgb uint8 buffer, [JpegInfo]); image i is
+        rgb[info.rgb_off : info.rgb_off + info.rgb_len].reshape(info.shape)."""
+        arr, keep = _jpeg_array(files)
+        raw = (_capi.jgpu_jpeg_info * len(files))()
+        if rgb is None:
+            total = _capi.lib().jgpu_jpegs_probe(arr, len(files), raw)
+            if total < 0:
+                raise RuntimeError(f"jgpu_jpegs_probe failed: {_capi.last_error()}")
+            rgb = np.zeros(max(int(total), 1), dtype=np.uint8)
+        cap = rgb.numel() if hasattr(rgb, "numel") else rgb.size
+        rc = _capi.lib().jgpu_decode_jpegs(self._h, arr, len(files), nthreads, _addr(rgb), cap, raw)
+        infos = _jpeg_infos(raw)
+        del keep
+        if rc != 0 and (strict or all(i.status for i in infos)):
+            raise RuntimeError(f"jgpu_decode_jpegs failed: {_capi.last_error()}")
+        return rgb, infos
 
     def decode_batch_host_packed(self, descs: List[ImageDesc], pack, pack_off: np.ndarray, index,
                                  qtabs: np.ndarray, rgb=None, yuv=None, force_generic: bool = False) -> None:

@@ -24,6 +24,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include "jgpu_internal.h"
+#include "jgpu_front.h"
 
 /* zig-zag position -> natural (row-major) position, T.81 figure A.6 */
 static const unsigned char kNatural[64] = {
@@ -361,14 +362,10 @@ static int restart(jfront_ctx *c, scan_comp *sc, int ncomps, int *expected) {
   return 0;
 }
 
-static int decode_scan(jfront_ctx *c, image *img, jpeg_decode_out out) {
-  scan_comp sc[NCOMPS_MAX];
-  int len, ns, i, j, v, mbx, mby;
-  int mcus_left, rst_expected = 0;
-  int pack_index = 0;
-  short *pack = img->coef;
-  long long w0x8 = (long long)img->plane[0].width << 3;
-
+/* Parses the SOS header (T.81 B.2.3), binds the scan components to their tables and planes
+ * and leaves c->ecs_pos at the first entropy-coded byte with an empty bit accumulator. */
+static int scan_setup(jfront_ctx *c, image *img, scan_comp *sc, int *ns_out) {
+  int len, ns, i, j, v;
   c->pos = c->sos_pos;
   if (get_u16(c, &len) || get_u8(c, &ns)) return 1;
   if (ns != c->ncomps) {
@@ -400,70 +397,90 @@ static int decode_scan(jfront_ctx *c, image *img, jpeg_decode_out out) {
   if (get_u8(c, &v) || v != 0) return fail(c, "Error SOS expected Ss value 0.");
   if (get_u8(c, &v) || v != 63) return fail(c, "Error SOS expected Se value 63.");
   if (get_u8(c, &v) || v != 0) return fail(c, "Error SOS expected Ah/Al value 0.");
-
   c->ecs_pos = c->pos;
   c->acc = 0;
   c->nbits = 0;
   c->hit_marker = 0;
+  *ns_out = ns;
+  return 0;
+}
+
+/* One MCU: the blocks of every scan component in the order of src/xjpeg.c:462-472. */
+static int decode_mcu(jfront_ctx *c, scan_comp *sc, int ns, jpeg_decode_out out, int mbx, int mby,
+                      short *pack, int *pack_index, long long w0x8) {
+  int i, v;
+  for (i = 0; i < ns; i++) {
+    scan_comp *s = &sc[i];
+    image_plane *ip = s->plane;
+    int sby, sbx;
+    for (sby = 0; sby < s->fc->vsamp; sby++) {
+      for (sbx = 0; sbx < s->fc->hsamp; sbx++) {
+        short block[64];
+        int by = mby * s->fc->vsamp + sby;
+        int bx = mbx * s->fc->hsamp + sbx;
+        int k = 0, sym;
+        memset(block, 0, sizeof(block));
+        sym = decode_symbol(c, s->dc);
+        s->pred = (short)(s->pred + (short)receive_extend(c, sym & 15));
+        if (out == JPEG_DECODE_PACK) {
+          /* src/xjpeg.c:484-496 */
+          ip->index[by * (ip->ystride >> 3) + bx] = *pack_index;
+          ip->packed++;
+          pack[(*pack_index)++] = (short)(s->pred & 0xfff);
+        }
+        block[0] = out == JPEG_DECODE_DCT ? (short)(s->pred * s->q[0]) : s->pred;
+        do {
+          sym = decode_symbol(c, s->ac);
+          if (sym == 0) { /* EOB */
+            if (out == JPEG_DECODE_PACK) {
+              ip->packed++;
+              pack[(*pack_index)++] = 0;
+            }
+            break;
+          }
+          k += (sym >> 4) + 1;
+          v = receive_extend(c, sym & 15);
+          if (k > 63) {
+            fail(c, "Error indexing outside block.");
+            break;
+          }
+          if (out == JPEG_DECODE_PACK) {
+            ip->packed++;
+            pack[(*pack_index)++] = (short)(((sym >> 4) << 12) | (v & 0xfff));
+          } else if (out == JPEG_DECODE_DCT) {
+            block[kNatural[k]] = (short)((short)v * s->q[kNatural[k]]);
+          } else {
+            block[kNatural[k]] = (short)v;
+          }
+        } while (k < 63);
+        if (c->error) return 1;
+        if (out != JPEG_DECODE_PACK) {
+          /* src/xjpeg.c:550-563 */
+          long long off = w0x8 * (by >> ip->xdec) +
+                          (w0x8 >> ip->xdec) * (by & ((1 << ip->xdec) - 1)) +
+                          ((long long)bx << 6);
+          memcpy(ip->coef + off, block, sizeof(block));
+        }
+      }
+    }
+  }
+  return 0;
+}
+
+static int decode_scan(jfront_ctx *c, image *img, jpeg_decode_out out) {
+  scan_comp sc[NCOMPS_MAX];
+  int ns, mbx, mby;
+  int mcus_left, rst_expected = 0;
+  int pack_index = 0;
+  short *pack = img->coef;
+  long long w0x8 = (long long)img->plane[0].width << 3;
+
+  if (scan_setup(c, img, sc, &ns)) return 1;
   mcus_left = c->restart_interval;
 
   for (mby = 0; mby < c->nvmb; mby++) {
     for (mbx = 0; mbx < c->nhmb; mbx++) {
-      for (i = 0; i < ns; i++) {
-        scan_comp *s = &sc[i];
-        image_plane *ip = s->plane;
-        int sby, sbx;
-        for (sby = 0; sby < s->fc->vsamp; sby++) {
-          for (sbx = 0; sbx < s->fc->hsamp; sbx++) {
-            short block[64];
-            int by = mby * s->fc->vsamp + sby;
-            int bx = mbx * s->fc->hsamp + sbx;
-            int k = 0, sym;
-            memset(block, 0, sizeof(block));
-            sym = decode_symbol(c, s->dc);
-            s->pred = (short)(s->pred + (short)receive_extend(c, sym & 15));
-            if (out == JPEG_DECODE_PACK) {
-              /* src/xjpeg.c:484-496 */
-              ip->index[by * (ip->ystride >> 3) + bx] = pack_index;
-              ip->packed++;
-              pack[pack_index++] = (short)(s->pred & 0xfff);
-            }
-            block[0] = out == JPEG_DECODE_DCT ? (short)(s->pred * s->q[0]) : s->pred;
-            do {
-              sym = decode_symbol(c, s->ac);
-              if (sym == 0) { /* EOB */
-                if (out == JPEG_DECODE_PACK) {
-                  ip->packed++;
-                  pack[pack_index++] = 0;
-                }
-                break;
-              }
-              k += (sym >> 4) + 1;
-              v = receive_extend(c, sym & 15);
-              if (k > 63) {
-                fail(c, "Error indexing outside block.");
-                break;
-              }
-              if (out == JPEG_DECODE_PACK) {
-                ip->packed++;
-                pack[pack_index++] = (short)(((sym >> 4) << 12) | (v & 0xfff));
-              } else if (out == JPEG_DECODE_DCT) {
-                block[kNatural[k]] = (short)((short)v * s->q[kNatural[k]]);
-              } else {
-                block[kNatural[k]] = (short)v;
-              }
-            } while (k < 63);
-            if (c->error) return 1;
-            if (out != JPEG_DECODE_PACK) {
-              /* src/xjpeg.c:550-563 */
-              long long off = w0x8 * (by >> ip->xdec) +
-                              (w0x8 >> ip->xdec) * (by & ((1 << ip->xdec) - 1)) +
-                              ((long long)bx << 6);
-              memcpy(ip->coef + off, block, sizeof(block));
-            }
-          }
-        }
-      }
+      if (decode_mcu(c, sc, ns, out, mbx, mby, pack, &pack_index, w0x8)) return 1;
       if (c->restart_interval && --mcus_left == 0) {
         int r = restart(c, sc, ns, &rst_expected);
         if (r == 1) return 1;
@@ -473,6 +490,103 @@ static int decode_scan(jfront_ctx *c, image *img, jpeg_decode_out out) {
     }
   }
   return 0;
+}
+
+/* ---- restart-interval parallel decoding (jgpu_front.h) ---------------------- */
+
+/* Restart intervals are independently decodable (T.81 F.1.1.5: predictors reset, bits byte
+ * aligned), so a scan with DRI can be cut at its RSTn markers and the pieces decoded by
+ * different threads.  Finds the pieces: seg_pos[k] = first entropy-coded byte of interval k.
+ * Returns 0 and nseg >= 1, or 1 when the markers are not where a well-formed file has them
+ * (the caller then decodes sequentially, which reports the error the reference's way). */
+int jfront_find_segments(jpeg_decode_ctx *ctx, jfront_segments *out) {
+  jfront_ctx *c = (jfront_ctx *)ctx;
+  jfront_ctx w;
+  scan_comp sc[NCOMPS_MAX];
+  image dummy;
+  int ns, total, nseg, k, pos;
+  memset(out, 0, sizeof(*out));
+  if (!c->have_frame || !c->sos_pos) return 1;
+  w = *c;
+  w.error = NULL;
+  memset(&dummy, 0, sizeof(dummy));
+  if (scan_setup(&w, &dummy, sc, &ns)) return 1;
+  total = c->nhmb * c->nvmb;
+  out->total_mcus = total;
+  if (!c->restart_interval) {
+    out->mcus_per_seg = total;
+    out->nseg = 1;
+    out->seg_pos = (int *)malloc(sizeof(int));
+    if (!out->seg_pos) return 1;
+    out->seg_pos[0] = w.ecs_pos;
+    return 0;
+  }
+  nseg = (total + c->restart_interval - 1) / c->restart_interval;
+  out->mcus_per_seg = c->restart_interval;
+  out->seg_pos = (int *)malloc(sizeof(int) * (size_t)nseg);
+  if (!out->seg_pos) return 1;
+  out->seg_pos[0] = pos = w.ecs_pos;
+  for (k = 1; k < nseg; k++) {
+    /* next marker that is neither a stuffed 0xFF00 nor a fill byte */
+    for (;;) {
+      const unsigned char *p;
+      if (pos >= c->size) goto malformed;
+      p = (const unsigned char *)memchr(c->buf + pos, 0xFF, (size_t)(c->size - pos));
+      if (!p || p + 1 >= c->buf + c->size) goto malformed;
+      pos = (int)(p - c->buf);
+      if (c->buf[pos + 1] == 0x00) { pos += 2; continue; }
+      if (c->buf[pos + 1] == 0xFF) { pos += 1; continue; }
+      break;
+    }
+    if (c->buf[pos + 1] != 0xD0 + ((k - 1) & 7)) goto malformed;
+    pos += 2;
+    out->seg_pos[k] = pos;
+  }
+  out->nseg = nseg;
+  return 0;
+malformed:
+  free(out->seg_pos);
+  memset(out, 0, sizeof(*out));
+  return 1;
+}
+
+void jfront_segments_free(jfront_segments *s) {
+  free(s->seg_pos);
+  memset(s, 0, sizeof(*s));
+}
+
+/* Decodes restart intervals [s0, s1) into img (QUANT or DCT planes).  Works on a private copy
+ * of the reader state, so several threads may run it on the same ctx and image at once: the
+ * blocks of different intervals are disjoint.  Returns 0, or 1 with *error set to a static
+ * message. */
+int jfront_decode_segments(const jpeg_decode_ctx *ctx, image *img, jpeg_decode_out out,
+                           const jfront_segments *segs, int s0, int s1, const char **error) {
+  jfront_ctx w = *(const jfront_ctx *)ctx;
+  scan_comp sc[NCOMPS_MAX];
+  int ns, s, i, pack_index = 0;
+  const long long w0x8 = (long long)img->plane[0].width << 3;
+  w.error = NULL;
+  if (out != JPEG_DECODE_QUANT && out != JPEG_DECODE_DCT) {
+    *error = "Error, parallel decoding produces quant or dct planes only";
+    return 1;
+  }
+  if (scan_setup(&w, img, sc, &ns)) goto failed;
+  for (s = s0; s < s1; s++) {
+    int m = s * segs->mcus_per_seg;
+    const int m_end = m + segs->mcus_per_seg < segs->total_mcus ? m + segs->mcus_per_seg : segs->total_mcus;
+    w.ecs_pos = segs->seg_pos[s];
+    w.acc = 0;
+    w.nbits = 0;
+    w.hit_marker = 0;
+    for (i = 0; i < ns; i++) sc[i].pred = 0;
+    for (; m < m_end; m++) {
+      if (decode_mcu(&w, sc, ns, out, m % w.nhmb, m / w.nhmb, NULL, &pack_index, w0x8)) goto failed;
+    }
+  }
+  return 0;
+failed:
+  *error = w.error ? w.error : "Error decoding scan";
+  return 1;
 }
 
 /* ---- vtable ---------------------------------------------------------------- */

@@ -291,6 +291,15 @@ __device__ __forceinline__ uint32_t chroma_clamped(pair32 v) {
  * colour offset).  Arithmetic is colour_offsets() of jgpu_kernels.cuh, i.e. the oracle's
  * jgo_colour_offsets, with the two samples riding in the two lanes of the packed binary32
  * instructions (each lane is one IEEE operation, products via fma(a, b, -0.0)). */
+/* Byte I of w, sign-extended: one PRMT whose selector nibbles 1..3 carry the replicate-sign bit
+ * (PTX prmt default mode; __byte_perm documents only three selector bits, so spell it in PTX). */
+template <int I>
+__device__ __forceinline__ int sext_byte(uint32_t w) {
+  int d;
+  asm("prmt.b32 %0, %1, %1, %2;" : "=r"(d) : "r"(w), "n"((8 + I) * 0x1110 + I));
+  return d;
+}
+
 /* PRMT selectors that turn two offset words into one s16x2 operand: (x, x) and (x, y).  The
  * binary32 forms leave the offset in the low half of the word, the fixed-point form in the high. */
 constexpr uint32_t kSelRep = JGPU_COLOUR_INT ? 0x3232u : 0x1010u;
@@ -301,8 +310,7 @@ __device__ __forceinline__ void chroma_offsets_bits2(uint32_t w, uint32_t (&r)[2
 #if JGPU_COLOUR_INT
   /* sign-extending byte extracts (PRMT with the replicate-sign selector bit), then
    * jgpu_colour_offsets_fixed: bit-identical to the binary32 definition for every input */
-  const int cb0 = (int)__byte_perm(w, 0u, 0x8880u), cr0 = (int)__byte_perm(w, 0u, 0x9991u);
-  const int cb1 = (int)__byte_perm(w, 0u, 0xaaa2u), cr1 = ((int)w) >> 24;
+  const int cb0 = sext_byte<0>(w), cr0 = sext_byte<1>(w), cb1 = sext_byte<2>(w), cr1 = ((int)w) >> 24;
   int r0, g0, b0, r1, g1, b1;
   jgpu_colour_offsets_fixed(cb0, cr0, &r0, &g0, &b0);
   jgpu_colour_offsets_fixed(cb1, cr1, &r1, &g1, &b1);

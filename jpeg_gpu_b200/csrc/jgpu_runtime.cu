@@ -781,3 +781,301 @@ extern "C" int jgpu_decode_image(jgpu_ctx *ctx, const jpeg_header *header, image
   }
   return EXIT_SUCCESS;
 }
+
+/* -------------------------------------------------------------------------- */
+/* JPEG files in, RGB out                                                     */
+
+#include <atomic>
+#include <thread>
+
+#include "jgpu_front.h"
+
+namespace {
+
+/* One file after header parsing. */
+struct JpegItem {
+  jpeg_info info;                 /* points at the caller's bytes */
+  jpeg_decode_ctx *front = nullptr;
+  jpeg_header header;
+  jgpu_image_desc desc;
+  jgpu_layout lay;
+  jfront_segments segs;
+  bool have_segs = false;
+  int first_task = 0, ntasks = 0;
+  std::atomic<int> tasks_left{0};
+  std::atomic<int> failed{0};
+  const char *message = nullptr;
+};
+
+struct JpegTask {
+  int item;
+  int s0, s1;   /* restart intervals; s0 < 0: whole image through the sequential reader */
+};
+
+/* An `image` whose coefficient planes live in caller-provided memory (what image_init would
+ * lay out, src/image.c:24-97, minus the allocations the QUANT path never touches). */
+void bind_image(image *img, const jgpu_image_desc &d, const jgpu_layout &lay, short *coef) {
+  memset(img, 0, sizeof(*img));
+  img->width = (unsigned short)d.width;
+  img->height = (unsigned short)d.height;
+  img->nplanes = d.ncomps;
+  img->coef = coef;
+  for (int p = 0; p < d.ncomps; p++) {
+    image_plane *ip = &img->plane[p];
+    ip->width = (unsigned short)lay.plane[p].width;
+    ip->height = (unsigned short)lay.plane[p].height;
+    ip->xstride = 1;
+    ip->ystride = ip->width;
+    ip->xdec = (unsigned char)lay.plane[p].xdec;
+    ip->ydec = (unsigned char)lay.plane[p].ydec;
+    ip->cstride = lay.plane[p].cstride;
+    ip->coef = coef + lay.plane[p].coef_off;
+  }
+}
+
+/* Parses one header; on rejection sets message and returns false. */
+bool probe_one(const jgpu_jpeg &f, JpegItem &it, jgpu_jpeg_info &out, bool keep_front) {
+  const jpeg_decode_ctx_vtbl &v = JFRONT_DECODE_CTX_VTBL;
+  memset(&out, 0, sizeof(out));
+  out.status = 1;
+  if (!f.data || f.size <= 0 || f.size > 0x7fffffff) {
+    out.message = "Error, empty or oversized jpeg buffer";
+    return false;
+  }
+  it.info.buf = const_cast<unsigned char *>(f.data);
+  it.info.size = (int)f.size;
+  it.front = v.decode_alloc(&it.info);
+  if (!it.front) {
+    out.message = "Error, out of memory";
+    return false;
+  }
+  bool ok = v.decode_header(it.front, &it.header) == EXIT_SUCCESS;
+  if (!ok) out.message = "Error reading jpeg headers";
+  if (ok && (jgpu_desc_from_header(&it.header, &it.desc) || jgpu_layout_query(&it.desc, &it.lay))) {
+    ok = false;
+    out.message = "Unsupported component layout";
+  }
+  if (ok) {
+    out.status = 0;
+    out.width = it.desc.width;
+    out.height = it.desc.height;
+    out.ncomps = it.desc.ncomps;
+    out.hsamp0 = it.desc.hsamp[0];
+    out.vsamp0 = it.desc.vsamp[0];
+    out.restart_interval = it.header.restart_interval;
+    out.rgb_len = it.lay.rgb_len;
+  }
+  if (!ok || !keep_front) {
+    v.decode_free(it.front);
+    it.front = nullptr;
+  }
+  return ok;
+}
+
+}  // namespace
+
+extern "C" int64_t jgpu_jpegs_probe(const jgpu_jpeg *files, int n, jgpu_jpeg_info *info) {
+  if (!files || !info || n <= 0) {
+    jgpu_fail("jgpu_jpegs_probe: bad arguments");
+    return -1;
+  }
+  int64_t off = 0;
+  for (int i = 0; i < n; i++) {
+    JpegItem it;
+    if (probe_one(files[i], it, info[i], false)) {
+      info[i].rgb_off = off;
+      off += (info[i].rgb_len + 255) & ~(int64_t)255;
+    }
+  }
+  return off;
+}
+
+extern "C" int jgpu_decode_jpegs(jgpu_ctx *ctx, const jgpu_jpeg *files, int n, int nthreads,
+                                 uint8_t *h_rgb, int64_t rgb_cap, jgpu_jpeg_info *info) {
+  if (!ctx || !files || n <= 0 || !h_rgb || !info) return jgpu_fail("jgpu_decode_jpegs: bad arguments");
+  CU_TRY(cudaSetDevice(ctx->device));
+  const jpeg_decode_ctx_vtbl &v = JFRONT_DECODE_CTX_VTBL;
+  if (nthreads <= 0) nthreads = (int)std::thread::hardware_concurrency();
+  if (nthreads <= 0) nthreads = 1;
+
+  /* ---- headers, layout ------------------------------------------------------ */
+  std::vector<JpegItem> items(n);
+  std::vector<int> ok;              /* indices of accepted files, in order */
+  std::vector<jgpu_image_desc> descs;
+  std::vector<uint16_t> qtabs;
+  int64_t rgb_off = 0, coef_off = 0;
+  for (int i = 0; i < n; i++) {
+    JpegItem &it = items[i];
+    if (!probe_one(files[i], it, info[i], true)) continue;
+    info[i].rgb_off = rgb_off;
+    it.desc.rgb_off = rgb_off;
+    it.desc.coef_off = coef_off;
+    it.desc.yuv_off = -1;
+    it.desc.qtab_set = (int32_t)ok.size();
+    rgb_off += (it.lay.rgb_len + 255) & ~(int64_t)255;
+    coef_off += it.lay.coef_len;   /* a multiple of 64 */
+    for (int t = 0; t < NQUANT_MAX; t++) {
+      qtabs.insert(qtabs.end(), it.header.quant[t].tbl, it.header.quant[t].tbl + 64);
+    }
+    descs.push_back(it.desc);
+    ok.push_back(i);
+  }
+  auto release_fronts = [&]() {
+    for (JpegItem &it : items) {
+      if (it.have_segs) jfront_segments_free(&it.segs);
+      if (it.front) v.decode_free(it.front);
+      it.front = nullptr;
+      it.have_segs = false;
+    }
+  };
+  if (ok.empty()) {
+    release_fronts();
+    return jgpu_fail("jgpu_decode_jpegs: no decodable file in the batch");
+  }
+  if (rgb_off > rgb_cap) {
+    release_fronts();
+    return jgpu_fail("jgpu_decode_jpegs: output needs %lld bytes, buffer has %lld", (long long)rgb_off,
+                     (long long)rgb_cap);
+  }
+  const int m = (int)ok.size();
+
+  /* ---- plan and buffers ------------------------------------------------------- */
+  const unsigned flags = JGPU_OUT_RGB;
+  if (!ctx->cached_plan || ctx->cached_flags != flags || !same_descs(ctx->cached_descs, descs.data(), m)) {
+    if (ctx->cached_plan) jgpu_plan_destroy(ctx->cached_plan);
+    ctx->cached_plan = jgpu_plan_create(ctx, descs.data(), m, flags);
+    if (!ctx->cached_plan) {
+      release_fronts();
+      return EXIT_FAILURE;
+    }
+    ctx->cached_descs = descs;
+    ctx->cached_flags = flags;
+  }
+  jgpu_plan *plan = ctx->cached_plan;
+  Buffer &stage = ctx->h_in[0];   /* pinned: the front end decodes straight into it */
+  if (stage.reserve((size_t)coef_off * 2 + 256) || ctx->d_coef.reserve((size_t)coef_off * 2 + 256) ||
+      ctx->d_qtabs.reserve(qtabs.size() * 2) || ctx->d_rgb.reserve((size_t)rgb_off + 256)) {
+    release_fronts();
+    return EXIT_FAILURE;
+  }
+  int16_t *h_coef = (int16_t *)stage.ptr;
+  int16_t *d_coef = (int16_t *)ctx->d_coef.ptr;
+  uint16_t *d_qtabs = (uint16_t *)ctx->d_qtabs.ptr;
+  uint8_t *d_rgb = (uint8_t *)ctx->d_rgb.ptr;
+
+  /* ---- entropy-decode tasks ---------------------------------------------------- */
+  std::vector<JpegTask> tasks;
+  const int kMinMcusPerTask = 1024;
+  for (int k = 0; k < m; k++) {
+    JpegItem &it = items[ok[k]];
+    it.first_task = (int)tasks.size();
+    if (jfront_find_segments(it.front, &it.segs) == 0) {
+      it.have_segs = true;
+      int pieces = std::max(1, std::min(it.segs.nseg, it.segs.total_mcus / kMinMcusPerTask));
+      for (int p = 0; p < pieces; p++) {
+        JpegTask t = {ok[k], (int)((int64_t)it.segs.nseg * p / pieces), (int)((int64_t)it.segs.nseg * (p + 1) / pieces)};
+        tasks.push_back(t);
+      }
+    } else {
+      JpegTask t = {ok[k], -1, -1};   /* malformed restart markers: let the sequential reader judge */
+      tasks.push_back(t);
+    }
+    it.ntasks = (int)tasks.size() - it.first_task;
+    it.tasks_left.store(it.ntasks, std::memory_order_relaxed);
+    info[ok[k]].tasks = it.ntasks;
+  }
+  std::atomic<int> next_task{0};
+  auto worker = [&]() {
+    for (;;) {
+      const int ti = next_task.fetch_add(1, std::memory_order_relaxed);
+      if (ti >= (int)tasks.size()) return;
+      const JpegTask &t = tasks[ti];
+      JpegItem &it = items[t.item];
+      image img;
+      bind_image(&img, it.desc, it.lay, h_coef + it.desc.coef_off);
+      const char *err = nullptr;
+      int rc;
+      if (t.s0 >= 0) {
+        rc = jfront_decode_segments(it.front, &img, JPEG_DECODE_QUANT, &it.segs, t.s0, t.s1, &err);
+      } else {
+        rc = v.decode_image(it.front, &img, JPEG_DECODE_QUANT);
+        if (rc) err = "Error decoding scan";
+      }
+      if (rc) {
+        it.message = err;
+        it.failed.store(1, std::memory_order_relaxed);
+      }
+      it.tasks_left.fetch_sub(1, std::memory_order_release);
+    }
+  };
+  std::vector<std::thread> pool;
+  const int nworkers = std::min<int>(nthreads, (int)tasks.size());
+  for (int t = 0; t < nworkers; t++) pool.emplace_back(worker);
+  auto join_all = [&]() {
+    for (std::thread &t : pool) t.join();
+    pool.clear();
+  };
+
+  /* ---- GPU pipeline: chunk k is uploaded as soon as its images are decoded ------- */
+  int rc = EXIT_SUCCESS;
+  auto gpu_part = [&]() -> int {
+    CU_TRY(cudaMemcpyAsync(d_qtabs, qtabs.data(), qtabs.size() * 2, cudaMemcpyHostToDevice, ctx->streams[0]));
+    CU_TRY(cudaEventRecord(ctx->events[0], ctx->streams[0]));
+    for (int s = 1; s < kHostStreams; s++) CU_TRY(cudaStreamWaitEvent(ctx->streams[s], ctx->events[0], 0));
+    /* the tables come from pageable memory: the copy above has completed on the host side */
+    const int64_t chunk_bytes = 48ll << 20;
+    int i0 = 0, chunk = 0;
+    while (i0 < m) {
+      int i1 = i0;
+      int64_t acc = 0;
+      while (i1 < m && (i1 == i0 || acc + plan->layouts[i1].coef_len * 2 <= chunk_bytes)) {
+        acc += plan->layouts[i1].coef_len * 2;
+        i1++;
+      }
+      for (int k = i0; k < i1; k++) {
+        JpegItem &it = items[ok[k]];
+        while (it.tasks_left.load(std::memory_order_acquire) > 0) std::this_thread::yield();
+      }
+      cudaStream_t st = ctx->streams[chunk % kHostStreams];
+      CU_TRY(cudaMemcpyAsync(d_coef + descs[i0].coef_off, h_coef + descs[i0].coef_off, (size_t)acc,
+                             cudaMemcpyHostToDevice, st));
+      if (plan_run_range(plan, i0, i1, d_coef, d_qtabs, m, d_rgb, nullptr, st)) return EXIT_FAILURE;
+      {
+        /* pinned destination: asynchronous; pageable: the call returns when the data is there */
+        const int64_t lo = descs[i0].rgb_off;
+        const int64_t hi = descs[i1 - 1].rgb_off + plan->layouts[i1 - 1].rgb_len;
+        CU_TRY(cudaMemcpyAsync(h_rgb + lo, d_rgb + lo, (size_t)(hi - lo), cudaMemcpyDeviceToHost, st));
+      }
+      i0 = i1;
+      chunk++;
+    }
+    for (int s = 0; s < kHostStreams; s++) CU_TRY(cudaStreamSynchronize(ctx->streams[s]));
+    return EXIT_SUCCESS;
+  };
+  rc = gpu_part();
+  join_all();
+  if (rc != EXIT_SUCCESS) {
+    /* drain whatever is in flight before the staging buffers can be reused */
+    cudaDeviceSynchronize();
+  }
+  for (int k = 0; k < m; k++) {
+    JpegItem &it = items[ok[k]];
+    if (it.failed.load()) {
+      info[ok[k]].status = 1;
+      info[ok[k]].message = it.message ? it.message : "Error decoding scan";
+      rc = EXIT_FAILURE;
+    }
+  }
+  if (m != n) rc = EXIT_FAILURE;
+  release_fronts();
+  if (rc != EXIT_SUCCESS) {
+    /* name the first bad file (a CUDA failure has left its own message and no bad file) */
+    for (int i = 0; i < n; i++) {
+      if (info[i].status) {
+        jgpu_fail("file %d: %s", i, info[i].message ? info[i].message : "rejected");
+        break;
+      }
+    }
+  }
+  return rc;
+}

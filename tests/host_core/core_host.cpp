@@ -24,3 +24,18 @@ extern "C" void core_idct_pairs(const short *in, short *out, long long npairs) {
       }
   }
 }
+
+// The fixed-point colour offsets the fused kernel uses (jgpu_colour_fixed.h), for every
+// (Cb, Cr) in 0..255: out[(cb*256 + cr)*3 + {0,1,2}] = R, G, B offsets.
+#include "jgpu_colour_fixed.h"
+extern "C" void core_colour_fixed_all(int *out) {
+  for (int cb = 0; cb < 256; cb++)
+    for (int cr = 0; cr < 256; cr++) {
+      int r, g, b;
+      jgpu_colour_offsets_fixed(cb - 128, cr - 128, &r, &g, &b);
+      int *o = out + (cb * 256 + cr) * 3;
+      o[0] = r >> 16;
+      o[1] = g >> 16;
+      o[2] = b >> 16;
+    }
+}

@@ -11,12 +11,32 @@ from golden_util import blocks
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def test_device_core_operation_order(tmp_path, port):
+def _build(tmp_path):
     so = tmp_path / "core_host.so"
     subprocess.run(["g++", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-I",
                     os.path.join(ROOT, "jpeg_gpu_b200", "csrc"), "-o", str(so),
                     os.path.join(ROOT, "tests", "host_core", "core_host.cpp")], check=True)
-    lib = C.CDLL(str(so))
+    return C.CDLL(str(so))
+
+
+def test_fixed_point_colour_offsets_equal_the_binary32_definition_everywhere(tmp_path, port):
+    """jgpu_colour_fixed.h (what the fused kernel executes) against the oracle's binary32
+    definition (jgo_colour_offsets, res/yuv.fs.glsl:11-23) for ALL 65536 (Cb, Cr): exact."""
+    import oracle
+    lib = _build(tmp_path)
+    got = np.zeros((256, 256, 3), dtype=np.int32)
+    lib.core_colour_fixed_all(C.c_void_p(got.ctypes.data))
+    cb, cr = np.meshgrid(np.arange(256), np.arange(256), indexing="ij")
+    ro, go, bo = oracle.np_colour_offsets(cb, cr)
+    assert np.array_equal(got[..., 0], ro) and np.array_equal(got[..., 1], go) and np.array_equal(got[..., 2], bo)
+    # and the C oracle itself, every input (the numpy mirror is only spot-checked elsewhere)
+    for c in range(256):
+        for r in range(0, 256):
+            assert tuple(got[c, r]) == port.colour_offsets(c, r), (c, r)
+
+
+def test_device_core_operation_order(tmp_path, port):
+    lib = _build(tmp_path)
     coef, want = blocks()
     rng = np.random.default_rng(2)
     more = rng.integers(-2048, 2048, size=(20000, 8, 8), dtype=np.int16)
