@@ -110,13 +110,41 @@ def measured_traffic(workload: str):
     return None
 
 
-def build_batch(workload: str):
+MIXED_PER_GPU = 96   # BASELINE config 5: images per GPU of the mixed-resolution stress batch
+
+
+def mixed_shapes(world: int):
+    """BASELINE config 5: a seed-fixed shuffle of {512^2, 1080p, 4K} x {gray, 4:4:4,
+    4:2:0, 4:2:2} plus odd sizes that exercise cropping and tails; MIXED_PER_GPU x world images."""
+    rng = np.random.default_rng(20261017)
+    sizes = [(512, 512), (1920, 1080), (3840, 2160), (70, 50), (1000, 563), (1537, 771)]
+    kinds = ["gray", "444", "420", "422"]
+    out = []
+    for _ in range(MIXED_PER_GPU * world):
+        w, h = sizes[int(rng.choice(len(sizes), p=[0.25, 0.3, 0.25, 0.05, 0.1, 0.05]))]
+        out.append((w, h, kinds[int(rng.integers(len(kinds)))]))
+    return out
+
+
+def build_batch(workload: str, rank: int = 0, world: int = 1):
+    """Returns (descs, coef_len, rgb_len, global image indices of this rank)."""
     import jpeg_gpu_b200 as J
-    w, h, ss, n = WORKLOADS[workload]
-    hs, vs = J.SUBSAMPLINGS[ss]
-    descs = [J.ImageDesc(w, h, hs, vs, tq=(0, 1, 1)[:len(hs)]) for _ in range(n)]
+    from jpeg_gpu_b200 import shard
+    if workload == "mixed_stress":
+        shapes = mixed_shapes(world)
+        mine = shard.shard_lpt([w * h for (w, h, _) in shapes], world)[rank]
+        descs = []
+        for i in mine:
+            w, h, ss = shapes[i]
+            hs, vs = J.SUBSAMPLINGS[ss]
+            descs.append(J.ImageDesc(w, h, hs, vs, tq=(0, 1, 1)[:len(hs)]))
+    else:
+        w, h, ss, n = WORKLOADS[workload]
+        hs, vs = J.SUBSAMPLINGS[ss]
+        descs = [J.ImageDesc(w, h, hs, vs, tq=(0, 1, 1)[:len(hs)]) for _ in range(n)]
+        mine = list(range(rank * n, (rank + 1) * n))
     coef_len, rgb_len, _ = J.pack_batch(descs)
-    return descs, coef_len, rgb_len
+    return descs, coef_len, rgb_len, mine
 
 
 def cpu_reference_run(workload: str, sample_images: int, repeats: int, threads: int):
@@ -156,13 +184,29 @@ def cpu_reference_run(workload: str, sample_images: int, repeats: int, threads: 
     return lib.kind, mpx, times
 
 
+class JsonStdout:
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its
+    version banner on stdout at init), so everything else is sent to stderr: fd 1 is pointed at
+    fd 2 for the life of the process and the line goes out through the saved descriptor."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self._fd = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, obj) -> None:
+        sys.stdout.flush()
+        os.write(self._fd, (json.dumps(obj) + "\n").encode())
+
+
 def main():
+    out = JsonStdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="4k420_b256", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="4k420_b256", choices=sorted(WORKLOADS) + ["mixed_stress"])
     ap.add_argument("--e2e-steps", type=int, default=None, help="steps of the host-buffer leg (default: min(steps, 5))")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -173,7 +217,15 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    w, h, ss, n_img = WORKLOADS[args.workload]
+    mixed = args.workload == "mixed_stress"
+    if mixed:
+        w = h = 0
+        ss, n_img = "mixed", MIXED_PER_GPU
+        args.no_e2e = True    # the host-buffer legs are measured on the uniform workloads
+        if args.impl == "reference":
+            raise SystemExit("--impl reference runs the uniform workloads")
+    else:
+        w, h, ss, n_img = WORKLOADS[args.workload]
     threads = os.cpu_count() or 1
 
     # ---------------------------------------------------------------- reference arm
@@ -198,7 +250,7 @@ def main():
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
         }
-        print(json.dumps(line))
+        out.emit(line)
         return 0
 
     # ---------------------------------------------------------------- our arm
@@ -214,16 +266,18 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 
-    descs, coef_len, rgb_len = build_batch(args.workload)
+    descs, coef_len, rgb_len, mine = build_batch(args.workload, rank, world)
     # quantisation tables: rank 0's copy is THE copy (one broadcast)
     q = shard.broadcast_tables(synth.quality_tables(85), device=dev)
     d_q = torch.from_numpy(q.astype(np.int16).reshape(-1)).to(dev)
     # per-rank batch: image seeds continue across ranks
-    d_coef = synth.torch_batch_coefficients(descs, coef_len, q, dev, first_index=rank * n_img)
+    d_coef = synth.torch_batch_coefficients(descs, coef_len, q, dev, first_index=mine[0] if mine else 0)
     d_rgb = torch.zeros(rgb_len, dtype=torch.uint8, device=dev)
     ctx = J.Context(local_rank)
     plan = ctx.plan(descs, rgb=True, yuv=False, force_generic=args.force_generic)
-    px_per_step = n_img * w * h
+    px_rank = sum(d.width * d.height for d in descs)
+    px_total = shard.sum_over_ranks(float(px_rank), dev)     # all ranks' pixels per step
+    px_per_step = px_rank
 
     def barrier():
         if world > 1:
@@ -244,12 +298,30 @@ def main():
     ms = ev0.elapsed_time(ev1)
     ms = shard.max_over_ranks(ms, dev)
     ms_per_step = ms / args.steps
-    value = world * px_per_step / 1e6 / (ms_per_step / 1e3)
+    value = px_total / 1e6 / (ms_per_step / 1e3)
+
+    # config 5: every 8th image of this rank is checked against the CPU oracle, bit for bit
+    parity = None
+    if mixed:
+        import oracle
+        lib = oracle.best()
+        bad = checked = 0
+        for k in range(0, len(descs), 8):
+            d = descs[k]
+            lay = d.query_layout()
+            g = oracle.geometry(d.width, d.height, d.hsamp, d.vsamp)
+            c = d_coef[d.coef_off:d.coef_off + lay.coef_len].cpu().numpy()
+            want, _ = lib.decode_image(g, c, q, d.tq, nthreads=min(threads, 16))
+            got = d_rgb[d.rgb_off:d.rgb_off + lay.rgb_len].cpu().numpy()
+            bad += int(not np.array_equal(got, want.reshape(-1)))
+            checked += 1
+        parity = {"checked": int(shard.sum_over_ranks(float(checked), dev)),
+                  "mismatching_images": int(shard.sum_over_ranks(float(bad), dev)), "oracle": lib.kind}
 
     # roofline of the dominant kernel: algorithmic bytes / device time of the step
     peak, peak_src = peaks()
     achieved = plan.bytes / (ms_per_step * 1e-3) / 1e9
-    coef_bytes = sum(128 * d.query_layout().coded_blocks for d in descs)
+    coef_bytes = sum(128 * d.query_layout().coded_blocks for d in descs)   # this rank's launch
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": measured_traffic(args.workload), "peak_source": peak_src,
                 "read_only_frac": coef_bytes / (ms_per_step * 1e-3) / 1e9 / peak,
@@ -352,7 +424,7 @@ def main():
             e2e_jpeg = None
 
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
+    if rank == 0 and world == 1 and not args.no_cpu and not mixed:
         kind, mpx, times = cpu_reference_run(args.workload, 16, 4, threads)
         best = min(times[1:])
         cpu = {"value": mpx / best, "unit": UNIT, "cores": threads, "kind": kind,
@@ -363,14 +435,17 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{w}x{h} {ss}, batch {n_img} per GPU, synthetic coefficient planes (SURVEY 8d)",
+            "config": {"workload": (f"mixed-resolution stress (BASELINE config 5): {MIXED_PER_GPU} images per GPU of "
+                                    "{512^2,1080p,4K,70x50,1000x563,1537x771} x {gray,444,420,422}, LPT-sharded by pixels"
+                                    if mixed else
+                                    f"{w}x{h} {ss}, batch {n_img} per GPU, synthetic coefficient planes (SURVEY 8d)"),
                        "l2": "inputs larger than L2 (%.2f GB coef + %.2f GB rgb per GPU)" % (coef_len * 2 / 1e9, rgb_len / 1e9),
                        "path": "generic (2 kernels)" if args.force_generic else "fused kernel",
                        "kernel_launches_per_step": plan.launches, "parallelism": f"images sharded x{world}"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_pack": e2e_pack, "e2e_jpeg": e2e_jpeg,
-            "gpu_launches": args.steps * plan.launches, "clocks": clk.summary(),
+            "gpu_launches": args.steps * plan.launches, "clocks": clk.summary(), "parity": parity,
         }
-        print(json.dumps(line))
+        out.emit(line)
     plan.close()
     ctx.close()
     if world > 1:

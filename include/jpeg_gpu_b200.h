@@ -70,6 +70,13 @@ void cuda_decode_set_frontend(const jpeg_decode_ctx_vtbl *frontend);
  * $JGPU_DEVICE). */
 void cuda_decode_set_device(int device);
 
+/* What the backend pulls from its front end and sends to the device for YUV/RGB output:
+ * JPEG_DECODE_QUANT (default; dense planes, 128 bytes per block) or JPEG_DECODE_PACK (the
+ * zero-run packed stream, ~20 bytes per block, expanded on the device) -- the choice the
+ * reference offers with `-o quant` / `-o pack` (src/jpeg_gpu.c:556-566,759-830).  Affects
+ * contexts allocated later.  Returns EXIT_FAILURE for any other value. */
+int cuda_decode_set_upload(jpeg_decode_out format);
+
 /* Output-surface helpers with the semantics of the reference's
  * image_init / image_zero / image_clear (src/image.c:24-123) and
  * jpeg_info_init / jpeg_info_clear (src/jpeg_info.c:31-61), for callers that
@@ -256,6 +263,12 @@ int64_t jgpu_jpegs_probe(const jgpu_jpeg *files, int n, jgpu_jpeg_info *info);
  * decoded). */
 int jgpu_decode_jpegs(jgpu_ctx *ctx, const jgpu_jpeg *files, int n, int nthreads,
                       uint8_t *h_rgb, int64_t rgb_cap, jgpu_jpeg_info *info);
+
+/* One image on the reference's structs with the PACK stream in img->coef / img->index, as a
+ * reader leaves them after decode_image(..., JPEG_DECODE_PACK); words = sum of
+ * img->plane[i].packed.  out = JPEG_DECODE_YUV or JPEG_DECODE_RGB.  Synchronous. */
+int jgpu_decode_image_packed(jgpu_ctx *ctx, const jpeg_header *header, image *img,
+                             int64_t words, jpeg_decode_out out);
 
 /* Page-locked host memory for the batch entry points. */
 void *jgpu_host_alloc(size_t bytes);

@@ -41,6 +41,7 @@
 #include <cuda_runtime.h>
 #include <stddef.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
 #include <vector>
@@ -733,6 +734,13 @@ cudaError_t configure_mode(int mode) {
   mi.cwarps = C::kCWarps;
   mi.channels = C::kChannels;
   mi.smem = C::kSmemBytes;
+  /* experiment knob: pad the dynamic shared memory to lower the CTAs per SM (occupancy
+   * sensitivity runs, profiles/r1_ab_notes.md); never set in production */
+  if (const char *pad = getenv("JGPU_FUSED_PAD_SMEM")) {
+    mi.smem = std::min<size_t>(mi.smem + (size_t)atoi(pad), 227 * 1024);
+    cudaFuncSetAttribute(&k_fused<HS, VS, GRAY, mode_groups(HS, VS, GRAY), true>,
+                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mi.smem);
+  }
   cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mi.smem);
   if (e != cudaSuccess) return e;
   int n = 0;

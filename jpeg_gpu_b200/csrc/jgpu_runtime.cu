@@ -782,6 +782,54 @@ extern "C" int jgpu_decode_image(jgpu_ctx *ctx, const jpeg_header *header, image
   return EXIT_SUCCESS;
 }
 
+/* Same, with the PACK stream in img->coef / img->index (what a front end leaves there after
+ * decode_image(..., JPEG_DECODE_PACK), src/xjpeg.c:484-496): `words` = sum of plane[i].packed. */
+extern "C" int jgpu_decode_image_packed(jgpu_ctx *ctx, const jpeg_header *header, image *img,
+                                        int64_t words, jpeg_decode_out out) {
+  if (!ctx || !header || !img) return jgpu_fail("jgpu_decode_image_packed: NULL argument");
+  if (out != JPEG_DECODE_YUV && out != JPEG_DECODE_RGB) {
+    return jgpu_fail("jgpu_decode_image_packed: output must be yuv or rgb");
+  }
+  jgpu_image_desc d;
+  jgpu_layout lay;
+  if (jgpu_desc_from_header(header, &d) || jgpu_layout_query(&d, &lay)) return EXIT_FAILURE;
+  if (img->nplanes != d.ncomps || img->width != d.width || img->height != d.height || !img->coef ||
+      !img->index) {
+    return jgpu_fail("jgpu_decode_image_packed: image surface does not match the header");
+  }
+  if (words < 0 || words > lay.coef_len) {
+    return jgpu_fail("jgpu_decode_image_packed: %lld words do not fit image.coef", (long long)words);
+  }
+  for (int p = 0; p < d.ncomps; p++) {
+    if (img->plane[p].index - img->index != lay.plane[p].coef_off / 64) {
+      return jgpu_fail("jgpu_decode_image_packed: plane %d index layout differs from image_init's", p);
+    }
+  }
+  uint16_t qt[NQUANT_MAX * 64];
+  for (int t = 0; t < NQUANT_MAX; t++) memcpy(qt + 64 * t, header->quant[t].tbl, 128);
+  const int64_t pack_off[2] = {0, words};
+  d.coef_off = 0;
+  d.qtab_set = 0;
+  if (out == JPEG_DECODE_RGB) {
+    d.rgb_off = 0;
+    d.yuv_off = -1;
+    return jgpu_decode_batch_host_packed(ctx, &d, 1, JGPU_OUT_RGB, (const uint16_t *)img->coef, pack_off,
+                                         img->index, qt, 1, img->pixels, nullptr);
+  }
+  d.yuv_off = 0;
+  Buffer &stage = ctx->h_out[kHostStreams - 1];
+  if (stage.reserve((size_t)lay.data_len)) return EXIT_FAILURE;
+  if (jgpu_decode_batch_host_packed(ctx, &d, 1, JGPU_OUT_YUV, (const uint16_t *)img->coef, pack_off, img->index,
+                                    qt, 1, nullptr, (uint8_t *)stage.ptr)) {
+    return EXIT_FAILURE;
+  }
+  for (int p = 0; p < d.ncomps; p++) {
+    memcpy(img->plane[p].data, (uint8_t *)stage.ptr + lay.plane[p].data_off,
+           (size_t)lay.plane[p].width * lay.plane[p].height);
+  }
+  return EXIT_SUCCESS;
+}
+
 /* -------------------------------------------------------------------------- */
 /* JPEG files in, RGB out                                                     */
 

@@ -15,6 +15,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <stdint.h>
 #include "jgpu_internal.h"
 
 static const jpeg_decode_ctx_vtbl *g_frontend = NULL;
@@ -23,12 +24,23 @@ static int g_device = -1;
 void cuda_decode_set_frontend(const jpeg_decode_ctx_vtbl *frontend) { g_frontend = frontend; }
 void cuda_decode_set_device(int device) { g_device = device; }
 
+static jpeg_decode_out g_upload = JPEG_DECODE_QUANT;
+int cuda_decode_set_upload(jpeg_decode_out format) {
+  if (format != JPEG_DECODE_QUANT && format != JPEG_DECODE_PACK) {
+    fprintf(stderr, "Unsupported upload format %i for cuda wrapper.\n", (int)format);
+    return EXIT_FAILURE;
+  }
+  g_upload = format;
+  return EXIT_SUCCESS;
+}
+
 typedef struct cuda_decode_ctx {
   jpeg_decode_ctx_vtbl front;
   jpeg_decode_ctx *front_ctx;
   jgpu_ctx *gpu;        /* created on the first YUV/RGB decode, kept across resets */
   int device;
   int have_header;
+  jpeg_decode_out upload; /* what crosses to the device: QUANT planes or the PACK stream */
   jpeg_header header;   /* copy taken in decode_header; decode_image needs the tables */
 } cuda_decode_ctx;
 
@@ -37,6 +49,7 @@ static cuda_decode_ctx *cuda_decode_alloc(jpeg_info *info) {
   if (ctx == NULL) return NULL;
   ctx->front = g_frontend ? *g_frontend : JFRONT_DECODE_CTX_VTBL;
   ctx->device = g_device;
+  ctx->upload = g_upload;
   if (ctx->device < 0) {
     const char *env = getenv("JGPU_DEVICE");
     ctx->device = env ? atoi(env) : 0;
@@ -67,6 +80,8 @@ static int cuda_decode_header(cuda_decode_ctx *ctx, jpeg_header *header) {
 }
 
 static int cuda_decode_image(cuda_decode_ctx *ctx, image *img, jpeg_decode_out out) {
+  int i, rc;
+  int64_t words = 0;
   switch (out) {
     case JPEG_DECODE_PACK:
     case JPEG_DECODE_QUANT:
@@ -84,7 +99,11 @@ static int cuda_decode_image(cuda_decode_ctx *ctx, image *img, jpeg_decode_out o
     fprintf(stderr, "Error, decode_image called before decode_header\n");
     return EXIT_FAILURE;
   }
-  if ((*ctx->front.decode_image)(ctx->front_ctx, img, JPEG_DECODE_QUANT) != EXIT_SUCCESS) {
+  if (ctx->upload == JPEG_DECODE_PACK) {
+    /* the reader counts words into plane[i].packed (src/xjpeg.c:492,515,532); start from zero */
+    for (i = 0; i < img->nplanes && i < NPLANES_MAX; i++) img->plane[i].packed = 0;
+  }
+  if ((*ctx->front.decode_image)(ctx->front_ctx, img, ctx->upload) != EXIT_SUCCESS) {
     return EXIT_FAILURE;
   }
   if (ctx->gpu == NULL) {
@@ -94,7 +113,14 @@ static int cuda_decode_image(cuda_decode_ctx *ctx, image *img, jpeg_decode_out o
       return EXIT_FAILURE;
     }
   }
-  if (jgpu_decode_image(ctx->gpu, &ctx->header, img, out) != EXIT_SUCCESS) {
+  if (ctx->upload == JPEG_DECODE_PACK) {
+    for (i = 0; i < img->nplanes && i < NPLANES_MAX; i++) words += img->plane[i].packed;
+    img->packed = (int)words; /* as the reference's caller does, src/jpeg_gpu.c:766-770 */
+    rc = jgpu_decode_image_packed(ctx->gpu, &ctx->header, img, words, out);
+  } else {
+    rc = jgpu_decode_image(ctx->gpu, &ctx->header, img, out);
+  }
+  if (rc != EXIT_SUCCESS) {
     fprintf(stderr, "%s\n", jgpu_last_error());
     return EXIT_FAILURE;
   }

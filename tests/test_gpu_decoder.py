@@ -37,6 +37,26 @@ def test_cuda_backend_yuv_and_rgb(name):
         assert np.array_equal(dec.decode_image("quant")["coef"], z["quant"])   # forwarded to the front end
 
 
+@pytest.mark.parametrize("name", NAMES)
+def test_cuda_backend_with_pack_upload(name):
+    """cuda_decode_set_upload(JPEG_DECODE_PACK): the reference's `-o pack` choice -- the run/level
+    stream crosses to the device and is expanded there; same planes, same pixels."""
+    from jpeg_gpu_b200 import _capi
+    jpg, z, g = load(name)
+    assert _capi.lib().cuda_decode_set_upload(_capi.JPEG_DECODE_PACK) == 0
+    try:
+        with J.Decoder(jpg, impl="cuda") as dec:
+            dec.decode_header()
+            planes = dec.decode_image("yuv")["planes"]
+            assert np.array_equal(np.concatenate([p.ravel() for p in planes]), z["yuv"])
+            dec.decode_reset()
+            dec.decode_header()
+            assert np.array_equal(dec.decode_image("rgb")["pixels"].reshape(-1), z["rgb"])
+    finally:
+        assert _capi.lib().cuda_decode_set_upload(_capi.JPEG_DECODE_QUANT) == 0
+    assert _capi.lib().cuda_decode_set_upload(_capi.JPEG_DECODE_RGB) == 1   # not an upload format
+
+
 def test_cuda_backend_error_convention():
     jpg, _, _ = load("c420_64x48")
     with J.Decoder(jpg, impl="cuda") as dec:
