@@ -409,17 +409,17 @@ def main():
                                       restart_marker_blocks=w // 16)
             files = [bio.getvalue()] * 32
             total, _ = J.probe_jpegs(files)
-            out = torch.zeros(total, dtype=torch.uint8).pin_memory()
-            ctx.decode_jpegs(files, out, nthreads=threads)   # warm-up (plan, staging)
+            jpeg_rgb = torch.zeros(total, dtype=torch.uint8).pin_memory()
+            ctx.decode_jpegs(files, jpeg_rgb, nthreads=threads)   # warm-up (plan, staging)
             t0 = time.perf_counter()
             for _ in range(3):
-                ctx.decode_jpegs(files, out, nthreads=threads)
+                ctx.decode_jpegs(files, jpeg_rgb, nthreads=threads)
             dt = time.perf_counter() - t0
             e2e_jpeg = {"value": 3 * len(files) * w * h / 1e6 / dt, "unit": UNIT, "files_per_step": len(files),
                         "steps": 3, "host_threads": threads, "jpeg_bytes": len(files[0]),
                         "input": f"{w}x{h} {ss} baseline JPEG (Pillow, q85, one restart interval per MCU row), "
                                  "Huffman decoding on the host threads, block decode on the GPU"}
-            del out
+            del jpeg_rgb
         except ImportError:
             e2e_jpeg = None
 
