@@ -410,15 +410,20 @@ def main():
             files = [bio.getvalue()] * 32
             total, _ = J.probe_jpegs(files)
             jpeg_rgb = torch.zeros(total, dtype=torch.uint8).pin_memory()
-            ctx.decode_jpegs(files, jpeg_rgb, nthreads=threads)   # warm-up (plan, staging)
-            t0 = time.perf_counter()
-            for _ in range(3):
-                ctx.decode_jpegs(files, jpeg_rgb, nthreads=threads)
-            dt = time.perf_counter() - t0
-            e2e_jpeg = {"value": 3 * len(files) * w * h / 1e6 / dt, "unit": UNIT, "files_per_step": len(files),
-                        "steps": 3, "host_threads": threads, "jpeg_bytes": len(files[0]),
+            e2e_jpeg = {"unit": UNIT, "files_per_step": len(files), "steps": 3, "host_threads": threads,
+                        "jpeg_bytes": len(files[0]),
                         "input": f"{w}x{h} {ss} baseline JPEG (Pillow, q85, one restart interval per MCU row), "
-                                 "Huffman decoding on the host threads, block decode on the GPU"}
+                                 "host buffers in and out",
+                        "h2d_bytes_per_step": len(files) * len(files[0]), "d2h_bytes_per_step": int(total)}
+            for key, entropy in (("value", "gpu"), ("cpu_entropy_value", "cpu")):
+                ctx.decode_jpegs(files, jpeg_rgb, nthreads=threads, entropy=entropy)   # warm-up (plan, staging)
+                t0 = time.perf_counter()
+                for _ in range(3):
+                    ctx.decode_jpegs(files, jpeg_rgb, nthreads=threads, entropy=entropy)
+                dt = time.perf_counter() - t0
+                e2e_jpeg[key] = 3 * len(files) * w * h / 1e6 / dt
+            e2e_jpeg["entropy"] = ("value: Huffman decoding on the GPU (jgpu_huff.cu), host threads only unstuff; "
+                                   "cpu_entropy_value: Huffman decoding on the host threads")
             del jpeg_rgb
         except ImportError:
             e2e_jpeg = None

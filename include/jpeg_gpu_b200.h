@@ -264,6 +264,24 @@ int64_t jgpu_jpegs_probe(const jgpu_jpeg *files, int n, jgpu_jpeg_info *info);
 int jgpu_decode_jpegs(jgpu_ctx *ctx, const jgpu_jpeg *files, int n, int nthreads,
                       uint8_t *h_rgb, int64_t rgb_cap, jgpu_jpeg_info *info);
 
+/* The same with the entropy decoder chosen explicitly:
+ *   JGPU_ENTROPY_GPU   Huffman decoding on the GPU (jgpu_huff.cu: self-synchronising parallel
+ *                      decoding of 1024-bit subsequences, replaces the scan loop of
+ *                      src/xjpeg.c:449-632).  Host threads only strip the byte stuffing and cut
+ *                      the scan at its restart markers; the compressed scan is what crosses
+ *                      the link.  Every file is verified on the device; a file the decoder does
+ *                      not take or flags (corrupt, truncated) goes through the sequential
+ *                      reader, so results and error reports are those of JGPU_ENTROPY_CPU.
+ *                      info[i].tasks = 1024-bit subsequences decoded in parallel (1 = the file
+ *                      went through the sequential reader).
+ *   JGPU_ENTROPY_CPU   the host-thread reader described above.
+ *   JGPU_ENTROPY_AUTO  $JGPU_ENTROPY ("cpu" / "gpu"), default gpu; what jgpu_decode_jpegs uses. */
+#define JGPU_ENTROPY_AUTO 0u
+#define JGPU_ENTROPY_CPU 1u
+#define JGPU_ENTROPY_GPU 2u
+int jgpu_decode_jpegs_ex(jgpu_ctx *ctx, const jgpu_jpeg *files, int n, int nthreads, unsigned flags,
+                         uint8_t *h_rgb, int64_t rgb_cap, jgpu_jpeg_info *info);
+
 /* One image on the reference's structs with the PACK stream in img->coef / img->index, as a
  * reader leaves them after decode_image(..., JPEG_DECODE_PACK); words = sum of
  * img->plane[i].packed.  out = JPEG_DECODE_YUV or JPEG_DECODE_RGB.  Synchronous. */

@@ -133,6 +133,8 @@ EXPORTS = [
     ("jgpu_jpegs_probe", C.c_int64, [C.POINTER(jgpu_jpeg), C.c_int, C.POINTER(jgpu_jpeg_info)]),
     ("jgpu_decode_jpegs", C.c_int, [C.c_void_p, C.POINTER(jgpu_jpeg), C.c_int, C.c_int, C.c_void_p, C.c_int64,
                                     C.POINTER(jgpu_jpeg_info)]),
+    ("jgpu_decode_jpegs_ex", C.c_int, [C.c_void_p, C.POINTER(jgpu_jpeg), C.c_int, C.c_int, C.c_uint, C.c_void_p,
+                                       C.c_int64, C.POINTER(jgpu_jpeg_info)]),
     ("jgpu_host_alloc", C.c_void_p, [C.c_size_t]),
     ("jgpu_host_free", None, [C.c_void_p]),
 ]

@@ -159,9 +159,10 @@ def _jpeg_array(files: Sequence[bytes]):
     arr = (_capi.jgpu_jpeg * len(files))()
     keep = []
     for i, f in enumerate(files):
-        buf = (C.c_ubyte * max(len(f), 1)).from_buffer_copy(f if len(f) else b"\0")
-        keep.append(buf)
-        arr[i].data = C.addressof(buf)
+        # no copy: the C side reads the bytes object's own buffer (kept alive by `keep`)
+        f = bytes(f) if not isinstance(f, bytes) else f
+        keep.append(f)
+        arr[i].data = C.cast(C.c_char_p(f if len(f) else b"\0"), C.c_void_p).value
         arr[i].size = len(f)
     return arr, keep
 
@@ -229,9 +230,13 @@ class Context:
             raise RuntimeError(f"jgpu_decode_batch_host failed: {_capi.last_error()}")
 
 
-    def decode_jpegs(self, files: Sequence[bytes], rgb=None, nthreads: int = 0, strict: bool = True):
-        """JPEG files in, RGB out (jgpu_decode_jpegs): multi-threaded entropy front end feeding the
-        GPU back end.  Returns (rgb uint8 buffer, [JpegInfo]); image i is
+    ENTROPY = {"auto": 0, "cpu": 1, "gpu": 2}
+
+    def decode_jpegs(self, files: Sequence[bytes], rgb=None, nthreads: int = 0, strict: bool = True,
+                     entropy: str = "auto"):
+        """JPEG files in, RGB out (jgpu_decode_jpegs_ex).  entropy="gpu": Huffman decoding on the
+        device (jgpu_huff.cu); "cpu": the multi-threaded host reader; "auto": $JGPU_ENTROPY, default
+        gpu.  Returns (rgb uint8 buffer, [JpegInfo]); image i is
         rgb[info.rgb_off : info.rgb_off + info.rgb_len].reshape(info.shape)."""
         arr, keep = _jpeg_array(files)
         raw = (_capi.jgpu_jpeg_info * len(files))()
@@ -241,7 +246,8 @@ class Context:
                 raise RuntimeError(f"jgpu_jpegs_probe failed: {_capi.last_error()}")
             rgb = np.zeros(max(int(total), 1), dtype=np.uint8)
         cap = rgb.numel() if hasattr(rgb, "numel") else rgb.size
-        rc = _capi.lib().jgpu_decode_jpegs(self._h, arr, len(files), nthreads, _addr(rgb), cap, raw)
+        rc = _capi.lib().jgpu_decode_jpegs_ex(self._h, arr, len(files), nthreads, self.ENTROPY[entropy], _addr(rgb),
+                                              cap, raw)
         infos = _jpeg_infos(raw)
         del keep
         if rc != 0 and (strict or all(i.status for i in infos)):

@@ -25,6 +25,7 @@
 #include <string.h>
 #include "jgpu_internal.h"
 #include "jgpu_front.h"
+#include "jgpu_huff_core.h"
 
 /* zig-zag position -> natural (row-major) position, T.81 figure A.6 */
 static const unsigned char kNatural[64] = {
@@ -37,6 +38,7 @@ static const unsigned char kNatural[64] = {
 
 typedef struct huff_table {
   int valid;
+  unsigned char counts[16]; /* codes of each length, as the DHT segment lists them */
   unsigned char symbols[256];
   /* fast[peek] = (length << 8) | symbol for codes of <= FAST_BITS bits, else 0 */
   unsigned short fast[1 << FAST_BITS];
@@ -119,6 +121,7 @@ static int parse_dqt(jfront_ctx *c) {
 static int build_huffman(huff_table *h, const unsigned char counts[16]) {
   int code = 0, k = 0, len, i;
   memset(h->fast, 0, sizeof(h->fast));
+  memcpy(h->counts, counts, 16);
   for (len = 1; len <= 16; len++) {
     int n = counts[len - 1];
     h->valptr[len] = k;
@@ -587,6 +590,144 @@ int jfront_decode_segments(const jpeg_decode_ctx *ctx, image *img, jpeg_decode_o
 failed:
   *error = w.error ? w.error : "Error decoding scan";
   return 1;
+}
+
+/* ---- preparation for the GPU entropy decoder (jgpu_huff_core.h) ------------------- */
+
+/* Copies `n` bytes, growing *out; returns 1 when the destination is too small. */
+static int put_bytes(unsigned char *dst, long long cap, long long *out, const unsigned char *src, long long n) {
+  if (*out + n > cap) return 1;
+  memcpy(dst + *out, src, (size_t)n);
+  *out += n;
+  return 0;
+}
+
+/* After decode_header: fills what the GPU decoder needs for this file.
+ *   stream     the entropy-coded bytes with the stuffed zeros (T.81 F.1.2.3) and the RSTn
+ *              markers removed; every restart interval starts on a subsequence boundary and is
+ *              zero-padded to the next one (a reader that meets a marker feeds zeros, refill()
+ *              above), 16 guard bytes follow the last one
+ *   seg_first  subsequence each restart interval starts at, n_seg + 1 entries
+ *   tables     JGPU_HUFF_TABLES decoder tables: (DC, AC) of plane 0, 1, 2
+ *   file       geometry fields (n_subseq, n_seg, mcus_per_seg, total_mcus, nhmb, bpm, ncomps,
+ *              hs, vs, blk_*); the caller places it in the batch (word0, plane_off, ...)
+ * Returns the bytes written to stream, or -1 with *why set when the file is not one the GPU
+ * path takes (the caller then uses the sequential reader, which reports errors the
+ * reference's way). */
+long long jfront_huff_prepare(jpeg_decode_ctx *ctx, int subseq_words, unsigned char *stream,
+                              long long stream_cap, unsigned int *seg_first, int seg_cap,
+                              jgpu_huff_table *tables, jgpu_huff_file *file, const char **why) {
+  jfront_ctx *c = (jfront_ctx *)ctx;
+  jfront_ctx w;
+  scan_comp sc[NCOMPS_MAX];
+  image dummy;
+  int ns, i, k, nseg, pos, bpm = 0;
+  long long out = 0;
+  const long long sub = 4ll * subseq_words;
+  *why = "Error decoding scan";
+  if (!c->have_frame || !c->sos_pos) return -1;
+  w = *c;
+  w.error = NULL;
+  memset(&dummy, 0, sizeof(dummy));
+  if (scan_setup(&w, &dummy, sc, &ns)) {
+    *why = w.error ? w.error : *why;
+    return -1;
+  }
+  memset(file->blk_comp, 0, sizeof(file->blk_comp));
+  memset(file->blk_dx, 0, sizeof(file->blk_dx));
+  memset(file->blk_dy, 0, sizeof(file->blk_dy));
+  for (i = 0; i < ns; i++) {
+    const int plane = (int)(sc[i].fc - w.comp);
+    int dx, dy;
+    if (jgpu_huff_build_table(&tables[2 * plane], sc[i].dc->counts, sc[i].dc->symbols) ||
+        jgpu_huff_build_table(&tables[2 * plane + 1], sc[i].ac->counts, sc[i].ac->symbols)) {
+      *why = "Error invalid DHT.";
+      return -1;
+    }
+    file->hs[plane] = sc[i].fc->hsamp;
+    file->vs[plane] = sc[i].fc->vsamp;
+    for (dy = 0; dy < sc[i].fc->vsamp; dy++) {
+      for (dx = 0; dx < sc[i].fc->hsamp; dx++) {
+        if (bpm >= JGPU_HUFF_MAX_BLOCKS) {
+          *why = "Error, more than 10 blocks per MCU";
+          return -1;
+        }
+        file->blk_comp[bpm] = (unsigned char)plane;
+        file->blk_dx[bpm] = (unsigned char)dx;
+        file->blk_dy[bpm] = (unsigned char)dy;
+        bpm++;
+      }
+    }
+  }
+  file->bpm = bpm;
+  file->ncomps = ns;
+  file->nhmb = c->nhmb;
+  file->total_mcus = c->nhmb * c->nvmb;
+  file->mcus_per_seg = c->restart_interval ? c->restart_interval : file->total_mcus;
+  nseg = (file->total_mcus + file->mcus_per_seg - 1) / file->mcus_per_seg;
+  /* coefficient slots of an interval are counted in 32 bits on the device */
+  if ((long long)file->mcus_per_seg * bpm * 64 >= 0x7fffffffll || nseg + 1 > seg_cap) {
+    *why = "Error, scan too large for the GPU entropy decoder";
+    return -1;
+  }
+  pos = w.ecs_pos;
+  for (k = 0; k < nseg; k++) {
+    const long long seg_start = out;
+    seg_first[k] = (unsigned int)(out / sub);
+    for (;;) { /* up to the next marker */
+      const unsigned char *p;
+      long long run;
+      if (pos >= c->size) break;
+      p = (const unsigned char *)memchr(c->buf + pos, 0xFF, (size_t)(c->size - pos));
+      run = p ? p - (c->buf + pos) : c->size - pos;
+      if (put_bytes(stream, stream_cap, &out, c->buf + pos, run)) goto too_small;
+      pos += (int)run;
+      if (!p) break;
+      if (pos + 1 < c->size && c->buf[pos + 1] == 0x00) {
+        const unsigned char ff = 0xFF;
+        if (put_bytes(stream, stream_cap, &out, &ff, 1)) goto too_small;
+        pos += 2;
+        continue;
+      }
+      break;
+    }
+    { /* zero padding to the next boundary; an empty interval still gets one subsequence */
+      long long pad = (sub - (out - seg_start) % sub) % sub;
+      if (out == seg_start) pad = sub;
+      if (out + pad > stream_cap) goto too_small;
+      memset(stream + out, 0, (size_t)pad);
+      out += pad;
+    }
+    if (k + 1 < nseg) { /* RSTn, T.81 E.2.4 */
+      while (pos + 1 < c->size && c->buf[pos + 1] == 0xFF) pos++; /* fill bytes */
+      if (pos + 1 >= c->size || c->buf[pos] != 0xFF || c->buf[pos + 1] != 0xD0 + (k & 7)) {
+        *why = "Error, restart markers are not where the header says";
+        return -1;
+      }
+      pos += 2;
+    }
+  }
+  seg_first[nseg] = (unsigned int)(out / sub);
+  file->n_seg = (unsigned int)nseg;
+  file->n_subseq = seg_first[nseg];
+  if (out + 16 > stream_cap) goto too_small;
+  memset(stream + out, 0, 16);
+  out += 16;
+  *why = NULL;
+  return out;
+too_small:
+  *why = "Error, stream buffer too small";
+  return -1;
+}
+
+/* Upper bound of what jfront_huff_prepare writes for this file, and of its restart intervals. */
+long long jfront_huff_bound(const jpeg_decode_ctx *ctx, int subseq_words, int *nseg_out) {
+  const jfront_ctx *c = (const jfront_ctx *)ctx;
+  const long long total = (long long)c->nhmb * c->nvmb;
+  const long long per = c->restart_interval ? c->restart_interval : total;
+  const long long nseg = per > 0 ? (total + per - 1) / per : 1;
+  if (nseg_out) *nseg_out = (int)nseg;
+  return (long long)c->size + (nseg + 1) * 4ll * subseq_words + 32;
 }
 
 /* ---- vtable ---------------------------------------------------------------- */

@@ -4,6 +4,7 @@
 #define JGPU_FRONT_H
 
 #include "jpeg_gpu_b200.h"
+#include "jgpu_huff_core.h"
 
 #ifdef __cplusplus
 extern "C" {
@@ -22,6 +23,12 @@ int jfront_find_segments(jpeg_decode_ctx *ctx, jfront_segments *out);
 void jfront_segments_free(jfront_segments *s);
 int jfront_decode_segments(const jpeg_decode_ctx *ctx, image *img, jpeg_decode_out out,
                            const jfront_segments *segs, int s0, int s1, const char **error);
+
+/* Preparation for the GPU entropy decoder (jgpu_huff.cu); see jgpu_front.c. */
+long long jfront_huff_prepare(jpeg_decode_ctx *ctx, int subseq_words, unsigned char *stream,
+                              long long stream_cap, unsigned int *seg_first, int seg_cap,
+                              jgpu_huff_table *tables, jgpu_huff_file *file, const char **why);
+long long jfront_huff_bound(const jpeg_decode_ctx *ctx, int subseq_words, int *nseg_out);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,345 @@
+/* jgpu_huff.cu — Huffman decoding of baseline JPEG scans on the GPU (sm_100a): the kernels
+ * around the per-thread loop of jgpu_huff_core.h.  See that header for the method; this file
+ * is the mapping to the machine.
+ *
+ *   k_huff_sync   one CTA = 256 consecutive subsequences of one file.  The file's six decoder
+ *                 tables (14.6 KB) and the CTA's 32 KB of scan words are staged in shared
+ *                 memory (words XOR-swizzled by subsequence so that 32 threads reading "their
+ *                 j-th word" hit 32 banks); states pass from thread to thread through shared
+ *                 memory until the CTA is stable, and to the next CTA through a carry array
+ *                 that the next launch of the kernel picks up.
+ *   k_huff_scan   one CTA per file: segmented exclusive scan of the slot counts (restart
+ *                 intervals are the segments).
+ *   k_huff_write  the same staging; stores coefficients, verifies the chain of states.
+ *   k_huff_dc     one CTA per (restart interval, component): prefix sum of DC differences.
+ */
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <algorithm>
+
+#include "jgpu_huff.h"
+#include "jgpu_internal.h"
+
+namespace jgpu {
+
+namespace {
+
+constexpr int kCta = JGPU_HUFF_CTA;
+constexpr int kGuardWords = 4;
+
+__constant__ unsigned char c_zigzag[64] = JGPU_HUFF_ZIGZAG_NATURAL;
+
+template <int S>
+struct SyncSmem {
+  jgpu_huff_table tabs[JGPU_HUFF_TABLES];
+  uint32_t words[(kCta + 1) * S];
+  uint32_t s_out[kCta + 1];
+  jgpu_huff_file file;
+  unsigned char zz[64];
+};
+
+template <int S>
+struct SmemWords {
+  const uint32_t *w;
+  uint32_t base; /* file-relative index of the CTA's first word */
+  __device__ __forceinline__ uint32_t operator()(uint32_t idx) const {
+    const uint32_t l = idx - base, row = l / S, col = l % S;
+    return w[row * S + (col ^ (row & (S - 1)))];
+  }
+};
+
+/* Stages the file descriptor, its tables and the CTA's words.  `count` subsequences. */
+template <int S>
+__device__ __forceinline__ void stage(SyncSmem<S> &sm, const jgpu_huff_file *files, const uint32_t *stream,
+                                      const jgpu_huff_table *tables, int first, int count) {
+  const int t = threadIdx.x;
+  {
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(files + blockIdx.y);
+    uint32_t *dst = reinterpret_cast<uint32_t *>(&sm.file);
+    for (int i = t; i < (int)(sizeof(jgpu_huff_file) / 4); i += kCta) dst[i] = src[i];
+    if (t < 64) sm.zz[t] = c_zigzag[t];
+  }
+  __syncthreads();
+  {
+    const uint4 *src = reinterpret_cast<const uint4 *>(tables + sm.file.table0);
+    uint4 *dst = reinterpret_cast<uint4 *>(sm.tabs);
+    for (int i = t; i < (int)(sizeof(jgpu_huff_table) * JGPU_HUFF_TABLES / 16); i += kCta) dst[i] = src[i];
+  }
+  {
+    const uint4 *src = reinterpret_cast<const uint4 *>(stream + sm.file.word0 + (size_t)first * S);
+    const int nvec = (count * S + kGuardWords) / 4;
+    for (int i = t; i < nvec; i += kCta) {
+      const uint4 v = src[i];
+      const uint32_t l = 4u * i, row = l / S, col = l % S, sw = row & (S - 1);
+      uint32_t *r = sm.words + row * S;
+      r[(col + 0) ^ sw] = __byte_perm(v.x, 0, 0x0123);
+      r[(col + 1) ^ sw] = __byte_perm(v.y, 0, 0x0123);
+      r[(col + 2) ^ sw] = __byte_perm(v.z, 0, 0x0123);
+      r[(col + 3) ^ sw] = __byte_perm(v.w, 0, 0x0123);
+    }
+  }
+  __syncthreads();
+}
+
+template <int S>
+__global__ void __launch_bounds__(kCta)
+k_huff_sync(const jgpu_huff_file *__restrict__ files, const uint32_t *__restrict__ stream,
+            const jgpu_huff_table *__restrict__ tables, const uint32_t *__restrict__ seg_first,
+            uint32_t *__restrict__ state, uint32_t *__restrict__ nslots, uint32_t *__restrict__ segid,
+            const uint32_t *__restrict__ carry_in, uint32_t *__restrict__ carry_out, int pass) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SyncSmem<S> &sm = *reinterpret_cast<SyncSmem<S> *>(smem_raw);
+  const jgpu_huff_file &gf = files[blockIdx.y];
+  const int first = (int)blockIdx.x * kCta;
+  if (first >= (int)gf.n_subseq) return;
+  const int count = min(kCta, (int)gf.n_subseq - first);
+  const int t = threadIdx.x;
+  const uint32_t gi = gf.subseq0 + (uint32_t)first + (uint32_t)min(t, count - 1);
+  const uint32_t cslot = gf.cta0 + blockIdx.x;
+  uint32_t new0 = 0;
+  if (pass > 0) {
+    /* Did the state handed to this CTA change since the last launch?  If not, neither does
+     * anything it computes. */
+    const uint32_t g0 = gf.subseq0 + (uint32_t)first;
+    new0 = (nslots[g0] >> 31) ? 0u : carry_in[cslot];
+    if (new0 == state[g0]) {
+      if (t == 0) carry_out[cslot + 1] = carry_in[cslot + 1];
+      return;
+    }
+  }
+  stage<S>(sm, files, stream, tables, first, count);
+
+  bool is_first;
+  uint32_t s_in, n = 0;
+  bool need;
+  if (pass == 0) {
+    /* restart interval of this subsequence: the last entry of seg_first[] not above it */
+    const uint32_t i = (uint32_t)(first + min(t, count - 1));
+    const uint32_t *sf = seg_first + gf.seg0;
+    uint32_t lo = 0, hi = gf.n_seg; /* answer in [lo, hi) */
+    while (hi - lo > 1) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (sf[mid] <= i) lo = mid; else hi = mid;
+    }
+    is_first = sf[lo] == i;
+    if (t < count) segid[gi] = lo;
+    s_in = 0;
+    need = true;
+  } else {
+    const uint32_t v = nslots[gi];
+    is_first = (v >> 31) != 0;
+    n = v & 0x7fffffffu;
+    s_in = t == 0 ? new0 : state[gi];
+    need = t == 0;
+  }
+  sm.s_out[t] = s_in;
+  __syncthreads();
+  /* what this CTA hands on stays what it was unless its last subsequence is redone */
+  if (t == 0) sm.s_out[count] = pass > 0 ? carry_in[cslot + 1] : 0u;
+  __syncthreads();
+
+  const SmemWords<S> words = {sm.words, (uint32_t)first * S};
+  for (;;) {
+    if (need && t < count) {
+      huff::NullSink sink;
+      uint32_t err = 0;
+      sm.s_out[t + 1] = huff::decode_subsequence(sm.tabs, sm.file.blk_comp, sm.file.bpm, words,
+                                                 (uint32_t)(first + t) * S, S, s_in, sink, &n, &err);
+    }
+    __syncthreads();
+    const uint32_t ni = (t == 0 || is_first) ? s_in : sm.s_out[t];
+    need = ni != s_in;
+    s_in = ni;
+    if (!__syncthreads_or(need ? 1 : 0)) break;
+  }
+  if (t < count) {
+    state[gi] = s_in;
+    nslots[gi] = n | (is_first ? 0x80000000u : 0u);
+    if (t == count - 1) carry_out[cslot + 1] = sm.s_out[count];
+  }
+}
+
+/* Segmented exclusive scan of the slot counts: slots[i] = slots the restart interval has
+ * advanced before subsequence i.  One CTA of 1024 threads per file. */
+__global__ void __launch_bounds__(1024)
+k_huff_scan(const jgpu_huff_file *__restrict__ files, const uint32_t *__restrict__ nslots,
+            uint32_t *__restrict__ slots) {
+  __shared__ uint32_t w_val[32], w_flag[32];
+  __shared__ uint32_t s_carry;
+  const jgpu_huff_file &f = files[blockIdx.x];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  if (t == 0) s_carry = 0;
+  __syncthreads();
+  for (uint32_t base = 0; base < f.n_subseq; base += 1024) {
+    const uint32_t i = base + t;
+    const uint32_t raw = i < f.n_subseq ? nslots[f.subseq0 + i] : 0u;
+    const uint32_t own_flag = raw >> 31, own_val = raw & 0x7fffffffu;
+    uint32_t val = own_val, flag = own_flag;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t v2 = __shfl_up_sync(0xffffffffu, val, d), f2 = __shfl_up_sync(0xffffffffu, flag, d);
+      if (lane >= d) {
+        if (!flag) val += v2;
+        flag |= f2;
+      }
+    }
+    if (lane == 31) {
+      w_val[warp] = val;
+      w_flag[warp] = flag;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      uint32_t v = w_val[lane], g = w_flag[lane];
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t v2 = __shfl_up_sync(0xffffffffu, v, d), g2 = __shfl_up_sync(0xffffffffu, g, d);
+        if (lane >= d) {
+          if (!g) v += v2;
+          g |= g2;
+        }
+      }
+      w_val[lane] = v;   /* inclusive over warps 0..lane */
+      w_flag[lane] = g;
+    }
+    __syncthreads();
+    /* what precedes this thread's warp inside the chunk, then what precedes the chunk */
+    uint32_t pre = 0, pre_flag = 0;
+    if (warp > 0) {
+      pre = w_val[warp - 1];
+      pre_flag = w_flag[warp - 1];
+    }
+    if (!pre_flag) pre += s_carry;
+    if (!flag) val += pre;
+    if (i < f.n_subseq) slots[f.subseq0 + i] = own_flag ? 0u : val - own_val;
+    __syncthreads();
+    if (t == 1023) s_carry = val;
+    __syncthreads();
+  }
+}
+
+template <int S>
+__global__ void __launch_bounds__(kCta)
+k_huff_write(const jgpu_huff_file *__restrict__ files, const uint32_t *__restrict__ stream,
+             const jgpu_huff_table *__restrict__ tables, const uint32_t *__restrict__ seg_first,
+             const uint32_t *__restrict__ state, const uint32_t *__restrict__ nslots,
+             const uint32_t *__restrict__ slots, const uint32_t *__restrict__ segid,
+             int16_t *__restrict__ coef, uint32_t *__restrict__ status) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SyncSmem<S> &sm = *reinterpret_cast<SyncSmem<S> *>(smem_raw);
+  const jgpu_huff_file &gf = files[blockIdx.y];
+  const int first = (int)blockIdx.x * kCta;
+  if (first >= (int)gf.n_subseq) return;
+  const int count = min(kCta, (int)gf.n_subseq - first);
+  const int t = threadIdx.x;
+  stage<S>(sm, files, stream, tables, first, count);
+  if (t >= count) return;
+  const jgpu_huff_file &f = sm.file;
+  const uint32_t i = (uint32_t)(first + t), gi = f.subseq0 + i;
+  const uint32_t seg = segid[gi];
+  const int seg_mcu0 = (int)seg * f.mcus_per_seg;
+  const int64_t seg_blocks = (int64_t)min(f.mcus_per_seg, f.total_mcus - seg_mcu0) * f.bpm;
+  const uint32_t slot0 = slots[gi], st = state[gi];
+  const int64_t g0 = slot0 >> 6;
+  uint32_t flags = 0;
+  if ((slot0 & 63u) != JGPU_HUFF_STATE_Z(st) || (uint32_t)(g0 % f.bpm) != JGPU_HUFF_STATE_C(st)) {
+    flags = JGPU_HUFF_ERR_SYNC;
+  } else if (g0 < seg_blocks) {
+    huff::StoreSink sink;
+    sink.start(&f, sm.zz, coef, seg_mcu0, g0, seg_blocks);
+    const SmemWords<S> words = {sm.words, (uint32_t)first * S};
+    uint32_t n = 0, err = 0;
+    const uint32_t out = huff::decode_subsequence(sm.tabs, f.blk_comp, f.bpm, words, i * S, S, st, sink, &n, &err);
+    if (err) flags |= JGPU_HUFF_ERR_CODE;
+    if (sink.g < seg_blocks) {
+      /* the interval goes on: into the next subsequence, which must start where this one ended */
+      if (i + 1 == seg_first[f.seg0 + seg + 1]) flags |= JGPU_HUFF_ERR_SHORT;
+      else if (out != state[gi + 1] || n != (nslots[gi] & 0x7fffffffu)) flags |= JGPU_HUFF_ERR_SYNC;
+    }
+  }
+  if (flags) atomicOr(status + f.status_slot, flags);
+}
+
+/* DC differences -> DC values: the reference's `pred += diff` in a 16-bit accumulator
+ * (src/xjpeg.c:430,479), reset at every restart interval (src/xjpeg.c:593-629). */
+__global__ void __launch_bounds__(256)
+k_huff_dc(const jgpu_huff_file *__restrict__ files, int16_t *__restrict__ coef) {
+  __shared__ int w_sum[8];
+  __shared__ int s_carry;
+  const jgpu_huff_file &f = files[blockIdx.y];
+  const uint32_t seg = blockIdx.x / (uint32_t)f.ncomps;
+  const int comp = (int)(blockIdx.x % (uint32_t)f.ncomps);
+  if (seg >= f.n_seg) return;
+  const int seg_mcu0 = (int)seg * f.mcus_per_seg;
+  const int cnt = min(f.mcus_per_seg, f.total_mcus - seg_mcu0) * f.hs[comp] * f.vs[comp];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  if (t == 0) s_carry = 0;
+  __syncthreads();
+  for (int base = 0; base < cnt; base += 256) {
+    const int e = base + t;
+    int16_t *p = nullptr;
+    int v = 0;
+    if (e < cnt) {
+      p = coef + huff::dc_element_offset(f, comp, seg_mcu0, e);
+      v = *p;
+    }
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int v2 = __shfl_up_sync(0xffffffffu, v, d);
+      if (lane >= d) v += v2;
+    }
+    if (lane == 31) w_sum[warp] = v;
+    __syncthreads();
+    int pre = s_carry;
+    for (int w = 0; w < warp; w++) pre += w_sum[w];
+    v += pre;
+    if (p) *p = (int16_t)v;
+    __syncthreads();
+    if (t == 255) s_carry = v;
+    __syncthreads();
+  }
+}
+
+template <int S>
+cudaError_t configure_kernels() {
+  cudaError_t e = cudaFuncSetAttribute(k_huff_sync<S>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)sizeof(SyncSmem<S>));
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(k_huff_write<S>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)sizeof(SyncSmem<S>));
+}
+
+}  // namespace
+
+cudaError_t huff_configure() { return configure_kernels<kHuffSubseqWords>(); }
+
+int huff_launches(const HuffLaunch &l) { return l.sync_passes + 3; }
+
+/* Enqueues the whole entropy decode of a group of files.  The coefficient range the files
+ * cover must have been zeroed on the same stream. */
+int huff_launch(const HuffLaunch &l, cudaStream_t st) {
+  constexpr int S = kHuffSubseqWords;
+  if (l.n_files <= 0 || l.max_subseq <= 0) return 0;
+  const dim3 grid((unsigned)((l.max_subseq + kCta - 1) / kCta), (unsigned)l.n_files);
+  const size_t smem = sizeof(SyncSmem<S>);
+  cudaError_t e;
+  if ((e = cudaMemsetAsync(l.d_carry[0] + l.carry0, 0, sizeof(uint32_t) * l.n_carry, st)) != cudaSuccess ||
+      (e = cudaMemsetAsync(l.d_carry[1] + l.carry0, 0, sizeof(uint32_t) * l.n_carry, st)) != cudaSuccess ||
+      (e = cudaMemsetAsync(l.d_status + l.status0, 0, sizeof(uint32_t) * l.n_files, st)) != cudaSuccess) {
+    return jgpu_fail("entropy decoder: memset failed (%s)", cudaGetErrorString(e));
+  }
+  for (int pass = 0; pass < l.sync_passes; pass++) {
+    k_huff_sync<S><<<grid, kCta, smem, st>>>(l.d_files, l.d_stream, l.d_tables, l.d_seg_first, l.d_state,
+                                             l.d_nslots, l.d_segid, l.d_carry[(pass + 1) & 1],
+                                             l.d_carry[pass & 1], pass);
+  }
+  k_huff_scan<<<l.n_files, 1024, 0, st>>>(l.d_files, l.d_nslots, l.d_slots);
+  k_huff_write<S><<<grid, kCta, smem, st>>>(l.d_files, l.d_stream, l.d_tables, l.d_seg_first, l.d_state,
+                                            l.d_nslots, l.d_slots, l.d_segid, l.d_coef, l.d_status);
+  const dim3 dc_grid((unsigned)std::max(1, l.max_dc_jobs), (unsigned)l.n_files);
+  k_huff_dc<<<dc_grid, 256, 0, st>>>(l.d_files, l.d_coef);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return jgpu_fail("entropy decoder: launch failed (%s)", cudaGetErrorString(e));
+  return 0;
+}
+
+}  // namespace jgpu

@@ -1,0 +1,288 @@
+/* jgpu_huff_core.h — entropy (Huffman) decoding of a baseline JPEG scan on the GPU: the data
+ * structures and the per-thread decoding loop, shared by the CUDA kernels (jgpu_huff.cu), the
+ * host-side preparation (jgpu_huff_prep.c) and a host emulation used by the CPU tests
+ * (tests/host_core/huff_host.cpp), so the logic is checked without a GPU.
+ *
+ * What it replaces: the reference's sequential reader, src/xjpeg.c:449-632 (scan loop),
+ * :163-205 (XJPEG_DECODE_HUFF), :311-336 (table build), producing the JPEG_DECODE_QUANT planes
+ * of src/xjpeg.c:497-499,520-523,550-563 — SURVEY 8(f) rank 4.
+ *
+ * Parallelisation.  A Huffman stream has no random access, but decoders that start at a wrong
+ * bit tend to fall into step with the true decoding after a few symbols (self-synchronisation;
+ * Klein & Wiseman 2003, applied to GPUs by Weissenberger & Schmidt, ICPP 2018).  The
+ * byte-unstuffed scan of a file is cut into SUBSEQUENCES of a fixed number of 32-bit words;
+ * restart intervals (T.81 E.2.4) start on a subsequence boundary, where the decoder state is
+ * known.  State at a subsequence boundary = (p, c, z): p = bits by which the symbol straddling
+ * the boundary overshoots it, c = block of the MCU being decoded, z = zig-zag index of the next
+ * coefficient (0: a DC symbol comes next).
+ *   sync pass   thread i decodes subsequence i from its current estimate of the state at its
+ *               start and hands the state it ends in to thread i+1; repeated (inside a CTA
+ *               through shared memory, across CTAs by relaunching) until nothing changes.
+ *               It also counts n_i, the coefficient slots the subsequence advances.
+ *   scan        exclusive prefix sum of n_i inside each restart interval -> the absolute
+ *               coefficient slot every subsequence starts at.
+ *   write pass  thread i decodes once more, now storing each non-zero coefficient (DC as the
+ *               difference it is coded as) at its place in the reference's plane layout, and
+ *               VERIFIES that it ends in exactly the state subsequence i+1 starts from.  With
+ *               the first state of every interval known, that check proves every state by
+ *               induction, so a file either decodes exactly as a sequential reader would or is
+ *               flagged and handed to the CPU reader.
+ *   DC pass     per restart interval and component, a prefix sum over the DC differences in
+ *               scan order (the predictor is a 16-bit accumulator, src/xjpeg.c:430,479).
+ */
+#ifndef JGPU_HUFF_CORE_H
+#define JGPU_HUFF_CORE_H
+
+#include <stdint.h>
+
+#define JGPU_HUFF_LUT_BITS 10
+#define JGPU_HUFF_MAX_BLOCKS 10   /* blocks per MCU, T.81 B.2.3 */
+#define JGPU_HUFF_TABLES 6        /* per file: (DC, AC) of each of up to 3 scan components */
+#define JGPU_HUFF_CTA 256         /* subsequences per CTA of the sync / write kernels */
+
+/* One Huffman table prepared for the decoder. */
+typedef struct jgpu_huff_table {
+  /* (length << 8) | symbol for every JGPU_HUFF_LUT_BITS-bit window whose leading bits are a
+   * code of at most that many bits; 0 otherwise */
+  uint16_t lut[1 << JGPU_HUFF_LUT_BITS];
+  /* canonical decoding of the longer codes (T.81 F.2.2.3) on a 16-bit window W:
+   * the code has length L for the smallest L with W < limit[L]; its symbol is
+   * symbols[(W >> (16 - L)) + delta[L]] */
+  uint32_t limit[18];
+  int32_t delta[18];
+  uint8_t symbols[256];
+} jgpu_huff_table;
+
+/* One file of a batch, as the kernels see it. */
+typedef struct jgpu_huff_file {
+  uint32_t word0;        /* first 32-bit word of its unstuffed scan in the stream buffer */
+  uint32_t n_subseq;     /* subsequences of the scan */
+  uint32_t subseq0;      /* index of its first subsequence in the per-subsequence arrays */
+  uint32_t seg0;         /* index of its first entry in the segment table */
+  uint32_t n_seg;        /* restart intervals (1 without DRI); the table has n_seg+1 entries */
+  uint32_t cta0;         /* index of its first entry in the per-CTA carry arrays */
+  int32_t mcus_per_seg;  /* restart interval in MCUs, or all MCUs */
+  int32_t total_mcus;
+  int32_t nhmb;          /* MCUs per MCU row */
+  int32_t bpm;           /* blocks per MCU */
+  int32_t ncomps;
+  int32_t status_slot;   /* which entry of the status array the kernels flag */
+  int32_t hs[3], vs[3];  /* sampling factors */
+  int32_t hblocks[3];    /* blocks per block row of each plane */
+  int64_t plane_off[3];  /* first int16 of each plane in the coefficient buffer */
+  uint8_t blk_comp[JGPU_HUFF_MAX_BLOCKS + 2]; /* component of each block of the MCU */
+  uint8_t blk_dx[JGPU_HUFF_MAX_BLOCKS + 2];   /* its position inside the MCU, in blocks */
+  uint8_t blk_dy[JGPU_HUFF_MAX_BLOCKS + 2];
+  uint32_t table0;       /* index of its first jgpu_huff_table */
+  uint32_t reserved;
+} jgpu_huff_file;
+
+/* status bits the kernels raise per file */
+#define JGPU_HUFF_ERR_CODE 1u      /* invalid code or coefficient index past 63 in the true decoding */
+#define JGPU_HUFF_ERR_SYNC 2u      /* states did not settle within the sync passes */
+#define JGPU_HUFF_ERR_SHORT 4u     /* the scan ends before the interval's last MCU */
+
+/* boundary state, packed */
+#define JGPU_HUFF_STATE(p, c, z) ((uint32_t)(p) | ((uint32_t)(c) << 8) | ((uint32_t)(z) << 16))
+#define JGPU_HUFF_STATE_P(s) ((s) & 0xffu)
+#define JGPU_HUFF_STATE_C(s) (((s) >> 8) & 0xffu)
+#define JGPU_HUFF_STATE_Z(s) (((s) >> 16) & 0xffu)
+
+#ifdef __cplusplus
+
+#if defined(__CUDACC__)
+#define JGPU_HUFF_HD __host__ __device__ __forceinline__
+#else
+#define JGPU_HUFF_HD inline
+#endif
+
+namespace jgpu {
+namespace huff {
+
+/* Symbol at the head of the 16-bit window `look`: (length << 8) | symbol, or 0 for a bit
+ * pattern that is no code of the table. */
+JGPU_HUFF_HD uint32_t lookup(const jgpu_huff_table *t, uint32_t look) {
+  uint32_t e = t->lut[look >> (16 - JGPU_HUFF_LUT_BITS)];
+  if (e) return e;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+  for (int len = JGPU_HUFF_LUT_BITS + 1; len <= 16; len++) {
+    if (look < t->limit[len]) {
+      return ((uint32_t)len << 8) | t->symbols[(int)(look >> (16 - len)) + t->delta[len]];
+    }
+  }
+  return 0;
+}
+
+/* Decodes the symbols that START inside one subsequence.
+ *   word_at(w)    big-endian 32-bit word w of the file's unstuffed scan (may be asked for up to
+ *                 three words past the subsequence)
+ *   w0, nwords    the subsequence
+ *   state         packed (p, c, z) at its start
+ *   sink.coef(k, v)    a coefficient: zig-zag index k of the current block, value v (DC: the
+ *                      coded difference); called for non-zero v only
+ *   sink.block_done()  the current block is complete; returns true to stop (the restart
+ *                      interval has all its blocks)
+ * Returns the state at the end; *n_out = coefficient slots advanced; *err is raised on a bit
+ * pattern that is no code and on a run past coefficient 63 (the reference's reader does not
+ * check either, src/xjpeg.c:67-78; ours fails on both, jgpu_front.c decode_symbol/decode_mcu). */
+template <typename WordAt, typename Sink>
+JGPU_HUFF_HD uint32_t decode_subsequence(const jgpu_huff_table *tabs, const uint8_t *blk_comp, int bpm,
+                                         WordAt word_at, uint32_t w0, int nwords, uint32_t state,
+                                         Sink &sink, uint32_t *n_out, uint32_t *err) {
+  int pos = (int)JGPU_HUFF_STATE_P(state);
+  uint32_t c = JGPU_HUFF_STATE_C(state), z = JGPU_HUFF_STATE_Z(state);
+  const int end = 32 * nwords;
+  uint32_t n = 0, bad = 0;
+  /* 64-bit window, MSB first: `avail` valid bits */
+  uint32_t next = w0 + (uint32_t)(pos >> 5);
+  uint64_t buf = ((uint64_t)word_at(next) << 32) | word_at(next + 1);
+  next += 2;
+  buf <<= (pos & 31);
+  int avail = 64 - (pos & 31);
+  while (pos < end) {
+    if (avail < 32) {
+      buf |= (uint64_t)word_at(next++) << (32 - avail);
+      avail += 32;
+    }
+    const jgpu_huff_table *t = tabs + 2 * blk_comp[c] + (z != 0);
+    uint32_t e = lookup(t, (uint32_t)(buf >> 48));
+    if (!e) {
+      bad = 1;
+      e = 16u << 8;   /* skip the window like jgpu_front.c decode_symbol; symbol 0 */
+    }
+    const int len = (int)(e >> 8);
+    const uint32_t sym = e & 0xffu;
+    const int s = (int)(sym & 15u);
+    /* T.81 F.2.2.1 EXTEND on the s bits after the code */
+    const uint32_t hi = (uint32_t)((buf << len) >> 32);
+    int v = 0;
+    if (s) {
+      const uint32_t bits = hi >> (32 - s);
+      v = bits < (1u << (s - 1)) ? (int)bits - (1 << s) + 1 : (int)bits;
+    }
+    buf <<= (len + s);
+    avail -= len + s;
+    pos += len + s;
+    bool done = false;
+    if (z == 0) {
+      if (v) sink.coef(0, v);
+      z = 1;
+      n += 1;
+    } else if (sym == 0) { /* end of block */
+      n += 64 - z;
+      done = true;
+    } else {
+      const uint32_t k = z + (sym >> 4);
+      if (k > 63) {
+        bad = 1;
+        n += 64 - z;
+        done = true;
+      } else {
+        if (v) sink.coef((int)k, v);
+        n += k + 1 - z;
+        z = k + 1;
+        done = z == 64;
+      }
+    }
+    if (done) {
+      z = 0;
+      c = c + 1 == (uint32_t)bpm ? 0 : c + 1;
+      if (sink.block_done()) break;
+    }
+  }
+  *n_out = n;
+  if (bad) *err = 1;
+  return JGPU_HUFF_STATE(pos > end ? pos - end : 0, c, z);
+}
+
+/* Sink of the sync pass: nothing is stored. */
+struct NullSink {
+  JGPU_HUFF_HD void coef(int, int) {}
+  JGPU_HUFF_HD bool block_done() { return false; }
+};
+
+/* zig-zag position -> natural (row-major) position, T.81 figure A.6 (the users define their
+ * own array from this initialiser: __constant__ on the device, plain on the host) */
+#define JGPU_HUFF_ZIGZAG_NATURAL                                                                  \
+  {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48,        \
+   41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,        \
+   30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63}
+
+/* First int16 of block `c` of MCU `mcu` in the coefficient buffer: the placement of
+ * src/xjpeg.c:550-563 (block-linear inside a plane for power-of-two decimation). */
+JGPU_HUFF_HD int64_t block_offset(const jgpu_huff_file &f, int mcu, int c) {
+  const int comp = f.blk_comp[c];
+  const int mbx = mcu % f.nhmb, mby = mcu / f.nhmb;
+  const int bx = mbx * f.hs[comp] + f.blk_dx[c];
+  const int by = mby * f.vs[comp] + f.blk_dy[c];
+  return f.plane_off[comp] + ((int64_t)by * f.hblocks[comp] + bx) * 64;
+}
+
+/* Sink of the write pass: stores coefficients of the blocks [g, seg_blocks) of one restart
+ * interval, g counted in scan order from the interval's first block. */
+struct StoreSink {
+  const jgpu_huff_file *f;
+  const unsigned char *zz; /* JGPU_HUFF_ZIGZAG_NATURAL */
+  int16_t *base;     /* the batch's coefficient buffer */
+  int mcu;           /* current MCU (image-wide index) */
+  int c;             /* current block inside it */
+  int64_t g, seg_blocks;
+  int16_t *blk;      /* current block */
+  JGPU_HUFF_HD void start(const jgpu_huff_file *file, const unsigned char *zigzag, int16_t *coef_base, int seg_mcu0,
+                          int64_t g0, int64_t nblocks) {
+    f = file;
+    zz = zigzag;
+    base = coef_base;
+    g = g0;
+    seg_blocks = nblocks;
+    mcu = seg_mcu0 + (int)(g0 / file->bpm);
+    c = (int)(g0 % file->bpm);
+    blk = base + block_offset(*f, mcu, c);
+  }
+  JGPU_HUFF_HD void coef(int k, int v) { blk[zz[k]] = (int16_t)v; }
+  JGPU_HUFF_HD bool block_done() {
+    g++;
+    if (g >= seg_blocks) return true;
+    if (++c == f->bpm) {
+      c = 0;
+      mcu++;
+    }
+    blk = base + block_offset(*f, mcu, c);
+    return false;
+  }
+};
+
+/* Element e of the DC chain of component `comp` in the restart interval that starts at MCU
+ * seg_mcu0: scan order = MCU by MCU, the component's blocks of an MCU row-major
+ * (src/xjpeg.c:462-472). */
+JGPU_HUFF_HD int64_t dc_element_offset(const jgpu_huff_file &f, int comp, int seg_mcu0, int e) {
+  const int per = f.hs[comp] * f.vs[comp];
+  const int mcu = seg_mcu0 + e / per, j = e % per;
+  const int mbx = mcu % f.nhmb, mby = mcu / f.nhmb;
+  const int bx = mbx * f.hs[comp] + j % f.hs[comp];
+  const int by = mby * f.vs[comp] + j / f.hs[comp];
+  return f.plane_off[comp] + ((int64_t)by * f.hblocks[comp] + bx) * 64;
+}
+
+}  // namespace huff
+}  // namespace jgpu
+
+#endif /* __cplusplus */
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- host-side preparation (jgpu_huff_prep.c) -------------------------------------------- */
+
+/* Builds one decoder table from the canonical description a DHT segment gives (T.81 C.2):
+ * counts[L-1] codes of length L, their symbols in code order.  Returns 0, or 1 when the
+ * counts over-subscribe the code space. */
+int jgpu_huff_build_table(jgpu_huff_table *t, const unsigned char counts[16], const unsigned char *symbols);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

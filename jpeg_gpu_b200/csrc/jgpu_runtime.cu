@@ -9,6 +9,7 @@
 #include <new>
 #include <vector>
 
+#include "jgpu_huff.h"
 #include "jgpu_internal.h"
 #include "jgpu_launch.h"
 
@@ -77,6 +78,9 @@ struct jgpu_ctx {
   Buffer d_pack, d_index, d_pack_off; /* jgpu_decode_batch_host_packed */
   /* pinned bounce buffers for pageable host memory */
   Buffer h_in[kHostStreams], h_out[kHostStreams];
+  /* GPU entropy decoder (jgpu_decode_jpegs_ex): pinned staging and device arrays */
+  Buffer hz_stream, hz_files, hz_tables, hz_segs, hz_status, hz_coef;
+  Buffer dz_stream, dz_files, dz_tables, dz_segs, dz_status, dz_sub[4], dz_carry[2];
   /* last plan built by jgpu_decode_batch_host, reused while descs match */
   jgpu_plan *cached_plan = nullptr;
   std::vector<jgpu_image_desc> cached_descs;
@@ -148,6 +152,8 @@ extern "C" jgpu_ctx *jgpu_create(int device) {
   ctx->sm_count = prop.multiProcessorCount;
   for (int i = 0; i < kHostStreams; i++) {
     ctx->h_in[i].pinned_host = ctx->h_out[i].pinned_host = true;
+    ctx->hz_stream.pinned_host = ctx->hz_files.pinned_host = ctx->hz_tables.pinned_host = true;
+    ctx->hz_segs.pinned_host = ctx->hz_status.pinned_host = ctx->hz_coef.pinned_host = true;
     if (cudaStreamCreateWithFlags(&ctx->streams[i], cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->events[i], cudaEventDisableTiming) != cudaSuccess) {
       jgpu_fail("could not create CUDA streams");
@@ -157,6 +163,11 @@ extern "C" jgpu_ctx *jgpu_create(int device) {
   }
   if (fused_configure(device) != cudaSuccess) {
     jgpu_fail("could not configure the fused kernel (%s)", cudaGetErrorString(cudaGetLastError()));
+    jgpu_destroy(ctx);
+    return nullptr;
+  }
+  if (huff_configure() != cudaSuccess) {
+    jgpu_fail("could not configure the entropy decoder (%s)", cudaGetErrorString(cudaGetLastError()));
     jgpu_destroy(ctx);
     return nullptr;
   }
@@ -180,6 +191,12 @@ extern "C" void jgpu_destroy(jgpu_ctx *ctx) {
   ctx->d_pack.release();
   ctx->d_index.release();
   ctx->d_pack_off.release();
+  for (Buffer *b : {&ctx->hz_stream, &ctx->hz_files, &ctx->hz_tables, &ctx->hz_segs, &ctx->hz_status, &ctx->hz_coef,
+                    &ctx->dz_stream, &ctx->dz_files, &ctx->dz_tables, &ctx->dz_segs, &ctx->dz_status,
+                    &ctx->dz_sub[0], &ctx->dz_sub[1], &ctx->dz_sub[2], &ctx->dz_sub[3], &ctx->dz_carry[0],
+                    &ctx->dz_carry[1]}) {
+    b->release();
+  }
   delete ctx;
 }
 
@@ -834,6 +851,7 @@ extern "C" int jgpu_decode_image_packed(jgpu_ctx *ctx, const jpeg_header *header
 /* JPEG files in, RGB out                                                     */
 
 #include <atomic>
+#include <chrono>
 #include <thread>
 
 #include "jgpu_front.h"
@@ -938,9 +956,8 @@ extern "C" int64_t jgpu_jpegs_probe(const jgpu_jpeg *files, int n, jgpu_jpeg_inf
   return off;
 }
 
-extern "C" int jgpu_decode_jpegs(jgpu_ctx *ctx, const jgpu_jpeg *files, int n, int nthreads,
-                                 uint8_t *h_rgb, int64_t rgb_cap, jgpu_jpeg_info *info) {
-  if (!ctx || !files || n <= 0 || !h_rgb || !info) return jgpu_fail("jgpu_decode_jpegs: bad arguments");
+static int decode_jpegs_cpu_entropy(jgpu_ctx *ctx, const jgpu_jpeg *files, int n, int nthreads,
+                                    uint8_t *h_rgb, int64_t rgb_cap, jgpu_jpeg_info *info) {
   CU_TRY(cudaSetDevice(ctx->device));
   const jpeg_decode_ctx_vtbl &v = JFRONT_DECODE_CTX_VTBL;
   if (nthreads <= 0) nthreads = (int)std::thread::hardware_concurrency();
@@ -1046,6 +1063,9 @@ extern "C" int jgpu_decode_jpegs(jgpu_ctx *ctx, const jgpu_jpeg *files, int n, i
       if (t.s0 >= 0) {
         rc = jfront_decode_segments(it.front, &img, JPEG_DECODE_QUANT, &it.segs, t.s0, t.s1, &err);
       } else {
+        /* the sequential reader stops at a missing restart marker and leaves the rest of the
+         * planes alone; the reference hands it zeroed planes (image_zero, src/jpeg_gpu.c:1227) */
+        memset(h_coef + it.desc.coef_off, 0, (size_t)it.lay.coef_len * 2);
         rc = v.decode_image(it.front, &img, JPEG_DECODE_QUANT);
         if (rc) err = "Error decoding scan";
       }
@@ -1126,4 +1146,313 @@ extern "C" int jgpu_decode_jpegs(jgpu_ctx *ctx, const jgpu_jpeg *files, int n, i
     }
   }
   return rc;
+}
+
+/* -------------------------------------------------------------------------- */
+/* JPEG files in, RGB out, Huffman decoding on the GPU           */
+
+/* Host threads only strip the byte stuffing and cut the scan at its restart markers
+ * (jfront_huff_prepare, a memchr/memcpy pass); the entropy decoding itself runs in
+ * jgpu_huff.cu, followed on the same stream by the fused block decoder.  What crosses the
+ * link is the compressed scan in, the pixels out.  Files the GPU decoder does not take
+ * (more than 10 blocks per MCU, restart markers out of place) or flags (corrupt or truncated
+ * scans, states that did not settle) go through the sequential reader afterwards, which
+ * decodes or rejects them exactly as before. */
+static int decode_jpegs_gpu_entropy(jgpu_ctx *ctx, const jgpu_jpeg *files, int n, int nthreads,
+                                    uint8_t *h_rgb, int64_t rgb_cap, jgpu_jpeg_info *info) {
+  CU_TRY(cudaSetDevice(ctx->device));
+  const jpeg_decode_ctx_vtbl &v = JFRONT_DECODE_CTX_VTBL;
+  constexpr int S = kHuffSubseqWords;
+  /* JGPU_TRACE=1: host-side phase times of this call on stderr */
+  const bool trace = getenv("JGPU_TRACE") != nullptr;
+  const auto t_begin = std::chrono::steady_clock::now();
+  auto since = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(); };
+  double t_setup = 0, t_prepared = 0, t_enqueued = 0, t_synced = 0;
+  if (nthreads <= 0) nthreads = (int)std::thread::hardware_concurrency();
+  if (nthreads <= 0) nthreads = 1;
+
+  /* ---- headers, layout ------------------------------------------------------ */
+  std::vector<JpegItem> items(n);
+  std::vector<int> ok;
+  std::vector<jgpu_image_desc> descs;
+  std::vector<uint16_t> qtabs;
+  int64_t rgb_off = 0, coef_off = 0;
+  for (int i = 0; i < n; i++) {
+    JpegItem &it = items[i];
+    if (!probe_one(files[i], it, info[i], true)) continue;
+    info[i].rgb_off = rgb_off;
+    it.desc.rgb_off = rgb_off;
+    it.desc.coef_off = coef_off;
+    it.desc.yuv_off = -1;
+    it.desc.qtab_set = (int32_t)ok.size();
+    rgb_off += (it.lay.rgb_len + 255) & ~(int64_t)255;
+    coef_off += it.lay.coef_len;
+    for (int t = 0; t < NQUANT_MAX; t++) {
+      qtabs.insert(qtabs.end(), it.header.quant[t].tbl, it.header.quant[t].tbl + 64);
+    }
+    descs.push_back(it.desc);
+    ok.push_back(i);
+  }
+  auto release_fronts = [&]() {
+    for (JpegItem &it : items) {
+      if (it.front) v.decode_free(it.front);
+      it.front = nullptr;
+    }
+  };
+  if (ok.empty()) {
+    release_fronts();
+    return jgpu_fail("jgpu_decode_jpegs: no decodable file in the batch");
+  }
+  if (rgb_off > rgb_cap) {
+    release_fronts();
+    return jgpu_fail("jgpu_decode_jpegs: output needs %lld bytes, buffer has %lld", (long long)rgb_off,
+                     (long long)rgb_cap);
+  }
+  const int m = (int)ok.size();
+  const unsigned flags = JGPU_OUT_RGB;
+  if (!ctx->cached_plan || ctx->cached_flags != flags || !same_descs(ctx->cached_descs, descs.data(), m)) {
+    if (ctx->cached_plan) jgpu_plan_destroy(ctx->cached_plan);
+    ctx->cached_plan = jgpu_plan_create(ctx, descs.data(), m, flags);
+    if (!ctx->cached_plan) {
+      release_fronts();
+      return EXIT_FAILURE;
+    }
+    ctx->cached_descs = descs;
+    ctx->cached_flags = flags;
+  }
+  jgpu_plan *plan = ctx->cached_plan;
+
+  /* ---- where each file's pieces go (from upper bounds, so the files prepare independently) */
+  struct Slot {
+    int64_t stream_off;   /* bytes, multiple of 16 */
+    int64_t stream_cap;
+    uint32_t seg0, seg_cap, subseq0, cta0;
+  };
+  std::vector<Slot> slot(m + 1);
+  {
+    int64_t so = 0;
+    uint64_t seg = 0, sub = 0, cta = 0;
+    for (int k = 0; k < m; k++) {
+      int nseg = 0;
+      const int64_t bound = (jfront_huff_bound(items[ok[k]].front, S, &nseg) + 15) & ~(int64_t)15;
+      const uint64_t nsub = (uint64_t)(bound / (4 * S)) + 1;
+      slot[k] = {so, bound, (uint32_t)seg, (uint32_t)nseg + 2, (uint32_t)sub, (uint32_t)cta};
+      so += bound;
+      seg += (uint64_t)nseg + 2;
+      sub += nsub;
+      cta += (nsub + JGPU_HUFF_CTA - 1) / JGPU_HUFF_CTA + 1;
+    }
+    slot[m] = {so, 0, (uint32_t)seg, 0, (uint32_t)sub, (uint32_t)cta};
+    if (so / 4 >= 0xffffffffll || sub >= 0xffffffffull) {
+      release_fronts();
+      return jgpu_fail("jgpu_decode_jpegs: batch too large for 32-bit stream offsets; split it");
+    }
+  }
+  const size_t n_sub = slot[m].subseq0, n_seg = slot[m].seg0, n_cta = slot[m].cta0;
+  if (ctx->hz_stream.reserve((size_t)slot[m].stream_off + 16) || ctx->dz_stream.reserve((size_t)slot[m].stream_off + 16) ||
+      ctx->hz_files.reserve(sizeof(jgpu_huff_file) * m) || ctx->dz_files.reserve(sizeof(jgpu_huff_file) * m) ||
+      ctx->hz_tables.reserve(sizeof(jgpu_huff_table) * JGPU_HUFF_TABLES * m) ||
+      ctx->dz_tables.reserve(sizeof(jgpu_huff_table) * JGPU_HUFF_TABLES * m) ||
+      ctx->hz_segs.reserve(4 * n_seg + 16) || ctx->dz_segs.reserve(4 * n_seg + 16) ||
+      ctx->hz_status.reserve(4 * (size_t)m + 16) || ctx->dz_status.reserve(4 * (size_t)m + 16) ||
+      ctx->dz_sub[0].reserve(4 * n_sub + 16) || ctx->dz_sub[1].reserve(4 * n_sub + 16) ||
+      ctx->dz_sub[2].reserve(4 * n_sub + 16) || ctx->dz_sub[3].reserve(4 * n_sub + 16) ||
+      ctx->dz_carry[0].reserve(4 * n_cta + 16) || ctx->dz_carry[1].reserve(4 * n_cta + 16) ||
+      ctx->d_coef.reserve((size_t)coef_off * 2 + 256) || ctx->d_qtabs.reserve(qtabs.size() * 2) ||
+      ctx->d_rgb.reserve((size_t)rgb_off + 256)) {
+    release_fronts();
+    return EXIT_FAILURE;
+  }
+  unsigned char *h_stream = (unsigned char *)ctx->hz_stream.ptr;
+  jgpu_huff_file *h_files = (jgpu_huff_file *)ctx->hz_files.ptr;
+  jgpu_huff_table *h_tables = (jgpu_huff_table *)ctx->hz_tables.ptr;
+  uint32_t *h_segs = (uint32_t *)ctx->hz_segs.ptr;
+  uint32_t *h_status = (uint32_t *)ctx->hz_status.ptr;
+  int16_t *d_coef = (int16_t *)ctx->d_coef.ptr;
+  uint16_t *d_qtabs = (uint16_t *)ctx->d_qtabs.ptr;
+  uint8_t *d_rgb = (uint8_t *)ctx->d_rgb.ptr;
+
+  t_setup = since();
+  /* ---- host threads: unstuff, cut at the restart markers, build the tables ------- */
+  std::vector<char> on_gpu(m, 0);
+  for (int k = 0; k < m; k++) items[ok[k]].tasks_left.store(1, std::memory_order_relaxed);
+  std::atomic<int> next_file{0};
+  auto worker = [&]() {
+    for (;;) {
+      const int k = next_file.fetch_add(1, std::memory_order_relaxed);
+      if (k >= m) return;
+      JpegItem &it = items[ok[k]];
+      jgpu_huff_file &f = h_files[k];
+      memset(&f, 0, sizeof(f));
+      const char *why = nullptr;
+      const long long bytes = jfront_huff_prepare(it.front, S, h_stream + slot[k].stream_off, slot[k].stream_cap,
+                                                  h_segs + slot[k].seg0, (int)slot[k].seg_cap,
+                                                  h_tables + (size_t)JGPU_HUFF_TABLES * k, &f, &why);
+      if (bytes < 0) {
+        memset(&f, 0, sizeof(f));   /* no subsequences: the kernels skip it */
+      } else {
+        on_gpu[k] = 1;
+        for (int p = 0; p < it.desc.ncomps; p++) {
+          f.hblocks[p] = it.lay.plane[p].hblocks;
+          f.plane_off[p] = it.desc.coef_off + it.lay.plane[p].coef_off;
+        }
+      }
+      f.word0 = (uint32_t)(slot[k].stream_off / 4);
+      f.subseq0 = slot[k].subseq0;
+      f.seg0 = slot[k].seg0;
+      f.cta0 = slot[k].cta0;
+      f.table0 = (uint32_t)(JGPU_HUFF_TABLES * k);
+      f.status_slot = k;
+      it.tasks_left.store(0, std::memory_order_release);
+    }
+  };
+  std::vector<std::thread> pool;
+  const int nworkers = std::min(nthreads, m);
+  for (int t = 0; t < nworkers; t++) pool.emplace_back(worker);
+  auto join_all = [&]() {
+    for (std::thread &t : pool) t.join();
+    pool.clear();
+  };
+
+  /* ---- GPU pipeline ------------------------------------------------------------------ */
+  auto gpu_part = [&]() -> int {
+    CU_TRY(cudaMemcpyAsync(d_qtabs, qtabs.data(), qtabs.size() * 2, cudaMemcpyHostToDevice, ctx->streams[0]));
+    CU_TRY(cudaEventRecord(ctx->events[0], ctx->streams[0]));
+    for (int s = 1; s < kHostStreams; s++) CU_TRY(cudaStreamWaitEvent(ctx->streams[s], ctx->events[0], 0));
+    const int64_t chunk_bytes = 192ll << 20;   /* of coefficients */
+    int i0 = 0, chunk = 0;
+    while (i0 < m) {
+      int i1 = i0;
+      int64_t acc = 0;
+      while (i1 < m && (i1 == i0 || acc + plan->layouts[i1].coef_len * 2 <= chunk_bytes)) {
+        acc += plan->layouts[i1].coef_len * 2;
+        i1++;
+      }
+      HuffLaunch l;
+      for (int k = i0; k < i1; k++) {
+        JpegItem &it = items[ok[k]];
+        while (it.tasks_left.load(std::memory_order_acquire) > 0) std::this_thread::yield();
+        l.max_subseq = std::max(l.max_subseq, (int)h_files[k].n_subseq);
+        l.max_dc_jobs = std::max(l.max_dc_jobs, (int)h_files[k].n_seg * h_files[k].ncomps);
+        info[ok[k]].tasks = on_gpu[k] ? (int32_t)h_files[k].n_subseq : 1;
+      }
+      cudaStream_t st = ctx->streams[chunk % kHostStreams];
+      /* each file's actual stream is shorter than its slot; copy slot by slot what was written */
+      for (int k = i0; k < i1; k++) {
+        if (!on_gpu[k]) continue;
+        const size_t bytes = (size_t)h_files[k].n_subseq * 4 * S + 16;
+        CU_TRY(cudaMemcpyAsync((unsigned char *)ctx->dz_stream.ptr + slot[k].stream_off, h_stream + slot[k].stream_off,
+                               bytes, cudaMemcpyHostToDevice, st));
+      }
+      CU_TRY(cudaMemcpyAsync((jgpu_huff_file *)ctx->dz_files.ptr + i0, h_files + i0, sizeof(jgpu_huff_file) * (i1 - i0),
+                             cudaMemcpyHostToDevice, st));
+      CU_TRY(cudaMemcpyAsync((jgpu_huff_table *)ctx->dz_tables.ptr + (size_t)JGPU_HUFF_TABLES * i0,
+                             h_tables + (size_t)JGPU_HUFF_TABLES * i0,
+                             sizeof(jgpu_huff_table) * JGPU_HUFF_TABLES * (i1 - i0), cudaMemcpyHostToDevice, st));
+      CU_TRY(cudaMemcpyAsync((uint32_t *)ctx->dz_segs.ptr + slot[i0].seg0, h_segs + slot[i0].seg0,
+                             4 * (size_t)(slot[i1].seg0 - slot[i0].seg0), cudaMemcpyHostToDevice, st));
+      CU_TRY(cudaMemsetAsync(d_coef + descs[i0].coef_off, 0, (size_t)acc, st));
+      l.n_files = i1 - i0;
+      l.carry0 = slot[i0].cta0;
+      l.n_carry = slot[i1].cta0 - slot[i0].cta0;
+      l.status0 = i0;
+      l.d_files = (const jgpu_huff_file *)ctx->dz_files.ptr + i0;
+      l.d_stream = (const uint32_t *)ctx->dz_stream.ptr;
+      l.d_tables = (const jgpu_huff_table *)ctx->dz_tables.ptr;
+      l.d_seg_first = (const uint32_t *)ctx->dz_segs.ptr;
+      l.d_state = (uint32_t *)ctx->dz_sub[0].ptr;
+      l.d_nslots = (uint32_t *)ctx->dz_sub[1].ptr;
+      l.d_slots = (uint32_t *)ctx->dz_sub[2].ptr;
+      l.d_segid = (uint32_t *)ctx->dz_sub[3].ptr;
+      l.d_carry[0] = (uint32_t *)ctx->dz_carry[0].ptr;
+      l.d_carry[1] = (uint32_t *)ctx->dz_carry[1].ptr;
+      l.d_status = (uint32_t *)ctx->dz_status.ptr;
+      l.d_coef = d_coef;
+      if (huff_launch(l, st)) return EXIT_FAILURE;
+      if (plan_run_range(plan, i0, i1, d_coef, d_qtabs, m, d_rgb, nullptr, st)) return EXIT_FAILURE;
+      CU_TRY(cudaMemcpyAsync(h_status + i0, (uint32_t *)ctx->dz_status.ptr + i0, 4 * (size_t)(i1 - i0),
+                             cudaMemcpyDeviceToHost, st));
+      {
+        const int64_t lo = descs[i0].rgb_off;
+        const int64_t hi = descs[i1 - 1].rgb_off + plan->layouts[i1 - 1].rgb_len;
+        CU_TRY(cudaMemcpyAsync(h_rgb + lo, d_rgb + lo, (size_t)(hi - lo), cudaMemcpyDeviceToHost, st));
+      }
+      i0 = i1;
+      chunk++;
+      if (i0 >= m) t_prepared = since();
+    }
+    t_enqueued = since();
+    for (int s = 0; s < kHostStreams; s++) CU_TRY(cudaStreamSynchronize(ctx->streams[s]));
+    t_synced = since();
+    return EXIT_SUCCESS;
+  };
+  int rc = gpu_part();
+  join_all();
+  if (rc != EXIT_SUCCESS) {
+    cudaDeviceSynchronize();
+    release_fronts();
+    return rc;
+  }
+  if (trace) {
+    fprintf(stderr, "jgpu_decode_jpegs[gpu entropy]: %d files, setup %.2f ms, last file prepared %.2f, enqueued %.2f, "
+            "streams drained %.2f\n", m, t_setup, t_prepared, t_enqueued, t_synced);
+  }
+
+  /* ---- files the GPU decoder left to the sequential reader ---------------------------- */
+  for (int k = 0; k < m; k++) {
+    if (on_gpu[k] && h_status[k] == 0) continue;
+    JpegItem &it = items[ok[k]];
+    info[ok[k]].tasks = 1;
+    if (ctx->hz_coef.reserve((size_t)it.lay.coef_len * 2 + 256)) {
+      release_fronts();
+      return EXIT_FAILURE;
+    }
+    int16_t *h_coef = (int16_t *)ctx->hz_coef.ptr;
+    memset(h_coef, 0, (size_t)it.lay.coef_len * 2);
+    image img;
+    bind_image(&img, it.desc, it.lay, h_coef);
+    if (v.decode_image(it.front, &img, JPEG_DECODE_QUANT) != EXIT_SUCCESS) {
+      info[ok[k]].status = 1;
+      info[ok[k]].message = "Error decoding scan";
+      rc = EXIT_FAILURE;
+      continue;
+    }
+    cudaStream_t st = ctx->streams[0];
+    CU_TRY(cudaMemcpyAsync(d_coef + it.desc.coef_off, h_coef, (size_t)it.lay.coef_len * 2, cudaMemcpyHostToDevice, st));
+    if (plan_run_range(plan, k, k + 1, d_coef, d_qtabs, m, d_rgb, nullptr, st)) {
+      release_fronts();
+      return EXIT_FAILURE;
+    }
+    CU_TRY(cudaMemcpyAsync(h_rgb + it.desc.rgb_off, d_rgb + it.desc.rgb_off, (size_t)it.lay.rgb_len,
+                           cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+  }
+  if (m != n) rc = EXIT_FAILURE;
+  release_fronts();
+  if (rc != EXIT_SUCCESS) {
+    for (int i = 0; i < n; i++) {
+      if (info[i].status) {
+        jgpu_fail("file %d: %s", i, info[i].message ? info[i].message : "rejected");
+        break;
+      }
+    }
+  }
+  return rc;
+}
+
+extern "C" int jgpu_decode_jpegs_ex(jgpu_ctx *ctx, const jgpu_jpeg *files, int n, int nthreads, unsigned flags,
+                                    uint8_t *h_rgb, int64_t rgb_cap, jgpu_jpeg_info *info) {
+  if (!ctx || !files || n <= 0 || !h_rgb || !info) return jgpu_fail("jgpu_decode_jpegs: bad arguments");
+  if (flags == JGPU_ENTROPY_AUTO) {
+    const char *env = getenv("JGPU_ENTROPY");
+    flags = env && !strcmp(env, "cpu") ? JGPU_ENTROPY_CPU : JGPU_ENTROPY_GPU;
+  }
+  if (flags == JGPU_ENTROPY_CPU) return decode_jpegs_cpu_entropy(ctx, files, n, nthreads, h_rgb, rgb_cap, info);
+  if (flags == JGPU_ENTROPY_GPU) return decode_jpegs_gpu_entropy(ctx, files, n, nthreads, h_rgb, rgb_cap, info);
+  return jgpu_fail("jgpu_decode_jpegs_ex: unknown flags %u", flags);
+}
+
+extern "C" int jgpu_decode_jpegs(jgpu_ctx *ctx, const jgpu_jpeg *files, int n, int nthreads,
+                                 uint8_t *h_rgb, int64_t rgb_cap, jgpu_jpeg_info *info) {
+  return jgpu_decode_jpegs_ex(ctx, files, n, nthreads, JGPU_ENTROPY_AUTO, h_rgb, rgb_cap, info);
 }

@@ -1,0 +1,219 @@
+// TEST-ONLY host emulation of the GPU entropy decoder (jgpu_huff.cu): the per-thread loop, the
+// sinks and the address arithmetic are the product's own (jgpu_huff_core.h), the CTA-level
+// choreography (rounds through "shared memory", carries between CTAs and launches, segmented
+// scan, verification, DC pass) is restated here thread by thread, so the method and the shared
+// code are checked against the sequential reader without a GPU.  Built by
+// tests/test_huffman_host.py together with the product's C host sources; not part of the library.
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "jgpu_front.h"
+#include "jgpu_huff_core.h"
+#include "jgpu_internal.h"
+
+namespace {
+
+const unsigned char kZigzag[64] = JGPU_HUFF_ZIGZAG_NATURAL;
+
+struct HostWords {
+  const uint32_t *w;
+  uint32_t operator()(uint32_t idx) const { return __builtin_bswap32(w[idx]); }
+};
+
+}  // namespace
+
+// Decodes one JPEG file's scan into QUANT planes (reference layout) the way the kernels do.
+//   subseq_words, cta   the kernel's constants (32, 256), shrinkable so that small files still
+//                       exercise hand-overs between subsequences, CTAs and launches
+//   sync_passes         launches of the sync kernel
+//   stats[0] = subsequences, [1] = restart intervals, [2] = rounds of the busiest CTA,
+//   [3] = CTAs that recomputed in a later pass
+// Returns the coefficient count (int16 elements), -1 when the file is not eligible, and leaves
+// the kernels' status word in *status.
+extern "C" long long huff_emulate(const unsigned char *jpeg, int size, short *coef, long long coef_cap,
+                                  int subseq_words, int cta, int sync_passes, unsigned *status, int *stats) {
+  using namespace jgpu::huff;
+  const jpeg_decode_ctx_vtbl &v = JFRONT_DECODE_CTX_VTBL;
+  jpeg_info info;
+  memset(&info, 0, sizeof(info));
+  info.buf = const_cast<unsigned char *>(jpeg);
+  info.size = size;
+  jpeg_decode_ctx *front = v.decode_alloc(&info);
+  jpeg_header header;
+  jgpu_image_desc desc;
+  jgpu_layout lay;
+  if (!front) return -1;
+  if (v.decode_header(front, &header) != EXIT_SUCCESS || jgpu_desc_from_header(&header, &desc) ||
+      jgpu_layout_query(&desc, &lay) || lay.coef_len > coef_cap) {
+    v.decode_free(front);
+    return -1;
+  }
+  int nseg_bound = 0;
+  const long long cap = jfront_huff_bound(front, subseq_words, &nseg_bound);
+  std::vector<unsigned char> stream((size_t)cap);
+  std::vector<unsigned int> seg_first((size_t)nseg_bound + 2);
+  std::vector<jgpu_huff_table> tabs(JGPU_HUFF_TABLES);
+  jgpu_huff_file f;
+  memset(&f, 0, sizeof(f));
+  const char *why = nullptr;
+  const long long bytes = jfront_huff_prepare(front, subseq_words, stream.data(), cap, seg_first.data(),
+                                              nseg_bound + 2, tabs.data(), &f, &why);
+  v.decode_free(front);
+  if (bytes < 0) return -1;
+  for (int p = 0; p < desc.ncomps; p++) {
+    f.hblocks[p] = lay.plane[p].hblocks;
+    f.plane_off[p] = lay.plane[p].coef_off;
+  }
+  const HostWords words = {reinterpret_cast<const uint32_t *>(stream.data())};
+  const int S = subseq_words;
+  const int n = (int)f.n_subseq;
+  const int nctas = (n + cta - 1) / cta;
+  std::vector<uint32_t> state(n, 0), nslots(n, 0), slots(n, 0), segid(n, 0);
+  std::vector<uint32_t> carry[2] = {std::vector<uint32_t>(nctas + 1, 0), std::vector<uint32_t>(nctas + 1, 0)};
+  unsigned st_flags = 0;
+  int max_rounds = 0, recomputed = 0;
+
+  // ---- k_huff_sync, `sync_passes` launches ----
+  for (int pass = 0; pass < sync_passes; pass++) {
+    const std::vector<uint32_t> &cin = carry[(pass + 1) & 1];
+    std::vector<uint32_t> &cout = carry[pass & 1];
+    for (int x = 0; x < nctas; x++) {
+      const int first = x * cta, count = std::min(cta, n - first);
+      uint32_t new0 = 0;
+      if (pass > 0) {
+        new0 = (nslots[first] >> 31) ? 0u : cin[x];
+        if (new0 == state[first]) {
+          cout[x + 1] = cin[x + 1];
+          continue;
+        }
+        recomputed++;
+      }
+      std::vector<uint32_t> s_in(count), s_out(count + 1, 0), nn(count, 0);
+      std::vector<char> need(count), is_first(count);
+      for (int t = 0; t < count; t++) {
+        const uint32_t i = (uint32_t)(first + t);
+        if (pass == 0) {
+          uint32_t lo = 0, hi = f.n_seg;
+          while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (seg_first[mid] <= i) lo = mid; else hi = mid;
+          }
+          is_first[t] = seg_first[lo] == i;
+          segid[i] = lo;
+          s_in[t] = 0;
+          need[t] = 1;
+        } else {
+          is_first[t] = (nslots[i] >> 31) != 0;
+          nn[t] = nslots[i] & 0x7fffffffu;
+          s_in[t] = t == 0 ? new0 : state[i];
+          need[t] = t == 0;
+        }
+        s_out[t] = s_in[t];
+      }
+      s_out[count] = pass > 0 ? cin[x + 1] : 0u;
+      int rounds = 0;
+      for (;;) {
+        rounds++;
+        for (int t = 0; t < count; t++) {
+          if (!need[t]) continue;
+          NullSink sink;
+          uint32_t err = 0;
+          s_out[t + 1] = decode_subsequence(tabs.data(), f.blk_comp, f.bpm, words, (uint32_t)(first + t) * S, S,
+                                            s_in[t], sink, &nn[t], &err);
+        }
+        bool any = false;
+        for (int t = 0; t < count; t++) {
+          const uint32_t ni = (t == 0 || is_first[t]) ? s_in[t] : s_out[t];
+          need[t] = ni != s_in[t];
+          s_in[t] = ni;
+          any |= need[t] != 0;
+        }
+        if (!any) break;
+      }
+      max_rounds = std::max(max_rounds, rounds);
+      for (int t = 0; t < count; t++) {
+        state[first + t] = s_in[t];
+        nslots[first + t] = nn[t] | (is_first[t] ? 0x80000000u : 0u);
+      }
+      cout[x + 1] = s_out[count];
+    }
+  }
+  // ---- k_huff_scan ----
+  {
+    uint32_t acc = 0;
+    for (int i = 0; i < n; i++) {
+      if (nslots[i] >> 31) acc = 0;
+      slots[i] = acc;
+      acc += nslots[i] & 0x7fffffffu;
+    }
+  }
+  // ---- k_huff_write ----
+  memset(coef, 0, sizeof(short) * (size_t)lay.coef_len);
+  for (int i = 0; i < n; i++) {
+    const uint32_t seg = segid[i];
+    const int seg_mcu0 = (int)seg * f.mcus_per_seg;
+    const int64_t seg_blocks = (int64_t)std::min(f.mcus_per_seg, f.total_mcus - seg_mcu0) * f.bpm;
+    const uint32_t slot0 = slots[i], st = state[i];
+    const int64_t g0 = slot0 >> 6;
+    if ((slot0 & 63u) != JGPU_HUFF_STATE_Z(st) || (uint32_t)(g0 % f.bpm) != JGPU_HUFF_STATE_C(st)) {
+      st_flags |= JGPU_HUFF_ERR_SYNC;
+    } else if (g0 < seg_blocks) {
+      StoreSink sink;
+      sink.start(&f, kZigzag, coef, seg_mcu0, g0, seg_blocks);
+      uint32_t nn = 0, err = 0;
+      const uint32_t out = decode_subsequence(tabs.data(), f.blk_comp, f.bpm, words, (uint32_t)i * S, S, st, sink,
+                                              &nn, &err);
+      if (err) st_flags |= JGPU_HUFF_ERR_CODE;
+      if (sink.g < seg_blocks) {
+        if ((uint32_t)i + 1 == seg_first[seg + 1]) st_flags |= JGPU_HUFF_ERR_SHORT;
+        else if (out != state[i + 1] || nn != (nslots[i] & 0x7fffffffu)) st_flags |= JGPU_HUFF_ERR_SYNC;
+      }
+    }
+  }
+  // ---- k_huff_dc ----
+  for (uint32_t seg = 0; seg < f.n_seg; seg++) {
+    const int seg_mcu0 = (int)seg * f.mcus_per_seg;
+    for (int comp = 0; comp < f.ncomps; comp++) {
+      const int cnt = std::min(f.mcus_per_seg, f.total_mcus - seg_mcu0) * f.hs[comp] * f.vs[comp];
+      int acc = 0;
+      for (int e = 0; e < cnt; e++) {
+        short *p = coef + dc_element_offset(f, comp, seg_mcu0, e);
+        acc += *p;
+        *p = (short)acc;
+      }
+    }
+  }
+  *status = st_flags;
+  if (stats) {
+    stats[0] = n;
+    stats[1] = (int)f.n_seg;
+    stats[2] = max_rounds;
+    stats[3] = recomputed;
+  }
+  return lay.coef_len;
+}
+
+// jgpu_huff_build_table against a bit-by-bit canonical decoder: every 16-bit window.
+extern "C" int huff_table_selfcheck(const unsigned char *counts, const unsigned char *symbols) {
+  jgpu_huff_table t;
+  if (jgpu_huff_build_table(&t, counts, symbols)) return -1;
+  int mismatches = 0;
+  for (uint32_t look = 0; look < 65536; look++) {
+    // T.81 F.2.2.3 DECODE
+    int code = 0, k = 0, want = 0, first = 0;
+    for (int len = 1; len <= 16; len++) {
+      code = (int)(look >> (16 - len));
+      const int cnt = counts[len - 1];
+      if (code - first < cnt) {
+        want = (len << 8) | symbols[k + code - first];
+        break;
+      }
+      k += cnt;
+      first = (first + cnt) << 1;
+    }
+    if ((int)jgpu::huff::lookup(&t, look) != want) mismatches++;
+  }
+  return mismatches;
+}

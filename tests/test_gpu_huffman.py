@@ -1,0 +1,103 @@
+"""GPU: Huffman decoding on the device (jgpu_huff.cu) through jgpu_decode_jpegs_ex:
+pixels must equal what the sequential reader + the same back end give (and the oracle's), file by
+file, including files the device decoder has to hand back to the sequential reader."""
+import io
+
+import numpy as np
+import pytest
+
+import jpeg_gpu_b200 as J
+import oracle
+from golden_util import NAMES, load
+
+pytestmark = pytest.mark.gpu
+
+
+def _picture(w, h, seed, noise=40):
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:h, 0:w]
+    base = np.stack([(xx * 5 + yy * 3) % 256, (yy * 7 + xx) % 256, (xx * 2 + yy * 9) % 256], -1)
+    return np.clip(base + rng.integers(-noise, noise + 1, size=base.shape), 0, 255).astype(np.uint8)
+
+
+def _jpeg(w, h, ss, rst=0, q=85, optimize=False, seed=1, noise=40):
+    from PIL import Image
+    img = _picture(w, h, seed, noise)
+    bio = io.BytesIO()
+    if ss == "L":
+        Image.fromarray(img[..., 0]).save(bio, "JPEG", quality=q, restart_marker_blocks=rst, optimize=optimize)
+    else:
+        Image.fromarray(img).save(bio, "JPEG", quality=q, subsampling=ss, restart_marker_blocks=rst, optimize=optimize)
+    return bio.getvalue()
+
+
+def _expected_rgb(checker, jpg):
+    with J.Decoder(jpg, impl="jfront") as dec:
+        h = dec.decode_header()
+        quant = dec.decode_image("quant")["coef"]
+    g = oracle.geometry(h.width, h.height, h.hsamp, h.vsamp)
+    rgb, _ = checker.decode_image(g, quant, h.qtabs, h.tq, nthreads=8)
+    return rgb
+
+
+def test_files_of_every_kind_match_the_sequential_reader_and_the_oracle(gpu_ctx, checker):
+    pytest.importorskip("PIL")
+    files = [_jpeg(1920, 1080, 2), _jpeg(1920, 1080, 2, rst=120), _jpeg(1000, 563, 1, rst=7, q=60, optimize=True),
+             _jpeg(2048, 1536, 0, q=95), _jpeg(1537, 771, 2, rst=97, q=30), _jpeg(640, 480, "L", rst=80),
+             _jpeg(333, 222, "L", q=98, optimize=True), _jpeg(3840, 2160, 2, noise=24), _jpeg(3840, 2160, 2, rst=240),
+             _jpeg(17, 9, 2), _jpeg(64, 64, 2, rst=1)]
+    files += [load(n)[0] for n in NAMES]
+    got, gi = gpu_ctx.decode_jpegs(files, entropy="gpu")
+    ref, ri = gpu_ctx.decode_jpegs(files, entropy="cpu")
+    for k, (a, b) in enumerate(zip(gi, ri)):
+        assert a.status == 0 and b.status == 0, k
+        assert (a.rgb_off, a.rgb_len) == (b.rgb_off, b.rgb_len)
+        assert np.array_equal(got[a.rgb_off:a.rgb_off + a.rgb_len], ref[b.rgb_off:b.rgb_off + b.rgb_len]), k
+    # decoded on the device, in parallel pieces (not through the fallback)
+    assert gi[0].tasks > 1000 and gi[7].tasks > 10000 and gi[8].tasks > 10000
+    for k in (0, 2, 5, 9):
+        want = _expected_rgb(checker, files[k])
+        assert np.array_equal(got[gi[k].rgb_off:gi[k].rgb_off + gi[k].rgb_len].reshape(gi[k].shape), want), k
+
+
+def test_a_batch_larger_than_one_chunk(gpu_ctx):
+    """More coefficients than one 192 MB chunk: several groups on alternating streams, same
+    pixels as the sequential reader; run twice (buffers and the cached plan are reused)."""
+    pytest.importorskip("PIL")
+    base = [_jpeg(3840, 2160, 2, seed=s, noise=16) for s in range(3)] + [_jpeg(1280, 720, 1, rst=40, seed=9)]
+    files = [base[i % len(base)] for i in range(11)]
+    ref, ri = gpu_ctx.decode_jpegs(files, entropy="cpu")
+    for _ in range(2):
+        got, gi = gpu_ctx.decode_jpegs(files, entropy="gpu")
+        assert all(i.status == 0 and i.tasks > 1 for i in gi)
+        assert np.array_equal(got, ref)
+
+
+def test_damaged_scans_give_what_the_sequential_reader_gives(gpu_ctx, capfd):
+    """Bytes flipped inside the scan, a cut file, a file with its restart markers renumbered: the
+    device decoder must flag them and the outcome (pixels or rejection) must be the sequential
+    reader's."""
+    pytest.importorskip("PIL")
+    good = _jpeg(640, 480, 2, rst=20)
+    rng = np.random.default_rng(3)
+    bad = []
+    for k in range(6):
+        b = bytearray(good)
+        for pos in rng.integers(len(b) // 2, len(b) - 4, size=1 + k):
+            b[pos] = int(rng.integers(0, 255))
+        bad.append(bytes(b))
+    bad.append(good[:len(good) * 3 // 5])
+    renum = bytearray(good)
+    for i in range(len(renum) - 1):
+        if renum[i] == 0xFF and 0xD0 <= renum[i + 1] <= 0xD7:
+            renum[i + 1] = 0xD0 + ((renum[i + 1] - 0xD0 + 3) & 7)
+    bad.append(bytes(renum))
+    files = [good] + bad + [good]
+    got, gi = gpu_ctx.decode_jpegs(files, strict=False, entropy="gpu")
+    ref, ri = gpu_ctx.decode_jpegs(files, strict=False, entropy="cpu")
+    assert gi[0].status == 0 and gi[-1].status == 0 and gi[0].tasks > 1
+    for k, (a, b) in enumerate(zip(gi, ri)):
+        assert a.status == b.status, (k, a.status, b.status, a.message, b.message)
+        if a.status == 0:
+            assert np.array_equal(got[a.rgb_off:a.rgb_off + a.rgb_len], ref[b.rgb_off:b.rgb_off + b.rgb_len]), k
+    capfd.readouterr()

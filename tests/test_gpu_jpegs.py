@@ -23,9 +23,10 @@ def _expected_rgb(checker, jpg):
     return rgb
 
 
-def test_golden_files_decode_to_the_oracles_pixels(gpu_ctx):
+@pytest.mark.parametrize("entropy", ["cpu", "gpu"])
+def test_golden_files_decode_to_the_oracles_pixels(gpu_ctx, entropy):
     files = [load(n)[0] for n in NAMES]
-    rgb, infos = gpu_ctx.decode_jpegs(files, nthreads=4)
+    rgb, infos = gpu_ctx.decode_jpegs(files, nthreads=4, entropy=entropy)
     for name, inf in zip(NAMES, infos):
         _, z, _ = load(name)
         assert inf.status == 0
@@ -55,7 +56,7 @@ def test_large_files_split_by_restart_interval(gpu_ctx, checker):
     pytest.importorskip("PIL")
     files = _big_jpegs()
     for nthreads in (1, 16):
-        rgb, infos = gpu_ctx.decode_jpegs(files, nthreads=nthreads)
+        rgb, infos = gpu_ctx.decode_jpegs(files, nthreads=nthreads, entropy="cpu")
         assert infos[0].tasks == 1 and infos[1].tasks > 1 and infos[6].tasks > 8
         for jpg, inf in zip(files, infos):
             assert inf.status == 0
@@ -64,15 +65,16 @@ def test_large_files_split_by_restart_interval(gpu_ctx, checker):
             assert np.array_equal(got, want)
 
 
-def test_bad_files_do_not_stop_the_batch(gpu_ctx, capfd):
+@pytest.mark.parametrize("entropy", ["cpu", "gpu"])
+def test_bad_files_do_not_stop_the_batch(gpu_ctx, capfd, entropy):
     good = load("c420_64x48")[0]
     cut = load("c420_rst_80x48")[0][:600]          # scan runs out: decodes what is there, like the reference
     files = [good, b"junk", good, cut]
-    rgb, infos = gpu_ctx.decode_jpegs(files, strict=False)
+    rgb, infos = gpu_ctx.decode_jpegs(files, strict=False, entropy=entropy)
     assert [i.status for i in infos][:3] == [0, 1, 0]
     z = load("c420_64x48")[1]
     for i in (0, 2):
         assert np.array_equal(rgb[infos[i].rgb_off:infos[i].rgb_off + infos[i].rgb_len], z["rgb"])
     with pytest.raises(RuntimeError):
-        gpu_ctx.decode_jpegs([b"junk", b""])
+        gpu_ctx.decode_jpegs([b"junk", b""], entropy=entropy)
     capfd.readouterr()

@@ -1,0 +1,120 @@
+"""GPU entropy decoder, checked on the CPU: the per-thread decoding loop, sinks and address
+arithmetic of jgpu_huff_core.h (the code the kernels run) driven by a host emulation of the
+kernels' choreography (tests/host_core/huff_host.cpp), against the sequential reader and the
+reference reader's own QUANT planes (goldens, src/xjpeg.c:449-632)."""
+import ctypes as C
+import io
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import jpeg_gpu_b200 as J
+from golden_util import NAMES, load
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CSRC = os.path.join(ROOT, "jpeg_gpu_b200", "csrc")
+
+
+@pytest.fixture(scope="module")
+def emu(tmp_path_factory):
+    d = tmp_path_factory.mktemp("huff_host")
+    objs = []
+    inc = ["-I", CSRC, "-I", os.path.join(ROOT, "include")]
+    for src in ("jgpu_front.c", "jgpu_host.c", "jgpu_huff_prep.c"):
+        o = str(d / (src + ".o"))
+        subprocess.run(["gcc", "-std=c99", "-O2", "-fPIC", *inc, "-c", "-o", o, os.path.join(CSRC, src)], check=True)
+        objs.append(o)
+    so = str(d / "huff_host.so")
+    subprocess.run(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", *inc, "-o", so,
+                    os.path.join(ROOT, "tests", "host_core", "huff_host.cpp"), *objs], check=True)
+    lib = C.CDLL(so)
+    lib.huff_emulate.restype = C.c_longlong
+    lib.huff_emulate.argtypes = [C.c_char_p, C.c_int, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int,
+                                 C.POINTER(C.c_uint), C.POINTER(C.c_int)]
+    lib.huff_table_selfcheck.argtypes = [C.c_char_p, C.c_char_p]
+    return lib
+
+
+def emulate(lib, jpg, subseq_words=32, cta=256, passes=3):
+    cap = 1 << 26
+    coef = np.zeros(cap, dtype=np.int16)
+    status = C.c_uint(0)
+    stats = (C.c_int * 4)()
+    n = lib.huff_emulate(jpg, len(jpg), coef.ctypes.data_as(C.c_void_p), cap, subseq_words, cta, passes,
+                         C.byref(status), stats)
+    return n, coef[:max(n, 0)], status.value, list(stats)
+
+
+def sequential_quant(jpg):
+    with J.Decoder(jpg, impl="jfront") as dec:
+        dec.decode_header()
+        return dec.decode_image("quant")["coef"]
+
+
+def test_decoder_tables_agree_with_the_canonical_procedure(emu):
+    """jgpu_huff_build_table + lookup on all 65536 windows == T.81 F.2.2.3, for the Annex K
+    luminance AC table and for a skewed table with 16-bit codes."""
+    k5_counts = bytes([0, 2, 1, 3, 3, 2, 4, 3, 5, 5, 4, 4, 0, 0, 1, 0x7d])
+    k5_syms = bytes(range(162))
+    assert emu.huff_table_selfcheck(k5_counts, k5_syms) == 0
+    skew = bytes([1] * 15 + [2])
+    assert emu.huff_table_selfcheck(skew, bytes(range(17))) == 0
+    assert emu.huff_table_selfcheck(bytes([3] + [0] * 15), bytes(range(3))) == -1   # over-subscribed
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_golden_files_match_the_reference_readers_planes(emu, name):
+    """Kernel geometry shrunk (1-word subsequences, 4-thread CTAs) so that these small files
+    cross subsequence, CTA and launch boundaries; planes == xjpeg's own QUANT output."""
+    jpg, z, _ = load(name)
+    for (words, cta, passes) in ((1, 4, 400), (2, 8, 100), (4, 16, 12), (32, 256, 3)):
+        n, coef, status, stats = emulate(emu, jpg, words, cta, passes)
+        assert n == z["quant"].size and status == 0, (name, words, cta, status, stats)
+        assert np.array_equal(coef, z["quant"].reshape(-1)), (name, words, cta)
+
+
+def _photo_like(w, h, seed):
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:h, 0:w]
+    base = np.stack([(xx * 5 + yy * 3) % 256, (yy * 7 + xx) % 256, (xx * 2 + yy * 9) % 256], -1)
+    return np.clip(base + rng.integers(-40, 41, size=base.shape), 0, 255).astype(np.uint8)
+
+
+CASES = [(640, 480, 2, 0, 85), (640, 480, 2, 40, 85), (517, 389, 1, 7, 60), (512, 512, 0, 0, 95),
+         (333, 222, "L", 0, 75), (333, 222, "L", 5, 30), (1920, 1080, 2, 0, 85), (1280, 720, 2, 80, 50)]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[f"{c[0]}x{c[1]}_{c[2]}_rst{c[3]}_q{c[4]}" for c in CASES])
+def test_generated_files_match_the_sequential_reader(emu, case):
+    Image = pytest.importorskip("PIL.Image")
+    w, h, ss, rst, q = case
+    img = _photo_like(w, h, w + h)
+    bio = io.BytesIO()
+    if ss == "L":
+        Image.fromarray(img[..., 0]).save(bio, "JPEG", quality=q, restart_marker_blocks=rst)
+    else:
+        Image.fromarray(img).save(bio, "JPEG", quality=q, subsampling=ss, restart_marker_blocks=rst,
+                                  optimize=(q == 60))
+    jpg = bio.getvalue()
+    want = sequential_quant(jpg)
+    n, coef, status, stats = emulate(emu, jpg)
+    assert n == want.size and status == 0, (status, stats)
+    assert np.array_equal(coef, want)
+    # the states settle in a handful of rounds: that is what makes the method parallel
+    assert stats[2] <= 24, stats
+
+
+def test_too_few_sync_launches_are_detected_not_decoded_wrong(emu):
+    """With tiny CTAs and a single sync launch the states cannot cross CTA boundaries: the
+    write pass must flag the file (the runtime then falls back to the sequential reader)."""
+    jpg, z, _ = load("c420_q10_96x64")
+    n, coef, status, stats = emulate(emu, jpg, 1, 2, 1)
+    assert n > 0 and (status & 2), (status, stats)
+
+
+def test_truncated_scan_is_flagged(emu):
+    jpg = load("c420_64x48")[0]
+    n, coef, status, stats = emulate(emu, jpg[:len(jpg) * 2 // 3])
+    assert n > 0 and (status & 4), (status, stats)
