@@ -14,6 +14,7 @@
  *   k_huff_dc     one CTA per (restart interval, component): prefix sum of DC differences.
  */
 #include <cuda_runtime.h>
+#include <stddef.h>
 #include <stdint.h>
 #include <algorithm>
 
@@ -38,15 +39,92 @@ struct SyncSmem {
   unsigned char zz[64];
 };
 
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds_u16(uint32_t a) {
+  uint32_t v;
+  asm volatile("{\n\t.reg .u16 t;\n\tld.shared.u16 t, [%1];\n\tcvt.u32.u16 %0, t;\n\t}" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds_u8(uint32_t a) {
+  uint32_t v;
+  asm volatile("{\n\t.reg .u16 t;\n\tld.shared.u8 t, [%1];\n\tcvt.u32.u16 %0, t;\n\t}" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ unsigned long long lds_u64(uint32_t a) {
+  unsigned long long v;
+  asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a));
+  return v;
+}
+
+/* The accessor jgpu_huff_core.h asks for, over 32-bit shared-memory addresses computed once
+ * per thread: explicit ld.shared, so the hot loop holds no generic pointer for the compiler to
+ * convert (it re-read %ctaid / the shared window base inside the loop when it did). */
 template <int S>
-struct SmemWords {
-  const uint32_t *w;
-  uint32_t base; /* file-relative index of the CTA's first word */
-  __device__ __forceinline__ uint32_t operator()(uint32_t idx) const {
-    const uint32_t l = idx - base, row = l / S, col = l % S;
-    return w[row * S + (col ^ (row & (S - 1)))];
+struct DevMem {
+  uint32_t words;      /* shared address of SyncSmem::words */
+  uint32_t base_word;  /* file-relative index of the CTA's first word */
+  uint32_t tabs, file, zz;
+  __device__ __forceinline__ uint32_t word(uint32_t i) const {
+    const uint32_t l = i - base_word, row = l / S;
+    return lds_u32(words + 4u * ((l & ~(uint32_t)(S - 1)) | ((l ^ row) & (S - 1))));
   }
+  __device__ __forceinline__ uint32_t lut(uint32_t t, uint32_t i) const {
+    return lds_u16(tabs + t * (uint32_t)sizeof(jgpu_huff_table) + 2u * i);
+  }
+  __device__ __forceinline__ uint32_t limit(uint32_t t, int len) const {
+    return lds_u32(tabs + t * (uint32_t)sizeof(jgpu_huff_table) + (uint32_t)offsetof(jgpu_huff_table, limit) + 4u * len);
+  }
+  __device__ __forceinline__ int32_t delta(uint32_t t, int len) const {
+    return (int32_t)lds_u32(tabs + t * (uint32_t)sizeof(jgpu_huff_table) + (uint32_t)offsetof(jgpu_huff_table, delta) + 4u * len);
+  }
+  __device__ __forceinline__ uint32_t symbol(uint32_t t, int i) const {
+    return lds_u8(tabs + t * (uint32_t)sizeof(jgpu_huff_table) + (uint32_t)offsetof(jgpu_huff_table, symbols) + (uint32_t)i);
+  }
+  __device__ __forceinline__ uint32_t blk_table(uint32_t c) const {
+    return 2u * lds_u8(file + (uint32_t)offsetof(jgpu_huff_file, blk_comp) + c);
+  }
+  __device__ __forceinline__ int64_t blk_base(int c) const {
+    return (int64_t)lds_u64(file + (uint32_t)offsetof(jgpu_huff_file, blk_base) + 8u * c);
+  }
+  __device__ __forceinline__ int32_t blk_xs(int c) const {
+    return (int32_t)lds_u32(file + (uint32_t)offsetof(jgpu_huff_file, blk_xs) + 4u * c);
+  }
+  __device__ __forceinline__ int32_t blk_ys(int c) const {
+    return (int32_t)lds_u32(file + (uint32_t)offsetof(jgpu_huff_file, blk_ys) + 4u * c);
+  }
+  __device__ __forceinline__ uint32_t zigzag(int k) const { return lds_u8(zz + (uint32_t)k); }
 };
+
+/* A value the compiler must keep in a register: what comes out of a volatile asm cannot be
+ * recomputed, and these addresses are otherwise rebuilt from special registers (S2R, tens of
+ * cycles on the short scoreboard) at every use inside the loop. */
+__device__ __forceinline__ uint32_t pinned(uint32_t v) {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(v));
+  return r;
+}
+
+template <int S>
+__device__ __forceinline__ DevMem<S> dev_mem(const SyncSmem<S> &sm, int first) {
+  DevMem<S> m;
+  m.words = pinned((uint32_t)__cvta_generic_to_shared(sm.words));
+  m.base_word = pinned((uint32_t)first * S);
+  m.tabs = pinned((uint32_t)__cvta_generic_to_shared(sm.tabs));
+  m.file = pinned((uint32_t)__cvta_generic_to_shared(&sm.file));
+  m.zz = pinned((uint32_t)__cvta_generic_to_shared(sm.zz));
+  return m;
+}
+
+/* %ctaid.x, read once (a plain blockIdx.x is cheap to re-read, so the compiler does, in loops) */
+__device__ __forceinline__ int cta_x() {
+  int v;
+  asm volatile("mov.u32 %0, %%ctaid.x;" : "=r"(v));
+  return v;
+}
 
 /* Stages the file descriptor, its tables and the CTA's words.  `count` subsequences. */
 template <int S>
@@ -82,7 +160,7 @@ __device__ __forceinline__ void stage(SyncSmem<S> &sm, const jgpu_huff_file *fil
 }
 
 template <int S>
-__global__ void __launch_bounds__(kCta)
+__global__ void __launch_bounds__(kCta, 4)
 k_huff_sync(const jgpu_huff_file *__restrict__ files, const uint32_t *__restrict__ stream,
             const jgpu_huff_table *__restrict__ tables, const uint32_t *__restrict__ seg_first,
             uint32_t *__restrict__ state, uint32_t *__restrict__ nslots, uint32_t *__restrict__ segid,
@@ -90,12 +168,13 @@ k_huff_sync(const jgpu_huff_file *__restrict__ files, const uint32_t *__restrict
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SyncSmem<S> &sm = *reinterpret_cast<SyncSmem<S> *>(smem_raw);
   const jgpu_huff_file &gf = files[blockIdx.y];
-  const int first = (int)blockIdx.x * kCta;
+  const int bx = cta_x();
+  const int first = bx * kCta;
   if (first >= (int)gf.n_subseq) return;
   const int count = min(kCta, (int)gf.n_subseq - first);
   const int t = threadIdx.x;
   const uint32_t gi = gf.subseq0 + (uint32_t)first + (uint32_t)min(t, count - 1);
-  const uint32_t cslot = gf.cta0 + blockIdx.x;
+  const uint32_t cslot = gf.cta0 + (uint32_t)bx;
   uint32_t new0 = 0;
   if (pass > 0) {
     /* Did the state handed to this CTA change since the last launch?  If not, neither does
@@ -138,13 +217,13 @@ k_huff_sync(const jgpu_huff_file *__restrict__ files, const uint32_t *__restrict
   if (t == 0) sm.s_out[count] = pass > 0 ? carry_in[cslot + 1] : 0u;
   __syncthreads();
 
-  const SmemWords<S> words = {sm.words, (uint32_t)first * S};
+  const DevMem<S> mem = dev_mem<S>(sm, first);
+  const int bpm = sm.file.bpm;
   for (;;) {
     if (need && t < count) {
       huff::NullSink sink;
       uint32_t err = 0;
-      sm.s_out[t + 1] = huff::decode_subsequence(sm.tabs, sm.file.blk_comp, sm.file.bpm, words,
-                                                 (uint32_t)(first + t) * S, S, s_in, sink, &n, &err);
+      sm.s_out[t + 1] = huff::decode_subsequence(mem, bpm, (uint32_t)(first + t) * S, S, s_in, sink, &n, &err);
     }
     __syncthreads();
     const uint32_t ni = (t == 0 || is_first) ? s_in : sm.s_out[t];
@@ -218,7 +297,7 @@ k_huff_scan(const jgpu_huff_file *__restrict__ files, const uint32_t *__restrict
 }
 
 template <int S>
-__global__ void __launch_bounds__(kCta)
+__global__ void __launch_bounds__(kCta, 4)
 k_huff_write(const jgpu_huff_file *__restrict__ files, const uint32_t *__restrict__ stream,
              const jgpu_huff_table *__restrict__ tables, const uint32_t *__restrict__ seg_first,
              const uint32_t *__restrict__ state, const uint32_t *__restrict__ nslots,
@@ -227,7 +306,7 @@ k_huff_write(const jgpu_huff_file *__restrict__ files, const uint32_t *__restric
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SyncSmem<S> &sm = *reinterpret_cast<SyncSmem<S> *>(smem_raw);
   const jgpu_huff_file &gf = files[blockIdx.y];
-  const int first = (int)blockIdx.x * kCta;
+  const int first = cta_x() * kCta;
   if (first >= (int)gf.n_subseq) return;
   const int count = min(kCta, (int)gf.n_subseq - first);
   const int t = threadIdx.x;
@@ -244,11 +323,11 @@ k_huff_write(const jgpu_huff_file *__restrict__ files, const uint32_t *__restric
   if ((slot0 & 63u) != JGPU_HUFF_STATE_Z(st) || (uint32_t)(g0 % f.bpm) != JGPU_HUFF_STATE_C(st)) {
     flags = JGPU_HUFF_ERR_SYNC;
   } else if (g0 < seg_blocks) {
-    huff::StoreSink sink;
-    sink.start(&f, sm.zz, coef, seg_mcu0, g0, seg_blocks);
-    const SmemWords<S> words = {sm.words, (uint32_t)first * S};
+    const DevMem<S> mem = dev_mem<S>(sm, first);
+    huff::StoreSink<DevMem<S>> sink;
+    sink.start(&mem, f.bpm, f.nhmb, coef, seg_mcu0, g0, seg_blocks);
     uint32_t n = 0, err = 0;
-    const uint32_t out = huff::decode_subsequence(sm.tabs, f.blk_comp, f.bpm, words, i * S, S, st, sink, &n, &err);
+    const uint32_t out = huff::decode_subsequence(mem, f.bpm, i * S, S, st, sink, &n, &err);
     if (err) flags |= JGPU_HUFF_ERR_CODE;
     if (sink.g < seg_blocks) {
       /* the interval goes on: into the next subsequence, which must start where this one ended */

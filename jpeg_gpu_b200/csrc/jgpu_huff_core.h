@@ -75,6 +75,10 @@ typedef struct jgpu_huff_file {
   uint8_t blk_dy[JGPU_HUFF_MAX_BLOCKS + 2];
   uint32_t table0;       /* index of its first jgpu_huff_table */
   uint32_t reserved;
+  /* address of block c of MCU (mbx, mby), in int16 from the coefficient buffer's start:
+   * blk_base[c] + mbx * blk_xs[c] + mby * blk_ys[c]  (jgpu_huff_file_finish) */
+  int64_t blk_base[JGPU_HUFF_MAX_BLOCKS + 2];
+  int32_t blk_xs[JGPU_HUFF_MAX_BLOCKS + 2], blk_ys[JGPU_HUFF_MAX_BLOCKS + 2];
 } jgpu_huff_file;
 
 /* status bits the kernels raise per file */
@@ -99,25 +103,51 @@ typedef struct jgpu_huff_file {
 namespace jgpu {
 namespace huff {
 
+/* The decoding loop reaches its data through a small accessor object, so that the kernels can
+ * hand it 32-bit shared-memory addresses (explicit ld.shared, nothing for the compiler to
+ * re-derive inside the loop) while the host emulation hands it plain pointers:
+ *   word(i)            big-endian 32-bit word i of the file's unstuffed scan
+ *   lut(t, i)          jgpu_huff_table[t].lut[i]          t = 2 * component + (AC ? 1 : 0)
+ *   limit(t, L), delta(t, L), symbol(t, i)                the canonical part of table t
+ *   blk_table(c)       2 * component of block c of the MCU
+ *   blk_base(c), blk_xs(c), blk_ys(c), zigzag(k)          write pass only */
+struct HostMem {
+  const uint32_t *words;   /* the file's scan, as stored (big-endian bytes) */
+  const jgpu_huff_table *tabs;
+  const jgpu_huff_file *f;
+  const unsigned char *zz;
+  uint32_t word(uint32_t i) const { return __builtin_bswap32(words[i]); }
+  uint32_t lut(uint32_t t, uint32_t i) const { return tabs[t].lut[i]; }
+  uint32_t limit(uint32_t t, int len) const { return tabs[t].limit[len]; }
+  int32_t delta(uint32_t t, int len) const { return tabs[t].delta[len]; }
+  uint32_t symbol(uint32_t t, int i) const { return tabs[t].symbols[i]; }
+  uint32_t blk_table(uint32_t c) const { return 2u * f->blk_comp[c]; }
+  int64_t blk_base(int c) const { return f->blk_base[c]; }
+  int32_t blk_xs(int c) const { return f->blk_xs[c]; }
+  int32_t blk_ys(int c) const { return f->blk_ys[c]; }
+  uint32_t zigzag(int k) const { return zz[k]; }
+};
+
 /* Symbol at the head of the 16-bit window `look`: (length << 8) | symbol, or 0 for a bit
  * pattern that is no code of the table. */
-JGPU_HUFF_HD uint32_t lookup(const jgpu_huff_table *t, uint32_t look) {
-  uint32_t e = t->lut[look >> (16 - JGPU_HUFF_LUT_BITS)];
+template <typename Mem>
+JGPU_HUFF_HD uint32_t lookup(const Mem &mem, uint32_t t, uint32_t look) {
+  uint32_t e = mem.lut(t, look >> (16 - JGPU_HUFF_LUT_BITS));
   if (e) return e;
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
   for (int len = JGPU_HUFF_LUT_BITS + 1; len <= 16; len++) {
-    if (look < t->limit[len]) {
-      return ((uint32_t)len << 8) | t->symbols[(int)(look >> (16 - len)) + t->delta[len]];
+    if (look < mem.limit(t, len)) {
+      return ((uint32_t)len << 8) | mem.symbol(t, (int)(look >> (16 - len)) + mem.delta(t, len));
     }
   }
   return 0;
 }
 
 /* Decodes the symbols that START inside one subsequence.
- *   word_at(w)    big-endian 32-bit word w of the file's unstuffed scan (may be asked for up to
- *                 three words past the subsequence)
+ *   mem           accessor (above); word() may be asked for up to three words past the
+ *                 subsequence
  *   w0, nwords    the subsequence
  *   state         packed (p, c, z) at its start
  *   sink.coef(k, v)    a coefficient: zig-zag index k of the current block, value v (DC: the
@@ -127,9 +157,8 @@ JGPU_HUFF_HD uint32_t lookup(const jgpu_huff_table *t, uint32_t look) {
  * Returns the state at the end; *n_out = coefficient slots advanced; *err is raised on a bit
  * pattern that is no code and on a run past coefficient 63 (the reference's reader does not
  * check either, src/xjpeg.c:67-78; ours fails on both, jgpu_front.c decode_symbol/decode_mcu). */
-template <typename WordAt, typename Sink>
-JGPU_HUFF_HD uint32_t decode_subsequence(const jgpu_huff_table *tabs, const uint8_t *blk_comp, int bpm,
-                                         WordAt word_at, uint32_t w0, int nwords, uint32_t state,
+template <typename Mem, typename Sink>
+JGPU_HUFF_HD uint32_t decode_subsequence(const Mem &mem, int bpm, uint32_t w0, int nwords, uint32_t state,
                                          Sink &sink, uint32_t *n_out, uint32_t *err) {
   int pos = (int)JGPU_HUFF_STATE_P(state);
   uint32_t c = JGPU_HUFF_STATE_C(state), z = JGPU_HUFF_STATE_Z(state);
@@ -137,58 +166,47 @@ JGPU_HUFF_HD uint32_t decode_subsequence(const jgpu_huff_table *tabs, const uint
   uint32_t n = 0, bad = 0;
   /* 64-bit window, MSB first: `avail` valid bits */
   uint32_t next = w0 + (uint32_t)(pos >> 5);
-  uint64_t buf = ((uint64_t)word_at(next) << 32) | word_at(next + 1);
+  uint64_t buf = ((uint64_t)mem.word(next) << 32) | mem.word(next + 1);
   next += 2;
   buf <<= (pos & 31);
   int avail = 64 - (pos & 31);
+  uint32_t tdc = mem.blk_table(c);   /* DC table of the current block; its AC table follows */
+  /* The body is written without branches on the kind of symbol (DC / AC / end of block): the
+   * threads of a warp sit at unrelated places of their blocks, and every divergent branch
+   * would be paid by all of them. */
   while (pos < end) {
     if (avail < 32) {
-      buf |= (uint64_t)word_at(next++) << (32 - avail);
+      buf |= (uint64_t)mem.word(next++) << (32 - avail);
       avail += 32;
     }
-    const jgpu_huff_table *t = tabs + 2 * blk_comp[c] + (z != 0);
-    uint32_t e = lookup(t, (uint32_t)(buf >> 48));
-    if (!e) {
-      bad = 1;
-      e = 16u << 8;   /* skip the window like jgpu_front.c decode_symbol; symbol 0 */
-    }
+    const uint32_t ac = z != 0;
+    uint32_t e = lookup(mem, tdc + ac, (uint32_t)(buf >> 48));
+    bad |= e == 0;
+    e = e ? e : (16u << 8);   /* no code: skip the window like jgpu_front.c decode_symbol; symbol 0 */
     const int len = (int)(e >> 8);
     const uint32_t sym = e & 0xffu;
     const int s = (int)(sym & 15u);
-    /* T.81 F.2.2.1 EXTEND on the s bits after the code */
+    /* T.81 F.2.2.1 EXTEND on the s bits after the code (s = 0 gives 0) */
     const uint32_t hi = (uint32_t)((buf << len) >> 32);
-    int v = 0;
-    if (s) {
-      const uint32_t bits = hi >> (32 - s);
-      v = bits < (1u << (s - 1)) ? (int)bits - (1 << s) + 1 : (int)bits;
-    }
+    const uint32_t bits = (hi >> 1) >> (31 - s);
+    const uint32_t half = (1u << s) >> 1;
+    const int v = bits < half ? (int)bits - (1 << s) + 1 : (int)bits;
     buf <<= (len + s);
     avail -= len + s;
     pos += len + s;
-    bool done = false;
-    if (z == 0) {
-      if (v) sink.coef(0, v);
-      z = 1;
-      n += 1;
-    } else if (sym == 0) { /* end of block */
-      n += 64 - z;
-      done = true;
-    } else {
-      const uint32_t k = z + (sym >> 4);
-      if (k > 63) {
-        bad = 1;
-        n += 64 - z;
-        done = true;
-      } else {
-        if (v) sink.coef((int)k, v);
-        n += k + 1 - z;
-        z = k + 1;
-        done = z == 64;
-      }
-    }
-    if (done) {
+    /* where the coefficient goes and where the block stands afterwards */
+    const uint32_t k = z + (ac ? sym >> 4 : 0u);       /* DC: z = 0, k = 0 */
+    const uint32_t over = k > 63u;                     /* run past the block: jgpu_front.c fails */
+    const uint32_t stop = (ac & (uint32_t)(sym == 0)) | over;   /* end of block */
+    bad |= over;
+    if (v != 0 && !stop) sink.coef((int)k, v);
+    const uint32_t znew = stop ? 64u : k + 1;
+    n += znew - z;
+    z = znew;
+    if (z == 64) {
       z = 0;
       c = c + 1 == (uint32_t)bpm ? 0 : c + 1;
+      tdc = mem.blk_table(c);
       if (sink.block_done()) break;
     }
   }
@@ -210,46 +228,48 @@ struct NullSink {
    41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,        \
    30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63}
 
-/* First int16 of block `c` of MCU `mcu` in the coefficient buffer: the placement of
- * src/xjpeg.c:550-563 (block-linear inside a plane for power-of-two decimation). */
-JGPU_HUFF_HD int64_t block_offset(const jgpu_huff_file &f, int mcu, int c) {
-  const int comp = f.blk_comp[c];
-  const int mbx = mcu % f.nhmb, mby = mcu / f.nhmb;
-  const int bx = mbx * f.hs[comp] + f.blk_dx[c];
-  const int by = mby * f.vs[comp] + f.blk_dy[c];
-  return f.plane_off[comp] + ((int64_t)by * f.hblocks[comp] + bx) * 64;
-}
-
 /* Sink of the write pass: stores coefficients of the blocks [g, seg_blocks) of one restart
- * interval, g counted in scan order from the interval's first block. */
+ * interval, g counted in scan order from the interval's first block.  Moving to the next block
+ * is a few adds (no division): the threads of a warp finish blocks at unrelated moments, so
+ * that step runs in almost every iteration of the warp. */
+template <typename Mem>
 struct StoreSink {
-  const jgpu_huff_file *f;
-  const unsigned char *zz; /* JGPU_HUFF_ZIGZAG_NATURAL */
+  const Mem *mem;
   int16_t *base;     /* the batch's coefficient buffer */
-  int mcu;           /* current MCU (image-wide index) */
+  int bpm, nhmb;
+  int mbx, mby;      /* current MCU */
   int c;             /* current block inside it */
   int64_t g, seg_blocks;
   int16_t *blk;      /* current block */
-  JGPU_HUFF_HD void start(const jgpu_huff_file *file, const unsigned char *zigzag, int16_t *coef_base, int seg_mcu0,
+  JGPU_HUFF_HD void locate() {
+    blk = base + mem->blk_base(c) + (int64_t)mbx * mem->blk_xs(c) + (int64_t)mby * mem->blk_ys(c);
+  }
+  JGPU_HUFF_HD void start(const Mem *m, int blocks_per_mcu, int mcus_per_row, int16_t *coef_base, int seg_mcu0,
                           int64_t g0, int64_t nblocks) {
-    f = file;
-    zz = zigzag;
+    mem = m;
+    bpm = blocks_per_mcu;
+    nhmb = mcus_per_row;
     base = coef_base;
     g = g0;
     seg_blocks = nblocks;
-    mcu = seg_mcu0 + (int)(g0 / file->bpm);
-    c = (int)(g0 % file->bpm);
-    blk = base + block_offset(*f, mcu, c);
+    const int mcu = seg_mcu0 + (int)(g0 / bpm);
+    c = (int)(g0 % bpm);
+    mbx = mcu % nhmb;
+    mby = mcu / nhmb;
+    locate();
   }
-  JGPU_HUFF_HD void coef(int k, int v) { blk[zz[k]] = (int16_t)v; }
+  JGPU_HUFF_HD void coef(int k, int v) { blk[mem->zigzag(k)] = (int16_t)v; }
   JGPU_HUFF_HD bool block_done() {
     g++;
     if (g >= seg_blocks) return true;
-    if (++c == f->bpm) {
+    if (++c == bpm) {
       c = 0;
-      mcu++;
+      if (++mbx == nhmb) {
+        mbx = 0;
+        mby++;
+      }
     }
-    blk = base + block_offset(*f, mcu, c);
+    locate();
     return false;
   }
 };
@@ -281,6 +301,9 @@ extern "C" {
  * counts[L-1] codes of length L, their symbols in code order.  Returns 0, or 1 when the
  * counts over-subscribe the code space. */
 int jgpu_huff_build_table(jgpu_huff_table *t, const unsigned char counts[16], const unsigned char *symbols);
+
+/* Derives blk_base / blk_xs / blk_ys once hs, vs, blk_*, hblocks and plane_off are set. */
+void jgpu_huff_file_finish(jgpu_huff_file *f);
 
 #ifdef __cplusplus
 }

@@ -31,3 +31,16 @@ int jgpu_huff_build_table(jgpu_huff_table *t, const unsigned char counts[16], co
   memcpy(t->symbols, symbols, (size_t)k);
   return 0;
 }
+
+/* The placement of src/xjpeg.c:550-563 (block-linear inside a plane), split into the terms the
+ * write pass adds up: block c of MCU (mbx, mby) sits at plane_off + ((mby*vs + dy) * hblocks +
+ * mbx*hs + dx) * 64. */
+void jgpu_huff_file_finish(jgpu_huff_file *f) {
+  int c;
+  for (c = 0; c < f->bpm; c++) {
+    const int comp = f->blk_comp[c];
+    f->blk_base[c] = f->plane_off[comp] + ((int64_t)f->blk_dy[c] * f->hblocks[comp] + f->blk_dx[c]) * 64;
+    f->blk_xs[c] = f->hs[comp] * 64;
+    f->blk_ys[c] = f->vs[comp] * f->hblocks[comp] * 64;
+  }
+}

@@ -1296,6 +1296,7 @@ static int decode_jpegs_gpu_entropy(jgpu_ctx *ctx, const jgpu_jpeg *files, int n
           f.hblocks[p] = it.lay.plane[p].hblocks;
           f.plane_off[p] = it.desc.coef_off + it.lay.plane[p].coef_off;
         }
+        jgpu_huff_file_finish(&f);
       }
       f.word0 = (uint32_t)(slot[k].stream_off / 4);
       f.subseq0 = slot[k].subseq0;

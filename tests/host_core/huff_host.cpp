@@ -17,10 +17,6 @@ namespace {
 
 const unsigned char kZigzag[64] = JGPU_HUFF_ZIGZAG_NATURAL;
 
-struct HostWords {
-  const uint32_t *w;
-  uint32_t operator()(uint32_t idx) const { return __builtin_bswap32(w[idx]); }
-};
 
 }  // namespace
 
@@ -66,7 +62,8 @@ extern "C" long long huff_emulate(const unsigned char *jpeg, int size, short *co
     f.hblocks[p] = lay.plane[p].hblocks;
     f.plane_off[p] = lay.plane[p].coef_off;
   }
-  const HostWords words = {reinterpret_cast<const uint32_t *>(stream.data())};
+  jgpu_huff_file_finish(&f);
+  const HostMem mem = {reinterpret_cast<const uint32_t *>(stream.data()), tabs.data(), &f, kZigzag};
   const int S = subseq_words;
   const int n = (int)f.n_subseq;
   const int nctas = (n + cta - 1) / cta;
@@ -120,8 +117,7 @@ extern "C" long long huff_emulate(const unsigned char *jpeg, int size, short *co
           if (!need[t]) continue;
           NullSink sink;
           uint32_t err = 0;
-          s_out[t + 1] = decode_subsequence(tabs.data(), f.blk_comp, f.bpm, words, (uint32_t)(first + t) * S, S,
-                                            s_in[t], sink, &nn[t], &err);
+          s_out[t + 1] = decode_subsequence(mem, f.bpm, (uint32_t)(first + t) * S, S, s_in[t], sink, &nn[t], &err);
         }
         bool any = false;
         for (int t = 0; t < count; t++) {
@@ -160,11 +156,10 @@ extern "C" long long huff_emulate(const unsigned char *jpeg, int size, short *co
     if ((slot0 & 63u) != JGPU_HUFF_STATE_Z(st) || (uint32_t)(g0 % f.bpm) != JGPU_HUFF_STATE_C(st)) {
       st_flags |= JGPU_HUFF_ERR_SYNC;
     } else if (g0 < seg_blocks) {
-      StoreSink sink;
-      sink.start(&f, kZigzag, coef, seg_mcu0, g0, seg_blocks);
+      StoreSink<HostMem> sink;
+      sink.start(&mem, f.bpm, f.nhmb, coef, seg_mcu0, g0, seg_blocks);
       uint32_t nn = 0, err = 0;
-      const uint32_t out = decode_subsequence(tabs.data(), f.blk_comp, f.bpm, words, (uint32_t)i * S, S, st, sink,
-                                              &nn, &err);
+      const uint32_t out = decode_subsequence(mem, f.bpm, (uint32_t)i * S, S, st, sink, &nn, &err);
       if (err) st_flags |= JGPU_HUFF_ERR_CODE;
       if (sink.g < seg_blocks) {
         if ((uint32_t)i + 1 == seg_first[seg + 1]) st_flags |= JGPU_HUFF_ERR_SHORT;
@@ -213,7 +208,8 @@ extern "C" int huff_table_selfcheck(const unsigned char *counts, const unsigned 
       k += cnt;
       first = (first + cnt) << 1;
     }
-    if ((int)jgpu::huff::lookup(&t, look) != want) mismatches++;
+    const jgpu::huff::HostMem mem = {nullptr, &t, nullptr, nullptr};
+    if ((int)jgpu::huff::lookup(mem, 0, look) != want) mismatches++;
   }
   return mismatches;
 }
