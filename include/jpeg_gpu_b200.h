@@ -77,6 +77,13 @@ void cuda_decode_set_device(int device);
  * contexts allocated later.  Returns EXIT_FAILURE for any other value. */
 int cuda_decode_set_upload(jpeg_decode_out format);
 
+/* Where decode_image(..., JPEG_DECODE_RGB) does its Huffman decoding: 0 (default) on the host, in
+ * the front end; 1 on the device (jgpu_huff.cu, see jgpu_decode_jpegs_ex): the file's bytes are
+ * uploaded as they are and no coefficient ever exists on the host.  Applies to the built-in
+ * front end only (a front end set with cuda_decode_set_frontend keeps decoding on the host) and
+ * to contexts allocated later.  Returns EXIT_FAILURE for any other value. */
+int cuda_decode_set_entropy(int on_device);
+
 /* Output-surface helpers with the semantics of the reference's
  * image_init / image_zero / image_clear (src/image.c:24-123) and
  * jpeg_info_init / jpeg_info_clear (src/jpeg_info.c:31-61), for callers that

@@ -997,10 +997,15 @@ static int decode_jpegs_cpu_entropy(jgpu_ctx *ctx, const jgpu_jpeg *files, int n
     release_fronts();
     return jgpu_fail("jgpu_decode_jpegs: no decodable file in the batch");
   }
-  if (rgb_off > rgb_cap) {
-    release_fronts();
-    return jgpu_fail("jgpu_decode_jpegs: output needs %lld bytes, buffer has %lld", (long long)rgb_off,
-                     (long long)rgb_cap);
+  {
+    /* the last image ends at its own length, not at the next 256-byte boundary */
+    const JpegItem &last = items[ok.back()];
+    const int64_t need = last.desc.rgb_off + last.lay.rgb_len;
+    if (need > rgb_cap) {
+      release_fronts();
+      return jgpu_fail("jgpu_decode_jpegs: output needs %lld bytes, buffer has %lld", (long long)need,
+                       (long long)rgb_cap);
+    }
   }
   const int m = (int)ok.size();
 
@@ -1203,10 +1208,15 @@ static int decode_jpegs_gpu_entropy(jgpu_ctx *ctx, const jgpu_jpeg *files, int n
     release_fronts();
     return jgpu_fail("jgpu_decode_jpegs: no decodable file in the batch");
   }
-  if (rgb_off > rgb_cap) {
-    release_fronts();
-    return jgpu_fail("jgpu_decode_jpegs: output needs %lld bytes, buffer has %lld", (long long)rgb_off,
-                     (long long)rgb_cap);
+  {
+    /* the last image ends at its own length, not at the next 256-byte boundary */
+    const JpegItem &last = items[ok.back()];
+    const int64_t need = last.desc.rgb_off + last.lay.rgb_len;
+    if (need > rgb_cap) {
+      release_fronts();
+      return jgpu_fail("jgpu_decode_jpegs: output needs %lld bytes, buffer has %lld", (long long)need,
+                       (long long)rgb_cap);
+    }
   }
   const int m = (int)ok.size();
   const unsigned flags = JGPU_OUT_RGB;

@@ -34,9 +34,24 @@ int cuda_decode_set_upload(jpeg_decode_out format) {
   return EXIT_SUCCESS;
 }
 
+/* Where RGB decodes do their Huffman decoding: 0 = the CPU front end (default: it is the
+ * pluggable part), 1 = on the device (jgpu_huff.cu), for the built-in front end only. */
+static int g_entropy_on_device = 0;
+int cuda_decode_set_entropy(int on_device) {
+  if (on_device != 0 && on_device != 1) {
+    fprintf(stderr, "Unsupported entropy decoder %i for cuda wrapper.\n", on_device);
+    return EXIT_FAILURE;
+  }
+  g_entropy_on_device = on_device;
+  return EXIT_SUCCESS;
+}
+
 typedef struct cuda_decode_ctx {
   jpeg_decode_ctx_vtbl front;
   jpeg_decode_ctx *front_ctx;
+  const unsigned char *buf; /* the caller's file bytes (jpeg_info.buf), for the device entropy decoder */
+  int size;
+  int entropy_on_device;
   jgpu_ctx *gpu;        /* created on the first YUV/RGB decode, kept across resets */
   int device;
   int have_header;
@@ -50,6 +65,9 @@ static cuda_decode_ctx *cuda_decode_alloc(jpeg_info *info) {
   ctx->front = g_frontend ? *g_frontend : JFRONT_DECODE_CTX_VTBL;
   ctx->device = g_device;
   ctx->upload = g_upload;
+  ctx->entropy_on_device = g_entropy_on_device && g_frontend == NULL;
+  ctx->buf = info->buf;
+  ctx->size = info->size;
   if (ctx->device < 0) {
     const char *env = getenv("JGPU_DEVICE");
     ctx->device = env ? atoi(env) : 0;
@@ -99,6 +117,26 @@ static int cuda_decode_image(cuda_decode_ctx *ctx, image *img, jpeg_decode_out o
     fprintf(stderr, "Error, decode_image called before decode_header\n");
     return EXIT_FAILURE;
   }
+  if (ctx->entropy_on_device && out == JPEG_DECODE_RGB && img->pixels != NULL) {
+    /* the file's bytes go to the device as they are; nothing is decoded on the host */
+    jgpu_jpeg file;
+    jgpu_jpeg_info jinfo;
+    const int64_t cap = (int64_t)img->width * img->height * 3;
+    if (ctx->gpu == NULL) {
+      ctx->gpu = jgpu_create(ctx->device);
+      if (ctx->gpu == NULL) {
+        fprintf(stderr, "%s\n", jgpu_last_error());
+        return EXIT_FAILURE;
+      }
+    }
+    file.data = ctx->buf;
+    file.size = ctx->size;
+    if (jgpu_decode_jpegs_ex(ctx->gpu, &file, 1, 1, JGPU_ENTROPY_GPU, img->pixels, cap, &jinfo) != EXIT_SUCCESS) {
+      fprintf(stderr, "%s\n", jgpu_last_error());
+      return EXIT_FAILURE;
+    }
+    return EXIT_SUCCESS;
+  }
   if (ctx->upload == JPEG_DECODE_PACK) {
     /* the reader counts words into plane[i].packed (src/xjpeg.c:492,515,532); start from zero */
     for (i = 0; i < img->nplanes && i < NPLANES_MAX; i++) img->plane[i].packed = 0;
@@ -130,6 +168,8 @@ static int cuda_decode_image(cuda_decode_ctx *ctx, image *img, jpeg_decode_out o
 static void cuda_decode_reset(cuda_decode_ctx *ctx, jpeg_info *info) {
   /* device buffers, streams and the cached plan survive; only the parser restarts */
   (*ctx->front.decode_reset)(ctx->front_ctx, info);
+  ctx->buf = info->buf;
+  ctx->size = info->size;
   ctx->have_header = 0;
 }
 

@@ -57,6 +57,27 @@ def test_cuda_backend_with_pack_upload(name):
     assert _capi.lib().cuda_decode_set_upload(_capi.JPEG_DECODE_RGB) == 1   # not an upload format
 
 
+@pytest.mark.parametrize("name", NAMES)
+def test_cuda_backend_with_entropy_decoding_on_the_device(name):
+    """cuda_decode_set_entropy(1): decode_image(RGB) uploads the file as it is and decodes the
+    Huffman scan on the GPU; same pixels, same protocol; YUV still comes through the front end."""
+    from jpeg_gpu_b200 import _capi
+    jpg, z, g = load(name)
+    assert _capi.lib().cuda_decode_set_entropy(1) == 0
+    try:
+        with J.Decoder(jpg, impl="cuda") as dec:
+            for _ in range(2):
+                dec.decode_header()
+                assert np.array_equal(dec.decode_image("rgb")["pixels"].reshape(-1), z["rgb"])
+                dec.decode_reset()
+            dec.decode_header()
+            planes = dec.decode_image("yuv")["planes"]
+            assert np.array_equal(np.concatenate([p.ravel() for p in planes]), z["yuv"])
+    finally:
+        assert _capi.lib().cuda_decode_set_entropy(0) == 0
+    assert _capi.lib().cuda_decode_set_entropy(7) == 1
+
+
 def test_cuda_backend_error_convention():
     jpg, _, _ = load("c420_64x48")
     with J.Decoder(jpg, impl="cuda") as dec:

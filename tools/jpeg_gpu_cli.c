@@ -28,7 +28,7 @@ static const struct option OPTIONS[] = {
     {"help", no_argument, NULL, 'h'},     {"impl", required_argument, NULL, 'i'},
     {"out", required_argument, NULL, 'o'}, {"dump", no_argument, NULL, 'd'},
     {"header", no_argument, NULL, 'H'},   {"frames", required_argument, NULL, 'n'},
-    {NULL, 0, NULL, 0}};
+    {"entropy", required_argument, NULL, 'e'}, {NULL, 0, NULL, 0}};
 
 static void usage(void) {
   fprintf(stderr,
@@ -47,7 +47,10 @@ static void usage(void) {
           "  -d --dump                      Dump jpeg data in the output format.\n"
           "  -H --header                    Print the jpeg header.\n"
           "  -n --frames <count>            Run the decode loop <count> times and report\n"
-          "                                  the time per frame.\n\n"
+          "                                  the time per frame.\n"
+          "  -e --entropy <where>           Where -i cuda -o rgb decodes the Huffman scan.\n"
+          "                                 cpu (default) => in the front end, on the host\n"
+          "                                 gpu => on the device; the file is uploaded as it is\n\n"
           " %s accepts only 8-bit non-hierarchical baseline JPEG files.\n\n",
           NAME, NAME);
 }
@@ -67,7 +70,7 @@ int main(int argc, char *argv[]) {
   image img;
   jpeg_decode_ctx *dec;
 
-  while ((c = getopt_long(argc, argv, "hi:o:dHn:", OPTIONS, NULL)) != EOF) {
+  while ((c = getopt_long(argc, argv, "hi:o:dHn:e:", OPTIONS, NULL)) != EOF) {
     switch (c) {
       case 'i':
         if (strcmp("cuda", optarg) == 0) vtbl = CUDA_DECODE_CTX_VTBL;
@@ -92,6 +95,14 @@ int main(int argc, char *argv[]) {
       case 'd': dump = 1; break;
       case 'H': head = 1; break;
       case 'n': frames = atoi(optarg); break;
+      case 'e':
+        if (strcmp("cpu", optarg) != 0 && strcmp("gpu", optarg) != 0) {
+          fprintf(stderr, "Invalid entropy decoder: %s\n", optarg);
+          usage();
+          return EXIT_FAILURE;
+        }
+        cuda_decode_set_entropy(strcmp("gpu", optarg) == 0);
+        break;
       case 'h':
       default: usage(); return EXIT_FAILURE;
     }
