@@ -422,6 +422,35 @@ def main():
                     ctx.decode_jpegs(files, jpeg_rgb, nthreads=threads, entropy=entropy)
                 dt = time.perf_counter() - t0
                 e2e_jpeg[key] = 3 * len(files) * w * h / 1e6 / dt
+            # the same with the pixels left in device memory (callers whose next stage runs on the GPU):
+            # only the compressed files cross the link
+            jpeg_dev = torch.empty(total, dtype=torch.uint8, device=dev)
+            ctx.decode_jpegs(files, jpeg_dev, nthreads=threads, entropy="gpu")
+            t0 = time.perf_counter()
+            for _ in range(3):
+                ctx.decode_jpegs(files, jpeg_dev, nthreads=threads, entropy="gpu")
+            dt = time.perf_counter() - t0
+            e2e_jpeg["device_out_value"] = 3 * len(files) * w * h / 1e6 / dt
+            del jpeg_dev
+            # the reference's own CPU path for the same files: xjpeg_decode_image(YUV), i.e. Huffman +
+            # dequant + IDCT into planes (no colour conversion: the xjpeg backend has none), one file
+            # per thread on all host cores (oracle/_ref; checker code, timed here as the baseline)
+            try:
+                import oracle
+                from concurrent.futures import ThreadPoolExecutor
+                if oracle.have_reference():
+                    ref = oracle.reference()
+                    k = min(len(files), threads)
+                    ref.ref_decode(files[0], "yuv")
+                    t0 = time.perf_counter()
+                    with ThreadPoolExecutor(threads) as ex:
+                        list(ex.map(lambda f: ref.ref_decode(f, "yuv"), files[:k]))
+                    dt = time.perf_counter() - t0
+                    e2e_jpeg["cpu_reference_value"] = k * w * h / 1e6 / dt
+                    e2e_jpeg["cpu_reference"] = (f"xjpeg_decode_image(YUV) of the compiled reference, {k} files on "
+                                                 f"{threads} threads, planes only (it has no RGB output)")
+            except Exception as exc:   # the checker is optional for this leg
+                e2e_jpeg["cpu_reference"] = f"unavailable: {exc}"
             e2e_jpeg["entropy"] = ("value: Huffman decoding on the GPU (jgpu_huff.cu), host threads only unstuff; "
                                    "cpu_entropy_value: Huffman decoding on the host threads")
             del jpeg_rgb

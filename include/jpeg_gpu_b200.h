@@ -286,6 +286,10 @@ int jgpu_decode_jpegs(jgpu_ctx *ctx, const jgpu_jpeg *files, int n, int nthreads
 #define JGPU_ENTROPY_AUTO 0u
 #define JGPU_ENTROPY_CPU 1u
 #define JGPU_ENTROPY_GPU 2u
+/* OR-ed into flags: h_rgb is DEVICE memory (256-byte aligned) and the pixels stay there -- for
+ * callers whose next stage runs on the GPU.  Implies the GPU entropy decoder; the call still
+ * returns only when the pixels are complete. */
+#define JGPU_JPEGS_DEVICE_OUT 0x100u
 int jgpu_decode_jpegs_ex(jgpu_ctx *ctx, const jgpu_jpeg *files, int n, int nthreads, unsigned flags,
                          uint8_t *h_rgb, int64_t rgb_cap, jgpu_jpeg_info *info);
 

@@ -246,8 +246,10 @@ class Context:
                 raise RuntimeError(f"jgpu_jpegs_probe failed: {_capi.last_error()}")
             rgb = np.zeros(max(int(total), 1), dtype=np.uint8)
         cap = rgb.numel() if hasattr(rgb, "numel") else rgb.size
-        rc = _capi.lib().jgpu_decode_jpegs_ex(self._h, arr, len(files), nthreads, self.ENTROPY[entropy], _addr(rgb),
-                                              cap, raw)
+        flags = self.ENTROPY[entropy]
+        if getattr(rgb, "is_cuda", False):
+            flags |= 0x100   # JGPU_JPEGS_DEVICE_OUT: the pixels stay on the device
+        rc = _capi.lib().jgpu_decode_jpegs_ex(self._h, arr, len(files), nthreads, flags, _addr(rgb), cap, raw)
         infos = _jpeg_infos(raw)
         del keep
         if rc != 0 and (strict or all(i.status for i in infos)):

@@ -35,7 +35,9 @@
 
 #include <stdint.h>
 
+#ifndef JGPU_HUFF_LUT_BITS
 #define JGPU_HUFF_LUT_BITS 10
+#endif
 #define JGPU_HUFF_MAX_BLOCKS 10   /* blocks per MCU, T.81 B.2.3 */
 #define JGPU_HUFF_TABLES 6        /* per file: (DC, AC) of each of up to 3 scan components */
 #define JGPU_HUFF_CTA 256         /* subsequences per CTA of the sync / write kernels */
@@ -258,7 +260,13 @@ struct StoreSink {
     mby = mcu / nhmb;
     locate();
   }
-  JGPU_HUFF_HD void coef(int k, int v) { blk[mem->zigzag(k)] = (int16_t)v; }
+  JGPU_HUFF_HD void coef(int k, int v) {
+#ifndef JGPU_HUFF_NO_STORE   /* experiment knob: the write pass without its stores (profiles/r1_ab_notes.md) */
+    blk[mem->zigzag(k)] = (int16_t)v;
+#else
+    (void)k; (void)v;
+#endif
+  }
   JGPU_HUFF_HD bool block_done() {
     g++;
     if (g >= seg_blocks) return true;

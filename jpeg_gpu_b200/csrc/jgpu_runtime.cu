@@ -1164,7 +1164,7 @@ static int decode_jpegs_cpu_entropy(jgpu_ctx *ctx, const jgpu_jpeg *files, int n
  * scans, states that did not settle) go through the sequential reader afterwards, which
  * decodes or rejects them exactly as before. */
 static int decode_jpegs_gpu_entropy(jgpu_ctx *ctx, const jgpu_jpeg *files, int n, int nthreads,
-                                    uint8_t *h_rgb, int64_t rgb_cap, jgpu_jpeg_info *info) {
+                                    uint8_t *h_rgb, int64_t rgb_cap, jgpu_jpeg_info *info, bool device_out) {
   CU_TRY(cudaSetDevice(ctx->device));
   const jpeg_decode_ctx_vtbl &v = JFRONT_DECODE_CTX_VTBL;
   constexpr int S = kHuffSubseqWords;
@@ -1269,7 +1269,7 @@ static int decode_jpegs_gpu_entropy(jgpu_ctx *ctx, const jgpu_jpeg *files, int n
       ctx->dz_sub[2].reserve(4 * n_sub + 16) || ctx->dz_sub[3].reserve(4 * n_sub + 16) ||
       ctx->dz_carry[0].reserve(4 * n_cta + 16) || ctx->dz_carry[1].reserve(4 * n_cta + 16) ||
       ctx->d_coef.reserve((size_t)coef_off * 2 + 256) || ctx->d_qtabs.reserve(qtabs.size() * 2) ||
-      ctx->d_rgb.reserve((size_t)rgb_off + 256)) {
+      (!device_out && ctx->d_rgb.reserve((size_t)rgb_off + 256))) {
     release_fronts();
     return EXIT_FAILURE;
   }
@@ -1280,7 +1280,8 @@ static int decode_jpegs_gpu_entropy(jgpu_ctx *ctx, const jgpu_jpeg *files, int n
   uint32_t *h_status = (uint32_t *)ctx->hz_status.ptr;
   int16_t *d_coef = (int16_t *)ctx->d_coef.ptr;
   uint16_t *d_qtabs = (uint16_t *)ctx->d_qtabs.ptr;
-  uint8_t *d_rgb = (uint8_t *)ctx->d_rgb.ptr;
+  /* JGPU_JPEGS_DEVICE_OUT: the caller's buffer is device memory and the kernels write into it */
+  uint8_t *d_rgb = device_out ? h_rgb : (uint8_t *)ctx->d_rgb.ptr;
 
   t_setup = since();
   /* ---- host threads: unstuff, cut at the restart markers, build the tables ------- */
@@ -1330,11 +1331,14 @@ static int decode_jpegs_gpu_entropy(jgpu_ctx *ctx, const jgpu_jpeg *files, int n
     CU_TRY(cudaMemcpyAsync(d_qtabs, qtabs.data(), qtabs.size() * 2, cudaMemcpyHostToDevice, ctx->streams[0]));
     CU_TRY(cudaEventRecord(ctx->events[0], ctx->streams[0]));
     for (int s = 1; s < kHostStreams; s++) CU_TRY(cudaStreamWaitEvent(ctx->streams[s], ctx->events[0], 0));
-    const int64_t chunk_bytes = 192ll << 20;   /* of coefficients */
+    /* groups grow from 48 MB to 192 MB of coefficients: a small first group gets the read-back
+     * (the slowest stage) going early, large later ones keep the kernels' grids full */
+    int64_t chunk_bytes = 48ll << 20;
     int i0 = 0, chunk = 0;
     while (i0 < m) {
       int i1 = i0;
       int64_t acc = 0;
+      if (chunk > 0 && chunk_bytes < (192ll << 20)) chunk_bytes *= 2;
       while (i1 < m && (i1 == i0 || acc + plan->layouts[i1].coef_len * 2 <= chunk_bytes)) {
         acc += plan->layouts[i1].coef_len * 2;
         i1++;
@@ -1383,7 +1387,7 @@ static int decode_jpegs_gpu_entropy(jgpu_ctx *ctx, const jgpu_jpeg *files, int n
       if (plan_run_range(plan, i0, i1, d_coef, d_qtabs, m, d_rgb, nullptr, st)) return EXIT_FAILURE;
       CU_TRY(cudaMemcpyAsync(h_status + i0, (uint32_t *)ctx->dz_status.ptr + i0, 4 * (size_t)(i1 - i0),
                              cudaMemcpyDeviceToHost, st));
-      {
+      if (!device_out) {
         const int64_t lo = descs[i0].rgb_off;
         const int64_t hi = descs[i1 - 1].rgb_off + plan->layouts[i1 - 1].rgb_len;
         CU_TRY(cudaMemcpyAsync(h_rgb + lo, d_rgb + lo, (size_t)(hi - lo), cudaMemcpyDeviceToHost, st));
@@ -1434,8 +1438,10 @@ static int decode_jpegs_gpu_entropy(jgpu_ctx *ctx, const jgpu_jpeg *files, int n
       release_fronts();
       return EXIT_FAILURE;
     }
-    CU_TRY(cudaMemcpyAsync(h_rgb + it.desc.rgb_off, d_rgb + it.desc.rgb_off, (size_t)it.lay.rgb_len,
-                           cudaMemcpyDeviceToHost, st));
+    if (!device_out) {
+      CU_TRY(cudaMemcpyAsync(h_rgb + it.desc.rgb_off, d_rgb + it.desc.rgb_off, (size_t)it.lay.rgb_len,
+                             cudaMemcpyDeviceToHost, st));
+    }
     CU_TRY(cudaStreamSynchronize(st));
   }
   if (m != n) rc = EXIT_FAILURE;
@@ -1454,13 +1460,22 @@ static int decode_jpegs_gpu_entropy(jgpu_ctx *ctx, const jgpu_jpeg *files, int n
 extern "C" int jgpu_decode_jpegs_ex(jgpu_ctx *ctx, const jgpu_jpeg *files, int n, int nthreads, unsigned flags,
                                     uint8_t *h_rgb, int64_t rgb_cap, jgpu_jpeg_info *info) {
   if (!ctx || !files || n <= 0 || !h_rgb || !info) return jgpu_fail("jgpu_decode_jpegs: bad arguments");
-  if (flags == JGPU_ENTROPY_AUTO) {
+  const bool device_out = (flags & JGPU_JPEGS_DEVICE_OUT) != 0;
+  unsigned entropy = flags & ~JGPU_JPEGS_DEVICE_OUT;
+  if (entropy == JGPU_ENTROPY_AUTO) {
     const char *env = getenv("JGPU_ENTROPY");
-    flags = env && !strcmp(env, "cpu") ? JGPU_ENTROPY_CPU : JGPU_ENTROPY_GPU;
+    entropy = env && !strcmp(env, "cpu") && !device_out ? JGPU_ENTROPY_CPU : JGPU_ENTROPY_GPU;
   }
-  if (flags == JGPU_ENTROPY_CPU) return decode_jpegs_cpu_entropy(ctx, files, n, nthreads, h_rgb, rgb_cap, info);
-  if (flags == JGPU_ENTROPY_GPU) return decode_jpegs_gpu_entropy(ctx, files, n, nthreads, h_rgb, rgb_cap, info);
-  return jgpu_fail("jgpu_decode_jpegs_ex: unknown flags %u", flags);
+  if (entropy == JGPU_ENTROPY_CPU && !device_out) {
+    return decode_jpegs_cpu_entropy(ctx, files, n, nthreads, h_rgb, rgb_cap, info);
+  }
+  if (entropy == JGPU_ENTROPY_GPU) {
+    if (device_out && (reinterpret_cast<uintptr_t>(h_rgb) & 255)) {
+      return jgpu_fail("jgpu_decode_jpegs_ex: a device output buffer must be 256-byte aligned");
+    }
+    return decode_jpegs_gpu_entropy(ctx, files, n, nthreads, h_rgb, rgb_cap, info, device_out);
+  }
+  return jgpu_fail("jgpu_decode_jpegs_ex: unsupported flags %u", flags);
 }
 
 extern "C" int jgpu_decode_jpegs(jgpu_ctx *ctx, const jgpu_jpeg *files, int n, int nthreads,

@@ -5,6 +5,7 @@
 // code are checked against the sequential reader without a GPU.  Built by
 // tests/test_huffman_host.py together with the product's C host sources; not part of the library.
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -113,6 +114,16 @@ extern "C" long long huff_emulate(const unsigned char *jpeg, int size, short *co
       int rounds = 0;
       for (;;) {
         rounds++;
+        if (getenv("HUFF_EMU_TRACE") && pass == 0) {
+          int act = 0, warps = 0;
+          for (int t = 0; t < count; t += 32) {
+            int a = 0;
+            for (int u = t; u < std::min(count, t + 32); u++) a += need[u] != 0;
+            act += a;
+            warps += a > 0;
+          }
+          fprintf(stderr, "cta %d round %d active %d warps %d\n", x, rounds, act, warps);
+        }
         for (int t = 0; t < count; t++) {
           if (!need[t]) continue;
           NullSink sink;

@@ -101,3 +101,18 @@ def test_damaged_scans_give_what_the_sequential_reader_gives(gpu_ctx, capfd):
         if a.status == 0:
             assert np.array_equal(got[a.rgb_off:a.rgb_off + a.rgb_len], ref[b.rgb_off:b.rgb_off + b.rgb_len]), k
     capfd.readouterr()
+
+
+def test_pixels_can_stay_on_the_device(gpu_ctx):
+    """JGPU_JPEGS_DEVICE_OUT: the output buffer is device memory; same bytes as the host-output call."""
+    pytest.importorskip("PIL")
+    import torch
+    files = [_jpeg(1920, 1080, 2, rst=120), _jpeg(333, 222, "L"), load("c444_40x24")[0], _jpeg(1280, 720, 1)]
+    ref, ri = gpu_ctx.decode_jpegs(files, entropy="gpu")
+    total, _ = J.probe_jpegs(files)
+    dev = torch.zeros(total, dtype=torch.uint8, device="cuda:0")
+    out, gi = gpu_ctx.decode_jpegs(files, dev, entropy="gpu")
+    got = out.cpu().numpy()
+    for a, b in zip(gi, ri):
+        assert a.status == 0 and (a.rgb_off, a.rgb_len) == (b.rgb_off, b.rgb_len)
+        assert np.array_equal(got[a.rgb_off:a.rgb_off + a.rgb_len], ref[b.rgb_off:b.rgb_off + b.rgb_len])

@@ -27,7 +27,8 @@ def main():
     Image.fromarray(pic).save(bio, "JPEG", quality=85, subsampling=2, restart_marker_blocks=rst)
     files = [bio.getvalue()] * n
     total, _ = J.probe_jpegs(files)
-    out = torch.zeros(total, dtype=torch.uint8).pin_memory()
+    device_out = os.environ.get("PROFILE_DEVICE_OUT") == "1"
+    out = torch.zeros(total, dtype=torch.uint8, device="cuda:0") if device_out else torch.zeros(total, dtype=torch.uint8).pin_memory()
     ctx = J.Context(0)
     ctx.decode_jpegs(files, out, entropy=entropy)
     for _ in range(reps):
