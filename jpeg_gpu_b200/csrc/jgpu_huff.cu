@@ -11,7 +11,8 @@
  *   k_huff_scan   one CTA per file: segmented exclusive scan of the slot counts (restart
  *                 intervals are the segments).
  *   k_huff_write  the same staging; stores coefficients, verifies the chain of states.
- *   k_huff_dc     one CTA per (restart interval, component): prefix sum of DC differences.
+ *   k_huff_dc     one CTA per piece of a (restart interval, component) chain: prefix sum of the
+ *                 DC differences, in two launches when chains are longer than a piece.
  */
 #include <cuda_runtime.h>
 #include <stddef.h>
@@ -72,6 +73,7 @@ struct DevMem {
   uint32_t words;      /* shared address of SyncSmem::words */
   uint32_t base_word;  /* file-relative index of the CTA's first word */
   uint32_t tabs, file, zz;
+  uint32_t comps;      /* huff::comp_pack of the file */
   __device__ __forceinline__ uint32_t word(uint32_t i) const {
     const uint32_t l = i - base_word, row = l / S;
     return lds_u32(words + 4u * ((l & ~(uint32_t)(S - 1)) | ((l ^ row) & (S - 1))));
@@ -88,9 +90,7 @@ struct DevMem {
   __device__ __forceinline__ uint32_t symbol(uint32_t t, int i) const {
     return lds_u8(tabs + t * (uint32_t)sizeof(jgpu_huff_table) + (uint32_t)offsetof(jgpu_huff_table, symbols) + (uint32_t)i);
   }
-  __device__ __forceinline__ uint32_t blk_table(uint32_t c) const {
-    return 2u * lds_u8(file + (uint32_t)offsetof(jgpu_huff_file, blk_comp) + c);
-  }
+  __device__ __forceinline__ uint32_t blk_table(uint32_t c) const { return 2u * ((comps >> (2u * c)) & 3u); }
   __device__ __forceinline__ int64_t blk_base(int c) const {
     return (int64_t)lds_u64(file + (uint32_t)offsetof(jgpu_huff_file, blk_base) + 8u * c);
   }
@@ -120,6 +120,7 @@ __device__ __forceinline__ DevMem<S> dev_mem(const SyncSmem<S> &sm, int first) {
   m.tabs = pinned((uint32_t)__cvta_generic_to_shared(sm.tabs));
   m.file = pinned((uint32_t)__cvta_generic_to_shared(&sm.file));
   m.zz = pinned((uint32_t)__cvta_generic_to_shared(sm.zz));
+  m.comps = pinned(huff::comp_pack(sm.file));
   return m;
 }
 
@@ -365,25 +366,43 @@ k_huff_write(const jgpu_huff_file *__restrict__ files, const uint32_t *__restric
 }
 
 /* DC differences -> DC values: the reference's `pred += diff` in a 16-bit accumulator
- * (src/xjpeg.c:430,479), reset at every restart interval (src/xjpeg.c:593-629). */
+ * (src/xjpeg.c:430,479), reset at every restart interval (src/xjpeg.c:593-629).  A chain (one
+ * component of one restart interval, in scan order) is cut into pieces of kDcPiece elements so
+ * that a file without restart markers (one chain of 129 600 luma blocks at 4K) still spreads over
+ * the GPU: k_huff_dc<0> leaves each piece's sum in `partial`, k_huff_dc<1> adds up the sums of the
+ * pieces before its own and scans.  blockIdx.x = (interval * ncomps + component) * pieces + piece. */
+constexpr int kDcPiece = 2048;
+
+template <int APPLY>
 __global__ void __launch_bounds__(256)
-k_huff_dc(const jgpu_huff_file *__restrict__ files, int16_t *__restrict__ coef) {
+k_huff_dc(const jgpu_huff_file *__restrict__ files, int16_t *__restrict__ coef, int *__restrict__ partial,
+          int pieces, size_t partial_stride) {
   __shared__ int w_sum[8];
   __shared__ int s_carry;
   const jgpu_huff_file &f = files[blockIdx.y];
-  const uint32_t seg = blockIdx.x / (uint32_t)f.ncomps;
-  const int comp = (int)(blockIdx.x % (uint32_t)f.ncomps);
-  if (seg >= f.n_seg) return;
+  const uint32_t job = blockIdx.x / (uint32_t)pieces, piece = blockIdx.x % (uint32_t)pieces;
+  const uint32_t seg = job / (uint32_t)f.ncomps;
+  const int comp = (int)(job % (uint32_t)f.ncomps);
+  if (seg >= f.n_seg || f.n_subseq == 0) return;
   const int seg_mcu0 = (int)seg * f.mcus_per_seg;
   const int cnt = min(f.mcus_per_seg, f.total_mcus - seg_mcu0) * f.hs[comp] * f.vs[comp];
+  const int e0 = (int)piece * kDcPiece, e1 = min(cnt, e0 + kDcPiece);
+  if (e0 >= cnt) return;
+  int *mine = partial + partial_stride * blockIdx.y + (size_t)job * pieces;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  if (t == 0) s_carry = 0;
+  if (t == 0) {
+    int c = 0;
+    if (APPLY) {
+      for (uint32_t p = 0; p < piece; p++) c += mine[p];
+    }
+    s_carry = c;
+  }
   __syncthreads();
-  for (int base = 0; base < cnt; base += 256) {
+  for (int base = e0; base < e1; base += 256) {
     const int e = base + t;
     int16_t *p = nullptr;
     int v = 0;
-    if (e < cnt) {
+    if (e < e1) {
       p = coef + huff::dc_element_offset(f, comp, seg_mcu0, e);
       v = *p;
     }
@@ -397,11 +416,12 @@ k_huff_dc(const jgpu_huff_file *__restrict__ files, int16_t *__restrict__ coef) 
     int pre = s_carry;
     for (int w = 0; w < warp; w++) pre += w_sum[w];
     v += pre;
-    if (p) *p = (int16_t)v;
+    if (APPLY && p) *p = (int16_t)v;
     __syncthreads();
     if (t == 255) s_carry = v;
     __syncthreads();
   }
+  if (!APPLY && t == 0) mine[piece] = s_carry;
 }
 
 template <int S>
@@ -417,7 +437,11 @@ cudaError_t configure_kernels() {
 
 cudaError_t huff_configure() { return configure_kernels<kHuffSubseqWords>(); }
 
-int huff_launches(const HuffLaunch &l) { return l.sync_passes + 3; }
+int huff_launches(const HuffLaunch &l) { return l.sync_passes + 3 + (l.max_dc_chain > kDcPiece ? 1 : 0); }
+
+size_t huff_dc_partial_ints(int max_dc_jobs, int max_dc_chain) {
+  return (size_t)std::max(1, max_dc_jobs) * (size_t)std::max(1, (max_dc_chain + kDcPiece - 1) / kDcPiece);
+}
 
 /* Enqueues the whole entropy decode of a group of files.  The coefficient range the files
  * cover must have been zeroed on the same stream. */
@@ -440,8 +464,12 @@ int huff_launch(const HuffLaunch &l, cudaStream_t st) {
   k_huff_scan<<<l.n_files, 1024, 0, st>>>(l.d_files, l.d_nslots, l.d_slots);
   k_huff_write<S><<<grid, kCta, smem, st>>>(l.d_files, l.d_stream, l.d_tables, l.d_seg_first, l.d_state,
                                             l.d_nslots, l.d_slots, l.d_segid, l.d_coef, l.d_status);
-  const dim3 dc_grid((unsigned)std::max(1, l.max_dc_jobs), (unsigned)l.n_files);
-  k_huff_dc<<<dc_grid, 256, 0, st>>>(l.d_files, l.d_coef);
+  const int pieces = std::max(1, (l.max_dc_chain + kDcPiece - 1) / kDcPiece);
+  const dim3 dc_grid((unsigned)(std::max(1, l.max_dc_jobs) * pieces), (unsigned)l.n_files);
+  if (pieces > 1) {
+    k_huff_dc<0><<<dc_grid, 256, 0, st>>>(l.d_files, l.d_coef, l.d_dc_partial, pieces, l.dc_partial_stride);
+  }
+  k_huff_dc<1><<<dc_grid, 256, 0, st>>>(l.d_files, l.d_coef, l.d_dc_partial, pieces, l.dc_partial_stride);
   e = cudaGetLastError();
   if (e != cudaSuccess) return jgpu_fail("entropy decoder: launch failed (%s)", cudaGetErrorString(e));
   return 0;

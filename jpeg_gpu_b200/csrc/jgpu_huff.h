@@ -16,6 +16,9 @@ struct HuffLaunch {
   int n_files = 0;
   int max_subseq = 0;      /* largest n_subseq of the group */
   int max_dc_jobs = 0;     /* largest n_seg * ncomps of the group */
+  int max_dc_chain = 0;    /* longest DC chain: blocks of one component in one restart interval */
+  int *d_dc_partial = nullptr;      /* n_files x dc_partial_stride ints of scratch */
+  size_t dc_partial_stride = 0;     /* >= huff_dc_partial_ints(max_dc_jobs, max_dc_chain) */
   int sync_passes = kHuffSyncPasses;
   size_t carry0 = 0, n_carry = 0;   /* the group's part of each carry array */
   int status0 = 0;         /* first status word of the group (n_files words are cleared) */
@@ -31,6 +34,7 @@ struct HuffLaunch {
 
 cudaError_t huff_configure();
 int huff_launches(const HuffLaunch &l);
+size_t huff_dc_partial_ints(int max_dc_jobs, int max_dc_chain);
 /* Returns 0 or 1 (jgpu_fail).  The coefficient range of the files must be zero. */
 int huff_launch(const HuffLaunch &l, cudaStream_t stream);
 

@@ -108,11 +108,18 @@ namespace huff {
 /* The decoding loop reaches its data through a small accessor object, so that the kernels can
  * hand it 32-bit shared-memory addresses (explicit ld.shared, nothing for the compiler to
  * re-derive inside the loop) while the host emulation hands it plain pointers:
- *   word(i)            big-endian 32-bit word i of the file's unstuffed scan
+ *   word(i)            big-endian 32-bit word i of the file's unstuffed scan (16 guard bytes follow it)
  *   lut(t, i)          jgpu_huff_table[t].lut[i]          t = 2 * component + (AC ? 1 : 0)
  *   limit(t, L), delta(t, L), symbol(t, i)                the canonical part of table t
  *   blk_table(c)       2 * component of block c of the MCU
  *   blk_base(c), blk_xs(c), blk_ys(c), zigzag(k)          write pass only */
+/* Component of every block of the MCU, two bits each: lives in a register in the kernels. */
+JGPU_HUFF_HD uint32_t comp_pack(const jgpu_huff_file &f) {
+  uint32_t v = 0;
+  for (int c = 0; c < f.bpm && c < JGPU_HUFF_MAX_BLOCKS; c++) v |= (uint32_t)(f.blk_comp[c] & 3u) << (2 * c);
+  return v;
+}
+
 struct HostMem {
   const uint32_t *words;   /* the file's scan, as stored (big-endian bytes) */
   const jgpu_huff_table *tabs;
@@ -123,7 +130,7 @@ struct HostMem {
   uint32_t limit(uint32_t t, int len) const { return tabs[t].limit[len]; }
   int32_t delta(uint32_t t, int len) const { return tabs[t].delta[len]; }
   uint32_t symbol(uint32_t t, int i) const { return tabs[t].symbols[i]; }
-  uint32_t blk_table(uint32_t c) const { return 2u * f->blk_comp[c]; }
+  uint32_t blk_table(uint32_t c) const { return 2u * ((comp_pack(*f) >> (2 * c)) & 3u); }
   int64_t blk_base(int c) const { return f->blk_base[c]; }
   int32_t blk_xs(int c) const { return f->blk_xs[c]; }
   int32_t blk_ys(int c) const { return f->blk_ys[c]; }
@@ -148,7 +155,7 @@ JGPU_HUFF_HD uint32_t lookup(const Mem &mem, uint32_t t, uint32_t look) {
 }
 
 /* Decodes the symbols that START inside one subsequence.
- *   mem           accessor (above); word() may be asked for up to three words past the
+ *   mem           accessor (above); word() may be asked for up to four words past the
  *                 subsequence
  *   w0, nwords    the subsequence
  *   state         packed (p, c, z) at its start
@@ -172,14 +179,16 @@ JGPU_HUFF_HD uint32_t decode_subsequence(const Mem &mem, int bpm, uint32_t w0, i
   next += 2;
   buf <<= (pos & 31);
   int avail = 64 - (pos & 31);
+  uint32_t ahead = mem.word(next);   /* the word the next refill needs, fetched one refill early */
   uint32_t tdc = mem.blk_table(c);   /* DC table of the current block; its AC table follows */
   /* The body is written without branches on the kind of symbol (DC / AC / end of block): the
    * threads of a warp sit at unrelated places of their blocks, and every divergent branch
    * would be paid by all of them. */
   while (pos < end) {
     if (avail < 32) {
-      buf |= (uint64_t)mem.word(next++) << (32 - avail);
+      buf |= (uint64_t)ahead << (32 - avail);
       avail += 32;
+      ahead = mem.word(++next);
     }
     const uint32_t ac = z != 0;
     uint32_t e = lookup(mem, tdc + ac, (uint32_t)(buf >> 48));

@@ -80,7 +80,7 @@ struct jgpu_ctx {
   Buffer h_in[kHostStreams], h_out[kHostStreams];
   /* GPU entropy decoder (jgpu_decode_jpegs_ex): pinned staging and device arrays */
   Buffer hz_stream, hz_files, hz_tables, hz_segs, hz_status, hz_coef;
-  Buffer dz_stream, dz_files, dz_tables, dz_segs, dz_status, dz_sub[4], dz_carry[2];
+  Buffer dz_stream, dz_files, dz_tables, dz_segs, dz_status, dz_sub[4], dz_carry[2], dz_dc[kHostStreams];
   /* last plan built by jgpu_decode_batch_host, reused while descs match */
   jgpu_plan *cached_plan = nullptr;
   std::vector<jgpu_image_desc> cached_descs;
@@ -194,7 +194,7 @@ extern "C" void jgpu_destroy(jgpu_ctx *ctx) {
   for (Buffer *b : {&ctx->hz_stream, &ctx->hz_files, &ctx->hz_tables, &ctx->hz_segs, &ctx->hz_status, &ctx->hz_coef,
                     &ctx->dz_stream, &ctx->dz_files, &ctx->dz_tables, &ctx->dz_segs, &ctx->dz_status,
                     &ctx->dz_sub[0], &ctx->dz_sub[1], &ctx->dz_sub[2], &ctx->dz_sub[3], &ctx->dz_carry[0],
-                    &ctx->dz_carry[1]}) {
+                    &ctx->dz_carry[1], &ctx->dz_dc[0], &ctx->dz_dc[1], &ctx->dz_dc[2]}) {
     b->release();
   }
   delete ctx;
@@ -1349,6 +1349,7 @@ static int decode_jpegs_gpu_entropy(jgpu_ctx *ctx, const jgpu_jpeg *files, int n
         while (it.tasks_left.load(std::memory_order_acquire) > 0) std::this_thread::yield();
         l.max_subseq = std::max(l.max_subseq, (int)h_files[k].n_subseq);
         l.max_dc_jobs = std::max(l.max_dc_jobs, (int)h_files[k].n_seg * h_files[k].ncomps);
+        l.max_dc_chain = std::max(l.max_dc_chain, h_files[k].mcus_per_seg * h_files[k].hs[0] * h_files[k].vs[0]);
         info[ok[k]].tasks = on_gpu[k] ? (int32_t)h_files[k].n_subseq : 1;
       }
       cudaStream_t st = ctx->streams[chunk % kHostStreams];
@@ -1367,6 +1368,17 @@ static int decode_jpegs_gpu_entropy(jgpu_ctx *ctx, const jgpu_jpeg *files, int n
       CU_TRY(cudaMemcpyAsync((uint32_t *)ctx->dz_segs.ptr + slot[i0].seg0, h_segs + slot[i0].seg0,
                              4 * (size_t)(slot[i1].seg0 - slot[i0].seg0), cudaMemcpyHostToDevice, st));
       CU_TRY(cudaMemsetAsync(d_coef + descs[i0].coef_off, 0, (size_t)acc, st));
+      {
+        /* scratch of the DC pass, one buffer per stream (groups on one stream run in order) */
+        Buffer &dc = ctx->dz_dc[chunk % kHostStreams];
+        l.dc_partial_stride = huff_dc_partial_ints(l.max_dc_jobs, l.max_dc_chain);
+        if (dc.cap < l.dc_partial_stride * 4 * (size_t)(i1 - i0)) {
+          /* growing means freeing: wait for the groups that may still use the old buffer */
+          CU_TRY(cudaStreamSynchronize(st));
+          if (dc.reserve(l.dc_partial_stride * 4 * (size_t)(i1 - i0) + 16)) return EXIT_FAILURE;
+        }
+        l.d_dc_partial = (int *)dc.ptr;
+      }
       l.n_files = i1 - i0;
       l.carry0 = slot[i0].cta0;
       l.n_carry = slot[i1].cta0 - slot[i0].cta0;
