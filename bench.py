@@ -31,6 +31,11 @@ WORKLOADS = {
     "4k422_b128": (3840, 2160, "422", 128),
     "1080p420_b1": (1920, 1080, "420", 1),
     "4k420_b16": (3840, 2160, "420", 16),
+    # the other sampling modes of the fused kernel (tuning runs; not BASELINE configurations)
+    "4k444_b64": (3840, 2160, "444", 64),
+    "4kgray_b256": (3840, 2160, "gray", 256),
+    "4k440_b128": (3840, 2160, "440", 128),
+    "1080p420_b512": (1920, 1080, "420", 512),
 }
 METRIC = "Mpixels/s decoded (coeff->RGB)"
 UNIT = "Mpixels/s"

@@ -66,15 +66,31 @@ namespace jgpu {
 #ifndef JGPU_COLOUR_INT
 #define JGPU_COLOUR_INT 1       /* 1: colour offsets in fixed point (jgpu_colour_fixed.h), no I2F / FMUL / FADD */
 #endif
+/* Tile shapes of the other sampling modes, measured on 4K batches (profiles/r1_ab_notes.md): what
+ * counts is how evenly 3840 (1920) pixels divide into tiles, not the warps per CTA. */
+#ifndef JGPU_FUSED_GRAY_WARPS
+#define JGPU_FUSED_GRAY_WARPS 2 /* warps of 64 blocks per grey tile: 1024 px (3 warps = 1536 px left 4K rows 2.5 tiles wide) */
+#endif
+#ifndef JGPU_FUSED_G444
+#define JGPU_FUSED_G444 1       /* column groups, luma 1x1: 512 px tiles */
+#endif
+#ifndef JGPU_FUSED_G440
+#define JGPU_FUSED_G440 2       /* luma 1x2: 1024 px tiles */
+#endif
+#ifndef JGPU_FUSED_G422
+#define JGPU_FUSED_G422 2       /* luma 2x1: 1024 px tiles (3 groups = 1536 px: 2.5 tiles per 4K row) */
+#endif
 #ifndef JGPU_FUSED_MINCTAS
 #define JGPU_FUSED_MINCTAS 0    /* 0: size registers for 12 warps per SM */
 #endif
 
-/* Column groups per tile, chosen per sampling mode so that a CTA has 6 warps where shared
- * memory lets two such CTAs share an SM (12 warps, the most 168 registers per thread allow):
- * 4:2:0 -> 4 luma + 2 chroma warps, 4:2:2 -> 3 + 3; the chroma-heavy modes stay at one group. */
+/* Column groups per tile, per sampling mode.  Every choice keeps 12 warps per SM (the most 168
+ * registers per thread allow): 4:2:0 -> 4 luma + 2 chroma warps x 2 CTAs, 4:2:2 -> 2 + 2 x 3 CTAs, ... */
 constexpr int mode_groups(int hs, int vs, bool gray) {
-  return JGPU_FUSED_G > 0 ? JGPU_FUSED_G : gray ? 1 : (hs == 2 ? (vs == 2 ? 2 : 3) : 1);
+  return JGPU_FUSED_G > 0 ? JGPU_FUSED_G
+         : gray           ? 1
+         : hs == 2        ? (vs == 2 ? 2 : JGPU_FUSED_G422)
+                          : (vs == 2 ? JGPU_FUSED_G440 : JGPU_FUSED_G444);
 }
 
 constexpr int kBoxRows = 32;                 /* blocks per TMA box */
@@ -106,7 +122,7 @@ static_assert(sizeof(TileDesc) == 128, "TileDesc is copied with cp.async.bulk an
 /* HS, VS: luma sampling factors (chroma is 1x1); G: 32-pair column groups per tile. */
 template <int HS, int VS, bool GRAY, int G>
 struct Cfg {
-  static constexpr int kYWarps = (GRAY ? 3 : VS) * G;
+  static constexpr int kYWarps = (GRAY ? JGPU_FUSED_GRAY_WARPS : VS) * G;
   static constexpr int kCWarps = GRAY ? 0 : (2 / HS) * G;
   static constexpr int kWarps = kYWarps + kCWarps;
   static constexpr int kThreads = 32 * kWarps;
