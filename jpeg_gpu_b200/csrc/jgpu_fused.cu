@@ -686,6 +686,143 @@ k_fused(const __grid_constant__ CUtensorMap tm_rows,   /* (64, rows)            
   }
 }
 
+/* ---- grey, one block per thread ---------------------------------------------
+ * The kernel above keeps TWO blocks per thread (the two lanes of the packed instructions are
+ * two blocks): 128 registers of transform state, 168 in all, 12 warps per SM.  Here a thread
+ * owns ONE block and the packed lanes are two ROWS of it (r and r+4) in the row pass, two
+ * COLUMNS (c and c+4) in the column pass, with a 2x2 exchange of register halves in between
+ * (16 pairs of MOVs; no shuffle, no shared memory).  64 registers of state, about 100 in all,
+ * 20 warps per SM: the occupancy experiment of DESIGN 6 (T = 1.96 ms + 11.5 ms / warps) says
+ * latency, not issue slots, is what the two-block form is short of.  Arithmetic is the same
+ * bit-exact sequence: prescale (y*S[r])*S[c] with S[r] different in the two lanes, inv_pass8,
+ * +0.5 on the vertical DC term, inv_pass8, floor, +128, clamp.
+ * A warp = 32 consecutive blocks of one block row (one TMA box, 4 KB, 128-byte swizzle) and
+ * writes 256 contiguous bytes per pixel row with one 8-byte store per thread. */
+constexpr int kTpbWarps = 4;
+constexpr int kTpbThreads = 32 * kTpbWarps;
+constexpr int kTpbOffTab = kTpbWarps * kBoxBytes;
+constexpr int kTpbOffDesc = kTpbOffTab + kTpbWarps * kQtabBytes;
+constexpr int kTpbOffBar = kTpbOffDesc + kDescSlots * (int)sizeof(TileDesc);
+constexpr int kTpbSmemBytes = kTpbOffBar + 8 * (kTpbWarps + kDescSlots);
+
+#ifndef JGPU_TPB_MINCTAS
+#define JGPU_TPB_MINCTAS 5
+#endif
+template <bool WIDE>
+__global__ void __launch_bounds__(kTpbThreads, JGPU_TPB_MINCTAS)
+k_gray_tpb(const __grid_constant__ CUtensorMap tm_rows, const TileDesc *__restrict__ descs, int n_tiles,
+           const uint32_t *__restrict__ qint, const uint32_t *__restrict__ wide_flag,
+           uint8_t *__restrict__ rgb, int rgb_aligned) {
+  if ((*wide_flag != 0) != WIDE) return;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem0 = smem_u32(smem_raw);
+  if (smem0 & 1023u) __trap();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bar_data = smem0 + kTpbOffBar + 8 * warp;
+  const uint32_t bar_desc0 = smem0 + kTpbOffBar + 8 * kTpbWarps;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kTpbWarps + kDescSlots; i++) mbar_init(smem0 + kTpbOffBar + 8 * i, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int my_tiles = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  auto fetch_desc = [&](int n) {   /* thread 0 only */
+    const uint32_t slot = (uint32_t)n % kDescSlots;
+    mbar_expect_tx(bar_desc0 + 8 * slot, (uint32_t)sizeof(TileDesc));
+    bulk_load(smem0 + kTpbOffDesc + slot * (uint32_t)sizeof(TileDesc), descs + (blockIdx.x + (size_t)n * gridDim.x),
+              (uint32_t)sizeof(TileDesc), bar_desc0 + 8 * slot);
+  };
+  auto wait_desc = [&](int n) -> uint32_t {
+    const uint32_t slot = (uint32_t)n % kDescSlots;
+    mbar_wait(bar_desc0 + 8 * slot, ((uint32_t)n / kDescSlots) & 1u);
+    return smem0 + kTpbOffDesc + slot * (uint32_t)sizeof(TileDesc);
+  };
+  const uint32_t wbox = smem0 + warp * kBoxBytes, wtab = smem0 + kTpbOffTab + warp * kQtabBytes;
+  auto fire = [&](int n) {   /* lane 0 of each warp: this warp's 32 blocks and its table */
+    const uint32_t d = wait_desc(n);
+    const int first = (int)lds32(d + offsetof(TileDesc, yfirst) + 4 * warp);
+    const int qy = (int)lds32(d + offsetof(TileDesc, qidx));
+    mbar_expect_tx(bar_data, kBoxBytes + kQtabBytes);
+    tma_load_2d(wbox, &tm_rows, 0, first, bar_data);
+    bulk_load(wtab, qint + (size_t)qy * 64, kQtabBytes, bar_data);
+  };
+  if (threadIdx.x == 0) {
+    fetch_desc(0);
+    if (my_tiles > 1) fetch_desc(1);
+  }
+  if (lane == 0) fire(0);
+  const uint8_t *const box = smem_raw + warp * kBoxBytes + 128 * lane;
+  const uint4 *const q = reinterpret_cast<const uint4 *>(smem_raw + kTpbOffTab + warp * kQtabBytes);
+  const int sw = lane & 7;
+  const int px_x = 8 * (32 * warp + lane);
+
+  for (int it = 0; it < my_tiles; it++) {
+    /* the warps of a CTA stay within a tile of each other: the descriptor ring relies on it */
+    named_sync(1, kTpbThreads);
+    if (threadIdx.x == 0 && it + 2 < my_tiles) fetch_desc(it + 2);
+    const uint32_t da = wait_desc(it);
+    const uint4 h0 = lds128(da);
+    const uint2 h1 = lds64(da + 16);
+    const bool active = px_x < (int)h0.z;
+    mbar_wait(bar_data, (uint32_t)it & 1u);
+    pair32 m[4][8];
+    if (active) {
+#pragma unroll
+      for (int r = 0; r < 4; r++) {
+        const uint4 a = *reinterpret_cast<const uint4 *>(box + 16 * (r ^ sw));
+        const uint4 b = *reinterpret_cast<const uint4 *>(box + 16 * ((r + 4) ^ sw));
+        const uint4 z = make_uint4(0, 0, 0, 0);
+        load_two_rows_packed<WIDE>(m[r], a, b, q[r], q[r + 4], WIDE ? q[8 + r] : z, WIDE ? q[12 + r] : z, r);
+        inv_pass8(m[r]);
+      }
+    }
+    __syncwarp();
+    if (lane == 0 && it + 1 < my_tiles) fire(it + 1);
+    if (!active) continue;
+    const pair32 magic = p_make_bits(kMagicBits, kMagicBits);
+    uint32_t w[8][4];   /* clamped samples: w[k][c] = (x[k][c], x[k][c+4]) as two 16-bit halves */
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      pair32 v[8];
+#pragma unroll
+      for (int r = 0; r < 4; r++) {
+        uint32_t alo, ahi, blo, bhi;
+        p_split_bits(m[r][c], alo, ahi);
+        p_split_bits(m[r][c + 4], blo, bhi);
+        v[r] = p_make_bits(alo, blo);       /* row r:     columns c, c+4 */
+        v[r + 4] = p_make_bits(ahi, bhi);   /* row r + 4: columns c, c+4 */
+      }
+      v[0] = p_add_half(v[0]);
+      inv_pass8(v);
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        uint32_t lo, hi;
+        p_split_bits(p_add_rm(v[k], magic), lo, hi);
+        w[k][c] = clamp_pair_u8(lo, hi);
+      }
+    }
+    const long long rgb_base = (long long)(((unsigned long long)h0.y << 32) | h0.x);
+    const int pitch = (int)h1.x;
+    const int vis_px = min(8, (int)h0.z - px_x), vis_rows = min(8, (int)h0.w);
+    const bool fast = (h1.y & (uint32_t)rgb_aligned & 1u) != 0 && vis_px == 8;
+    uint8_t *dst = rgb + rgb_base + px_x;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      if (k < vis_rows) {
+        const uint32_t p = __byte_perm(w[k][0], w[k][1], 0x6240);   /* x0 x1 x4 x5 */
+        const uint32_t t = __byte_perm(w[k][2], w[k][3], 0x6240);   /* x2 x3 x6 x7 */
+        const uint32_t o0 = __byte_perm(p, t, 0x5410), o1 = __byte_perm(p, t, 0x7632);
+        if (fast) {
+          asm volatile("st.global.cs.v2.u32 [%0], {%1, %2};" ::"l"(dst), "r"(o0), "r"(o1) : "memory");
+        } else {
+          for (int i = 0; i < vis_px; i++) dst[i] = (uint8_t)((i < 4 ? o0 : o1) >> (8 * (i & 3)));
+        }
+      }
+      dst += pitch;
+    }
+  }
+}
+
 /* u16 tables -> packed tables for IDP.2A (one tiny launch per run).  Per table 64 words:
  * word r*4+i        = (q[r][2i] & 255)  | (q[r][2i+1] & 255) << 24      (low bytes)
  * word 32 + r*4+i   = (q[r][2i] >> 8)   | (q[r][2i+1] >> 8)  << 24      (high bytes) */
@@ -732,6 +869,7 @@ struct ModeInfo {
 
 ModeInfo g_modes[kNumFusedModes];
 bool g_configured = false;
+bool g_gray_tpb = false;   /* grey images go through k_gray_tpb (JGPU_GRAY_TPB=1, experiment) */
 
 template <int HS, int VS, bool GRAY>
 cudaError_t configure_mode(int mode) {
@@ -790,6 +928,21 @@ cudaError_t fused_configure(int device) {
   if ((e = configure_mode<2, 1, false>(kMode422)) != cudaSuccess) return e;
   if ((e = configure_mode<2, 2, false>(kMode420)) != cudaSuccess) return e;
   if ((e = configure_mode<1, 2, false>(kMode440)) != cudaSuccess) return e;
+  if (const char *tpb = getenv("JGPU_GRAY_TPB")) g_gray_tpb = atoi(tpb) != 0;
+  if (g_gray_tpb) {
+    ModeInfo &mi = g_modes[kModeGray];
+    if ((e = cudaFuncSetAttribute(&k_gray_tpb<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTpbSmemBytes)) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(&k_gray_tpb<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTpbSmemBytes)) != cudaSuccess) {
+      return e;
+    }
+    mi.tile_mcus = 32 * kTpbWarps;
+    mi.threads = kTpbThreads;
+    mi.ywarps = kTpbWarps;
+    mi.smem = kTpbSmemBytes;
+    int n = 0;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, &k_gray_tpb<false>, kTpbThreads, kTpbSmemBytes)) != cudaSuccess) return e;
+    mi.ctas_per_sm = std::max(n, 1);
+  }
   g_configured = true;
   return cudaSuccess;
 }
@@ -852,7 +1005,7 @@ int fused_plan_build(FusedPlan &fp, const jgpu_image_desc *descs, const jgpu_lay
         for (int c = 0; c < d.ncomps; c++) t.qidx[c] = d.qtab_set * 4 + d.tq[c];
         for (int w = 0; w < mi.ywarps; w++) {
           if (mi.gray) {
-            t.yfirst[w] = block0[0] + r * hblocks[0] + x + 64 * w;
+            t.yfirst[w] = block0[0] + r * hblocks[0] + x + (mi.tile_mcus / mi.ywarps) * w;
           } else {
             t.yfirst[w] = block0[0] + (r * mi.vs + w / mi.groups) * hblocks[0] + x * mi.hs + 64 * (w % mi.groups);
           }
@@ -983,7 +1136,15 @@ int fused_plan_launch(FusedPlan &fp, int i0, int i1, const int16_t *coef, const 
     const TileDesc *descs = static_cast<const TileDesc *>(p->d_descs[m]) + t0;
     const uint32_t *qint = static_cast<const uint32_t *>(p->d_qint);
     switch (m) {
-      case kModeGray: e = launch_mode<1, 1, true>(grid, mi.smem, stream, p->tm_rows, p->tm_pairs, descs, t1 - t0, qint, wide_flag, rgb, rgb_aligned); break;
+      case kModeGray:
+        if (g_gray_tpb) {
+          k_gray_tpb<false><<<grid, kTpbThreads, mi.smem, stream>>>(p->tm_rows, descs, t1 - t0, qint, wide_flag, rgb, rgb_aligned);
+          k_gray_tpb<true><<<grid, kTpbThreads, mi.smem, stream>>>(p->tm_rows, descs, t1 - t0, qint, wide_flag, rgb, rgb_aligned);
+          e = cudaGetLastError();
+        } else {
+          e = launch_mode<1, 1, true>(grid, mi.smem, stream, p->tm_rows, p->tm_pairs, descs, t1 - t0, qint, wide_flag, rgb, rgb_aligned);
+        }
+        break;
       case kMode444: e = launch_mode<1, 1, false>(grid, mi.smem, stream, p->tm_rows, p->tm_pairs, descs, t1 - t0, qint, wide_flag, rgb, rgb_aligned); break;
       case kMode422: e = launch_mode<2, 1, false>(grid, mi.smem, stream, p->tm_rows, p->tm_pairs, descs, t1 - t0, qint, wide_flag, rgb, rgb_aligned); break;
       case kMode420: e = launch_mode<2, 2, false>(grid, mi.smem, stream, p->tm_rows, p->tm_pairs, descs, t1 - t0, qint, wide_flag, rgb, rgb_aligned); break;

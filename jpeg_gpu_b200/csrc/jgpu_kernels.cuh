@@ -115,6 +115,29 @@ JGPU_DEV void load_row_pair_packed(pair32 (&row)[8], uint4 a, uint4 b, uint4 qa,
   }
 }
 
+/* The same for ONE block: rows r and r + 4 of it ride in the two lanes (k_gray_tpb), so the
+ * first prescale factor differs between the lanes: (y*S[r])*S[c] and (y*S[r+4])*S[c]. */
+template <bool WIDE>
+JGPU_DEV void load_two_rows_packed(pair32 (&row)[8], uint4 a, uint4 b, uint4 qa, uint4 qb, uint4 qah, uint4 qbh, int r) {
+  const uint32_t wa[4] = {a.x, a.y, a.z, a.w}, wb[4] = {b.x, b.y, b.z, b.w};
+  const uint32_t ka[4] = {qa.x, qa.y, qa.z, qa.w}, kb[4] = {qb.x, qb.y, qb.z, qb.w};
+  const uint32_t ha[4] = {qah.x, qah.y, qah.z, qah.w}, hb[4] = {qbh.x, qbh.y, qbh.z, qbh.w};
+  const pair32 sr = p_make_bits(scale_bits(r), scale_bits(r + 4));
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    int a0 = dp2a_lo_s16_u8(wa[i], ka[i]), a1 = dp2a_hi_s16_u8(wa[i], ka[i]);
+    int b0 = dp2a_lo_s16_u8(wb[i], kb[i]), b1 = dp2a_hi_s16_u8(wb[i], kb[i]);
+    if (WIDE) {
+      a0 += dp2a_lo_s16_u8(wa[i], ha[i]) << 8;
+      a1 += dp2a_hi_s16_u8(wa[i], ha[i]) << 8;
+      b0 += dp2a_lo_s16_u8(wb[i], hb[i]) << 8;
+      b1 += dp2a_hi_s16_u8(wb[i], hb[i]) << 8;
+    }
+    row[2 * i] = p_mulc(p_mul(p_make((float)(short)a0, (float)(short)b0), sr), scale_bits(2 * i));
+    row[2 * i + 1] = p_mulc(p_mul(p_make((float)(short)a1, (float)(short)b1), sr), scale_bits(2 * i + 1));
+  }
+}
+
 /* Two un-floored samples (same block, adjacent columns) -> two clamped u8
  * samples in the halves of a 32-bit word:
  *   floor            src/dct.c:118 ((short)floor(t): low 16 bits of the integer)

@@ -126,3 +126,27 @@ def test_host_batch_api(gpu_ctx, checker):
     p_rgb = torch.zeros(rgb_len, dtype=torch.uint8).pin_memory()
     gpu_ctx.decode_batch_host(descs, p_coef, q, p_rgb, None)  # pinned buffers
     compare_batch(descs, p_rgb.numpy(), None, exp_rgb, None)
+
+
+def test_grey_one_block_per_thread_variant(checker, monkeypatch):
+    """JGPU_GRAY_TPB=1 (experiment, profiles/r1_ab_notes.md): k_gray_tpb keeps one block per thread
+    (rows r / r+4, then columns c / c+4 in the packed lanes).  Same bits as the oracle, including
+    cropped and unaligned images, 16-bit tables and the adversarial coefficient kinds."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    monkeypatch.setenv("JGPU_GRAY_TPB", "1")
+    ctx = J.Context(0)           # the fused kernels are configured per context creation
+    try:
+        shapes = [(w, h, "gray") for (w, h) in SIZES] + [(4096, 1024, "gray"), (1537, 9, "gray"), (1920, 1080, "gray")]
+        descs, coef_len, rgb_len, _ = make_batch(shapes, want_yuv=False)
+        for q in (synth.quality_tables(85), synth.quality_tables(85) * 3):   # 8-bit and 16-bit entries
+            q = q.astype(np.uint16)
+            coef = synth.batch_coefficients(descs, coef_len, q, kinds=KINDS)
+            exp_rgb, _ = oracle_batch(checker, descs, coef, q, rgb_len, 0, nthreads=8)
+            got_rgb, _ = gpu_batch(ctx, descs, coef, q, rgb_len, 0)
+            compare_batch(descs, got_rgb, None, exp_rgb, None)
+    finally:
+        ctx.close()
+        monkeypatch.delenv("JGPU_GRAY_TPB")
+        J.Context(0).close()     # back to the product configuration for the tests that follow
