@@ -36,7 +36,7 @@ int cuda_decode_set_upload(jpeg_decode_out format) {
 
 /* Where RGB decodes do their Huffman decoding: 0 = the CPU front end (default: it is the
  * pluggable part), 1 = on the device (jgpu_huff.cu), for the built-in front end only. */
-static int g_entropy_on_device = 0;
+static int g_entropy_on_device = -1;   /* -1: not set, $JGPU_ENTROPY=gpu turns it on */
 int cuda_decode_set_entropy(int on_device) {
   if (on_device != 0 && on_device != 1) {
     fprintf(stderr, "Unsupported entropy decoder %i for cuda wrapper.\n", on_device);
@@ -65,7 +65,14 @@ static cuda_decode_ctx *cuda_decode_alloc(jpeg_info *info) {
   ctx->front = g_frontend ? *g_frontend : JFRONT_DECODE_CTX_VTBL;
   ctx->device = g_device;
   ctx->upload = g_upload;
-  ctx->entropy_on_device = g_entropy_on_device && g_frontend == NULL;
+  {
+    int on = g_entropy_on_device;
+    if (on < 0) {
+      const char *env = getenv("JGPU_ENTROPY");
+      on = env != NULL && strcmp(env, "gpu") == 0;
+    }
+    ctx->entropy_on_device = on && g_frontend == NULL;
+  }
   ctx->buf = info->buf;
   ctx->size = info->size;
   if (ctx->device < 0) {
