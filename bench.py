@@ -267,7 +267,10 @@ def main():
         raise SystemExit("bench.py --impl ours needs a CUDA device; there is no CPU fallback")
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
+    numa = None
     if world > 1:
+        # one process per GPU: keep its host buffers and copy threads next to its GPU's PCIe root
+        numa = shard.bind_to_gpu_numa_node(local_rank)
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 
@@ -480,7 +483,8 @@ def main():
                                     f"{w}x{h} {ss}, batch {n_img} per GPU, synthetic coefficient planes (SURVEY 8d)"),
                        "l2": "inputs larger than L2 (%.2f GB coef + %.2f GB rgb per GPU)" % (coef_len * 2 / 1e9, rgb_len / 1e9),
                        "path": "generic (2 kernels)" if args.force_generic else "fused kernel",
-                       "kernel_launches_per_step": plan.launches, "parallelism": f"images sharded x{world}"},
+                       "kernel_launches_per_step": plan.launches, "parallelism": f"images sharded x{world}",
+                       "host_binding": numa},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_pack": e2e_pack, "e2e_jpeg": e2e_jpeg,
             "gpu_launches": args.steps * plan.launches, "clocks": clk.summary(), "parity": parity,
         }

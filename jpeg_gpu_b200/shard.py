@@ -66,3 +66,36 @@ def sum_over_ranks(value: float, device=None) -> float:
     t = torch.tensor([value], dtype=torch.float64, device=device if device is not None else "cpu")
     dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return float(t.item())
+
+
+def bind_to_gpu_numa_node(device_index: int) -> dict:
+    """One process per GPU: run this process on the CPUs of the NUMA node its GPU hangs off, so that
+    the pinned host buffers it allocates afterwards (first touch) and its copy threads are local to
+    the GPU's PCIe root.  Reads the GPU's PCI address from NVML and the node's CPU list from sysfs;
+    does nothing when either is unavailable.  Returns what it found (for the bench's JSON line)."""
+    import os
+    info = {"numa_node": None, "cpus": None}
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        index = int(visible.split(",")[device_index]) if visible and visible.split(",")[device_index].isdigit() \
+            else device_index
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(index)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        sysfs = "/sys/bus/pci/devices/" + bus.lower()[-12:]
+        node = int(open(sysfs + "/numa_node").read())
+        info["numa_node"] = node
+        if node < 0:
+            return info
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            info["cpus"] = len(cpus)
+    except Exception as exc:   # no NVML, no sysfs, containers without the files: stay unbound
+        info["error"] = str(exc)[:80]
+    return info
