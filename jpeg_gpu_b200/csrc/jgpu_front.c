@@ -607,7 +607,8 @@ static int put_bytes(unsigned char *dst, long long cap, long long *out, const un
  *              markers removed; every restart interval starts on a subsequence boundary and is
  *              zero-padded to the next one (a reader that meets a marker feeds zeros, refill()
  *              above), 16 guard bytes follow the last one
- *   seg_first  subsequence each restart interval starts at, n_seg + 1 entries
+ *   seg_first  subsequence each restart interval starts at, n_seg + 1 entries, then the
+ *              entropy-coded bits of each interval, n_seg entries (0xffffffff: not to be checked)
  *   tables     JGPU_HUFF_TABLES decoder tables: (DC, AC) of plane 0, 1, 2
  *   file       geometry fields (n_subseq, n_seg, mcus_per_seg, total_mcus, nhmb, bpm, ncomps,
  *              hs, vs, blk_*); the caller places it in the batch (word0, plane_off, ...)
@@ -666,7 +667,7 @@ long long jfront_huff_prepare(jpeg_decode_ctx *ctx, int subseq_words, unsigned c
   file->mcus_per_seg = c->restart_interval ? c->restart_interval : file->total_mcus;
   nseg = (file->total_mcus + file->mcus_per_seg - 1) / file->mcus_per_seg;
   /* coefficient slots of an interval are counted in 32 bits on the device */
-  if ((long long)file->mcus_per_seg * bpm * 64 >= 0x7fffffffll || nseg + 1 > seg_cap) {
+  if ((long long)file->mcus_per_seg * bpm * 64 >= 0x7fffffffll || 2 * nseg + 1 > seg_cap) {
     *why = "Error, scan too large for the GPU entropy decoder";
     return -1;
   }
@@ -691,6 +692,15 @@ long long jfront_huff_prepare(jpeg_decode_ctx *ctx, int subseq_words, unsigned c
       }
       break;
     }
+    /* entropy-coded bits of the interval, for the "nothing left over" check: only where the
+     * sequential reader looks for a marker after the interval (restart() above) */
+    if ((out - seg_start) * 8 >= 0xffffffffll) {
+      *why = "Error, scan too large for the GPU entropy decoder";
+      return -1;
+    }
+    seg_first[nseg + 1 + k] = (k + 1 < nseg || (c->restart_interval && file->total_mcus % c->restart_interval == 0))
+                                  ? (unsigned int)((out - seg_start) * 8)
+                                  : 0xffffffffu;
     { /* zero padding to the next boundary; an empty interval still gets one subsequence */
       long long pad = (sub - (out - seg_start) % sub) % sub;
       if (out == seg_start) pad = sub;
@@ -705,6 +715,14 @@ long long jfront_huff_prepare(jpeg_decode_ctx *ctx, int subseq_words, unsigned c
         return -1;
       }
       pos += 2;
+    } else if (c->restart_interval && file->total_mcus % c->restart_interval == 0) {
+      /* the sequential reader looks for a marker after a complete last interval too (restart()
+       * above): the end of the file, EOI or the next RSTn pass, anything else is its error */
+      while (pos + 1 < c->size && c->buf[pos + 1] == 0xFF) pos++;
+      if (pos + 1 < c->size && c->buf[pos + 1] != 0xD9 && c->buf[pos + 1] != 0xD0 + (k & 7)) {
+        *why = "Error, unknown marker found in scan.";
+        return -1;
+      }
     }
   }
   seg_first[nseg] = (unsigned int)(out / sub);
@@ -727,7 +745,7 @@ long long jfront_huff_bound(const jpeg_decode_ctx *ctx, int subseq_words, int *n
   const long long per = c->restart_interval ? c->restart_interval : total;
   const long long nseg = per > 0 ? (total + per - 1) / per : 1;
   if (nseg_out) *nseg_out = (int)nseg;
-  return (long long)c->size + (nseg + 1) * 4ll * subseq_words + 32;
+  return (long long)c->size + (nseg + 1) * 4ll * subseq_words + 32;   /* the segment table needs 2*nseg + 1 entries */
 }
 
 /* ---- vtable ---------------------------------------------------------------- */

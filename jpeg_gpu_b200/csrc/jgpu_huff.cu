@@ -354,8 +354,17 @@ k_huff_write(const jgpu_huff_file *__restrict__ files, const uint32_t *__restric
     huff::StoreSink<DevMem<S>> sink;
     sink.start(&mem, f.bpm, f.nhmb, coef, seg_mcu0, g0, seg_blocks);
     uint32_t n = 0, err = 0;
-    const uint32_t out = huff::decode_subsequence(mem, f.bpm, i * S, S, st, sink, &n, &err);
+    int pos = 0;
+    const uint32_t out = huff::decode_subsequence(mem, f.bpm, i * S, S, st, sink, &n, &err, &pos);
     if (err) flags |= JGPU_HUFF_ERR_CODE;
+    if (sink.g >= seg_blocks) {
+      /* this thread decoded the interval's last block: whole bytes left over are the sequential
+       * reader's to judge */
+      const uint32_t *sf = seg_first + f.seg0;
+      const uint32_t bits = sf[f.n_seg + 1 + seg];
+      const long long used = (long long)(i - sf[seg]) * (32 * S) + pos;
+      if (bits != 0xffffffffu && (long long)bits - used >= 8) flags |= JGPU_HUFF_ERR_TRAIL;
+    }
     if (sink.g < seg_blocks) {
       /* the interval goes on: into the next subsequence, which must start where this one ended */
       if (i + 1 == seg_first[f.seg0 + seg + 1]) flags |= JGPU_HUFF_ERR_SHORT;

@@ -61,7 +61,8 @@ typedef struct jgpu_huff_file {
   uint32_t n_subseq;     /* subsequences of the scan */
   uint32_t subseq0;      /* index of its first subsequence in the per-subsequence arrays */
   uint32_t seg0;         /* index of its first entry in the segment table */
-  uint32_t n_seg;        /* restart intervals (1 without DRI); the table has n_seg+1 entries */
+  uint32_t n_seg;        /* restart intervals (1 without DRI); the table holds n_seg+1 first
+                            subsequences, then n_seg data lengths in bits (0xffffffff: not checked) */
   uint32_t cta0;         /* index of its first entry in the per-CTA carry arrays */
   int32_t mcus_per_seg;  /* restart interval in MCUs, or all MCUs */
   int32_t total_mcus;
@@ -87,6 +88,9 @@ typedef struct jgpu_huff_file {
 #define JGPU_HUFF_ERR_CODE 1u      /* invalid code or coefficient index past 63 in the true decoding */
 #define JGPU_HUFF_ERR_SYNC 2u      /* states did not settle within the sync passes */
 #define JGPU_HUFF_ERR_SHORT 4u     /* the scan ends before the interval's last MCU */
+#define JGPU_HUFF_ERR_TRAIL 8u     /* a restart interval has whole bytes left after its last MCU: the
+                                      sequential reader resynchronises there (jgpu_front.c restart())
+                                      and may reject the file; its call */
 
 /* boundary state, packed */
 #define JGPU_HUFF_STATE(p, c, z) ((uint32_t)(p) | ((uint32_t)(c) << 8) | ((uint32_t)(z) << 16))
@@ -163,12 +167,13 @@ JGPU_HUFF_HD uint32_t lookup(const Mem &mem, uint32_t t, uint32_t look) {
  *                      coded difference); called for non-zero v only
  *   sink.block_done()  the current block is complete; returns true to stop (the restart
  *                      interval has all its blocks)
- * Returns the state at the end; *n_out = coefficient slots advanced; *err is raised on a bit
+ * Returns the state at the end; *n_out = coefficient slots advanced; *pos_out = bits consumed
+ * from the start of the subsequence when decoding stopped; *err is raised on a bit
  * pattern that is no code and on a run past coefficient 63 (the reference's reader does not
  * check either, src/xjpeg.c:67-78; ours fails on both, jgpu_front.c decode_symbol/decode_mcu). */
 template <typename Mem, typename Sink>
 JGPU_HUFF_HD uint32_t decode_subsequence(const Mem &mem, int bpm, uint32_t w0, int nwords, uint32_t state,
-                                         Sink &sink, uint32_t *n_out, uint32_t *err) {
+                                         Sink &sink, uint32_t *n_out, uint32_t *err, int *pos_out = nullptr) {
   int pos = (int)JGPU_HUFF_STATE_P(state);
   uint32_t c = JGPU_HUFF_STATE_C(state), z = JGPU_HUFF_STATE_Z(state);
   const int end = 32 * nwords;
@@ -223,6 +228,7 @@ JGPU_HUFF_HD uint32_t decode_subsequence(const Mem &mem, int bpm, uint32_t w0, i
   }
   *n_out = n;
   if (bad) *err = 1;
+  if (pos_out) *pos_out = pos;   /* bits from the start of the subsequence to where decoding stopped */
   return JGPU_HUFF_STATE(pos > end ? pos - end : 0, c, z);
 }
 

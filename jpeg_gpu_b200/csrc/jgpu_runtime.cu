@@ -1246,9 +1246,9 @@ static int decode_jpegs_gpu_entropy(jgpu_ctx *ctx, const jgpu_jpeg *files, int n
       int nseg = 0;
       const int64_t bound = (jfront_huff_bound(items[ok[k]].front, S, &nseg) + 15) & ~(int64_t)15;
       const uint64_t nsub = (uint64_t)(bound / (4 * S)) + 1;
-      slot[k] = {so, bound, (uint32_t)seg, (uint32_t)nseg + 2, (uint32_t)sub, (uint32_t)cta};
+      slot[k] = {so, bound, (uint32_t)seg, 2 * (uint32_t)nseg + 3, (uint32_t)sub, (uint32_t)cta};
       so += bound;
-      seg += (uint64_t)nseg + 2;
+      seg += 2 * (uint64_t)nseg + 3;
       sub += nsub;
       cta += (nsub + JGPU_HUFF_CTA - 1) / JGPU_HUFF_CTA + 1;
     }

@@ -50,13 +50,13 @@ extern "C" long long huff_emulate(const unsigned char *jpeg, int size, short *co
   int nseg_bound = 0;
   const long long cap = jfront_huff_bound(front, subseq_words, &nseg_bound);
   std::vector<unsigned char> stream((size_t)cap);
-  std::vector<unsigned int> seg_first((size_t)nseg_bound + 2);
+  std::vector<unsigned int> seg_first(2 * (size_t)nseg_bound + 3);
   std::vector<jgpu_huff_table> tabs(JGPU_HUFF_TABLES);
   jgpu_huff_file f;
   memset(&f, 0, sizeof(f));
   const char *why = nullptr;
   const long long bytes = jfront_huff_prepare(front, subseq_words, stream.data(), cap, seg_first.data(),
-                                              nseg_bound + 2, tabs.data(), &f, &why);
+                                              2 * nseg_bound + 3, tabs.data(), &f, &why);
   v.decode_free(front);
   if (bytes < 0) return -1;
   for (int p = 0; p < desc.ncomps; p++) {
@@ -170,8 +170,14 @@ extern "C" long long huff_emulate(const unsigned char *jpeg, int size, short *co
       StoreSink<HostMem> sink;
       sink.start(&mem, f.bpm, f.nhmb, coef, seg_mcu0, g0, seg_blocks);
       uint32_t nn = 0, err = 0;
-      const uint32_t out = decode_subsequence(mem, f.bpm, (uint32_t)i * S, S, st, sink, &nn, &err);
+      int pos = 0;
+      const uint32_t out = decode_subsequence(mem, f.bpm, (uint32_t)i * S, S, st, sink, &nn, &err, &pos);
       if (err) st_flags |= JGPU_HUFF_ERR_CODE;
+      if (sink.g >= seg_blocks) {
+        const uint32_t bits = seg_first[f.n_seg + 1 + seg];
+        const long long used = (long long)((uint32_t)i - seg_first[seg]) * (32 * S) + pos;
+        if (bits != 0xffffffffu && (long long)bits - used >= 8) st_flags |= JGPU_HUFF_ERR_TRAIL;
+      }
       if (sink.g < seg_blocks) {
         if ((uint32_t)i + 1 == seg_first[seg + 1]) st_flags |= JGPU_HUFF_ERR_SHORT;
         else if (out != state[i + 1] || nn != (nslots[i] & 0x7fffffffu)) st_flags |= JGPU_HUFF_ERR_SYNC;

@@ -118,3 +118,32 @@ def test_truncated_scan_is_flagged(emu):
     jpg = load("c420_64x48")[0]
     n, coef, status, stats = emulate(emu, jpg[:len(jpg) * 2 // 3])
     assert n > 0 and (status & 4), (status, stats)
+
+
+def test_corrupted_scans_are_flagged_or_decode_like_the_sequential_reader(emu, capfd):
+    """The write pass's verification, fuzzed: bytes flipped anywhere after the headers.  Whenever
+    the emulated kernels report a clean status, the sequential reader must accept the file too and
+    produce the same planes -- a damaged file may be handed to the fallback, never decoded wrong."""
+    rng = np.random.default_rng(11)
+    clean = flagged = 0
+    for name in ("c420_64x48", "c420_rst_80x48", "c444_q100_24x24", "gray_48x40", "c422_rst_33x17"):
+        jpg = load(name)[0]
+        sos = jpg.index(b"\xff\xda")
+        for trial in range(40):
+            b = bytearray(jpg)
+            for pos in rng.integers(sos + 14, len(b) - 2, size=int(rng.integers(1, 4))):
+                b[pos] = int(rng.integers(0, 256))
+            bad = bytes(b)
+            words, cta = ((32, 256), (2, 8))[trial & 1]
+            n, coef, status, stats = emulate(emu, bad, words, cta, 64)
+            if n < 0:
+                flagged += 1          # not eligible (e.g. a restart marker was hit): sequential reader's job
+                continue
+            if status != 0:
+                flagged += 1
+                continue
+            clean += 1
+            want = sequential_quant(bad)      # raises if the sequential reader rejects the file
+            assert np.array_equal(coef, want), (name, trial)
+    assert clean > 20 and flagged > 20, (clean, flagged)
+    capfd.readouterr()
