@@ -440,6 +440,18 @@ def main():
             dt = time.perf_counter() - t0
             e2e_jpeg["device_out_value"] = 3 * len(files) * w * h / 1e6 / dt
             del jpeg_dev
+            # planes instead of pixels (what the reference's xjpeg backend itself produces): half the
+            # read-back for 4:2:0
+            yuv_total, _ = J.probe_jpegs(files, out="yuv")
+            jpeg_yuv = torch.zeros(yuv_total, dtype=torch.uint8).pin_memory()
+            ctx.decode_jpegs(files, jpeg_yuv, nthreads=threads, entropy="gpu", out="yuv")
+            t0 = time.perf_counter()
+            for _ in range(3):
+                ctx.decode_jpegs(files, jpeg_yuv, nthreads=threads, entropy="gpu", out="yuv")
+            dt = time.perf_counter() - t0
+            e2e_jpeg["yuv_out_value"] = 3 * len(files) * w * h / 1e6 / dt
+            e2e_jpeg["yuv_d2h_bytes_per_step"] = yuv_total
+            del jpeg_yuv
             # the reference's own CPU path for the same files: xjpeg_decode_image(YUV), i.e. Huffman +
             # dequant + IDCT into planes (no colour conversion: the xjpeg backend has none), one file
             # per thread on all host cores (oracle/_ref; checker code, timed here as the baseline)

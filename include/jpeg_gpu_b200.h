@@ -77,7 +77,7 @@ void cuda_decode_set_device(int device);
  * contexts allocated later.  Returns EXIT_FAILURE for any other value. */
 int cuda_decode_set_upload(jpeg_decode_out format);
 
-/* Where decode_image(..., JPEG_DECODE_RGB) does its Huffman decoding: 0 (default) on the host, in
+/* Where decode_image(..., JPEG_DECODE_RGB / JPEG_DECODE_YUV) does its Huffman decoding: 0 (default) on the host, in
  * the front end; 1 on the device (jgpu_huff.cu, see jgpu_decode_jpegs_ex): the file's bytes are
  * uploaded as they are and no coefficient ever exists on the host.  Applies to the built-in
  * front end only (a front end set with cuda_decode_set_frontend keeps decoding on the host) and
@@ -263,6 +263,8 @@ typedef struct jgpu_jpeg_info {
 /* Host only.  Parses the headers, assigns rgb_off back to back (256-byte aligned) and
  * returns the output buffer size in bytes (rejected files take no space), or -1. */
 int64_t jgpu_jpegs_probe(const jgpu_jpeg *files, int n, jgpu_jpeg_info *info);
+/* The same for the output selected by flags (0 or JGPU_JPEGS_OUT_YUV; other bits are ignored). */
+int64_t jgpu_jpegs_probe_ex(const jgpu_jpeg *files, int n, unsigned flags, jgpu_jpeg_info *info);
 
 /* Decodes every accepted file into h_rgb + info[i].rgb_off (interleaved RGB8, or grey8 for
  * 1-component files).  h_rgb may be pageable or pinned.  nthreads <= 0: all host cores.
@@ -291,6 +293,12 @@ int jgpu_decode_jpegs(jgpu_ctx *ctx, const jgpu_jpeg *files, int n, int nthreads
  * callers whose next stage runs on the GPU.  Implies the GPU entropy decoder; the call still
  * returns only when the pixels are complete. */
 #define JGPU_JPEGS_DEVICE_OUT 0x100u
+/* OR-ed into flags: the output is what the reference's xjpeg backend produces for JPEG_DECODE_YUV
+ * (src/xjpeg.c:565-584) instead of pixels -- per file the padded u8 planes Y | Cb | Cr back to
+ * back (jgpu_layout.plane[i].data_off / width / height, jgpu_layout.data_len bytes), bit-exact
+ * with it, at info[i].rgb_off with info[i].rgb_len = data_len.  Half the read-back of RGB for
+ * 4:2:0.  Implies the GPU entropy decoder.  jgpu_jpegs_probe_ex sizes the buffer. */
+#define JGPU_JPEGS_OUT_YUV 0x200u
 int jgpu_decode_jpegs_ex(jgpu_ctx *ctx, const jgpu_jpeg *files, int n, int nthreads, unsigned flags,
                          uint8_t *h_rgb, int64_t rgb_cap, jgpu_jpeg_info *info);
 

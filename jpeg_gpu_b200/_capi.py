@@ -132,6 +132,7 @@ EXPORTS = [
                                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                                 C.c_void_p, C.c_void_p]),
     ("jgpu_jpegs_probe", C.c_int64, [C.POINTER(jgpu_jpeg), C.c_int, C.POINTER(jgpu_jpeg_info)]),
+    ("jgpu_jpegs_probe_ex", C.c_int64, [C.POINTER(jgpu_jpeg), C.c_int, C.c_uint, C.POINTER(jgpu_jpeg_info)]),
     ("jgpu_decode_jpegs", C.c_int, [C.c_void_p, C.POINTER(jgpu_jpeg), C.c_int, C.c_int, C.c_void_p, C.c_int64,
                                     C.POINTER(jgpu_jpeg_info)]),
     ("jgpu_decode_jpegs_ex", C.c_int, [C.c_void_p, C.POINTER(jgpu_jpeg), C.c_int, C.c_int, C.c_uint, C.c_void_p,

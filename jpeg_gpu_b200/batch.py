@@ -172,11 +172,12 @@ def _jpeg_infos(raw) -> List[JpegInfo]:
                      r.rgb_off, r.rgb_len, r.message.decode() if r.message else None) for r in raw]
 
 
-def probe_jpegs(files: Sequence[bytes]):
-    """Headers only (host, no GPU): returns (output bytes needed, [JpegInfo])."""
+def probe_jpegs(files: Sequence[bytes], out: str = "rgb"):
+    """Headers only (host, no GPU): returns (output bytes needed, [JpegInfo]); out="yuv" sizes the
+    buffer for the padded Y|Cb|Cr planes (JGPU_JPEGS_OUT_YUV) instead of pixels."""
     arr, keep = _jpeg_array(files)
     raw = (_capi.jgpu_jpeg_info * len(files))()
-    total = _capi.lib().jgpu_jpegs_probe(arr, len(files), raw)
+    total = _capi.lib().jgpu_jpegs_probe_ex(arr, len(files), {"rgb": 0, "yuv": 0x200}[out], raw)
     if total < 0:
         raise RuntimeError(f"jgpu_jpegs_probe failed: {_capi.last_error()}")
     del keep
@@ -233,20 +234,21 @@ class Context:
     ENTROPY = {"auto": 0, "cpu": 1, "gpu": 2}
 
     def decode_jpegs(self, files: Sequence[bytes], rgb=None, nthreads: int = 0, strict: bool = True,
-                     entropy: str = "auto"):
+                     entropy: str = "auto", out: str = "rgb"):
         """JPEG files in, RGB out (jgpu_decode_jpegs_ex).  entropy="gpu": Huffman decoding on the
         device (jgpu_huff.cu); "cpu": the multi-threaded host reader; "auto": $JGPU_ENTROPY, default
         gpu.  Returns (rgb uint8 buffer, [JpegInfo]); image i is
         rgb[info.rgb_off : info.rgb_off + info.rgb_len].reshape(info.shape)."""
         arr, keep = _jpeg_array(files)
         raw = (_capi.jgpu_jpeg_info * len(files))()
+        out_flag = {"rgb": 0, "yuv": 0x200}[out]   # JGPU_JPEGS_OUT_YUV: padded Y|Cb|Cr planes per file
         if rgb is None:
-            total = _capi.lib().jgpu_jpegs_probe(arr, len(files), raw)
+            total = _capi.lib().jgpu_jpegs_probe_ex(arr, len(files), out_flag, raw)
             if total < 0:
                 raise RuntimeError(f"jgpu_jpegs_probe failed: {_capi.last_error()}")
             rgb = np.zeros(max(int(total), 1), dtype=np.uint8)
         cap = rgb.numel() if hasattr(rgb, "numel") else rgb.size
-        flags = self.ENTROPY[entropy]
+        flags = self.ENTROPY[entropy] | out_flag
         if getattr(rgb, "is_cuda", False):
             flags |= 0x100   # JGPU_JPEGS_DEVICE_OUT: the pixels stay on the device
         rc = _capi.lib().jgpu_decode_jpegs_ex(self._h, arr, len(files), nthreads, flags, _addr(rgb), cap, raw)

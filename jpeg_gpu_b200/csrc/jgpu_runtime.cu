@@ -940,7 +940,7 @@ bool probe_one(const jgpu_jpeg &f, JpegItem &it, jgpu_jpeg_info &out, bool keep_
 
 }  // namespace
 
-extern "C" int64_t jgpu_jpegs_probe(const jgpu_jpeg *files, int n, jgpu_jpeg_info *info) {
+extern "C" int64_t jgpu_jpegs_probe_ex(const jgpu_jpeg *files, int n, unsigned flags, jgpu_jpeg_info *info) {
   if (!files || !info || n <= 0) {
     jgpu_fail("jgpu_jpegs_probe: bad arguments");
     return -1;
@@ -949,11 +949,16 @@ extern "C" int64_t jgpu_jpegs_probe(const jgpu_jpeg *files, int n, jgpu_jpeg_inf
   for (int i = 0; i < n; i++) {
     JpegItem it;
     if (probe_one(files[i], it, info[i], false)) {
+      if (flags & JGPU_JPEGS_OUT_YUV) info[i].rgb_len = it.lay.data_len;   /* padded Y|Cb|Cr planes */
       info[i].rgb_off = off;
       off += (info[i].rgb_len + 255) & ~(int64_t)255;
     }
   }
   return off;
+}
+
+extern "C" int64_t jgpu_jpegs_probe(const jgpu_jpeg *files, int n, jgpu_jpeg_info *info) {
+  return jgpu_jpegs_probe_ex(files, n, 0, info);
 }
 
 static int decode_jpegs_cpu_entropy(jgpu_ctx *ctx, const jgpu_jpeg *files, int n, int nthreads,
@@ -1164,7 +1169,8 @@ static int decode_jpegs_cpu_entropy(jgpu_ctx *ctx, const jgpu_jpeg *files, int n
  * scans, states that did not settle) go through the sequential reader afterwards, which
  * decodes or rejects them exactly as before. */
 static int decode_jpegs_gpu_entropy(jgpu_ctx *ctx, const jgpu_jpeg *files, int n, int nthreads,
-                                    uint8_t *h_rgb, int64_t rgb_cap, jgpu_jpeg_info *info, bool device_out) {
+                                    uint8_t *h_rgb, int64_t rgb_cap, jgpu_jpeg_info *info, bool device_out,
+                                    bool yuv_out) {
   CU_TRY(cudaSetDevice(ctx->device));
   const jpeg_decode_ctx_vtbl &v = JFRONT_DECODE_CTX_VTBL;
   constexpr int S = kHuffSubseqWords;
@@ -1185,12 +1191,15 @@ static int decode_jpegs_gpu_entropy(jgpu_ctx *ctx, const jgpu_jpeg *files, int n
   for (int i = 0; i < n; i++) {
     JpegItem &it = items[i];
     if (!probe_one(files[i], it, info[i], true)) continue;
+    /* one output buffer either way: pixels, or (JGPU_JPEGS_OUT_YUV) the padded Y|Cb|Cr planes */
+    const int64_t out_len = yuv_out ? it.lay.data_len : it.lay.rgb_len;
     info[i].rgb_off = rgb_off;
-    it.desc.rgb_off = rgb_off;
+    info[i].rgb_len = out_len;
+    it.desc.rgb_off = yuv_out ? 0 : rgb_off;
     it.desc.coef_off = coef_off;
-    it.desc.yuv_off = -1;
+    it.desc.yuv_off = yuv_out ? rgb_off : -1;
     it.desc.qtab_set = (int32_t)ok.size();
-    rgb_off += (it.lay.rgb_len + 255) & ~(int64_t)255;
+    rgb_off += (out_len + 255) & ~(int64_t)255;
     coef_off += it.lay.coef_len;
     for (int t = 0; t < NQUANT_MAX; t++) {
       qtabs.insert(qtabs.end(), it.header.quant[t].tbl, it.header.quant[t].tbl + 64);
@@ -1211,7 +1220,7 @@ static int decode_jpegs_gpu_entropy(jgpu_ctx *ctx, const jgpu_jpeg *files, int n
   {
     /* the last image ends at its own length, not at the next 256-byte boundary */
     const JpegItem &last = items[ok.back()];
-    const int64_t need = last.desc.rgb_off + last.lay.rgb_len;
+    const int64_t need = yuv_out ? last.desc.yuv_off + last.lay.data_len : last.desc.rgb_off + last.lay.rgb_len;
     if (need > rgb_cap) {
       release_fronts();
       return jgpu_fail("jgpu_decode_jpegs: output needs %lld bytes, buffer has %lld", (long long)need,
@@ -1219,7 +1228,7 @@ static int decode_jpegs_gpu_entropy(jgpu_ctx *ctx, const jgpu_jpeg *files, int n
     }
   }
   const int m = (int)ok.size();
-  const unsigned flags = JGPU_OUT_RGB;
+  const unsigned flags = yuv_out ? JGPU_OUT_YUV : JGPU_OUT_RGB;
   if (!ctx->cached_plan || ctx->cached_flags != flags || !same_descs(ctx->cached_descs, descs.data(), m)) {
     if (ctx->cached_plan) jgpu_plan_destroy(ctx->cached_plan);
     ctx->cached_plan = jgpu_plan_create(ctx, descs.data(), m, flags);
@@ -1396,12 +1405,14 @@ static int decode_jpegs_gpu_entropy(jgpu_ctx *ctx, const jgpu_jpeg *files, int n
       l.d_status = (uint32_t *)ctx->dz_status.ptr;
       l.d_coef = d_coef;
       if (huff_launch(l, st)) return EXIT_FAILURE;
-      if (plan_run_range(plan, i0, i1, d_coef, d_qtabs, m, d_rgb, nullptr, st)) return EXIT_FAILURE;
+      if (plan_run_range(plan, i0, i1, d_coef, d_qtabs, m, yuv_out ? nullptr : d_rgb, yuv_out ? d_rgb : nullptr, st)) {
+        return EXIT_FAILURE;
+      }
       CU_TRY(cudaMemcpyAsync(h_status + i0, (uint32_t *)ctx->dz_status.ptr + i0, 4 * (size_t)(i1 - i0),
                              cudaMemcpyDeviceToHost, st));
       if (!device_out) {
-        const int64_t lo = descs[i0].rgb_off;
-        const int64_t hi = descs[i1 - 1].rgb_off + plan->layouts[i1 - 1].rgb_len;
+        const int64_t lo = info[ok[i0]].rgb_off;
+        const int64_t hi = info[ok[i1 - 1]].rgb_off + info[ok[i1 - 1]].rgb_len;
         CU_TRY(cudaMemcpyAsync(h_rgb + lo, d_rgb + lo, (size_t)(hi - lo), cudaMemcpyDeviceToHost, st));
       }
       i0 = i1;
@@ -1446,12 +1457,12 @@ static int decode_jpegs_gpu_entropy(jgpu_ctx *ctx, const jgpu_jpeg *files, int n
     }
     cudaStream_t st = ctx->streams[0];
     CU_TRY(cudaMemcpyAsync(d_coef + it.desc.coef_off, h_coef, (size_t)it.lay.coef_len * 2, cudaMemcpyHostToDevice, st));
-    if (plan_run_range(plan, k, k + 1, d_coef, d_qtabs, m, d_rgb, nullptr, st)) {
+    if (plan_run_range(plan, k, k + 1, d_coef, d_qtabs, m, yuv_out ? nullptr : d_rgb, yuv_out ? d_rgb : nullptr, st)) {
       release_fronts();
       return EXIT_FAILURE;
     }
     if (!device_out) {
-      CU_TRY(cudaMemcpyAsync(h_rgb + it.desc.rgb_off, d_rgb + it.desc.rgb_off, (size_t)it.lay.rgb_len,
+      CU_TRY(cudaMemcpyAsync(h_rgb + info[ok[k]].rgb_off, d_rgb + info[ok[k]].rgb_off, (size_t)info[ok[k]].rgb_len,
                              cudaMemcpyDeviceToHost, st));
     }
     CU_TRY(cudaStreamSynchronize(st));
@@ -1473,19 +1484,20 @@ extern "C" int jgpu_decode_jpegs_ex(jgpu_ctx *ctx, const jgpu_jpeg *files, int n
                                     uint8_t *h_rgb, int64_t rgb_cap, jgpu_jpeg_info *info) {
   if (!ctx || !files || n <= 0 || !h_rgb || !info) return jgpu_fail("jgpu_decode_jpegs: bad arguments");
   const bool device_out = (flags & JGPU_JPEGS_DEVICE_OUT) != 0;
-  unsigned entropy = flags & ~JGPU_JPEGS_DEVICE_OUT;
+  const bool yuv_out = (flags & JGPU_JPEGS_OUT_YUV) != 0;
+  unsigned entropy = flags & ~(JGPU_JPEGS_DEVICE_OUT | JGPU_JPEGS_OUT_YUV);
   if (entropy == JGPU_ENTROPY_AUTO) {
     const char *env = getenv("JGPU_ENTROPY");
-    entropy = env && !strcmp(env, "cpu") && !device_out ? JGPU_ENTROPY_CPU : JGPU_ENTROPY_GPU;
+    entropy = env && !strcmp(env, "cpu") && !device_out && !yuv_out ? JGPU_ENTROPY_CPU : JGPU_ENTROPY_GPU;
   }
-  if (entropy == JGPU_ENTROPY_CPU && !device_out) {
+  if (entropy == JGPU_ENTROPY_CPU && !device_out && !yuv_out) {
     return decode_jpegs_cpu_entropy(ctx, files, n, nthreads, h_rgb, rgb_cap, info);
   }
   if (entropy == JGPU_ENTROPY_GPU) {
     if (device_out && (reinterpret_cast<uintptr_t>(h_rgb) & 255)) {
       return jgpu_fail("jgpu_decode_jpegs_ex: a device output buffer must be 256-byte aligned");
     }
-    return decode_jpegs_gpu_entropy(ctx, files, n, nthreads, h_rgb, rgb_cap, info, device_out);
+    return decode_jpegs_gpu_entropy(ctx, files, n, nthreads, h_rgb, rgb_cap, info, device_out, yuv_out);
   }
   return jgpu_fail("jgpu_decode_jpegs_ex: unsupported flags %u", flags);
 }

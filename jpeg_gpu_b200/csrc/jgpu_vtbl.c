@@ -52,6 +52,8 @@ typedef struct cuda_decode_ctx {
   const unsigned char *buf; /* the caller's file bytes (jpeg_info.buf), for the device entropy decoder */
   int size;
   int entropy_on_device;
+  uint8_t *planes;          /* pinned staging for YUV output of the device entropy path (grow-only) */
+  int64_t planes_cap;
   jgpu_ctx *gpu;        /* created on the first YUV/RGB decode, kept across resets */
   int device;
   int have_header;
@@ -144,6 +146,52 @@ static int cuda_decode_image(cuda_decode_ctx *ctx, image *img, jpeg_decode_out o
     }
     return EXIT_SUCCESS;
   }
+  if (ctx->entropy_on_device && out == JPEG_DECODE_YUV) {
+    /* planes come back packed Y | Cb | Cr; the surface holds them as separate allocations */
+    jgpu_jpeg file;
+    jgpu_jpeg_info jinfo;
+    jgpu_image_desc d;
+    jgpu_layout lay;
+    if (jgpu_desc_from_header(&ctx->header, &d) || jgpu_layout_query(&d, &lay)) {
+      fprintf(stderr, "%s\n", jgpu_last_error());
+      return EXIT_FAILURE;
+    }
+    for (i = 0; i < d.ncomps; i++) {
+      if (img->plane[i].data == NULL || img->plane[i].width != lay.plane[i].width ||
+          img->plane[i].height != lay.plane[i].height) {
+        fprintf(stderr, "Error, image surface does not match the jpeg header\n");
+        return EXIT_FAILURE;
+      }
+    }
+    if (ctx->gpu == NULL) {
+      ctx->gpu = jgpu_create(ctx->device);
+      if (ctx->gpu == NULL) {
+        fprintf(stderr, "%s\n", jgpu_last_error());
+        return EXIT_FAILURE;
+      }
+    }
+    if (ctx->planes_cap < lay.data_len) {
+      jgpu_host_free(ctx->planes);
+      ctx->planes = (uint8_t *)jgpu_host_alloc((size_t)lay.data_len);
+      ctx->planes_cap = ctx->planes ? lay.data_len : 0;
+      if (ctx->planes == NULL) {
+        fprintf(stderr, "%s\n", jgpu_last_error());
+        return EXIT_FAILURE;
+      }
+    }
+    file.data = ctx->buf;
+    file.size = ctx->size;
+    if (jgpu_decode_jpegs_ex(ctx->gpu, &file, 1, 1, JGPU_ENTROPY_GPU | JGPU_JPEGS_OUT_YUV, ctx->planes,
+                             ctx->planes_cap, &jinfo) != EXIT_SUCCESS) {
+      fprintf(stderr, "%s\n", jgpu_last_error());
+      return EXIT_FAILURE;
+    }
+    for (i = 0; i < d.ncomps; i++) {
+      memcpy(img->plane[i].data, ctx->planes + lay.plane[i].data_off,
+             (size_t)lay.plane[i].width * lay.plane[i].height);
+    }
+    return EXIT_SUCCESS;
+  }
   if (ctx->upload == JPEG_DECODE_PACK) {
     /* the reader counts words into plane[i].packed (src/xjpeg.c:492,515,532); start from zero */
     for (i = 0; i < img->nplanes && i < NPLANES_MAX; i++) img->plane[i].packed = 0;
@@ -183,6 +231,7 @@ static void cuda_decode_reset(cuda_decode_ctx *ctx, jpeg_info *info) {
 static void cuda_decode_free(cuda_decode_ctx *ctx) {
   if (ctx == NULL) return;
   (*ctx->front.decode_free)(ctx->front_ctx);
+  jgpu_host_free(ctx->planes);
   jgpu_destroy(ctx->gpu);
   free(ctx);
 }

@@ -60,7 +60,8 @@ def test_cuda_backend_with_pack_upload(name):
 @pytest.mark.parametrize("name", NAMES)
 def test_cuda_backend_with_entropy_decoding_on_the_device(name):
     """cuda_decode_set_entropy(1): decode_image(RGB) uploads the file as it is and decodes the
-    Huffman scan on the GPU; same pixels, same protocol; YUV still comes through the front end."""
+    Huffman scan on the GPU; same pixels and the same planes (bit-exact with xjpeg's YUV output),
+    same protocol."""
     from jpeg_gpu_b200 import _capi
     jpg, z, g = load(name)
     assert _capi.lib().cuda_decode_set_entropy(1) == 0
@@ -71,7 +72,7 @@ def test_cuda_backend_with_entropy_decoding_on_the_device(name):
                 assert np.array_equal(dec.decode_image("rgb")["pixels"].reshape(-1), z["rgb"])
                 dec.decode_reset()
             dec.decode_header()
-            planes = dec.decode_image("yuv")["planes"]
+            planes = dec.decode_image("yuv")["planes"]     # also decoded on the device, planes read back
             assert np.array_equal(np.concatenate([p.ravel() for p in planes]), z["yuv"])
     finally:
         assert _capi.lib().cuda_decode_set_entropy(0) == 0

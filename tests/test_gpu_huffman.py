@@ -116,3 +116,14 @@ def test_pixels_can_stay_on_the_device(gpu_ctx):
     for a, b in zip(gi, ri):
         assert a.status == 0 and (a.rgb_off, a.rgb_len) == (b.rgb_off, b.rgb_len)
         assert np.array_equal(got[a.rgb_off:a.rgb_off + a.rgb_len], ref[b.rgb_off:b.rgb_off + b.rgb_len])
+
+
+def test_planes_instead_of_pixels(gpu_ctx):
+    """JGPU_JPEGS_OUT_YUV: per file the padded Y|Cb|Cr planes, bit-exact with what the compiled
+    reference's xjpeg_decode_image(YUV) wrote for the golden files."""
+    files = [load(n)[0] for n in NAMES]
+    buf, infos = gpu_ctx.decode_jpegs(files, entropy="gpu", out="yuv")
+    for name, inf in zip(NAMES, infos):
+        z = load(name)[1]
+        assert inf.status == 0 and inf.rgb_len == z["yuv"].size, name
+        assert np.array_equal(buf[inf.rgb_off:inf.rgb_off + inf.rgb_len], z["yuv"]), name
