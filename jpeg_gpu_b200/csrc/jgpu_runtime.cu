@@ -1362,12 +1362,18 @@ static int decode_jpegs_gpu_entropy(jgpu_ctx *ctx, const jgpu_jpeg *files, int n
         info[ok[k]].tasks = on_gpu[k] ? (int32_t)h_files[k].n_subseq : 1;
       }
       cudaStream_t st = ctx->streams[chunk % kHostStreams];
-      /* each file's actual stream is shorter than its slot; copy slot by slot what was written */
-      for (int k = i0; k < i1; k++) {
-        if (!on_gpu[k]) continue;
-        const size_t bytes = (size_t)h_files[k].n_subseq * 4 * S + 16;
-        CU_TRY(cudaMemcpyAsync((unsigned char *)ctx->dz_stream.ptr + slot[k].stream_off, h_stream + slot[k].stream_off,
-                               bytes, cudaMemcpyHostToDevice, st));
+      /* each file's stream is a little shorter than its slot (headers, stuffing and markers are
+       * gone): large files are copied slot by slot, many small ones in one go, gaps included */
+      if (i1 - i0 > 16) {
+        CU_TRY(cudaMemcpyAsync((unsigned char *)ctx->dz_stream.ptr + slot[i0].stream_off, h_stream + slot[i0].stream_off,
+                               (size_t)(slot[i1].stream_off - slot[i0].stream_off), cudaMemcpyHostToDevice, st));
+      } else {
+        for (int k = i0; k < i1; k++) {
+          if (!on_gpu[k]) continue;
+          const size_t bytes = (size_t)h_files[k].n_subseq * 4 * S + 16;
+          CU_TRY(cudaMemcpyAsync((unsigned char *)ctx->dz_stream.ptr + slot[k].stream_off, h_stream + slot[k].stream_off,
+                                 bytes, cudaMemcpyHostToDevice, st));
+        }
       }
       CU_TRY(cudaMemcpyAsync((jgpu_huff_file *)ctx->dz_files.ptr + i0, h_files + i0, sizeof(jgpu_huff_file) * (i1 - i0),
                              cudaMemcpyHostToDevice, st));

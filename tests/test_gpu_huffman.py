@@ -127,3 +127,15 @@ def test_planes_instead_of_pixels(gpu_ctx):
         z = load(name)[1]
         assert inf.status == 0 and inf.rgb_len == z["yuv"].size, name
         assert np.array_equal(buf[inf.rgb_off:inf.rgb_off + inf.rgb_len], z["yuv"]), name
+
+
+def test_many_small_files_in_one_batch(gpu_ctx):
+    """Hundreds of small files: one group, one upload, a grid of (pieces x files) with mostly tiny
+    files next to a larger one; pixels as from the sequential reader."""
+    pytest.importorskip("PIL")
+    base = [load(n)[0] for n in NAMES] + [_jpeg(640, 480, 2, rst=20), _jpeg(96, 64, 0)]
+    files = [base[(7 * i) % len(base)] for i in range(400)]
+    got, gi = gpu_ctx.decode_jpegs(files, entropy="gpu")
+    ref, ri = gpu_ctx.decode_jpegs(files, entropy="cpu")
+    assert all(i.status == 0 for i in gi)
+    assert np.array_equal(got, ref)
