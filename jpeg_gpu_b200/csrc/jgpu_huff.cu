@@ -174,9 +174,11 @@ k_huff_sync(const jgpu_huff_file *__restrict__ files, const uint32_t *__restrict
   SyncSmem<S> &sm = *reinterpret_cast<SyncSmem<S> *>(smem_raw);
   const jgpu_huff_file &gf = files[blockIdx.y];
   const int bx = cta_x();
-  const int first = bx * kCta;
-  if (first >= (int)gf.n_subseq) return;
-  const int count = min(kCta, (int)gf.n_subseq - first);
+  const int own0 = bx * JGPU_HUFF_OWN;             /* first subsequence this CTA owns */
+  if (own0 >= (int)gf.n_subseq) return;
+  const int first = max(0, own0 - JGPU_HUFF_WARM);  /* first one it decodes */
+  const int lead = own0 - first;                    /* warm-up threads: their results are dropped */
+  const int count = min(lead + JGPU_HUFF_OWN, (int)gf.n_subseq - first);
   const int t = threadIdx.x;
   const uint32_t gi = gf.subseq0 + (uint32_t)first + (uint32_t)min(t, count - 1);
   const uint32_t cslot = gf.cta0 + (uint32_t)bx;
@@ -184,7 +186,7 @@ k_huff_sync(const jgpu_huff_file *__restrict__ files, const uint32_t *__restrict
   if (pass > 0) {
     /* Did the state handed to this CTA change since the last launch?  If not, neither does
      * anything it computes. */
-    const uint32_t g0 = gf.subseq0 + (uint32_t)first;
+    const uint32_t g0 = gf.subseq0 + (uint32_t)own0;
     new0 = (nslots[g0] >> 31) ? 0u : carry_in[cslot];
     if (new0 == state[g0]) {
       if (t == 0) carry_out[cslot + 1] = carry_in[cslot + 1];
@@ -196,6 +198,8 @@ k_huff_sync(const jgpu_huff_file *__restrict__ files, const uint32_t *__restrict
   bool is_first;
   uint32_t s_in, n = 0;
   bool need;
+  /* the thread whose start state is given, not derived from its left neighbour */
+  const int fixed = pass == 0 ? 0 : lead;
   if (pass == 0) {
     /* restart interval of this subsequence: the last entry of seg_first[] not above it */
     const uint32_t i = (uint32_t)(first + min(t, count - 1));
@@ -206,15 +210,19 @@ k_huff_sync(const jgpu_huff_file *__restrict__ files, const uint32_t *__restrict
       if (sf[mid] <= i) lo = mid; else hi = mid;
     }
     is_first = sf[lo] == i;
-    if (t < count) segid[gi] = lo;
+    if (t >= lead && t < count) segid[gi] = lo;
     s_in = 0;
     need = t < count;
-  } else {
+  } else if (t >= lead) {
     const uint32_t v = nslots[gi];
     is_first = (v >> 31) != 0;
     n = v & 0x7fffffffu;
-    s_in = t == 0 ? new0 : state[gi];
-    need = t == 0;
+    s_in = t == lead ? new0 : state[gi];
+    need = t == lead;
+  } else {
+    is_first = false;
+    s_in = 0;
+    need = false;
   }
   sm.s_out[t] = s_in;
   sm.s_in[t] = s_in;
@@ -247,7 +255,7 @@ k_huff_sync(const jgpu_huff_file *__restrict__ files, const uint32_t *__restrict
       sm.n[u] = nn;
     }
     __syncthreads();
-    const uint32_t ni = (t == 0 || is_first) ? s_in : sm.s_out[t];
+    const uint32_t ni = (t <= fixed || is_first) ? s_in : sm.s_out[t];
     need = ni != s_in && t < count;
     s_in = ni;
     sm.s_in[t] = ni;
@@ -258,7 +266,7 @@ k_huff_sync(const jgpu_huff_file *__restrict__ files, const uint32_t *__restrict
       __syncthreads();
     }
   }
-  if (t < count) {
+  if (t >= lead && t < count) {
     state[gi] = s_in;
     nslots[gi] = sm.n[t] | (is_first ? 0x80000000u : 0u);
     if (t == count - 1) carry_out[cslot + 1] = sm.s_out[count];
@@ -458,6 +466,7 @@ int huff_launch(const HuffLaunch &l, cudaStream_t st) {
   constexpr int S = kHuffSubseqWords;
   if (l.n_files <= 0 || l.max_subseq <= 0) return 0;
   const dim3 grid((unsigned)((l.max_subseq + kCta - 1) / kCta), (unsigned)l.n_files);
+  const dim3 sync_grid((unsigned)((l.max_subseq + JGPU_HUFF_OWN - 1) / JGPU_HUFF_OWN), (unsigned)l.n_files);
   const size_t smem = sizeof(SyncSmem<S>);
   cudaError_t e;
   if ((e = cudaMemsetAsync(l.d_carry[0] + l.carry0, 0, sizeof(uint32_t) * l.n_carry, st)) != cudaSuccess ||
@@ -466,7 +475,7 @@ int huff_launch(const HuffLaunch &l, cudaStream_t st) {
     return jgpu_fail("entropy decoder: memset failed (%s)", cudaGetErrorString(e));
   }
   for (int pass = 0; pass < l.sync_passes; pass++) {
-    k_huff_sync<S><<<grid, kCta, smem, st>>>(l.d_files, l.d_stream, l.d_tables, l.d_seg_first, l.d_state,
+    k_huff_sync<S><<<sync_grid, kCta, smem, st>>>(l.d_files, l.d_stream, l.d_tables, l.d_seg_first, l.d_state,
                                              l.d_nslots, l.d_segid, l.d_carry[(pass + 1) & 1],
                                              l.d_carry[pass & 1], pass);
   }

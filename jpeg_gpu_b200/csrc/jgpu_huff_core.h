@@ -41,6 +41,13 @@
 #define JGPU_HUFF_MAX_BLOCKS 10   /* blocks per MCU, T.81 B.2.3 */
 #define JGPU_HUFF_TABLES 6        /* per file: (DC, AC) of each of up to 3 scan components */
 #define JGPU_HUFF_CTA 256         /* subsequences per CTA of the sync / write kernels */
+/* Sync kernel: the first JGPU_HUFF_WARM threads of a CTA re-decode the last subsequences of the
+ * CTA before it, only to hand the first subsequence the CTA OWNS a start state that has already
+ * fallen into step (the chance that eight pieces in a row do not is about 0.1 % on 4:2:0 files).
+ * Without them every CTA's first state is a blind guess and nearly every CTA has to be redone
+ * in the second launch. */
+#define JGPU_HUFF_WARM 8
+#define JGPU_HUFF_OWN (JGPU_HUFF_CTA - JGPU_HUFF_WARM)   /* subsequences a sync CTA owns */
 
 /* One Huffman table prepared for the decoder. */
 typedef struct jgpu_huff_table {

@@ -1259,7 +1259,7 @@ static int decode_jpegs_gpu_entropy(jgpu_ctx *ctx, const jgpu_jpeg *files, int n
       so += bound;
       seg += 2 * (uint64_t)nseg + 3;
       sub += nsub;
-      cta += (nsub + JGPU_HUFF_CTA - 1) / JGPU_HUFF_CTA + 1;
+      cta += (nsub + JGPU_HUFF_OWN - 1) / JGPU_HUFF_OWN + 1;   /* carry slots of the sync kernel's CTAs */
     }
     slot[m] = {so, 0, (uint32_t)seg, 0, (uint32_t)sub, (uint32_t)cta};
     if (so / 4 >= 0xffffffffll || sub >= 0xffffffffull) {

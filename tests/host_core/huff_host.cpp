@@ -67,7 +67,11 @@ extern "C" long long huff_emulate(const unsigned char *jpeg, int size, short *co
   const HostMem mem = {reinterpret_cast<const uint32_t *>(stream.data()), tabs.data(), &f, kZigzag};
   const int S = subseq_words;
   const int n = (int)f.n_subseq;
-  const int nctas = (n + cta - 1) / cta;
+  // the sync kernel's CTAs overlap: `warm` threads re-decode the end of the previous CTA's range
+  // (JGPU_HUFF_WARM = 8 of 256 in the product; scaled down with the shrunken geometries)
+  const int warm = cta >= 32 ? JGPU_HUFF_WARM * cta / JGPU_HUFF_CTA : cta / 4;
+  const int own = cta - warm;
+  const int nctas = (n + own - 1) / own;
   std::vector<uint32_t> state(n, 0), nslots(n, 0), slots(n, 0), segid(n, 0);
   std::vector<uint32_t> carry[2] = {std::vector<uint32_t>(nctas + 1, 0), std::vector<uint32_t>(nctas + 1, 0)};
   unsigned st_flags = 0;
@@ -78,16 +82,19 @@ extern "C" long long huff_emulate(const unsigned char *jpeg, int size, short *co
     const std::vector<uint32_t> &cin = carry[(pass + 1) & 1];
     std::vector<uint32_t> &cout = carry[pass & 1];
     for (int x = 0; x < nctas; x++) {
-      const int first = x * cta, count = std::min(cta, n - first);
+      const int own0 = x * own;
+      const int first = std::max(0, own0 - warm), lead = own0 - first;
+      const int count = std::min(lead + own, n - first);
       uint32_t new0 = 0;
       if (pass > 0) {
-        new0 = (nslots[first] >> 31) ? 0u : cin[x];
-        if (new0 == state[first]) {
+        new0 = (nslots[own0] >> 31) ? 0u : cin[x];
+        if (new0 == state[own0]) {
           cout[x + 1] = cin[x + 1];
           continue;
         }
         recomputed++;
       }
+      const int fixed = pass == 0 ? 0 : lead;
       std::vector<uint32_t> s_in(count), s_out(count + 1, 0), nn(count, 0);
       std::vector<char> need(count), is_first(count);
       for (int t = 0; t < count; t++) {
@@ -99,14 +106,18 @@ extern "C" long long huff_emulate(const unsigned char *jpeg, int size, short *co
             if (seg_first[mid] <= i) lo = mid; else hi = mid;
           }
           is_first[t] = seg_first[lo] == i;
-          segid[i] = lo;
+          if (t >= lead) segid[i] = lo;
           s_in[t] = 0;
           need[t] = 1;
-        } else {
+        } else if (t >= lead) {
           is_first[t] = (nslots[i] >> 31) != 0;
           nn[t] = nslots[i] & 0x7fffffffu;
-          s_in[t] = t == 0 ? new0 : state[i];
-          need[t] = t == 0;
+          s_in[t] = t == lead ? new0 : state[i];
+          need[t] = t == lead;
+        } else {
+          is_first[t] = 0;
+          s_in[t] = 0;
+          need[t] = 0;
         }
         s_out[t] = s_in[t];
       }
@@ -132,7 +143,7 @@ extern "C" long long huff_emulate(const unsigned char *jpeg, int size, short *co
         }
         bool any = false;
         for (int t = 0; t < count; t++) {
-          const uint32_t ni = (t == 0 || is_first[t]) ? s_in[t] : s_out[t];
+          const uint32_t ni = (t <= fixed || is_first[t]) ? s_in[t] : s_out[t];
           need[t] = ni != s_in[t];
           s_in[t] = ni;
           any |= need[t] != 0;
@@ -140,7 +151,7 @@ extern "C" long long huff_emulate(const unsigned char *jpeg, int size, short *co
         if (!any) break;
       }
       max_rounds = std::max(max_rounds, rounds);
-      for (int t = 0; t < count; t++) {
+      for (int t = lead; t < count; t++) {
         state[first + t] = s_in[t];
         nslots[first + t] = nn[t] | (is_first[t] ? 0x80000000u : 0u);
       }
