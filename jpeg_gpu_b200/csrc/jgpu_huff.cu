@@ -2,7 +2,8 @@
  * around the per-thread loop of jgpu_huff_core.h.  See that header for the method; this file
  * is the mapping to the machine.
  *
- *   k_huff_sync   one CTA = 256 consecutive subsequences of one file.  The file's six decoder
+ *   k_huff_sync   one CTA = 248 consecutive subsequences of one file plus the 8 before them as
+ *                 a warm-up (JGPU_HUFF_WARM).  The file's six decoder
  *                 tables (14.6 KB) and the CTA's 32 KB of scan words are staged in shared
  *                 memory (words XOR-swizzled by subsequence so that 32 threads reading "their
  *                 j-th word" hit 32 banks); states pass from thread to thread through shared

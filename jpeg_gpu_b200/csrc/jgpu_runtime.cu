@@ -1455,11 +1455,25 @@ static int decode_jpegs_gpu_entropy(jgpu_ctx *ctx, const jgpu_jpeg *files, int n
     memset(h_coef, 0, (size_t)it.lay.coef_len * 2);
     image img;
     bind_image(&img, it.desc, it.lay, h_coef);
-    if (v.decode_image(it.front, &img, JPEG_DECODE_QUANT) != EXIT_SUCCESS) {
-      info[ok[k]].status = 1;
-      info[ok[k]].message = "Error decoding scan";
-      rc = EXIT_FAILURE;
-      continue;
+    {
+      /* exactly what the host-thread path does with this file: restart intervals cut at their
+       * markers when those are in place, else the sequential reader and its error reports */
+      jfront_segments segs;
+      const char *err = nullptr;
+      int frc;
+      if (jfront_find_segments(it.front, &segs) == 0) {
+        frc = jfront_decode_segments(it.front, &img, JPEG_DECODE_QUANT, &segs, 0, segs.nseg, &err);
+        jfront_segments_free(&segs);
+      } else {
+        frc = v.decode_image(it.front, &img, JPEG_DECODE_QUANT);
+        if (frc) err = "Error decoding scan";
+      }
+      if (frc) {
+        info[ok[k]].status = 1;
+        info[ok[k]].message = err ? err : "Error decoding scan";
+        rc = EXIT_FAILURE;
+        continue;
+      }
     }
     cudaStream_t st = ctx->streams[0];
     CU_TRY(cudaMemcpyAsync(d_coef + it.desc.coef_off, h_coef, (size_t)it.lay.coef_len * 2, cudaMemcpyHostToDevice, st));

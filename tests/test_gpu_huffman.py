@@ -139,3 +139,35 @@ def test_many_small_files_in_one_batch(gpu_ctx):
     ref, ri = gpu_ctx.decode_jpegs(files, entropy="cpu")
     assert all(i.status == 0 for i in gi)
     assert np.array_equal(got, ref)
+
+
+def test_fuzzed_files_agree_with_the_host_thread_path(gpu_ctx, capfd):
+    """tools/fuzz_jpegs_gpu.py in small: 240 files with flipped, deleted or cut-off bytes (and
+    undamaged ones): status and pixels of the device entropy path == those of the host path."""
+    pytest.importorskip("PIL")
+    rng = np.random.default_rng(21)
+    base = [load(n)[0] for n in NAMES] + [_jpeg(320, 240, 2, rst=20, seed=3), _jpeg(333, 222, 1, rst=5, seed=4),
+                                          _jpeg(200, 120, 0, seed=5)]
+    files = []
+    for i in range(240):
+        b = bytearray(base[i % len(base)])
+        sos = bytes(b).index(b"\xff\xda")
+        if i % 4 == 0:
+            for pos in rng.integers(sos + 14, len(b) - 2, size=int(rng.integers(1, 4))):
+                b[pos] = int(rng.integers(0, 256))
+        elif i % 4 == 1:
+            b = b[:int(rng.integers(sos + 20, len(b)))]
+        elif i % 4 == 2:
+            pos = int(rng.integers(sos + 14, len(b) - 4))
+            del b[pos:pos + int(rng.integers(1, 4))]
+        files.append(bytes(b))
+    got, gi = gpu_ctx.decode_jpegs(files, strict=False, entropy="gpu")
+    ref, ri = gpu_ctx.decode_jpegs(files, strict=False, entropy="cpu")
+    on_device = 0
+    for k, (a, b) in enumerate(zip(gi, ri)):
+        assert a.status == b.status, (k, a.message, b.message)
+        if a.status == 0:
+            on_device += a.tasks > 1
+            assert np.array_equal(got[a.rgb_off:a.rgb_off + a.rgb_len], ref[b.rgb_off:b.rgb_off + b.rgb_len]), k
+    assert on_device > 100
+    capfd.readouterr()
