@@ -81,8 +81,10 @@ int cuda_decode_set_upload(jpeg_decode_out format);
  * the front end; 1 on the device (jgpu_huff.cu, see jgpu_decode_jpegs_ex): the file's bytes are
  * uploaded as they are and no coefficient ever exists on the host.  Applies to the built-in
  * front end only (a front end set with cuda_decode_set_frontend keeps decoding on the host) and
- * to contexts allocated later.  Never called: $JGPU_ENTROPY=gpu turns it on.  Returns EXIT_FAILURE
- * for any other value. */
+ * to contexts allocated later.  Never called: $JGPU_ENTROPY=gpu turns it on.  Well-formed files
+ * give the same bytes either way; a damaged file the device decoder hands back is decoded as
+ * jgpu_decode_jpegs_ex(JGPU_ENTROPY_CPU) would (restart intervals at their markers), which accepts
+ * some files the strictly sequential front end rejects.  Returns EXIT_FAILURE for any other value. */
 int cuda_decode_set_entropy(int on_device);
 
 /* Output-surface helpers with the semantics of the reference's
