@@ -147,3 +147,36 @@ def test_corrupted_scans_are_flagged_or_decode_like_the_sequential_reader(emu, c
             assert np.array_equal(coef, want), (name, trial)
     assert clean > 20 and flagged > 20, (clean, flagged)
     capfd.readouterr()
+
+
+def _with_fill_bytes(jpg):
+    """0xFF fill bytes in front of every RSTn marker (legal, T.81 B.1.1.2)."""
+    out = bytearray()
+    i = 0
+    sos = jpg.index(b"\xff\xda")
+    while i < len(jpg):
+        if i > sos and jpg[i] == 0xFF and i + 1 < len(jpg) and 0xD0 <= jpg[i + 1] <= 0xD7:
+            out += b"\xff\xff"
+        out.append(jpg[i])
+        i += 1
+    return bytes(out)
+
+
+def test_marker_corner_cases_of_the_preparation(emu):
+    """Fill bytes before restart markers, more than eight restart intervals (the RSTn counter
+    wraps), a restart interval longer than the image, one MCU per interval: planes as from the
+    sequential reader, decoded by the emulated kernels (status 0, not through a fallback)."""
+    Image = pytest.importorskip("PIL.Image")
+    img = _photo_like(160, 96, 5)
+    cases = []
+    for ss, rst in ((2, 1), (2, 3), (1, 2), (0, 50), (2, 1000)):
+        bio = io.BytesIO()
+        Image.fromarray(img).save(bio, "JPEG", quality=80, subsampling=ss, restart_marker_blocks=rst)
+        cases.append(bio.getvalue())
+    cases += [_with_fill_bytes(c) for c in cases[:3]] + [_with_fill_bytes(load("c420_rst_80x48")[0])]
+    for k, jpg in enumerate(cases):
+        want = sequential_quant(jpg)
+        for words, cta, passes in ((32, 256, 3), (1, 8, 200)):
+            n, coef, status, stats = emulate(emu, jpg, words, cta, passes)
+            assert n == want.size and status == 0, (k, words, status, stats)
+            assert np.array_equal(coef, want), (k, words)
