@@ -7,7 +7,10 @@
 
 namespace jgpu {
 
-constexpr int kHuffSubseqWords = 32;   /* 1024 bits per subsequence */
+#ifndef JGPU_HUFF_S
+#define JGPU_HUFF_S 32
+#endif
+constexpr int kHuffSubseqWords = JGPU_HUFF_S;   /* 1024 bits per subsequence (16 and 64 measured, profiles/r1_ab_notes.md) */
 constexpr int kHuffSyncPasses = 3;     /* launches of k_huff_sync (1 + hand-overs across CTAs) */
 
 /* One group of files, everything on the device.  Per-subsequence arrays are indexed by
