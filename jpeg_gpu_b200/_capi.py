@@ -106,6 +106,7 @@ EXPORTS = [
     ("cuda_decode_set_device", None, [C.c_int]),
     ("cuda_decode_set_upload", C.c_int, [C.c_int]),
     ("cuda_decode_set_entropy", C.c_int, [C.c_int]),
+    ("jgpu_image_set_pinned", None, [C.c_int]),
     ("jgpu_decode_image_packed", C.c_int, [C.c_void_p, C.POINTER(jpeg_header), C.POINTER(image), C.c_int64, C.c_int]),
     ("jgpu_image_init", C.c_int, [C.POINTER(image), C.POINTER(jpeg_header)]),
     ("jgpu_image_zero", None, [C.POINTER(image)]),

@@ -48,6 +48,7 @@ class Decoder:
     def __init__(self, data: bytes, impl: str = "cuda"):
         if impl not in BACKENDS:
             raise ValueError(f"Invalid decoder implementation: {impl}")
+        self._impl = impl
         self._vt = _capi.vtbl(BACKENDS[impl])
         self._buf = (C.c_ubyte * len(data)).from_buffer_copy(data)  # owned by the caller, as in the reference
         self._info = _capi.jpeg_info(len(data), C.cast(self._buf, C.POINTER(C.c_ubyte)))
@@ -82,7 +83,11 @@ class Decoder:
             raise DecodeError("decode_image before decode_header")
         if self._img is None:
             self._img = _capi.image()
-            if _capi.lib().jgpu_image_init(C.byref(self._img), C.byref(self._hdr)) != 0:
+            # the CUDA backend reads pixels back into the surface: page-locked memory for it
+            _capi.lib().jgpu_image_set_pinned(1 if self._impl == "cuda" else 0)
+            rc = _capi.lib().jgpu_image_init(C.byref(self._img), C.byref(self._hdr))
+            _capi.lib().jgpu_image_set_pinned(0)
+            if rc != 0:
                 self._img = None
                 raise DecodeError("Error initializing image")
             # image_init leaves the buffers uninitialised (src/image.c:61-76); zero them once so

@@ -14,6 +14,10 @@
 #include "jgpu_huff_core.h"
 #include "jgpu_internal.h"
 
+// jgpu_host.c can ask the CUDA runtime glue for page-locked memory; this host-only build has none
+extern "C" void *jgpu_host_alloc(size_t) { return nullptr; }
+extern "C" void jgpu_host_free(void *) {}
+
 namespace {
 
 const unsigned char kZigzag[64] = JGPU_HUFF_ZIGZAG_NATURAL;

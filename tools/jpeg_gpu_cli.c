@@ -117,6 +117,8 @@ int main(int argc, char *argv[]) {
     return EXIT_FAILURE;
   }
 
+  /* the CUDA backend reads pixels back into the surface: give it page-locked memory */
+  jgpu_image_set_pinned(vtbl.decode_image == CUDA_DECODE_CTX_VTBL.decode_image && out == JPEG_DECODE_RGB);
   dec = (*vtbl.decode_alloc)(&info);
   if (dec == NULL) return EXIT_FAILURE;
   if ((*vtbl.decode_header)(dec, &header) != EXIT_SUCCESS) return EXIT_FAILURE;
