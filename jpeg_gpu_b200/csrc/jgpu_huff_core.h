@@ -150,10 +150,9 @@ struct HostMem {
 
 /* Symbol at the head of the 16-bit window `look`: (length << 8) | symbol, or 0 for a bit
  * pattern that is no code of the table. */
+/* Codes longer than the look-up table covers: canonical search by length. */
 template <typename Mem>
-JGPU_HUFF_HD uint32_t lookup(const Mem &mem, uint32_t t, uint32_t look) {
-  uint32_t e = mem.lut(t, look >> (16 - JGPU_HUFF_LUT_BITS));
-  if (e) return e;
+JGPU_HUFF_HD uint32_t lookup_long(const Mem &mem, uint32_t t, uint32_t look) {
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
@@ -163,6 +162,12 @@ JGPU_HUFF_HD uint32_t lookup(const Mem &mem, uint32_t t, uint32_t look) {
     }
   }
   return 0;
+}
+
+template <typename Mem>
+JGPU_HUFF_HD uint32_t lookup(const Mem &mem, uint32_t t, uint32_t look) {
+  const uint32_t e = mem.lut(t, look >> (16 - JGPU_HUFF_LUT_BITS));
+  return e ? e : lookup_long(mem, t, look);
 }
 
 /* Decodes the symbols that START inside one subsequence.
@@ -203,9 +208,15 @@ JGPU_HUFF_HD uint32_t decode_subsequence(const Mem &mem, int bpm, uint32_t w0, i
       ahead = mem.word(++next);
     }
     const uint32_t ac = z != 0;
-    uint32_t e = lookup(mem, tdc + ac, (uint32_t)(buf >> 48));
-    bad |= e == 0;
-    e = e ? e : (16u << 8);   /* no code: skip the window like jgpu_front.c decode_symbol; symbol 0 */
+    const uint32_t look = (uint32_t)(buf >> 48);
+    uint32_t e = mem.lut(tdc + ac, look >> (16 - JGPU_HUFF_LUT_BITS));
+    if (e == 0) {   /* rare per thread: everything about long and invalid codes stays off the main path */
+      e = lookup_long(mem, tdc + ac, look);
+      if (e == 0) {
+        bad = 1;
+        e = 16u << 8;   /* no code: skip the window like jgpu_front.c decode_symbol; symbol 0 */
+      }
+    }
     const int len = (int)(e >> 8);
     const uint32_t sym = e & 0xffu;
     const int s = (int)(sym & 15u);
