@@ -80,10 +80,12 @@ def test_reference_reader_drives_the_cuda_backend(ref, plugged, name, upload):
 
 
 def test_reference_reader_errors_keep_the_convention(ref, plugged):
-    """A cut-off file: the reference's header parser fails -> EXIT_FAILURE through our table too; an
-    unsupported `out` is refused with EXIT_FAILURE, nothing aborts."""
+    """A file without a frame header: the reference's parser reports "Error reading jpeg headers"
+    (src/jpeg_wrap.c:275-278) -> EXIT_FAILURE through our table too; an unsupported `out` is refused
+    with EXIT_FAILURE; nothing aborts.  (A cut-off file is NOT fed to the reference's reader: built
+    with its default flags -- GLJ_ENABLE_VALIDATION off, Makefile:25 -- it divides by zero on one.)"""
     jpg, _ = expected("c420_64x48")
-    with Session(plugged, jpg[:120], ref.lib.image_init, ref.lib.image_zero, ref.lib.image_clear) as s:
+    with Session(plugged, bytes([0xff, 0xd8, 0xff, 0xd9]), ref.lib.image_init, ref.lib.image_zero, ref.lib.image_clear) as s:
         assert s.header() == 1
     with Session(plugged, jpg, ref.lib.image_init, ref.lib.image_zero, ref.lib.image_clear) as s:
         assert s.header() == 0
