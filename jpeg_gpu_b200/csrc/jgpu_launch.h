@@ -45,5 +45,18 @@ int fused_plan_launches(const FusedPlan &fp);
 int fused_plan_launch(FusedPlan &fp, int i0, int i1, const int16_t *coef, const uint16_t *qtabs,
                       int n_sets, uint8_t *rgb, cudaStream_t stream);
 
+cudaError_t launch_prep_qtabs(const uint16_t *qtabs, uint32_t *qint, int n_tables, uint32_t *wide_flag,
+                              cudaStream_t stream);
+
+/* ---- fused path, one MCU column per thread (jgpu_mcu.cu) -------------------- */
+/* Same plan interface; `flags` selects pixels (JGPU_OUT_RGB) or planes (JGPU_OUT_YUV), not both. */
+cudaError_t mcu_configure(int device);
+int mcu_plan_build(FusedPlan &fp, const jgpu_image_desc *descs, const jgpu_layout *layouts,
+                   const int *modes, int n, unsigned flags, int sm_count);
+void mcu_plan_release(FusedPlan &fp);
+int mcu_plan_launches(const FusedPlan &fp);
+int mcu_plan_launch(FusedPlan &fp, int i0, int i1, const int16_t *coef, const uint16_t *qtabs,
+                    int n_sets, uint8_t *rgb, uint8_t *yuv, cudaStream_t stream);
+
 }  // namespace jgpu
 #endif

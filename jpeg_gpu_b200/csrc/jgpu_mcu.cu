@@ -1,0 +1,853 @@
+/* jgpu_mcu.cu — the fused coefficient -> pixels kernel, one MCU column per thread (sm_100a).
+ *
+ * Same work as the reference's three render passes (res/horz_quant_*.fs.glsl ->
+ * res/vert.fs.glsl -> res/unyuv.fs.glsl / ungrey.fs.glsl, driven by
+ * src/jpeg_gpu.c:1341-1363) and the same arithmetic as jgpu_fused.cu (its
+ * predecessor, kept as an A/B reference): dequantise, both IDCT passes, bias / clamp,
+ * nearest-neighbour chroma upsample, colour, crop, RGB8 store -- or the clamped planes
+ * themselves (src/xjpeg.c:565-584) when the plan asks for YUV.
+ *
+ * What is different: there are no warp roles and nothing is shared between warps.
+ *   unit   = a 16-pixel-wide column of one MCU row: one MCU for the 2x luma modes (4:2:0,
+ *            4:2:2), two MCUs for the 1x modes (4:4:4, 4:4:0), two blocks for grey.
+ *   thread = one unit, start to finish.  It runs the block-PAIR transform of
+ *            jgpu_idct_core.cuh once per "step": first the chroma pair(s) of its unit
+ *            (Cb and Cr of one MCU ride in the two packed lanes), whose clamped samples it
+ *            parks in a private strip of shared memory, then one luma pair per luma block
+ *            row (two horizontally adjacent blocks = 16 pixels), whose clamped samples stay
+ *            in registers while the colour offsets are added and the 48 bytes of each
+ *            pixel row are stored.
+ *   warp   = 32 consecutive units = 512 pixels of one MCU row: a "task".  Warps take tasks
+ *            round-robin and never wait for one another: each has its own TMA landing
+ *            zone (two 4 KB boxes, 128-byte swizzle), its own tables, its own mbarrier and
+ *            its own ring of task descriptors.
+ * In jgpu_fused.cu four luma warps and two chroma warps of a CTA met at named barriers once
+ * per tile; ncu showed the chroma warps asleep half of the time and the luma warps a tenth
+ * of theirs at the barrier (profiles/r2_notes.md).  Here every resident warp carries the
+ * same mix of work and the only waits left are on a warp's own loads.
+ *
+ * Data movement
+ *   HBM -> smem: cp.async.bulk.tensor boxes of 32 blocks x 128 B, as in jgpu_fused.cu: a 2-D
+ *     view (64, rows) for runs of consecutive blocks and a 3-D view (64, parity, pairs) that
+ *     gathers every second block, so that lane L owns blocks 2L and 2L+1 of a 64-block run.
+ *     A warp starts the loads of its next step as soon as the row pass has pulled the
+ *     current boxes into registers.
+ *   task descriptors: 128 bytes per task, built on the host, fetched two tasks ahead into a
+ *     per-warp 4-slot ring with cp.async.bulk.
+ *   regs -> HBM: per pixel row three 128-bit streaming stores per thread (a warp covers 1536
+ *     contiguous bytes); planes: 16 bytes of Y / 8 bytes of Cb and of Cr per thread and row.
+ */
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <algorithm>
+#include <vector>
+
+#include "jgpu_fused_common.cuh"
+#include "jgpu_internal.h"
+#include "jgpu_launch.h"
+
+namespace jgpu {
+
+#ifndef JGPU_MCU_WAIT_NS
+#define JGPU_MCU_WAIT_NS 0       /* suspend-time hint of the mbarrier waits; 0: plain try_wait (see mbar_try_wait_hint) */
+#endif
+#ifndef JGPU_MCU_L2_PREFETCH
+#define JGPU_MCU_L2_PREFETCH 0   /* 1: prefetch the step after next into L2 when a step's loads are issued */
+#endif
+
+#ifdef JGPU_MCU_TRACE
+/* debugging aid (never in the product build): per warp {SM id, start, end (globaltimer ns), steps} */
+__device__ unsigned long long g_mcu_trace[4 * 148 * 12];
+#endif
+
+constexpr int kZoneBytes = 2 * kBoxBytes;   /* a warp's TMA landing zone: box A, box B */
+constexpr int kRingSlots = 4;
+constexpr int kOutRgb = 1, kOutYuv = 2;
+
+/* One task = 32 units of one MCU row, as the host describes it (mcu_plan_build).  Block
+ * numbers are GLOBAL: the coefficient buffer viewed as rows of 64 int16. */
+struct __align__(16) WarpTask {
+  long long rgb_base;     /* byte offset in the rgb buffer of the task's top-left pixel */
+  int32_t width_left;     /* visible pixels from the task's left edge to the image's right edge */
+  int32_t rows_left;      /* visible rows from the task's top row to the image's bottom */
+  int32_t pitch;          /* bytes per rgb row */
+  int32_t flags;          /* bit 0: rgb rows are 16-byte aligned (given an aligned base pointer) */
+  int32_t qidx[3];        /* 64-entry table indices: qtab_set*4 + tq */
+  int32_t blocks_left;    /* luma blocks from the task's left edge to the padded plane's right edge */
+  int32_t yfirst[2];      /* first luma block of the task's run, luma block row 0 / 1 of the MCU row */
+  int32_t cfirst[2];      /* first Cb / Cr block of the task's run */
+  long long yuv_base[3];  /* planes output: byte offset of the task's top-left sample in Y / Cb / Cr */
+  int32_t yuv_pitch[2];   /* row stride of the Y plane / of the chroma planes */
+  int32_t pad[10];
+};
+static_assert(sizeof(WarpTask) == 128, "WarpTask is copied with cp.async.bulk and read with vector loads");
+
+/* Build knobs (A/B-tested on the GPU, profiles/r2_notes.md).
+ *   JGPU_MCU_WARPS 12: 168 registers per thread; row 0 of the register tile is parked in shared
+ *                      memory between the passes; the clamped luma is staged as BYTES.
+ *   JGPU_MCU_WARPS 11: 184 registers; nothing parked; luma staged as s16x2 words (no pack/unpack). */
+#ifndef JGPU_MCU_WARPS
+#define JGPU_MCU_WARPS 12
+#endif
+#ifndef JGPU_MCU_STAGE_BYTES
+#define JGPU_MCU_STAGE_BYTES (JGPU_MCU_WARPS >= 12)
+#endif
+#ifndef JGPU_MCU_PARK
+#define JGPU_MCU_PARK (JGPU_MCU_WARPS >= 12)
+#endif
+
+/* Per-warp shared memory.  Everything a thread parks is laid out [row][lane] (16-byte chunks of
+ * the 32 lanes side by side): 128-bit accesses of a warp are conflict-free without padding. */
+template <int HS, int VS, bool GRAY, bool WIDE>
+struct McuCfg {
+  static constexpr int kChromaSteps = GRAY ? 0 : (HS == 2 ? 1 : 2);
+  static constexpr int kLumaSteps = GRAY ? 1 : VS;
+  static constexpr int kSteps = kChromaSteps + kLumaSteps;
+  static constexpr int kChannels = GRAY ? 1 : 3;
+  static constexpr bool kStageBytes = JGPU_MCU_STAGE_BYTES != 0;
+  static constexpr bool kPark = JGPU_MCU_PARK != 0;
+  /* packed tables of a step: Cb and Cr (chroma) or one (luma); the high-byte halves only when the
+   * batch has 16-bit tables */
+  static constexpr int kTabBytes = WIDE ? kQtabBytes : kQtabBytes / 2;
+  /* chroma strip of one chroma step: 8 rows x [lane] x 8 samples x (Cb-128, Cr-128) signed bytes */
+  static constexpr int kChromaStep = 8 * 32 * 16;
+  /* luma staging: 8 rows x [lane] x 16 clamped samples, as bytes (A0-3 B0-3 A4-7 B4-7) or as
+   * s16x2 words (two 16-byte halves per row: a0 b0 a1 b1 | a2 b2 a3 b3) */
+  static constexpr int kStageRow = kStageBytes ? 32 * 16 : 2 * 32 * 16;
+  static constexpr int kStageBytesTotal = 8 * kStageRow;
+  static constexpr int kParkBytes = kPark ? 4 * 32 * 16 : 0;
+  static constexpr int kOffTab = 0;
+  static constexpr int kOffChroma = 2 * kTabBytes;
+  static constexpr int kOffStage = kOffChroma + kChromaSteps * kChromaStep;
+  static constexpr int kOffPark = kOffStage + kStageBytesTotal;
+  static constexpr int kOffRing = kOffPark + kParkBytes;
+  static constexpr int kOffBar = kOffRing + kRingSlots * (int)sizeof(WarpTask);   /* 5 mbarriers, then the loop counters */
+  static constexpr int kOffLoop = kOffBar + 48;
+  static constexpr int kWarpMisc = kOffBar + 64;
+  /* warps per CTA; one CTA per SM */
+  static constexpr int kFit = (227 * 1024) / (kZoneBytes + kWarpMisc);
+  static constexpr int kWarps = kFit < JGPU_MCU_WARPS ? kFit : JGPU_MCU_WARPS;
+  static constexpr int kThreads = 32 * kWarps;
+  static constexpr int kSmemBytes = kWarps * (kZoneBytes + kWarpMisc);
+  static_assert(kWarps >= 8, "shared memory budget");
+  static_assert(kWarpMisc % 16 == 0, "alignment");
+};
+
+__device__ __forceinline__ void stg64_stream(uint8_t *p, uint2 v) {
+  asm volatile("st.global.cs.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
+}
+
+/* pair_row_pass of jgpu_fused_common.cuh with the parked row laid out [chunk][lane], or not parked */
+template <bool WIDE, bool PARK>
+__device__ __forceinline__ void mcu_row_pass(pair32 (&m)[8][8], const uint8_t *box_a, const uint8_t *box_b,
+                                             int row, const uint4 *qa, const uint4 *qb, uint32_t park) {
+  const uint8_t *ra = box_a + 128 * row, *rb = box_b + 128 * row;
+  const int sw = row & 7;
+  constexpr int kHi = kQtabBytes / 2 / 16;   /* the high-byte rows follow the 8 low-byte rows */
+#pragma unroll
+  for (int r = 0; r < 8; r++) {
+    const int off = 16 * (r ^ sw);
+    const uint4 a = *reinterpret_cast<const uint4 *>(ra + off);
+    const uint4 b = *reinterpret_cast<const uint4 *>(rb + off);
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    load_row_pair_packed<WIDE>(m[r], a, b, qa[r], qb[r], WIDE ? qa[kHi + r] : z, WIDE ? qb[kHi + r] : z, r);
+    inv_pass8(m[r]);
+    if (PARK && r == 0) {
+      /* park row 0 in shared memory until the column pass asks for it, two pairs per chunk */
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        uint4 c;
+        p_split_bits(m[0][2 * j], c.x, c.y);
+        p_split_bits(m[0][2 * j + 1], c.z, c.w);
+        sts128(park + 512 * j, c);
+      }
+    }
+  }
+}
+
+template <int HS, int VS, bool GRAY, bool WIDE, int OUT>
+__global__ void __launch_bounds__(McuCfg<HS, VS, GRAY, WIDE>::kThreads, 1)
+k_mcu(const __grid_constant__ CUtensorMap tm_rows,   /* (64, rows)            */
+      const __grid_constant__ CUtensorMap tm_pairs,  /* (64, parity, pairs)   */
+      const WarpTask *__restrict__ tasks, int n_tasks, const uint32_t *__restrict__ qint,
+      const uint32_t *__restrict__ wide_flag, uint8_t *__restrict__ rgb, int rgb_aligned,
+      uint8_t *__restrict__ yuv) {
+  using C = McuCfg<HS, VS, GRAY, WIDE>;
+  if ((*wide_flag != 0) != WIDE) return;
+#ifdef JGPU_MCU_TRACE
+  unsigned long long trace_t0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(trace_t0));
+#endif
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem0 = smem_u32(smem_raw);
+  if (smem0 & 1023u) __trap();   /* the 128-byte swizzle needs the boxes 1 KB aligned */
+
+  /* Where this thread's things live.  Re-derived from a fresh, un-CSE-able read of %tid.x at
+   * every point of use instead of being kept in registers across the transform, where every
+   * register counts (128 of them hold the block pair). */
+  struct Geo {
+    int lane;
+    uint32_t zone;      /* the warp's landing zone: box A, box B */
+    uint32_t misc;      /* the warp's area behind the zones */
+    uint32_t mine;      /* misc + 16*lane: this lane's column of every [row][lane] array */
+    const uint8_t *zone_gen;
+    const uint4 *tab_gen;
+  };
+  auto geo = [&]() -> Geo {
+    uint32_t tid;
+    asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
+    const uint32_t w = tid >> 5;
+    Geo g;
+    g.lane = (int)(tid & 31);
+    g.zone = smem0 + w * kZoneBytes;
+    g.misc = smem0 + C::kWarps * kZoneBytes + w * C::kWarpMisc;
+    g.mine = g.misc + 16u * (uint32_t)g.lane;
+    g.zone_gen = smem_raw + w * kZoneBytes;
+    g.tab_gen = reinterpret_cast<const uint4 *>(smem_raw + C::kWarps * kZoneBytes + w * C::kWarpMisc + C::kOffTab);
+    return g;
+  };
+  /* mbarriers of a warp: [0] its coefficient loads, [1 + slot] its descriptor ring */
+  auto bar_data = [&](const Geo &g) { return g.misc + C::kOffBar; };
+  auto bar_ring = [&](const Geo &g, uint32_t slot) { return g.misc + C::kOffBar + 8 + 8 * slot; };
+  auto desc_addr = [&](const Geo &g, int n) { return g.misc + C::kOffRing + ((uint32_t)n % kRingSlots) * (uint32_t)sizeof(WarpTask); };
+
+  {
+    const Geo g = geo();
+    if (g.lane == 0) {
+      for (int i = 0; i < 1 + kRingSlots; i++) mbar_init(bar_data(g) + 8 * i, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+  }
+
+  /* this warp's tasks: gw, gw + nw, gw + 2 nw, ...; local task n lives in ring slot n % 4 */
+  auto fetch_desc = [&](const Geo &g, int n) {   /* lane 0 only */
+    const int gw = (int)blockIdx.x * C::kWarps + (int)(threadIdx.x >> 5), nw = (int)gridDim.x * C::kWarps;
+    const uint32_t slot = (uint32_t)n % kRingSlots;
+    mbar_expect_tx(bar_ring(g, slot), (uint32_t)sizeof(WarpTask));
+    bulk_load(desc_addr(g, n), tasks + (gw + (size_t)n * nw), (uint32_t)sizeof(WarpTask), bar_ring(g, slot));
+  };
+  auto wait_desc = [&](const Geo &g, int n) {
+    mbar_wait_hint<JGPU_MCU_WAIT_NS>(bar_ring(g, (uint32_t)n % kRingSlots), ((uint32_t)n / kRingSlots) & 1u);
+  };
+  /* start the loads of step s of local task n (lane 0 only; its descriptor must have landed).
+   * Tables: the low-byte half always, the high-byte half for 16-bit tables. */
+  auto load_table = [&](uint32_t dst, int q, uint32_t bar) {
+    bulk_load(dst, qint + (size_t)q * 64, C::kTabBytes, bar);
+  };
+  auto fire = [&](const Geo &g, int n, int s) {
+    const uint32_t d = desc_addr(g, n), bar = bar_data(g), tab = g.misc + C::kOffTab;
+    if (s < C::kChromaSteps) {
+      int f0 = (int)lds32(d + offsetof(WarpTask, cfirst));
+      int f1 = (int)lds32(d + offsetof(WarpTask, cfirst) + 4);
+      const int q1 = (int)lds32(d + offsetof(WarpTask, qidx) + 4);
+      const int q2 = (int)lds32(d + offsetof(WarpTask, qidx) + 8);
+      mbar_expect_tx(bar, 2 * kBoxBytes + 2 * C::kTabBytes);
+      if (HS == 2) {
+        /* Cb and Cr of 32 consecutive MCUs */
+        tma_load_2d(g.zone, &tm_rows, 0, f0, bar);
+        tma_load_2d(g.zone + kBoxBytes, &tm_rows, 0, f1, bar);
+      } else {
+        /* step s takes the MCUs of parity s: every second Cb block and every second Cr block */
+        f0 += s;
+        f1 += s;
+        tma_load_3d(g.zone, &tm_pairs, 0, f0 & 1, f0 >> 1, bar);
+        tma_load_3d(g.zone + kBoxBytes, &tm_pairs, 0, f1 & 1, f1 >> 1, bar);
+      }
+      load_table(tab, q1, bar);
+      load_table(tab + C::kTabBytes, q2, bar);
+    } else {
+      /* the 32 even-position and the 32 odd-position blocks of a 64-block luma run */
+      const int first = (int)lds32(d + offsetof(WarpTask, yfirst) + 4 * (s - C::kChromaSteps));
+      const int qy = (int)lds32(d + offsetof(WarpTask, qidx));
+      mbar_expect_tx(bar, 2 * kBoxBytes + C::kTabBytes);
+      tma_load_3d(g.zone, &tm_pairs, 0, first & 1, first >> 1, bar);
+      tma_load_3d(g.zone + kBoxBytes, &tm_pairs, 0, (first + 1) & 1, (first + 1) >> 1, bar);
+      load_table(tab, qy, bar);
+    }
+  };
+
+  /* steps of this warp: its tasks x steps per task.  The loop counters live in shared memory: no
+   * register is spent on them across the transform. */
+  {
+    const Geo g = geo();
+    const int gw = (int)blockIdx.x * C::kWarps + (int)(threadIdx.x >> 5), nw = (int)gridDim.x * C::kWarps;
+    const int my_tasks = gw < n_tasks ? (n_tasks - gw + nw - 1) / nw : 0;
+    if (my_tasks == 0) return;
+    sts64(g.misc + C::kOffLoop, make_uint2(0u, (uint32_t)(my_tasks * C::kSteps)));   /* every lane, same value */
+    if (g.lane == 0) {
+      fetch_desc(g, 0);
+      if (my_tasks > 1) fetch_desc(g, 1);
+      wait_desc(g, 0);
+      fire(g, 0, 0);
+    }
+  }
+
+#pragma unroll 1
+  for (;;) {
+    int step, total;
+    {
+      const Geo g = geo();
+      const uint2 lc = lds64(g.misc + C::kOffLoop);
+      step = (int)lc.x;
+      total = (int)lc.y;
+#ifdef JGPU_MCU_TRACE
+      if (step >= total && g.lane == 0) {
+        unsigned long long t1;
+        unsigned smid;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        unsigned long long *o = g_mcu_trace + 4 * ((size_t)blockIdx.x * C::kWarps + (threadIdx.x >> 5));
+        o[0] = smid; o[1] = trace_t0; o[2] = t1; o[3] = (unsigned long long)total;
+      }
+#endif
+      if (step >= total) break;
+      __syncwarp();
+      sts32(g.misc + C::kOffLoop, (uint32_t)step + 1u);
+    }
+    const int n = step / C::kSteps, s = step - n * C::kSteps;
+    const bool is_c = s < C::kChromaSteps;
+    const int yr = s - C::kChromaSteps;   /* luma block row inside the MCU row */
+    bool active;   /* does this lane's unit exist / show in this step? */
+    {
+      const Geo g = geo();
+      /* keep the ring two tasks ahead (the slot of task n-2: every lane is past it) */
+      if (s == 0 && g.lane == 0 && (n + 2) * C::kSteps < total) fetch_desc(g, n + 2);
+      wait_desc(g, n);
+      const uint32_t da = desc_addr(g, n);
+      const uint4 h0 = lds128(da);                                     /* rgb_base, width_left, rows_left */
+      if (OUT == kOutYuv) {
+        active = 2 * g.lane + ((HS == 1 && is_c) ? s : 0) < (int)lds32(da + offsetof(WarpTask, blocks_left));
+      } else {
+        active = 16 * g.lane + ((HS == 1 && is_c) ? 8 * s : 0) < (int)h0.z && (is_c || 8 * yr < (int)h0.w);
+      }
+      mbar_wait_hint<JGPU_MCU_WAIT_NS>(bar_data(g), (uint32_t)step & 1u);
+    }
+
+    {
+      pair32 m[8][8];
+      if (active) {
+        const Geo g = geo();
+        const uint4 *const qa = g.tab_gen;
+        const uint4 *const qb = is_c ? qa + C::kTabBytes / 16 : qa;   /* chroma: Cb table, then Cr table */
+        mcu_row_pass<WIDE, C::kPark>(m, g.zone_gen, g.zone_gen + kBoxBytes, g.lane, qa, qb, g.mine + C::kOffPark);
+      }
+      /* the boxes are in registers: start the loads of this warp's next step */
+      __syncwarp();
+      {
+        const Geo g = geo();
+        if (g.lane == 0 && step + 1 < total) {
+          if (s + 1 < C::kSteps) {
+            fire(g, n, s + 1);
+          } else {
+            wait_desc(g, n + 1);
+            fire(g, n + 1, 0);
+          }
+        }
+      }
+      if (!active) continue;
+
+      const pair32 magic = p_make_bits(kMagicBits, kMagicBits);
+      const Geo g = geo();
+      const uint32_t mine = g.mine;
+      auto row0 = [&](int j, pair32 &a, pair32 &b) {
+        const uint4 c = lds128(mine + C::kOffPark + 512 * j);
+        a = p_make_bits(c.x, c.y);
+        b = p_make_bits(c.z, c.w);
+      };
+      uint32_t keep_a[8];   /* the even column step's words, until the odd one completes them */
+      auto sink = [&](int j, pair32 (&u)[8], pair32 (&v)[8]) {
+        if (is_c) {
+          /* chroma: clamped samples of columns 2j, 2j+1 as four signed bytes (Cb, Cr, Cb, Cr);
+           * two column steps make 8 bytes of the strip's row */
+          const uint32_t strip = mine + C::kOffChroma + (uint32_t)s * C::kChromaStep;
+#pragma unroll
+          for (int k = 0; k < 8; k++) {
+            const uint32_t w = __byte_perm(chroma_clamped(u[k]), chroma_clamped(v[k]), 0x6420);
+            if ((j & 1) == 0) keep_a[k] = w;
+            else sts64(strip + 512 * k + 8 * (j >> 1), make_uint2(keep_a[k], w));
+          }
+        } else {
+          /* luma: (short)floor + 128, clamp: pixels 2j, 2j+1 of row k of block A and of block B */
+#pragma unroll
+          for (int k = 0; k < 8; k++) {
+            uint32_t ulo, uhi, vlo, vhi;
+            p_split_bits(p_add_rm(u[k], magic), ulo, uhi);
+            p_split_bits(p_add_rm(v[k], magic), vlo, vhi);
+            const uint32_t wa = clamp_pair_u8(ulo, vlo), wb = clamp_pair_u8(uhi, vhi);
+            if (C::kStageBytes) {
+              /* bytes (A2j A2j+1 B2j B2j+1); two column steps make 8 bytes of the staged row */
+              const uint32_t w = __byte_perm(wa, wb, 0x6420);
+              if ((j & 1) == 0) keep_a[k] = w;
+              else sts64(mine + C::kOffStage + C::kStageRow * k + 8 * (j >> 1), make_uint2(keep_a[k], w));
+            } else {
+              sts64(mine + C::kOffStage + C::kStageRow * k + 512 * (j >> 1) + 8 * (j & 1), make_uint2(wa, wb));
+            }
+          }
+        }
+      };
+      if (C::kPark) column_pass_by_pairs_parked(m, row0, sink);
+      else column_pass_by_pairs(m, sink);
+    }
+
+    const Geo g = geo();
+    const uint32_t da = desc_addr(g, n);
+    if (is_c) {
+      if (OUT == kOutYuv) {
+        /* planes: 8 Cb bytes and 8 Cr bytes per row, out of the strip */
+        const uint2 b1 = lds64(da + offsetof(WarpTask, yuv_base) + 8);
+        const uint2 b2 = lds64(da + offsetof(WarpTask, yuv_base) + 16);
+        const int cpitch = (int)lds32(da + offsetof(WarpTask, yuv_pitch) + 4);
+        const long long col = HS == 2 ? 8 * g.lane : 16 * g.lane + 8 * s;
+        uint8_t *pb = yuv + (long long)(((unsigned long long)b1.y << 32) | b1.x) + col;
+        uint8_t *pr = yuv + (long long)(((unsigned long long)b2.y << 32) | b2.x) + col;
+        const uint32_t strip = g.mine + C::kOffChroma + (uint32_t)s * C::kChromaStep;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+          const uint4 t = lds128(strip + 512 * k);
+          uint2 vb, vr;
+          vb.x = __byte_perm(t.x, t.y, 0x6420) ^ 0x80808080u;
+          vb.y = __byte_perm(t.z, t.w, 0x6420) ^ 0x80808080u;
+          vr.x = __byte_perm(t.x, t.y, 0x7531) ^ 0x80808080u;
+          vr.y = __byte_perm(t.z, t.w, 0x7531) ^ 0x80808080u;
+          stg64_stream(pb, vb);
+          stg64_stream(pr, vr);
+          pb += cpitch;
+          pr += cpitch;
+        }
+      }
+      continue;
+    }
+
+    /* one staged luma row -> s16x2 words: ya[0..3] = block A pixel pairs, yb[0..3] = block B */
+    auto staged_row = [&](int k, uint32_t (&ya)[4], uint32_t (&yb)[4]) {
+      const uint32_t row = g.mine + C::kOffStage + C::kStageRow * k;
+      if (C::kStageBytes) {
+        const uint4 t = lds128(row);   /* A01 B01 | A23 B23 | A45 B45 | A67 B67 */
+        ya[0] = __byte_perm(t.x, 0u, 0x4140); yb[0] = __byte_perm(t.x, 0u, 0x4342);
+        ya[1] = __byte_perm(t.y, 0u, 0x4140); yb[1] = __byte_perm(t.y, 0u, 0x4342);
+        ya[2] = __byte_perm(t.z, 0u, 0x4140); yb[2] = __byte_perm(t.z, 0u, 0x4342);
+        ya[3] = __byte_perm(t.w, 0u, 0x4140); yb[3] = __byte_perm(t.w, 0u, 0x4342);
+      } else {
+        const uint4 t0 = lds128(row), t1 = lds128(row + 512);   /* a0 b0 a1 b1 | a2 b2 a3 b3 */
+        ya[0] = t0.x; ya[1] = t0.z; ya[2] = t1.x; ya[3] = t1.z;
+        yb[0] = t0.y; yb[1] = t0.w; yb[2] = t1.y; yb[3] = t1.w;
+      }
+    };
+    /* ... and as 16 bytes in pixel order */
+    auto staged_row_bytes = [&](int k) -> uint4 {
+      const uint32_t row = g.mine + C::kOffStage + C::kStageRow * k;
+      if (C::kStageBytes) {
+        const uint4 t = lds128(row);
+        return make_uint4(__byte_perm(t.x, t.y, 0x5410), __byte_perm(t.z, t.w, 0x5410),
+                          __byte_perm(t.x, t.y, 0x7632), __byte_perm(t.z, t.w, 0x7632));
+      }
+      const uint4 t0 = lds128(row), t1 = lds128(row + 512);
+      return make_uint4(__byte_perm(t0.x, t0.z, 0x6420), __byte_perm(t1.x, t1.z, 0x6420),
+                        __byte_perm(t0.y, t0.w, 0x6420), __byte_perm(t1.y, t1.w, 0x6420));
+    };
+
+    if (OUT == kOutYuv) {
+      /* planes: 16 Y bytes per row (8 when the unit's second block lies beyond the padded plane) */
+      const uint2 b0 = lds64(da + offsetof(WarpTask, yuv_base));
+      const int ypitch = (int)lds32(da + offsetof(WarpTask, yuv_pitch));
+      const bool whole = 2 * g.lane + 1 < (int)lds32(da + offsetof(WarpTask, blocks_left));
+      const bool wide16 = whole && (ypitch & 8) == 0;   /* an odd number of blocks per row: rows are only 8-byte aligned */
+      uint8_t *py = yuv + (long long)(((unsigned long long)b0.y << 32) | b0.x) + (long long)(8 * yr) * ypitch + 16 * g.lane;
+#pragma unroll 2
+      for (int k = 0; k < 8; k++) {
+        const uint4 v = staged_row_bytes(k);
+        if (wide16) {
+          stg128_stream(py, v);
+        } else {
+          stg64_stream(py, make_uint2(v.x, v.y));
+          if (whole) stg64_stream(py + 8, make_uint2(v.z, v.w));
+        }
+        py += ypitch;
+      }
+      continue;
+    }
+
+    /* ---- colour offsets, pack, store --------------------------------------------------------- */
+    const uint4 h0 = lds128(da);
+    const uint2 h1 = lds64(da + 16);
+    const long long rgb_base = (long long)(((unsigned long long)h0.y << 32) | h0.x);
+    const int pitch = (int)h1.x;
+    const int vis_px = min(16, (int)h0.z - 16 * g.lane);
+    const int vis_rows = min(8, (int)h0.w - 8 * yr);
+    const bool fast = (h1.y & (uint32_t)rgb_aligned & 1u) != 0 && vis_px == 16;
+    uint8_t *dst = rgb + rgb_base + (long long)(8 * yr) * pitch + (long long)(16 * g.lane) * C::kChannels;
+    if (GRAY) {
+#pragma unroll 1
+      for (int k = 0; k < vis_rows; k++, dst += pitch) {
+        const uint4 v = staged_row_bytes(k);
+        if (fast) stg128_stream(dst, v);
+        else store_row_slow(dst, v, v, v, vis_px);
+      }
+    } else {
+      /* one iteration per chroma row = VS pixel rows */
+      const uint32_t crow0 = g.mine + C::kOffChroma + (VS == 2 ? 4u * 512u * (uint32_t)yr : 0u);
+#pragma unroll 1
+      for (int cr = 0; cr < 8 / VS; cr++) {
+        if (cr * VS >= vis_rows) break;
+        uint32_t ca[12], cb[12];   /* offsets for block A / block B: 4 pixel pairs x (R,G,B) */
+        if (HS == 2) {
+          /* 8 chroma samples, each serving one horizontal pixel pair of VS rows: offsets,
+           * replicated into both halves of an s16x2 word */
+          const uint4 t = lds128(crow0 + 512 * cr);
+          const uint32_t cs[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+            uint32_t *o = i < 2 ? ca : cb;
+            const int p = 6 * (i & 1);
+            uint32_t r[2], gg[2], b[2];
+            chroma_offsets_bits2(cs[i], r, gg, b);
+            o[p + 0] = __byte_perm(r[0], r[0], kSelRep);
+            o[p + 1] = __byte_perm(gg[0], gg[0], kSelRep);
+            o[p + 2] = __byte_perm(b[0], b[0], kSelRep);
+            o[p + 3] = __byte_perm(r[1], r[1], kSelRep);
+            o[p + 4] = __byte_perm(gg[1], gg[1], kSelRep);
+            o[p + 5] = __byte_perm(b[1], b[1], kSelRep);
+          }
+        } else {
+          /* block A = even MCU (strip of chroma step 0), block B = odd MCU (step 1): 8 samples
+           * each, one per pixel */
+#pragma unroll
+          for (int blk = 0; blk < 2; blk++) {
+            const uint4 t = lds128(crow0 + 512 * cr + (blk ? C::kChromaStep : 0));
+            const uint32_t cs[4] = {t.x, t.y, t.z, t.w};
+            uint32_t *o = blk == 0 ? ca : cb;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+              uint32_t r[2], gg[2], b[2];
+              chroma_offsets_bits2(cs[i], r, gg, b);
+              o[3 * i + 0] = __byte_perm(r[0], r[1], kSelPair);
+              o[3 * i + 1] = __byte_perm(gg[0], gg[1], kSelPair);
+              o[3 * i + 2] = __byte_perm(b[0], b[1], kSelPair);
+            }
+          }
+        }
+#pragma unroll
+        for (int sub = 0; sub < VS; sub++) {
+          const int k = cr * VS + sub;
+          if (k < vis_rows) {
+            uint32_t ya[4], yb[4], w[12];
+            staged_row(k, ya, yb);
+            rgb4(ya[0], ya[1], ca[0], ca[1], ca[2], ca[3], ca[4], ca[5], w[0], w[1], w[2]);
+            rgb4(ya[2], ya[3], ca[6], ca[7], ca[8], ca[9], ca[10], ca[11], w[3], w[4], w[5]);
+            rgb4(yb[0], yb[1], cb[0], cb[1], cb[2], cb[3], cb[4], cb[5], w[6], w[7], w[8]);
+            rgb4(yb[2], yb[3], cb[6], cb[7], cb[8], cb[9], cb[10], cb[11], w[9], w[10], w[11]);
+            const uint4 q0 = make_uint4(w[0], w[1], w[2], w[3]);
+            const uint4 q1 = make_uint4(w[4], w[5], w[6], w[7]);
+            const uint4 q2 = make_uint4(w[8], w[9], w[10], w[11]);
+            if (fast) {
+              stg128_stream(dst, q0);
+              stg128_stream(dst + 16, q1);
+              stg128_stream(dst + 32, q2);
+            } else {
+              store_row_slow(dst, q0, q1, q2, 3 * vis_px);
+            }
+            dst += pitch;
+          }
+        }
+      }
+    }
+  }
+}
+
+/* ---- host side ------------------------------------------------------------- */
+
+namespace {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
+                                  const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn mcu_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) == cudaSuccess &&
+        qr == cudaDriverEntryPointSuccess) {
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+  }
+  return fn;
+}
+
+struct McuMode {
+  int hs, vs, gray, channels;
+  int threads, warps;             /* the kernel for 8-bit tables */
+  size_t smem;
+  int threads_wide, warps_wide;   /* the kernel for 16-bit tables (more table bytes per warp) */
+  size_t smem_wide;
+};
+McuMode g_mcu[kNumFusedModes];
+bool g_mcu_configured = false;
+
+template <int HS, int VS, bool GRAY>
+cudaError_t mcu_configure_mode(int mode) {
+  using C = McuCfg<HS, VS, GRAY, false>;
+  using CW = McuCfg<HS, VS, GRAY, true>;
+  McuMode &mi = g_mcu[mode];
+  mi.hs = HS; mi.vs = VS; mi.gray = GRAY; mi.channels = C::kChannels;
+  mi.threads = C::kThreads; mi.warps = C::kWarps; mi.smem = C::kSmemBytes;
+  mi.threads_wide = CW::kThreads; mi.warps_wide = CW::kWarps; mi.smem_wide = CW::kSmemBytes;
+  cudaError_t e;
+  if ((e = cudaFuncSetAttribute(&k_mcu<HS, VS, GRAY, false, kOutRgb>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mi.smem)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(&k_mcu<HS, VS, GRAY, true, kOutRgb>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mi.smem_wide)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(&k_mcu<HS, VS, GRAY, false, kOutYuv>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mi.smem)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(&k_mcu<HS, VS, GRAY, true, kOutYuv>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mi.smem_wide)) != cudaSuccess) return e;
+  return cudaSuccess;
+}
+
+template <int HS, int VS, bool GRAY>
+cudaError_t mcu_launch_mode(bool planes, int sm_count, const McuMode &mi, cudaStream_t stream, const CUtensorMap &tm_rows,
+                            const CUtensorMap &tm_pairs, const WarpTask *tasks, int n_tasks, const uint32_t *qint,
+                            const uint32_t *wide_flag, uint8_t *rgb, int rgb_aligned, uint8_t *yuv) {
+  const int grid = std::min((n_tasks + mi.warps - 1) / mi.warps, sm_count);
+  const int grid_w = std::min((n_tasks + mi.warps_wide - 1) / mi.warps_wide, sm_count);
+  if (planes) {
+    k_mcu<HS, VS, GRAY, false, kOutYuv><<<grid, mi.threads, mi.smem, stream>>>(tm_rows, tm_pairs, tasks, n_tasks, qint, wide_flag, rgb, rgb_aligned, yuv);
+    k_mcu<HS, VS, GRAY, true, kOutYuv><<<grid_w, mi.threads_wide, mi.smem_wide, stream>>>(tm_rows, tm_pairs, tasks, n_tasks, qint, wide_flag, rgb, rgb_aligned, yuv);
+  } else {
+    k_mcu<HS, VS, GRAY, false, kOutRgb><<<grid, mi.threads, mi.smem, stream>>>(tm_rows, tm_pairs, tasks, n_tasks, qint, wide_flag, rgb, rgb_aligned, yuv);
+    k_mcu<HS, VS, GRAY, true, kOutRgb><<<grid_w, mi.threads_wide, mi.smem_wide, stream>>>(tm_rows, tm_pairs, tasks, n_tasks, qint, wide_flag, rgb, rgb_aligned, yuv);
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+#ifdef JGPU_MCU_TRACE
+extern "C" int jgpu_mcu_trace_read(unsigned long long *out, int n_words) {
+  return cudaMemcpyFromSymbol(out, g_mcu_trace, sizeof(unsigned long long) * (size_t)n_words) == cudaSuccess ? 0 : 1;
+}
+#endif
+
+cudaError_t mcu_configure(int device) {
+  (void)device;
+  cudaError_t e;
+  if ((e = mcu_configure_mode<1, 1, true>(kModeGray)) != cudaSuccess) return e;
+  if ((e = mcu_configure_mode<1, 1, false>(kMode444)) != cudaSuccess) return e;
+  if ((e = mcu_configure_mode<2, 1, false>(kMode422)) != cudaSuccess) return e;
+  if ((e = mcu_configure_mode<2, 2, false>(kMode420)) != cudaSuccess) return e;
+  if ((e = mcu_configure_mode<1, 2, false>(kMode440)) != cudaSuccess) return e;
+  g_mcu_configured = true;
+  return cudaSuccess;
+}
+
+struct McuPlanImpl {
+  int n = 0;
+  int sm_count = 0;
+  bool planes = false;   /* tasks cover the padded planes (YUV output) instead of the visible pixels */
+  void *d_tasks[kNumFusedModes] = {};
+  int n_tasks[kNumFusedModes] = {};
+  std::vector<int> first_task[kNumFusedModes]; /* per mode, n+1 entries */
+  void *d_qint = nullptr;
+  int qint_cap = 0; /* tables */
+  long long coef_rows = 0; /* 128-byte rows the batch touches */
+  const void *map_ptr = nullptr;
+  CUtensorMap tm_rows, tm_pairs;
+  cudaStream_t side[kNumFusedModes] = {};
+  cudaEvent_t fork = nullptr, join[kNumFusedModes] = {};
+};
+
+int mcu_plan_build(FusedPlan &fp, const jgpu_image_desc *descs, const jgpu_layout *layouts,
+                   const int *modes, int n, unsigned flags, int sm_count) {
+  if (!g_mcu_configured) return jgpu_fail("fused kernel not configured");
+  if (!mcu_encode_fn()) return jgpu_fail("cuTensorMapEncodeTiled is not available from this driver");
+  McuPlanImpl *p = new McuPlanImpl();
+  fp.impl = p;
+  p->n = n;
+  p->sm_count = sm_count;
+  p->planes = (flags & JGPU_OUT_YUV) != 0;
+  std::vector<WarpTask> tasks[kNumFusedModes];
+  for (int m = 0; m < kNumFusedModes; m++) p->first_task[m].assign(n + 1, 0);
+  for (int i = 0; i < n; i++) {
+    const jgpu_image_desc &d = descs[i];
+    const jgpu_layout &lay = layouts[i];
+    const McuMode &mi = g_mcu[modes[i]];
+    int block0[3] = {0, 0, 0}, hblocks[3] = {0, 0, 0};
+    for (int c = 0; c < d.ncomps; c++) {
+      block0[c] = (int)((d.coef_off + lay.plane[c].coef_off) / 64);
+      hblocks[c] = lay.plane[c].hblocks;
+    }
+    p->coef_rows = std::max<long long>(p->coef_rows, (d.coef_off + lay.coef_len + 63) / 64);
+    for (int m = 0; m < kNumFusedModes; m++) p->first_task[m][i] = (int)tasks[m].size();
+    /* MCU rows; a unit is two luma blocks wide, a task 32 units */
+    const int mcu_h = mi.gray ? 8 : 8 * mi.vs;
+    const int nv = mi.gray ? lay.plane[0].vblocks : lay.nvmb;
+    const int lblocks = hblocks[0];                       /* luma blocks per block row */
+    const int cper = mi.gray ? 0 : (mi.hs == 2 ? 32 : 64);  /* chroma blocks a task spans */
+    for (int r = 0; r < nv; r++) {
+      for (int b = 0; b < lblocks; b += 64) {
+        const int x0 = b * 8, y0 = r * mcu_h;
+        /* tasks wholly to the right of / below the visible image carry no pixels */
+        if (!p->planes && (x0 >= d.width || y0 >= d.height)) continue;
+        WarpTask t;
+        memset(&t, 0, sizeof(t));
+        t.pitch = d.width * mi.channels;
+        t.rgb_base = d.rgb_off + ((long long)y0 * d.width + x0) * mi.channels;
+        t.width_left = d.width - x0;
+        t.rows_left = d.height - y0;
+        t.flags = ((t.rgb_base & 15) == 0 && (t.pitch & 15) == 0) ? 1 : 0;
+        for (int c = 0; c < d.ncomps; c++) t.qidx[c] = d.qtab_set * 4 + d.tq[c];
+        t.blocks_left = lblocks - b;
+        const int lrows = mi.gray ? 1 : mi.vs;
+        for (int v = 0; v < lrows; v++) t.yfirst[v] = block0[0] + (r * lrows + v) * lblocks + b;
+        if (!mi.gray) {
+          const int cx = b / 64 * cper;
+          t.cfirst[0] = block0[1] + r * hblocks[1] + cx;
+          t.cfirst[1] = block0[2] + r * hblocks[2] + cx;
+        }
+        if (p->planes) {
+          t.yuv_pitch[0] = lay.plane[0].width;
+          t.yuv_base[0] = d.yuv_off + lay.plane[0].data_off + (long long)y0 * lay.plane[0].width + x0;
+          if (!mi.gray) {
+            t.yuv_pitch[1] = lay.plane[1].width;
+            const long long coff = (long long)(r * 8) * lay.plane[1].width + (b / 64) * cper * 8;
+            t.yuv_base[1] = d.yuv_off + lay.plane[1].data_off + coff;
+            t.yuv_base[2] = d.yuv_off + lay.plane[2].data_off + coff;
+          }
+        }
+        tasks[modes[i]].push_back(t);
+      }
+    }
+  }
+  for (int m = 0; m < kNumFusedModes; m++) p->first_task[m][n] = (int)tasks[m].size();
+  for (int m = 0; m < kNumFusedModes; m++) {
+    p->n_tasks[m] = (int)tasks[m].size();
+    if (tasks[m].empty()) continue;
+    if (cudaMalloc(&p->d_tasks[m], sizeof(WarpTask) * tasks[m].size()) != cudaSuccess ||
+        cudaMemcpy(p->d_tasks[m], tasks[m].data(), sizeof(WarpTask) * tasks[m].size(),
+                   cudaMemcpyHostToDevice) != cudaSuccess) {
+      return jgpu_fail("fused plan: task descriptor upload failed");
+    }
+  }
+  return 0;
+}
+
+void mcu_plan_release(FusedPlan &fp) {
+  McuPlanImpl *p = static_cast<McuPlanImpl *>(fp.impl);
+  if (!p) return;
+  for (int m = 0; m < kNumFusedModes; m++) {
+    cudaFree(p->d_tasks[m]);
+    if (p->side[m]) cudaStreamDestroy(p->side[m]);
+    if (p->join[m]) cudaEventDestroy(p->join[m]);
+  }
+  if (p->fork) cudaEventDestroy(p->fork);
+  cudaFree(p->d_qint);
+  delete p;
+  fp.impl = nullptr;
+}
+
+int mcu_plan_launches(const FusedPlan &fp) {
+  const McuPlanImpl *p = static_cast<const McuPlanImpl *>(fp.impl);
+  int n = 1; /* table conversion */
+  for (int m = 0; m < kNumFusedModes; m++) n += 2 * (p->n_tasks[m] > 0); /* 8-bit and 16-bit table variants */
+  return n;
+}
+
+static int mcu_build_maps(McuPlanImpl *p, const int16_t *coef) {
+  if (p->map_ptr == coef) return 0;
+  if (reinterpret_cast<uintptr_t>(coef) & 255) {
+    return jgpu_fail("fused path: the coefficient buffer must be 256-byte aligned");
+  }
+  EncodeTiledFn enc = mcu_encode_fn();
+  const cuuint64_t rows = (cuuint64_t)((p->coef_rows + 1) & ~1ll);
+  {
+    cuuint64_t dims[2] = {64, rows};
+    cuuint64_t strides[1] = {128};
+    cuuint32_t box[2] = {64, kBoxRows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&p->tm_rows, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<int16_t *>(coef), dims,
+                     strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return jgpu_fail("cuTensorMapEncodeTiled(rows) failed (%d)", (int)r);
+  }
+  {
+    cuuint64_t dims[3] = {64, 2, rows / 2};
+    cuuint64_t strides[2] = {128, 256};
+    cuuint32_t box[3] = {64, 1, kBoxRows};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(&p->tm_pairs, CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, const_cast<int16_t *>(coef), dims,
+                     strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return jgpu_fail("cuTensorMapEncodeTiled(pairs) failed (%d)", (int)r);
+  }
+  p->map_ptr = coef;
+  return 0;
+}
+
+int mcu_plan_launch(FusedPlan &fp, int i0, int i1, const int16_t *coef, const uint16_t *qtabs,
+                    int n_sets, uint8_t *rgb, uint8_t *yuv, cudaStream_t stream) {
+  McuPlanImpl *p = static_cast<McuPlanImpl *>(fp.impl);
+  if (mcu_build_maps(p, coef)) return 1;
+  const int n_tables = n_sets * 4;
+  if (n_tables > p->qint_cap) {
+    cudaFree(p->d_qint);
+    p->d_qint = nullptr;
+    if (cudaMalloc(&p->d_qint, (size_t)n_tables * 64 * 4 + 16) != cudaSuccess) {
+      return jgpu_fail("fused path: table buffer allocation failed");
+    }
+    p->qint_cap = n_tables;
+  }
+  /* the wide flag lives right behind the tables */
+  uint32_t *wide_flag = (uint32_t *)p->d_qint + (size_t)p->qint_cap * 64;
+  cudaError_t e = launch_prep_qtabs(qtabs, (uint32_t *)p->d_qint, n_tables, wide_flag, stream);
+  if (e != cudaSuccess) return jgpu_fail("k_prep_qtabs launch failed (%s)", cudaGetErrorString(e));
+  const int rgb_aligned = (reinterpret_cast<uintptr_t>(rgb) & 15) == 0 ? 1 : 0;
+  int n_modes = 0;
+  for (int m = 0; m < kNumFusedModes; m++) n_modes += p->first_task[m][i1] > p->first_task[m][i0];
+  const bool forked = n_modes > 1;
+  if (forked) {
+    if (!p->fork && cudaEventCreateWithFlags(&p->fork, cudaEventDisableTiming) != cudaSuccess) {
+      return jgpu_fail("fused path: event creation failed");
+    }
+    if (cudaEventRecord(p->fork, stream) != cudaSuccess) return jgpu_fail("fused path: event record failed");
+  }
+  cudaStream_t caller = stream;
+  bool first_mode = true;
+  for (int m = 0; m < kNumFusedModes; m++) {
+    const int t0 = p->first_task[m][i0], t1 = p->first_task[m][i1];
+    if (t1 <= t0) continue;
+    stream = caller;
+    if (forked && !first_mode) {
+      /* the first mode stays on the caller's stream, the others go to side streams */
+      if ((!p->side[m] && cudaStreamCreateWithFlags(&p->side[m], cudaStreamNonBlocking) != cudaSuccess) ||
+          (!p->join[m] && cudaEventCreateWithFlags(&p->join[m], cudaEventDisableTiming) != cudaSuccess) ||
+          cudaStreamWaitEvent(p->side[m], p->fork, 0) != cudaSuccess) {
+        return jgpu_fail("fused path: side stream setup failed");
+      }
+      stream = p->side[m];
+    }
+    first_mode = false;
+    const McuMode &mi = g_mcu[m];
+    const int grid = p->sm_count;
+    const WarpTask *tasks = static_cast<const WarpTask *>(p->d_tasks[m]) + t0;
+    const uint32_t *qint = static_cast<const uint32_t *>(p->d_qint);
+    switch (m) {
+      case kModeGray: e = mcu_launch_mode<1, 1, true>(p->planes, grid, mi, stream, p->tm_rows, p->tm_pairs, tasks, t1 - t0, qint, wide_flag, rgb, rgb_aligned, yuv); break;
+      case kMode444: e = mcu_launch_mode<1, 1, false>(p->planes, grid, mi, stream, p->tm_rows, p->tm_pairs, tasks, t1 - t0, qint, wide_flag, rgb, rgb_aligned, yuv); break;
+      case kMode422: e = mcu_launch_mode<2, 1, false>(p->planes, grid, mi, stream, p->tm_rows, p->tm_pairs, tasks, t1 - t0, qint, wide_flag, rgb, rgb_aligned, yuv); break;
+      case kMode420: e = mcu_launch_mode<2, 2, false>(p->planes, grid, mi, stream, p->tm_rows, p->tm_pairs, tasks, t1 - t0, qint, wide_flag, rgb, rgb_aligned, yuv); break;
+      case kMode440: e = mcu_launch_mode<1, 2, false>(p->planes, grid, mi, stream, p->tm_rows, p->tm_pairs, tasks, t1 - t0, qint, wide_flag, rgb, rgb_aligned, yuv); break;
+    }
+    if (e != cudaSuccess) return jgpu_fail("fused kernel launch failed (%s)", cudaGetErrorString(e));
+    if (stream != caller) {
+      if (cudaEventRecord(p->join[m], stream) != cudaSuccess || cudaStreamWaitEvent(caller, p->join[m], 0) != cudaSuccess) {
+        return jgpu_fail("fused path: join failed");
+      }
+    }
+  }
+  return 0;
+}
+
+}  // namespace jgpu

@@ -100,8 +100,9 @@ struct jgpu_plan {
   /* generic path */
   Buffer d_segs, d_pair_work, d_cimgs, d_colour_work, d_scratch;
   std::vector<int> img_first_pair_cta, img_first_colour_cta; /* size n+1 */
-  /* fused path */
+  /* fused path: jgpu_mcu.cu (pixels or planes), or its predecessor jgpu_fused.cu (pixels; JGPU_FUSED_IMPL=v9) */
   bool fused = false;
+  bool mcu = false;
   FusedPlan fp;
   /* PACK expansion: built when every coef_off is a multiple of 64 */
   bool can_unpack = false;
@@ -161,6 +162,11 @@ extern "C" jgpu_ctx *jgpu_create(int device) {
       return nullptr;
     }
   }
+  if (mcu_configure(device) != cudaSuccess) {
+    jgpu_fail("could not configure the fused kernel (%s)", cudaGetErrorString(cudaGetLastError()));
+    jgpu_destroy(ctx);
+    return nullptr;
+  }
   if (fused_configure(device) != cudaSuccess) {
     jgpu_fail("could not configure the fused kernel (%s)", cudaGetErrorString(cudaGetLastError()));
     jgpu_destroy(ctx);
@@ -217,6 +223,12 @@ extern "C" void jgpu_host_free(void *p) {
 /* -------------------------------------------------------------------------- */
 /* plans                                                                      */
 
+/* JGPU_FUSED_IMPL=v9 selects the warp-role kernel of jgpu_fused.cu (A/B runs); default: jgpu_mcu.cu */
+static bool use_v9() {
+  const char *e = getenv("JGPU_FUSED_IMPL");
+  return e != nullptr && strcmp(e, "v9") == 0;
+}
+
 static bool fused_eligible(const jgpu_image_desc &d, const jgpu_layout &lay, unsigned flags,
                            int *mode) {
   (void)lay;
@@ -230,8 +242,10 @@ static bool fused_eligible(const jgpu_image_desc &d, const jgpu_layout &lay, uns
     else if (d.hsamp[0] == 1 && d.vsamp[0] == 2) *mode = kMode440;
     else return false;
   }
-  /* the fused kernel writes RGB only and addresses coefficients by 128-byte row */
-  if ((flags & (JGPU_OUT_RGB | JGPU_OUT_YUV)) != JGPU_OUT_RGB) return false;
+  /* the fused kernels write pixels OR planes and address coefficients by 128-byte row */
+  const unsigned out = flags & (JGPU_OUT_RGB | JGPU_OUT_YUV);
+  if (out != JGPU_OUT_RGB && out != JGPU_OUT_YUV) return false;
+  if (out == JGPU_OUT_YUV && use_v9()) return false;
   if (d.coef_off & 63) return false;
   return true;
 }
@@ -320,8 +334,11 @@ extern "C" jgpu_plan *jgpu_plan_create(jgpu_ctx *ctx, const jgpu_image_desc *des
   if (build_unpack_lists(plan)) goto fail;
 
   if (plan->fused) {
-    if (fused_plan_build(plan->fp, plan->descs.data(), plan->layouts.data(), modes.data(), n,
-                         flags, ctx->sm_count)) {
+    plan->mcu = !use_v9();
+    if (plan->mcu ? mcu_plan_build(plan->fp, plan->descs.data(), plan->layouts.data(), modes.data(), n, flags,
+                                   ctx->sm_count)
+                  : fused_plan_build(plan->fp, plan->descs.data(), plan->layouts.data(), modes.data(), n, flags,
+                                     ctx->sm_count)) {
       goto fail;
     }
     return plan;
@@ -409,13 +426,14 @@ extern "C" void jgpu_plan_destroy(jgpu_plan *plan) {
   plan->d_scratch.release();
   plan->d_unpack_segs.release();
   plan->d_unpack_work.release();
-  fused_plan_release(plan->fp);
+  if (plan->mcu) mcu_plan_release(plan->fp);
+  else fused_plan_release(plan->fp);
   delete plan;
 }
 
 extern "C" int jgpu_plan_launches(const jgpu_plan *plan) {
   if (!plan) return 0;
-  if (plan->fused) return fused_plan_launches(plan->fp);
+  if (plan->fused) return plan->mcu ? mcu_plan_launches(plan->fp) : fused_plan_launches(plan->fp);
   return (plan->flags & JGPU_OUT_RGB) ? 2 : 1;
 }
 
@@ -427,6 +445,10 @@ static int plan_run_range(jgpu_plan *plan, int i0, int i1, const int16_t *d_coef
                           cudaStream_t stream) {
   if (i0 >= i1) return 0;
   if (plan->fused) {
+    if (plan->mcu && d_yuv && (reinterpret_cast<uintptr_t>(d_yuv) & 15)) {
+      return jgpu_fail("the planes buffer must be 16-byte aligned");
+    }
+    if (plan->mcu) return mcu_plan_launch(plan->fp, i0, i1, d_coef, d_qtabs, n_sets, d_rgb, d_yuv, stream);
     return fused_plan_launch(plan->fp, i0, i1, d_coef, d_qtabs, n_sets, d_rgb, stream);
   }
   uint8_t *planes = plan->use_scratch ? (uint8_t *)plan->d_scratch.ptr : d_yuv;
