@@ -65,26 +65,36 @@ __device__ unsigned long long g_mcu_trace[4 * 148 * 12];
 #endif
 
 constexpr int kZoneBytes = 2 * kBoxBytes;   /* a warp's TMA landing zone: box A, box B */
+constexpr int kHalfRows = 16;               /* blocks per TMA box: one half-task */
+constexpr int kHalfBoxBytes = kHalfRows * 128;
 constexpr int kRingSlots = 4;
 constexpr int kOutRgb = 1, kOutYuv = 2;
 
-/* One task = 32 units of one MCU row, as the host describes it (mcu_plan_build).  Block
- * numbers are GLOBAL: the coefficient buffer viewed as rows of 64 int16. */
+/* One half-task = up to 16 consecutive units of one MCU row of one image; a task = two of them
+ * (lanes 0-15 and lanes 16-31), consecutive in the image's row-major order, so that the second
+ * may be the start of the next MCU row: a 3840-pixel row is 15 half-tasks, and with whole-warp
+ * column groups every eighth warp would run half empty.  Block numbers are GLOBAL: the
+ * coefficient buffer viewed as rows of 64 int16.  Built on the host (mcu_plan_build). */
+struct McuHalf {
+  long long base0;        /* pixels: byte offset in the rgb buffer of the half-task's top-left pixel;
+                             planes: byte offset of its top-left Y sample */
+  long long base1;        /* planes: byte offset of its top-left Cb sample (Cr: + cr_delta) */
+  int32_t width_left;     /* visible pixels from its left edge to the image's right edge (0: no such half) */
+  int32_t rows_left;      /* visible rows from its top row to the image's bottom */
+  int32_t blocks_left;    /* luma blocks from its left edge to the padded plane's right edge (0: no such half) */
+  int32_t yfirst[2];      /* first luma block of its run, luma block row 0 / 1 of the MCU row */
+  int32_t cfirst[2];      /* first Cb / Cr block of its run */
+  int32_t pad;
+};
 struct __align__(16) WarpTask {
-  long long rgb_base;     /* byte offset in the rgb buffer of the task's top-left pixel */
-  int32_t width_left;     /* visible pixels from the task's left edge to the image's right edge */
-  int32_t rows_left;      /* visible rows from the task's top row to the image's bottom */
-  int32_t pitch;          /* bytes per rgb row */
+  McuHalf half[2];
+  long long cr_delta;     /* planes: Cr plane offset minus Cb plane offset */
+  int32_t pitch0;         /* bytes per rgb row / per Y plane row */
+  int32_t pitch1;         /* bytes per chroma plane row */
   int32_t flags;          /* bit 0: rgb rows are 16-byte aligned (given an aligned base pointer) */
   int32_t qidx[3];        /* 64-entry table indices: qtab_set*4 + tq */
-  int32_t blocks_left;    /* luma blocks from the task's left edge to the padded plane's right edge */
-  int32_t yfirst[2];      /* first luma block of the task's run, luma block row 0 / 1 of the MCU row */
-  int32_t cfirst[2];      /* first Cb / Cr block of the task's run */
-  long long yuv_base[3];  /* planes output: byte offset of the task's top-left sample in Y / Cb / Cr */
-  int32_t yuv_pitch[2];   /* row stride of the Y plane / of the chroma planes */
-  int32_t pad[10];
 };
-static_assert(sizeof(WarpTask) == 128, "WarpTask is copied with cp.async.bulk and read with vector loads");
+static_assert(sizeof(McuHalf) == 48 && sizeof(WarpTask) == 128, "WarpTask is copied with cp.async.bulk");
 
 /* Build knobs (A/B-tested on the GPU, profiles/r2_notes.md).
  *   JGPU_MCU_WARPS 12: 168 registers per thread; row 0 of the register tile is parked in shared
@@ -141,20 +151,23 @@ __device__ __forceinline__ void stg64_stream(uint8_t *p, uint2 v) {
   asm volatile("st.global.cs.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
 }
 
-/* pair_row_pass of jgpu_fused_common.cuh with the parked row laid out [chunk][lane], or not parked */
+/* pair_row_pass of jgpu_fused_common.cuh with 32-bit shared addresses (the generic pointers cost four
+ * more registers where none are free) and the parked row laid out [chunk][lane], or not parked.
+ * zone: the warp's two boxes; tab: table of block A; tab_b: table of block B. */
 template <bool WIDE, bool PARK>
-__device__ __forceinline__ void mcu_row_pass(pair32 (&m)[8][8], const uint8_t *box_a, const uint8_t *box_b,
-                                             int row, const uint4 *qa, const uint4 *qb, uint32_t park) {
-  const uint8_t *ra = box_a + 128 * row, *rb = box_b + 128 * row;
+__device__ __forceinline__ void mcu_row_pass(pair32 (&m)[8][8], uint32_t zone, int row, uint32_t tab, uint32_t tab_b,
+                                             uint32_t park) {
+  const uint32_t ra = zone + 128 * row, rb = ra + kBoxBytes;
   const int sw = row & 7;
-  constexpr int kHi = kQtabBytes / 2 / 16;   /* the high-byte rows follow the 8 low-byte rows */
+  constexpr int kHi = kQtabBytes / 2;   /* the high-byte rows follow the 8 low-byte rows */
 #pragma unroll
   for (int r = 0; r < 8; r++) {
     const int off = 16 * (r ^ sw);
-    const uint4 a = *reinterpret_cast<const uint4 *>(ra + off);
-    const uint4 b = *reinterpret_cast<const uint4 *>(rb + off);
+    const uint4 a = lds128(ra + off);
+    const uint4 b = lds128(rb + off);
     const uint4 z = make_uint4(0, 0, 0, 0);
-    load_row_pair_packed<WIDE>(m[r], a, b, qa[r], qb[r], WIDE ? qa[kHi + r] : z, WIDE ? qb[kHi + r] : z, r);
+    load_row_pair_packed<WIDE>(m[r], a, b, lds128(tab + 16 * r), lds128(tab_b + 16 * r),
+                               WIDE ? lds128(tab + kHi + 16 * r) : z, WIDE ? lds128(tab_b + kHi + 16 * r) : z, r);
     inv_pass8(m[r]);
     if (PARK && r == 0) {
       /* park row 0 in shared memory until the column pass asks for it, two pairs per chunk */
@@ -171,8 +184,8 @@ __device__ __forceinline__ void mcu_row_pass(pair32 (&m)[8][8], const uint8_t *b
 
 template <int HS, int VS, bool GRAY, bool WIDE, int OUT>
 __global__ void __launch_bounds__(McuCfg<HS, VS, GRAY, WIDE>::kThreads, 1)
-k_mcu(const __grid_constant__ CUtensorMap tm_rows,   /* (64, rows)            */
-      const __grid_constant__ CUtensorMap tm_pairs,  /* (64, parity, pairs)   */
+k_mcu(const __grid_constant__ CUtensorMap tm_rows,   /* (64, rows), boxes of 16 rows            */
+      const __grid_constant__ CUtensorMap tm_pairs,  /* (64, parity, pairs), boxes of 16 pairs  */
       const WarpTask *__restrict__ tasks, int n_tasks, const uint32_t *__restrict__ qint,
       const uint32_t *__restrict__ wide_flag, uint8_t *__restrict__ rgb, int rgb_aligned,
       uint8_t *__restrict__ yuv) {
@@ -194,8 +207,6 @@ k_mcu(const __grid_constant__ CUtensorMap tm_rows,   /* (64, rows)            */
     uint32_t zone;      /* the warp's landing zone: box A, box B */
     uint32_t misc;      /* the warp's area behind the zones */
     uint32_t mine;      /* misc + 16*lane: this lane's column of every [row][lane] array */
-    const uint8_t *zone_gen;
-    const uint4 *tab_gen;
   };
   auto geo = [&]() -> Geo {
     uint32_t tid;
@@ -206,14 +217,14 @@ k_mcu(const __grid_constant__ CUtensorMap tm_rows,   /* (64, rows)            */
     g.zone = smem0 + w * kZoneBytes;
     g.misc = smem0 + C::kWarps * kZoneBytes + w * C::kWarpMisc;
     g.mine = g.misc + 16u * (uint32_t)g.lane;
-    g.zone_gen = smem_raw + w * kZoneBytes;
-    g.tab_gen = reinterpret_cast<const uint4 *>(smem_raw + C::kWarps * kZoneBytes + w * C::kWarpMisc + C::kOffTab);
     return g;
   };
   /* mbarriers of a warp: [0] its coefficient loads, [1 + slot] its descriptor ring */
   auto bar_data = [&](const Geo &g) { return g.misc + C::kOffBar; };
   auto bar_ring = [&](const Geo &g, uint32_t slot) { return g.misc + C::kOffBar + 8 + 8 * slot; };
   auto desc_addr = [&](const Geo &g, int n) { return g.misc + C::kOffRing + ((uint32_t)n % kRingSlots) * (uint32_t)sizeof(WarpTask); };
+  /* this lane's half-task inside a descriptor */
+  auto half_addr = [&](const Geo &g, int n) { return desc_addr(g, n) + (uint32_t)(g.lane >> 4) * (uint32_t)sizeof(McuHalf); };
 
   {
     const Geo g = geo();
@@ -234,40 +245,44 @@ k_mcu(const __grid_constant__ CUtensorMap tm_rows,   /* (64, rows)            */
   auto wait_desc = [&](const Geo &g, int n) {
     mbar_wait_hint<JGPU_MCU_WAIT_NS>(bar_ring(g, (uint32_t)n % kRingSlots), ((uint32_t)n / kRingSlots) & 1u);
   };
-  /* start the loads of step s of local task n (lane 0 only; its descriptor must have landed).
-   * Tables: the low-byte half always, the high-byte half for 16-bit tables. */
-  auto load_table = [&](uint32_t dst, int q, uint32_t bar) {
-    bulk_load(dst, qint + (size_t)q * 64, C::kTabBytes, bar);
-  };
+  /* Start the loads of step s of local task n (lane 0 only; its descriptor must have landed): per
+   * half-task 16 rows of box A and 16 rows of box B (a half-task that does not exist repeats the
+   * other one's blocks, see mcu_plan_build), and the step's table(s): the low-byte half always, the
+   * high-byte half for 16-bit tables. */
   auto fire = [&](const Geo &g, int n, int s) {
     const uint32_t d = desc_addr(g, n), bar = bar_data(g), tab = g.misc + C::kOffTab;
-    if (s < C::kChromaSteps) {
-      int f0 = (int)lds32(d + offsetof(WarpTask, cfirst));
-      int f1 = (int)lds32(d + offsetof(WarpTask, cfirst) + 4);
-      const int q1 = (int)lds32(d + offsetof(WarpTask, qidx) + 4);
-      const int q2 = (int)lds32(d + offsetof(WarpTask, qidx) + 8);
-      mbar_expect_tx(bar, 2 * kBoxBytes + 2 * C::kTabBytes);
-      if (HS == 2) {
-        /* Cb and Cr of 32 consecutive MCUs */
-        tma_load_2d(g.zone, &tm_rows, 0, f0, bar);
-        tma_load_2d(g.zone + kBoxBytes, &tm_rows, 0, f1, bar);
+    const bool chroma = s < C::kChromaSteps;
+    mbar_expect_tx(bar, 2 * kBoxBytes + (chroma ? 2 : 1) * C::kTabBytes);
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const uint32_t hd = d + h * (uint32_t)sizeof(McuHalf);
+      const uint32_t dst = g.zone + h * kHalfBoxBytes;
+      if (chroma) {
+        int f0 = (int)lds32(hd + offsetof(McuHalf, cfirst));
+        int f1 = (int)lds32(hd + offsetof(McuHalf, cfirst) + 4);
+        if (HS == 2) {
+          /* Cb and Cr of 16 consecutive MCUs */
+          tma_load_2d(dst, &tm_rows, 0, f0, bar);
+          tma_load_2d(dst + kBoxBytes, &tm_rows, 0, f1, bar);
+        } else {
+          /* step s takes the MCUs of parity s: every second Cb block and every second Cr block */
+          f0 += s;
+          f1 += s;
+          tma_load_3d(dst, &tm_pairs, 0, f0 & 1, f0 >> 1, bar);
+          tma_load_3d(dst + kBoxBytes, &tm_pairs, 0, f1 & 1, f1 >> 1, bar);
+        }
       } else {
-        /* step s takes the MCUs of parity s: every second Cb block and every second Cr block */
-        f0 += s;
-        f1 += s;
-        tma_load_3d(g.zone, &tm_pairs, 0, f0 & 1, f0 >> 1, bar);
-        tma_load_3d(g.zone + kBoxBytes, &tm_pairs, 0, f1 & 1, f1 >> 1, bar);
+        /* the 16 even-position and the 16 odd-position blocks of a 32-block luma run */
+        const int first = (int)lds32(hd + offsetof(McuHalf, yfirst) + 4 * (s - C::kChromaSteps));
+        tma_load_3d(dst, &tm_pairs, 0, first & 1, first >> 1, bar);
+        tma_load_3d(dst + kBoxBytes, &tm_pairs, 0, (first + 1) & 1, (first + 1) >> 1, bar);
       }
-      load_table(tab, q1, bar);
-      load_table(tab + C::kTabBytes, q2, bar);
+    }
+    if (chroma) {
+      bulk_load(tab, qint + (size_t)lds32(d + offsetof(WarpTask, qidx) + 4) * 64, C::kTabBytes, bar);
+      bulk_load(tab + C::kTabBytes, qint + (size_t)lds32(d + offsetof(WarpTask, qidx) + 8) * 64, C::kTabBytes, bar);
     } else {
-      /* the 32 even-position and the 32 odd-position blocks of a 64-block luma run */
-      const int first = (int)lds32(d + offsetof(WarpTask, yfirst) + 4 * (s - C::kChromaSteps));
-      const int qy = (int)lds32(d + offsetof(WarpTask, qidx));
-      mbar_expect_tx(bar, 2 * kBoxBytes + C::kTabBytes);
-      tma_load_3d(g.zone, &tm_pairs, 0, first & 1, first >> 1, bar);
-      tma_load_3d(g.zone + kBoxBytes, &tm_pairs, 0, (first + 1) & 1, (first + 1) >> 1, bar);
-      load_table(tab, qy, bar);
+      bulk_load(tab, qint + (size_t)lds32(d + offsetof(WarpTask, qidx)) * 64, C::kTabBytes, bar);
     }
   };
 
@@ -289,12 +304,11 @@ k_mcu(const __grid_constant__ CUtensorMap tm_rows,   /* (64, rows)            */
 
 #pragma unroll 1
   for (;;) {
-    int step, total;
+    bool is_c, active;   /* a chroma step?  does this lane's unit exist / show in this step? */
     {
       const Geo g = geo();
       const uint2 lc = lds64(g.misc + C::kOffLoop);
-      step = (int)lc.x;
-      total = (int)lc.y;
+      const int step = (int)lc.x, total = (int)lc.y;
 #ifdef JGPU_MCU_TRACE
       if (step >= total && g.lane == 0) {
         unsigned long long t1;
@@ -308,22 +322,18 @@ k_mcu(const __grid_constant__ CUtensorMap tm_rows,   /* (64, rows)            */
       if (step >= total) break;
       __syncwarp();
       sts32(g.misc + C::kOffLoop, (uint32_t)step + 1u);
-    }
-    const int n = step / C::kSteps, s = step - n * C::kSteps;
-    const bool is_c = s < C::kChromaSteps;
-    const int yr = s - C::kChromaSteps;   /* luma block row inside the MCU row */
-    bool active;   /* does this lane's unit exist / show in this step? */
-    {
-      const Geo g = geo();
+      const int n = step / C::kSteps, s = step - n * C::kSteps;
+      is_c = s < C::kChromaSteps;
       /* keep the ring two tasks ahead (the slot of task n-2: every lane is past it) */
       if (s == 0 && g.lane == 0 && (n + 2) * C::kSteps < total) fetch_desc(g, n + 2);
       wait_desc(g, n);
-      const uint32_t da = desc_addr(g, n);
-      const uint4 h0 = lds128(da);                                     /* rgb_base, width_left, rows_left */
+      const uint32_t ha = half_addr(g, n);
+      const int u = g.lane & 15;
       if (OUT == kOutYuv) {
-        active = 2 * g.lane + ((HS == 1 && is_c) ? s : 0) < (int)lds32(da + offsetof(WarpTask, blocks_left));
+        active = 2 * u + ((HS == 1 && is_c) ? s : 0) < (int)lds32(ha + offsetof(McuHalf, blocks_left));
       } else {
-        active = 16 * g.lane + ((HS == 1 && is_c) ? 8 * s : 0) < (int)h0.z && (is_c || 8 * yr < (int)h0.w);
+        const uint2 wr = lds64(ha + offsetof(McuHalf, width_left));   /* width_left, rows_left */
+        active = 16 * u + ((HS == 1 && is_c) ? 8 * s : 0) < (int)wr.x && (is_c || 8 * (s - C::kChromaSteps) < (int)wr.y);
       }
       mbar_wait_hint<JGPU_MCU_WAIT_NS>(bar_data(g), (uint32_t)step & 1u);
     }
@@ -332,20 +342,21 @@ k_mcu(const __grid_constant__ CUtensorMap tm_rows,   /* (64, rows)            */
       pair32 m[8][8];
       if (active) {
         const Geo g = geo();
-        const uint4 *const qa = g.tab_gen;
-        const uint4 *const qb = is_c ? qa + C::kTabBytes / 16 : qa;   /* chroma: Cb table, then Cr table */
-        mcu_row_pass<WIDE, C::kPark>(m, g.zone_gen, g.zone_gen + kBoxBytes, g.lane, qa, qb, g.mine + C::kOffPark);
+        const uint32_t qa = g.misc + C::kOffTab;
+        const uint32_t qb = is_c ? qa + C::kTabBytes : qa;   /* chroma: Cb table, then Cr table */
+        mcu_row_pass<WIDE, C::kPark>(m, g.zone, g.lane, qa, qb, g.mine + C::kOffPark);
       }
       /* the boxes are in registers: start the loads of this warp's next step */
       __syncwarp();
       {
         const Geo g = geo();
-        if (g.lane == 0 && step + 1 < total) {
-          if (s + 1 < C::kSteps) {
-            fire(g, n, s + 1);
-          } else {
-            wait_desc(g, n + 1);
-            fire(g, n + 1, 0);
+        if (g.lane == 0) {
+          const uint2 lc = lds64(g.misc + C::kOffLoop);   /* (this step + 1, total) */
+          const int next = (int)lc.x;
+          if (next < (int)lc.y) {
+            const int n = next / C::kSteps, s = next - n * C::kSteps;
+            if (s == 0) wait_desc(g, n);
+            fire(g, n, s);
           }
         }
       }
@@ -354,6 +365,7 @@ k_mcu(const __grid_constant__ CUtensorMap tm_rows,   /* (64, rows)            */
       const pair32 magic = p_make_bits(kMagicBits, kMagicBits);
       const Geo g = geo();
       const uint32_t mine = g.mine;
+      const int s = ((int)lds32(g.misc + C::kOffLoop) - 1) % C::kSteps;
       auto row0 = [&](int j, pair32 &a, pair32 &b) {
         const uint4 c = lds128(mine + C::kOffPark + 512 * j);
         a = p_make_bits(c.x, c.y);
@@ -395,16 +407,24 @@ k_mcu(const __grid_constant__ CUtensorMap tm_rows,   /* (64, rows)            */
     }
 
     const Geo g = geo();
-    const uint32_t da = desc_addr(g, n);
+    const int u = g.lane & 15;   /* this lane's unit inside its half-task */
+    int n, s;
+    {
+      const int step = (int)lds32(g.misc + C::kOffLoop) - 1;
+      n = step / C::kSteps;
+      s = step - n * C::kSteps;
+    }
+    const int yr = s - C::kChromaSteps;   /* luma block row inside the MCU row */
+    const uint32_t da = desc_addr(g, n), ha = half_addr(g, n);
     if (is_c) {
       if (OUT == kOutYuv) {
         /* planes: 8 Cb bytes and 8 Cr bytes per row, out of the strip */
-        const uint2 b1 = lds64(da + offsetof(WarpTask, yuv_base) + 8);
-        const uint2 b2 = lds64(da + offsetof(WarpTask, yuv_base) + 16);
-        const int cpitch = (int)lds32(da + offsetof(WarpTask, yuv_pitch) + 4);
-        const long long col = HS == 2 ? 8 * g.lane : 16 * g.lane + 8 * s;
+        const uint2 b1 = lds64(ha + offsetof(McuHalf, base1));
+        const uint2 dl = lds64(da + offsetof(WarpTask, cr_delta));
+        const int cpitch = (int)lds32(da + offsetof(WarpTask, pitch1));
+        const long long col = HS == 2 ? 8 * u : 16 * u + 8 * s;
         uint8_t *pb = yuv + (long long)(((unsigned long long)b1.y << 32) | b1.x) + col;
-        uint8_t *pr = yuv + (long long)(((unsigned long long)b2.y << 32) | b2.x) + col;
+        uint8_t *pr = pb + (long long)(((unsigned long long)dl.y << 32) | dl.x);
         const uint32_t strip = g.mine + C::kOffChroma + (uint32_t)s * C::kChromaStep;
 #pragma unroll
         for (int k = 0; k < 8; k++) {
@@ -451,13 +471,14 @@ k_mcu(const __grid_constant__ CUtensorMap tm_rows,   /* (64, rows)            */
                         __byte_perm(t0.y, t0.w, 0x6420), __byte_perm(t1.y, t1.w, 0x6420));
     };
 
+    const uint2 b0 = lds64(ha + offsetof(McuHalf, base0));
+    const long long base0 = (long long)(((unsigned long long)b0.y << 32) | b0.x);
+    const int pitch = (int)lds32(da + offsetof(WarpTask, pitch0));
     if (OUT == kOutYuv) {
       /* planes: 16 Y bytes per row (8 when the unit's second block lies beyond the padded plane) */
-      const uint2 b0 = lds64(da + offsetof(WarpTask, yuv_base));
-      const int ypitch = (int)lds32(da + offsetof(WarpTask, yuv_pitch));
-      const bool whole = 2 * g.lane + 1 < (int)lds32(da + offsetof(WarpTask, blocks_left));
-      const bool wide16 = whole && (ypitch & 8) == 0;   /* an odd number of blocks per row: rows are only 8-byte aligned */
-      uint8_t *py = yuv + (long long)(((unsigned long long)b0.y << 32) | b0.x) + (long long)(8 * yr) * ypitch + 16 * g.lane;
+      const bool whole = 2 * u + 1 < (int)lds32(ha + offsetof(McuHalf, blocks_left));
+      const bool wide16 = whole && (pitch & 8) == 0;   /* an odd number of blocks per row: rows are only 8-byte aligned */
+      uint8_t *py = yuv + base0 + (long long)(8 * yr) * pitch + 16 * u;
 #pragma unroll 2
       for (int k = 0; k < 8; k++) {
         const uint4 v = staged_row_bytes(k);
@@ -467,20 +488,17 @@ k_mcu(const __grid_constant__ CUtensorMap tm_rows,   /* (64, rows)            */
           stg64_stream(py, make_uint2(v.x, v.y));
           if (whole) stg64_stream(py + 8, make_uint2(v.z, v.w));
         }
-        py += ypitch;
+        py += pitch;
       }
       continue;
     }
 
     /* ---- colour offsets, pack, store --------------------------------------------------------- */
-    const uint4 h0 = lds128(da);
-    const uint2 h1 = lds64(da + 16);
-    const long long rgb_base = (long long)(((unsigned long long)h0.y << 32) | h0.x);
-    const int pitch = (int)h1.x;
-    const int vis_px = min(16, (int)h0.z - 16 * g.lane);
-    const int vis_rows = min(8, (int)h0.w - 8 * yr);
-    const bool fast = (h1.y & (uint32_t)rgb_aligned & 1u) != 0 && vis_px == 16;
-    uint8_t *dst = rgb + rgb_base + (long long)(8 * yr) * pitch + (long long)(16 * g.lane) * C::kChannels;
+    const uint2 wr = lds64(ha + offsetof(McuHalf, width_left));   /* width_left, rows_left */
+    const int vis_px = min(16, (int)wr.x - 16 * u);
+    const int vis_rows = min(8, (int)wr.y - 8 * yr);
+    const bool fast = (lds32(da + offsetof(WarpTask, flags)) & (uint32_t)rgb_aligned & 1u) != 0 && vis_px == 16;
+    uint8_t *dst = rgb + base0 + (long long)(8 * yr) * pitch + (long long)(16 * u) * C::kChannels;
     if (GRAY) {
 #pragma unroll 1
       for (int k = 0; k < vis_rows; k++, dst += pitch) {
@@ -681,44 +699,64 @@ int mcu_plan_build(FusedPlan &fp, const jgpu_image_desc *descs, const jgpu_layou
     }
     p->coef_rows = std::max<long long>(p->coef_rows, (d.coef_off + lay.coef_len + 63) / 64);
     for (int m = 0; m < kNumFusedModes; m++) p->first_task[m][i] = (int)tasks[m].size();
-    /* MCU rows; a unit is two luma blocks wide, a task 32 units */
+    /* the image's half-tasks in row-major order: MCU rows x runs of 16 units (32 luma blocks) */
     const int mcu_h = mi.gray ? 8 : 8 * mi.vs;
     const int nv = mi.gray ? lay.plane[0].vblocks : lay.nvmb;
+    const int lrows = mi.gray ? 1 : mi.vs;                /* luma block rows per MCU row */
     const int lblocks = hblocks[0];                       /* luma blocks per block row */
-    const int cper = mi.gray ? 0 : (mi.hs == 2 ? 32 : 64);  /* chroma blocks a task spans */
+    const int cper = mi.gray ? 0 : (mi.hs == 2 ? 16 : 32);  /* chroma blocks a half-task spans */
+    std::vector<McuHalf> halves;
     for (int r = 0; r < nv; r++) {
-      for (int b = 0; b < lblocks; b += 64) {
+      for (int b = 0; b < lblocks; b += 32) {
         const int x0 = b * 8, y0 = r * mcu_h;
-        /* tasks wholly to the right of / below the visible image carry no pixels */
+        /* half-tasks wholly to the right of / below the visible image carry no pixels */
         if (!p->planes && (x0 >= d.width || y0 >= d.height)) continue;
-        WarpTask t;
-        memset(&t, 0, sizeof(t));
-        t.pitch = d.width * mi.channels;
-        t.rgb_base = d.rgb_off + ((long long)y0 * d.width + x0) * mi.channels;
-        t.width_left = d.width - x0;
-        t.rows_left = d.height - y0;
-        t.flags = ((t.rgb_base & 15) == 0 && (t.pitch & 15) == 0) ? 1 : 0;
-        for (int c = 0; c < d.ncomps; c++) t.qidx[c] = d.qtab_set * 4 + d.tq[c];
-        t.blocks_left = lblocks - b;
-        const int lrows = mi.gray ? 1 : mi.vs;
-        for (int v = 0; v < lrows; v++) t.yfirst[v] = block0[0] + (r * lrows + v) * lblocks + b;
+        McuHalf h;
+        memset(&h, 0, sizeof(h));
+        h.width_left = d.width - x0;
+        h.rows_left = d.height - y0;
+        h.blocks_left = lblocks - b;
+        for (int v = 0; v < lrows; v++) h.yfirst[v] = block0[0] + (r * lrows + v) * lblocks + b;
         if (!mi.gray) {
-          const int cx = b / 64 * cper;
-          t.cfirst[0] = block0[1] + r * hblocks[1] + cx;
-          t.cfirst[1] = block0[2] + r * hblocks[2] + cx;
+          const int cx = b / 32 * cper;
+          h.cfirst[0] = block0[1] + r * hblocks[1] + cx;
+          h.cfirst[1] = block0[2] + r * hblocks[2] + cx;
         }
         if (p->planes) {
-          t.yuv_pitch[0] = lay.plane[0].width;
-          t.yuv_base[0] = d.yuv_off + lay.plane[0].data_off + (long long)y0 * lay.plane[0].width + x0;
+          h.base0 = d.yuv_off + lay.plane[0].data_off + (long long)y0 * lay.plane[0].width + x0;
           if (!mi.gray) {
-            t.yuv_pitch[1] = lay.plane[1].width;
-            const long long coff = (long long)(r * 8) * lay.plane[1].width + (b / 64) * cper * 8;
-            t.yuv_base[1] = d.yuv_off + lay.plane[1].data_off + coff;
-            t.yuv_base[2] = d.yuv_off + lay.plane[2].data_off + coff;
+            h.base1 = d.yuv_off + lay.plane[1].data_off + (long long)(r * 8) * lay.plane[1].width + (b / 32) * cper * 8;
           }
+        } else {
+          h.base0 = d.rgb_off + ((long long)y0 * d.width + x0) * mi.channels;
         }
-        tasks[modes[i]].push_back(t);
+        halves.push_back(h);
       }
+    }
+    for (size_t k = 0; k < halves.size(); k += 2) {
+      WarpTask t;
+      memset(&t, 0, sizeof(t));
+      t.half[0] = halves[k];
+      if (k + 1 < halves.size()) {
+        t.half[1] = halves[k + 1];
+      } else {
+        /* no second half: its lanes stay idle; the loads repeat the first half's blocks */
+        t.half[1] = halves[k];
+        t.half[1].width_left = t.half[1].rows_left = t.half[1].blocks_left = 0;
+      }
+      if (p->planes) {
+        t.pitch0 = lay.plane[0].width;
+        if (!mi.gray) {
+          t.pitch1 = lay.plane[1].width;
+          t.cr_delta = lay.plane[2].data_off - lay.plane[1].data_off;
+        }
+      } else {
+        t.pitch0 = d.width * mi.channels;
+        /* every half-task starts at a multiple of 256 pixels of a row: aligned iff the image is */
+        t.flags = ((d.rgb_off & 15) == 0 && (t.pitch0 & 15) == 0) ? 1 : 0;
+      }
+      for (int c = 0; c < d.ncomps; c++) t.qidx[c] = d.qtab_set * 4 + d.tq[c];
+      tasks[modes[i]].push_back(t);
     }
   }
   for (int m = 0; m < kNumFusedModes; m++) p->first_task[m][n] = (int)tasks[m].size();
@@ -765,7 +803,7 @@ static int mcu_build_maps(McuPlanImpl *p, const int16_t *coef) {
   {
     cuuint64_t dims[2] = {64, rows};
     cuuint64_t strides[1] = {128};
-    cuuint32_t box[2] = {64, kBoxRows};
+    cuuint32_t box[2] = {64, kHalfRows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(&p->tm_rows, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<int16_t *>(coef), dims,
                      strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -775,7 +813,7 @@ static int mcu_build_maps(McuPlanImpl *p, const int16_t *coef) {
   {
     cuuint64_t dims[3] = {64, 2, rows / 2};
     cuuint64_t strides[2] = {128, 256};
-    cuuint32_t box[3] = {64, 1, kBoxRows};
+    cuuint32_t box[3] = {64, 1, kHalfRows};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(&p->tm_pairs, CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, const_cast<int16_t *>(coef), dims,
                      strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
