@@ -585,29 +585,33 @@ k_gray_tpb(const __grid_constant__ CUtensorMap tm_rows, const TileDesc *__restri
   }
 }
 
-/* u16 tables -> packed tables for IDP.2A (one tiny launch per run).  Per table 64 words:
+/* u16 tables -> packed tables for IDP.2A (one tiny launch per run) and the 16-bit flag.  Per table 64 words:
  * word r*4+i        = (q[r][2i] & 255)  | (q[r][2i+1] & 255) << 24      (low bytes)
  * word 32 + r*4+i   = (q[r][2i] >> 8)   | (q[r][2i+1] >> 8)  << 24      (high bytes) */
-__global__ void k_prep_qtabs(const uint16_t *__restrict__ q, uint32_t *__restrict__ out, int n_words,
-                             uint32_t *__restrict__ wide_flag) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_words) return;
-  const int table = i >> 6, w = i & 63, hi = w >> 5, idx = (w & 31) * 2;
-  const uint32_t q0 = q[table * 64 + idx], q1 = q[table * 64 + idx + 1];
-  const uint32_t v = hi ? ((q0 >> 8) | ((q1 >> 8) << 24)) : ((q0 & 255u) | ((q1 & 255u) << 24));
-  out[i] = v;
-  if (hi && v) atomicOr(wide_flag, 1u);   /* wide_flag is zeroed by the host before this launch */
+/* One CTA walks all the words, so that the flag is WRITTEN (0 or 1) rather than OR-ed into a word
+ * somebody must zero first: chunks of one batch run this on several streams at once with the same
+ * tables (jgpu_decode_batch_host), and every such launch stores the same bytes -- a zeroing memset
+ * from a later chunk could otherwise land between an earlier chunk's two kernel instantiations. */
+__global__ void __launch_bounds__(256) k_prep_qtabs(const uint16_t *__restrict__ q, uint32_t *__restrict__ out,
+                                                    int n_words, uint32_t *__restrict__ wide_flag) {
+  int wide = 0;
+  for (int i = threadIdx.x; i < n_words; i += blockDim.x) {
+    const int table = i >> 6, w = i & 63, hi = w >> 5, idx = (w & 31) * 2;
+    const uint32_t q0 = q[table * 64 + idx], q1 = q[table * 64 + idx + 1];
+    const uint32_t v = hi ? ((q0 >> 8) | ((q1 >> 8) << 24)) : ((q0 & 255u) | ((q1 & 255u) << 24));
+    out[i] = v;
+    wide |= (hi && v);
+  }
+  wide = __syncthreads_or(wide);
+  if (threadIdx.x == 0) *wide_flag = wide ? 1u : 0u;
 }
 
 /* ---- host side ------------------------------------------------------------- */
 
-/* u16 tables -> packed tables + the 16-bit flag, on `stream` (shared with jgpu_mcu.cu).  The flag
- * word is zeroed first; both writes are the same for the same tables, whoever issues them. */
+/* u16 tables -> packed tables + the 16-bit flag, on `stream` (shared with jgpu_mcu.cu). */
 cudaError_t launch_prep_qtabs(const uint16_t *qtabs, uint32_t *qint, int n_tables, uint32_t *wide_flag,
                               cudaStream_t stream) {
-  cudaError_t e = cudaMemsetAsync(wide_flag, 0, 4, stream);
-  if (e != cudaSuccess) return e;
-  k_prep_qtabs<<<(n_tables * 64 + 255) / 256, 256, 0, stream>>>(qtabs, qint, n_tables * 64, wide_flag);
+  k_prep_qtabs<<<1, 256, 0, stream>>>(qtabs, qint, n_tables * 64, wide_flag);
   return cudaGetLastError();
 }
 
@@ -870,9 +874,7 @@ int fused_plan_launch(FusedPlan &fp, int i0, int i1, const int16_t *coef, const 
   }
   /* the wide flag lives right behind the tables */
   uint32_t *wide_flag = (uint32_t *)p->d_qint + (size_t)p->qint_cap * 64;
-  if (cudaMemsetAsync(wide_flag, 0, 4, stream) != cudaSuccess) return jgpu_fail("fused path: memset failed");
-  k_prep_qtabs<<<(n_tables * 64 + 255) / 256, 256, 0, stream>>>(qtabs, (uint32_t *)p->d_qint, n_tables * 64, wide_flag);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = launch_prep_qtabs(qtabs, (uint32_t *)p->d_qint, n_tables, wide_flag, stream);
   if (e != cudaSuccess) return jgpu_fail("k_prep_qtabs launch failed (%s)", cudaGetErrorString(e));
   const int rgb_aligned = (reinterpret_cast<uintptr_t>(rgb) & 15) == 0 ? 1 : 0;
   int n_modes = 0;

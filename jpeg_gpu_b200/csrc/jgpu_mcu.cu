@@ -69,6 +69,7 @@ constexpr int kHalfRows = 16;               /* blocks per TMA box: one half-task
 constexpr int kHalfBoxBytes = kHalfRows * 128;
 constexpr int kRingSlots = 4;
 constexpr int kOutRgb = 1, kOutYuv = 2;
+constexpr unsigned kClaimSlots = 1024;
 
 /* One half-task = up to 16 consecutive units of one MCU row of one image; a task = two of them
  * (lanes 0-15 and lanes 16-31), consecutive in the image's row-major order, so that the second
@@ -135,9 +136,10 @@ struct McuCfg {
   static constexpr int kOffStage = kOffChroma + kChromaSteps * kChromaStep;
   static constexpr int kOffPark = kOffStage + kStageBytesTotal;
   static constexpr int kOffRing = kOffPark + kParkBytes;
-  static constexpr int kOffBar = kOffRing + kRingSlots * (int)sizeof(WarpTask);   /* 5 mbarriers, then the loop counters */
-  static constexpr int kOffLoop = kOffBar + 48;
-  static constexpr int kWarpMisc = kOffBar + 64;
+  static constexpr int kOffBar = kOffRing + kRingSlots * (int)sizeof(WarpTask);   /* 5 mbarriers */
+  static constexpr int kOffLoop = kOffBar + 48;   /* the warp's step counter */
+  static constexpr int kOffIdx = kOffBar + 64;    /* task index of each ring slot */
+  static constexpr int kWarpMisc = kOffBar + 96;
   /* warps per CTA; one CTA per SM */
   static constexpr int kFit = (227 * 1024) / (kZoneBytes + kWarpMisc);
   static constexpr int kWarps = kFit < JGPU_MCU_WARPS ? kFit : JGPU_MCU_WARPS;
@@ -188,7 +190,7 @@ k_mcu(const __grid_constant__ CUtensorMap tm_rows,   /* (64, rows), boxes of 16 
       const __grid_constant__ CUtensorMap tm_pairs,  /* (64, parity, pairs), boxes of 16 pairs  */
       const WarpTask *__restrict__ tasks, int n_tasks, const uint32_t *__restrict__ qint,
       const uint32_t *__restrict__ wide_flag, uint8_t *__restrict__ rgb, int rgb_aligned,
-      uint8_t *__restrict__ yuv) {
+      uint8_t *__restrict__ yuv, int *__restrict__ claim) {
   using C = McuCfg<HS, VS, GRAY, WIDE>;
   if ((*wide_flag != 0) != WIDE) return;
 #ifdef JGPU_MCU_TRACE
@@ -235,12 +237,19 @@ k_mcu(const __grid_constant__ CUtensorMap tm_rows,   /* (64, rows), boxes of 16 
     __syncwarp();
   }
 
-  /* this warp's tasks: gw, gw + nw, gw + 2 nw, ...; local task n lives in ring slot n % 4 */
-  auto fetch_desc = [&](const Geo &g, int n) {   /* lane 0 only */
-    const int gw = (int)blockIdx.x * C::kWarps + (int)(threadIdx.x >> 5), nw = (int)gridDim.x * C::kWarps;
+  /* This warp's tasks: the first two are gw and gw + nw; every later one is claimed from the
+   * launch's counter while the task two before it runs, so that warps which fall behind (their SM
+   * sees longer memory latencies; measured spread of a static split: 10 %) simply take fewer, and
+   * batches of mixed sizes balance themselves.
+   * Local task n lives in ring slot n % 4: its index (>= n_tasks: there is none) and its descriptor. */
+  auto idx_addr = [&](const Geo &g, int n) { return g.misc + C::kOffIdx + 4u * ((uint32_t)n % kRingSlots); };
+  auto fetch_desc = [&](const Geo &g, int n, int idx) {   /* lane 0 only */
     const uint32_t slot = (uint32_t)n % kRingSlots;
-    mbar_expect_tx(bar_ring(g, slot), (uint32_t)sizeof(WarpTask));
-    bulk_load(desc_addr(g, n), tasks + (gw + (size_t)n * nw), (uint32_t)sizeof(WarpTask), bar_ring(g, slot));
+    sts32(idx_addr(g, n), (uint32_t)idx);
+    if (idx < n_tasks) {
+      mbar_expect_tx(bar_ring(g, slot), (uint32_t)sizeof(WarpTask));
+      bulk_load(desc_addr(g, n), tasks + idx, (uint32_t)sizeof(WarpTask), bar_ring(g, slot));
+    }
   };
   auto wait_desc = [&](const Geo &g, int n) {
     mbar_wait_hint<JGPU_MCU_WAIT_NS>(bar_ring(g, (uint32_t)n % kRingSlots), ((uint32_t)n / kRingSlots) & 1u);
@@ -286,20 +295,20 @@ k_mcu(const __grid_constant__ CUtensorMap tm_rows,   /* (64, rows), boxes of 16 
     }
   };
 
-  /* steps of this warp: its tasks x steps per task.  The loop counters live in shared memory: no
-   * register is spent on them across the transform. */
+  /* The warp's step counter lives in shared memory: no register is spent on it across the
+   * transform.  Step = local task * steps per task + step inside the task. */
   {
     const Geo g = geo();
     const int gw = (int)blockIdx.x * C::kWarps + (int)(threadIdx.x >> 5), nw = (int)gridDim.x * C::kWarps;
-    const int my_tasks = gw < n_tasks ? (n_tasks - gw + nw - 1) / nw : 0;
-    if (my_tasks == 0) return;
-    sts64(g.misc + C::kOffLoop, make_uint2(0u, (uint32_t)(my_tasks * C::kSteps)));   /* every lane, same value */
+    if (gw >= n_tasks) return;
+    sts32(g.misc + C::kOffLoop, 0u);   /* every lane, same value */
     if (g.lane == 0) {
-      fetch_desc(g, 0);
-      if (my_tasks > 1) fetch_desc(g, 1);
+      fetch_desc(g, 0, gw);
+      fetch_desc(g, 1, gw + nw);
       wait_desc(g, 0);
       fire(g, 0, 0);
     }
+    __syncwarp();
   }
 
 #pragma unroll 1
@@ -307,25 +316,23 @@ k_mcu(const __grid_constant__ CUtensorMap tm_rows,   /* (64, rows), boxes of 16 
     bool is_c, active;   /* a chroma step?  does this lane's unit exist / show in this step? */
     {
       const Geo g = geo();
-      const uint2 lc = lds64(g.misc + C::kOffLoop);
-      const int step = (int)lc.x, total = (int)lc.y;
+      const int step = (int)lds32(g.misc + C::kOffLoop);
+      const int n = step / C::kSteps, s = step - n * C::kSteps;
+      const bool done = (int)lds32(idx_addr(g, n)) >= n_tasks;
 #ifdef JGPU_MCU_TRACE
-      if (step >= total && g.lane == 0) {
+      if (done && g.lane == 0) {
         unsigned long long t1;
         unsigned smid;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
         asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
         unsigned long long *o = g_mcu_trace + 4 * ((size_t)blockIdx.x * C::kWarps + (threadIdx.x >> 5));
-        o[0] = smid; o[1] = trace_t0; o[2] = t1; o[3] = (unsigned long long)total;
+        o[0] = smid; o[1] = trace_t0; o[2] = t1; o[3] = (unsigned long long)step;
       }
 #endif
-      if (step >= total) break;
+      if (done) break;
       __syncwarp();
       sts32(g.misc + C::kOffLoop, (uint32_t)step + 1u);
-      const int n = step / C::kSteps, s = step - n * C::kSteps;
       is_c = s < C::kChromaSteps;
-      /* keep the ring two tasks ahead (the slot of task n-2: every lane is past it) */
-      if (s == 0 && g.lane == 0 && (n + 2) * C::kSteps < total) fetch_desc(g, n + 2);
       wait_desc(g, n);
       const uint32_t ha = half_addr(g, n);
       const int u = g.lane & 15;
@@ -351,12 +358,13 @@ k_mcu(const __grid_constant__ CUtensorMap tm_rows,   /* (64, rows), boxes of 16 
       {
         const Geo g = geo();
         if (g.lane == 0) {
-          const uint2 lc = lds64(g.misc + C::kOffLoop);   /* (this step + 1, total) */
-          const int next = (int)lc.x;
-          if (next < (int)lc.y) {
-            const int n = next / C::kSteps, s = next - n * C::kSteps;
-            if (s == 0) wait_desc(g, n);
+          const int next = (int)lds32(g.misc + C::kOffLoop);   /* this step + 1 */
+          const int n = next / C::kSteps, s = next - n * C::kSteps;
+          if (s != 0) {
             fire(g, n, s);
+          } else if ((int)lds32(idx_addr(g, n)) < n_tasks) {
+            wait_desc(g, n);
+            fire(g, n, 0);
           }
         }
       }
@@ -443,22 +451,7 @@ k_mcu(const __grid_constant__ CUtensorMap tm_rows,   /* (64, rows), boxes of 16 
       continue;
     }
 
-    /* one staged luma row -> s16x2 words: ya[0..3] = block A pixel pairs, yb[0..3] = block B */
-    auto staged_row = [&](int k, uint32_t (&ya)[4], uint32_t (&yb)[4]) {
-      const uint32_t row = g.mine + C::kOffStage + C::kStageRow * k;
-      if (C::kStageBytes) {
-        const uint4 t = lds128(row);   /* A01 B01 | A23 B23 | A45 B45 | A67 B67 */
-        ya[0] = __byte_perm(t.x, 0u, 0x4140); yb[0] = __byte_perm(t.x, 0u, 0x4342);
-        ya[1] = __byte_perm(t.y, 0u, 0x4140); yb[1] = __byte_perm(t.y, 0u, 0x4342);
-        ya[2] = __byte_perm(t.z, 0u, 0x4140); yb[2] = __byte_perm(t.z, 0u, 0x4342);
-        ya[3] = __byte_perm(t.w, 0u, 0x4140); yb[3] = __byte_perm(t.w, 0u, 0x4342);
-      } else {
-        const uint4 t0 = lds128(row), t1 = lds128(row + 512);   /* a0 b0 a1 b1 | a2 b2 a3 b3 */
-        ya[0] = t0.x; ya[1] = t0.z; ya[2] = t1.x; ya[3] = t1.z;
-        yb[0] = t0.y; yb[1] = t0.w; yb[2] = t1.y; yb[3] = t1.w;
-      }
-    };
-    /* ... and as 16 bytes in pixel order */
+    /* one staged luma row as 16 bytes in pixel order */
     auto staged_row_bytes = [&](int k) -> uint4 {
       const uint32_t row = g.mine + C::kOffStage + C::kStageRow * k;
       if (C::kStageBytes) {
@@ -469,6 +462,17 @@ k_mcu(const __grid_constant__ CUtensorMap tm_rows,   /* (64, rows), boxes of 16 
       const uint4 t0 = lds128(row), t1 = lds128(row + 512);
       return make_uint4(__byte_perm(t0.x, t0.z, 0x6420), __byte_perm(t1.x, t1.z, 0x6420),
                         __byte_perm(t0.y, t0.w, 0x6420), __byte_perm(t1.y, t1.w, 0x6420));
+    };
+
+    /* First luma step of a task (lane 0 always takes part in it: its unit is the task's first):
+     * claim the task after next now, pick the answer up when this step's rows are stored -- the
+     * round trip to the counter hides behind them -- and request its descriptor, which then has
+     * more than a task's time to arrive. */
+    const bool claims = yr == 0 && g.lane == 0;
+    int claimed = 0;
+    if (claims) claimed = atomicAdd(claim, 1);
+    auto finish_claim = [&]() {
+      if (claims) fetch_desc(g, n + 2, 2 * (int)gridDim.x * C::kWarps + claimed);
     };
 
     const uint2 b0 = lds64(ha + offsetof(McuHalf, base0));
@@ -490,6 +494,7 @@ k_mcu(const __grid_constant__ CUtensorMap tm_rows,   /* (64, rows), boxes of 16 
         }
         py += pitch;
       }
+      finish_claim();
       continue;
     }
 
@@ -509,14 +514,26 @@ k_mcu(const __grid_constant__ CUtensorMap tm_rows,   /* (64, rows), boxes of 16 
     } else {
       /* one iteration per chroma row = VS pixel rows */
       const uint32_t crow0 = g.mine + C::kOffChroma + (VS == 2 ? 4u * 512u * (uint32_t)yr : 0u);
+      /* every shared-memory load is issued a stretch before its first use: the chroma row one
+       * iteration ahead, the staged luma rows at the top of the iteration (the offset arithmetic
+       * sits between them and the pixel rows that need them) */
+      uint4 tnext = lds128(crow0);
 #pragma unroll 1
       for (int cr = 0; cr < 8 / VS; cr++) {
         if (cr * VS >= vis_rows) break;
+        uint4 ty[VS][2];
+#pragma unroll
+        for (int sub = 0; sub < VS; sub++) {
+          const uint32_t row = g.mine + C::kOffStage + C::kStageRow * (cr * VS + sub);
+          ty[sub][0] = lds128(row);
+          ty[sub][1] = C::kStageBytes ? ty[sub][0] : lds128(row + 512);
+        }
         uint32_t ca[12], cb[12];   /* offsets for block A / block B: 4 pixel pairs x (R,G,B) */
         if (HS == 2) {
           /* 8 chroma samples, each serving one horizontal pixel pair of VS rows: offsets,
            * replicated into both halves of an s16x2 word */
-          const uint4 t = lds128(crow0 + 512 * cr);
+          const uint4 t = tnext;
+          tnext = lds128(crow0 + 512 * (cr + 1 < 8 / VS ? cr + 1 : cr));
           const uint32_t cs[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
           for (int i = 0; i < 4; i++) {
@@ -554,7 +571,17 @@ k_mcu(const __grid_constant__ CUtensorMap tm_rows,   /* (64, rows), boxes of 16 
           const int k = cr * VS + sub;
           if (k < vis_rows) {
             uint32_t ya[4], yb[4], w[12];
-            staged_row(k, ya, yb);
+            if (C::kStageBytes) {   /* A01 B01 | A23 B23 | A45 B45 | A67 B67 */
+              const uint4 t = ty[sub][0];
+              ya[0] = __byte_perm(t.x, 0u, 0x4140); yb[0] = __byte_perm(t.x, 0u, 0x4342);
+              ya[1] = __byte_perm(t.y, 0u, 0x4140); yb[1] = __byte_perm(t.y, 0u, 0x4342);
+              ya[2] = __byte_perm(t.z, 0u, 0x4140); yb[2] = __byte_perm(t.z, 0u, 0x4342);
+              ya[3] = __byte_perm(t.w, 0u, 0x4140); yb[3] = __byte_perm(t.w, 0u, 0x4342);
+            } else {                /* a0 b0 a1 b1 | a2 b2 a3 b3 */
+              const uint4 t0 = ty[sub][0], t1 = ty[sub][1];
+              ya[0] = t0.x; ya[1] = t0.z; ya[2] = t1.x; ya[3] = t1.z;
+              yb[0] = t0.y; yb[1] = t0.w; yb[2] = t1.y; yb[3] = t1.w;
+            }
             rgb4(ya[0], ya[1], ca[0], ca[1], ca[2], ca[3], ca[4], ca[5], w[0], w[1], w[2]);
             rgb4(ya[2], ya[3], ca[6], ca[7], ca[8], ca[9], ca[10], ca[11], w[3], w[4], w[5]);
             rgb4(yb[0], yb[1], cb[0], cb[1], cb[2], cb[3], cb[4], cb[5], w[6], w[7], w[8]);
@@ -574,6 +601,7 @@ k_mcu(const __grid_constant__ CUtensorMap tm_rows,   /* (64, rows), boxes of 16 
         }
       }
     }
+    finish_claim();
   }
 }
 
@@ -628,15 +656,15 @@ cudaError_t mcu_configure_mode(int mode) {
 template <int HS, int VS, bool GRAY>
 cudaError_t mcu_launch_mode(bool planes, int sm_count, const McuMode &mi, cudaStream_t stream, const CUtensorMap &tm_rows,
                             const CUtensorMap &tm_pairs, const WarpTask *tasks, int n_tasks, const uint32_t *qint,
-                            const uint32_t *wide_flag, uint8_t *rgb, int rgb_aligned, uint8_t *yuv) {
+                            const uint32_t *wide_flag, uint8_t *rgb, int rgb_aligned, uint8_t *yuv, int *claim) {
   const int grid = std::min((n_tasks + mi.warps - 1) / mi.warps, sm_count);
   const int grid_w = std::min((n_tasks + mi.warps_wide - 1) / mi.warps_wide, sm_count);
   if (planes) {
-    k_mcu<HS, VS, GRAY, false, kOutYuv><<<grid, mi.threads, mi.smem, stream>>>(tm_rows, tm_pairs, tasks, n_tasks, qint, wide_flag, rgb, rgb_aligned, yuv);
-    k_mcu<HS, VS, GRAY, true, kOutYuv><<<grid_w, mi.threads_wide, mi.smem_wide, stream>>>(tm_rows, tm_pairs, tasks, n_tasks, qint, wide_flag, rgb, rgb_aligned, yuv);
+    k_mcu<HS, VS, GRAY, false, kOutYuv><<<grid, mi.threads, mi.smem, stream>>>(tm_rows, tm_pairs, tasks, n_tasks, qint, wide_flag, rgb, rgb_aligned, yuv, claim);
+    k_mcu<HS, VS, GRAY, true, kOutYuv><<<grid_w, mi.threads_wide, mi.smem_wide, stream>>>(tm_rows, tm_pairs, tasks, n_tasks, qint, wide_flag, rgb, rgb_aligned, yuv, claim);
   } else {
-    k_mcu<HS, VS, GRAY, false, kOutRgb><<<grid, mi.threads, mi.smem, stream>>>(tm_rows, tm_pairs, tasks, n_tasks, qint, wide_flag, rgb, rgb_aligned, yuv);
-    k_mcu<HS, VS, GRAY, true, kOutRgb><<<grid_w, mi.threads_wide, mi.smem_wide, stream>>>(tm_rows, tm_pairs, tasks, n_tasks, qint, wide_flag, rgb, rgb_aligned, yuv);
+    k_mcu<HS, VS, GRAY, false, kOutRgb><<<grid, mi.threads, mi.smem, stream>>>(tm_rows, tm_pairs, tasks, n_tasks, qint, wide_flag, rgb, rgb_aligned, yuv, claim);
+    k_mcu<HS, VS, GRAY, true, kOutRgb><<<grid_w, mi.threads_wide, mi.smem_wide, stream>>>(tm_rows, tm_pairs, tasks, n_tasks, qint, wide_flag, rgb, rgb_aligned, yuv, claim);
   }
   return cudaGetLastError();
 }
@@ -670,6 +698,11 @@ struct McuPlanImpl {
   std::vector<int> first_task[kNumFusedModes]; /* per mode, n+1 entries */
   void *d_qint = nullptr;
   int qint_cap = 0; /* tables */
+  /* task counters: one int per kernel launch, taken round-robin from a ring (launches of one plan may
+   * be in flight on several streams: the chunks of jgpu_decode_batch_host) and zeroed on the launch's
+   * stream just before it */
+  int *d_claim = nullptr;
+  unsigned claim_next = 0;
   long long coef_rows = 0; /* 128-byte rows the batch touches */
   const void *map_ptr = nullptr;
   CUtensorMap tm_rows, tm_pairs;
@@ -782,6 +815,7 @@ void mcu_plan_release(FusedPlan &fp) {
   }
   if (p->fork) cudaEventDestroy(p->fork);
   cudaFree(p->d_qint);
+  cudaFree(p->d_claim);
   delete p;
   fp.impl = nullptr;
 }
@@ -869,14 +903,19 @@ int mcu_plan_launch(FusedPlan &fp, int i0, int i1, const int16_t *coef, const ui
     first_mode = false;
     const McuMode &mi = g_mcu[m];
     const int grid = p->sm_count;
+    if (!p->d_claim && cudaMalloc(&p->d_claim, sizeof(int) * kClaimSlots) != cudaSuccess) {
+      return jgpu_fail("fused path: counter allocation failed");
+    }
+    int *claim = p->d_claim + (p->claim_next++ % kClaimSlots);
+    if (cudaMemsetAsync(claim, 0, sizeof(int), stream) != cudaSuccess) return jgpu_fail("fused path: memset failed");
     const WarpTask *tasks = static_cast<const WarpTask *>(p->d_tasks[m]) + t0;
     const uint32_t *qint = static_cast<const uint32_t *>(p->d_qint);
     switch (m) {
-      case kModeGray: e = mcu_launch_mode<1, 1, true>(p->planes, grid, mi, stream, p->tm_rows, p->tm_pairs, tasks, t1 - t0, qint, wide_flag, rgb, rgb_aligned, yuv); break;
-      case kMode444: e = mcu_launch_mode<1, 1, false>(p->planes, grid, mi, stream, p->tm_rows, p->tm_pairs, tasks, t1 - t0, qint, wide_flag, rgb, rgb_aligned, yuv); break;
-      case kMode422: e = mcu_launch_mode<2, 1, false>(p->planes, grid, mi, stream, p->tm_rows, p->tm_pairs, tasks, t1 - t0, qint, wide_flag, rgb, rgb_aligned, yuv); break;
-      case kMode420: e = mcu_launch_mode<2, 2, false>(p->planes, grid, mi, stream, p->tm_rows, p->tm_pairs, tasks, t1 - t0, qint, wide_flag, rgb, rgb_aligned, yuv); break;
-      case kMode440: e = mcu_launch_mode<1, 2, false>(p->planes, grid, mi, stream, p->tm_rows, p->tm_pairs, tasks, t1 - t0, qint, wide_flag, rgb, rgb_aligned, yuv); break;
+      case kModeGray: e = mcu_launch_mode<1, 1, true>(p->planes, grid, mi, stream, p->tm_rows, p->tm_pairs, tasks, t1 - t0, qint, wide_flag, rgb, rgb_aligned, yuv, claim); break;
+      case kMode444: e = mcu_launch_mode<1, 1, false>(p->planes, grid, mi, stream, p->tm_rows, p->tm_pairs, tasks, t1 - t0, qint, wide_flag, rgb, rgb_aligned, yuv, claim); break;
+      case kMode422: e = mcu_launch_mode<2, 1, false>(p->planes, grid, mi, stream, p->tm_rows, p->tm_pairs, tasks, t1 - t0, qint, wide_flag, rgb, rgb_aligned, yuv, claim); break;
+      case kMode420: e = mcu_launch_mode<2, 2, false>(p->planes, grid, mi, stream, p->tm_rows, p->tm_pairs, tasks, t1 - t0, qint, wide_flag, rgb, rgb_aligned, yuv, claim); break;
+      case kMode440: e = mcu_launch_mode<1, 2, false>(p->planes, grid, mi, stream, p->tm_rows, p->tm_pairs, tasks, t1 - t0, qint, wide_flag, rgb, rgb_aligned, yuv, claim); break;
     }
     if (e != cudaSuccess) return jgpu_fail("fused kernel launch failed (%s)", cudaGetErrorString(e));
     if (stream != caller) {
