@@ -514,26 +514,14 @@ k_mcu(const __grid_constant__ CUtensorMap tm_rows,   /* (64, rows), boxes of 16 
     } else {
       /* one iteration per chroma row = VS pixel rows */
       const uint32_t crow0 = g.mine + C::kOffChroma + (VS == 2 ? 4u * 512u * (uint32_t)yr : 0u);
-      /* every shared-memory load is issued a stretch before its first use: the chroma row one
-       * iteration ahead, the staged luma rows at the top of the iteration (the offset arithmetic
-       * sits between them and the pixel rows that need them) */
-      uint4 tnext = lds128(crow0);
 #pragma unroll 1
       for (int cr = 0; cr < 8 / VS; cr++) {
         if (cr * VS >= vis_rows) break;
-        uint4 ty[VS][2];
-#pragma unroll
-        for (int sub = 0; sub < VS; sub++) {
-          const uint32_t row = g.mine + C::kOffStage + C::kStageRow * (cr * VS + sub);
-          ty[sub][0] = lds128(row);
-          ty[sub][1] = C::kStageBytes ? ty[sub][0] : lds128(row + 512);
-        }
         uint32_t ca[12], cb[12];   /* offsets for block A / block B: 4 pixel pairs x (R,G,B) */
         if (HS == 2) {
           /* 8 chroma samples, each serving one horizontal pixel pair of VS rows: offsets,
            * replicated into both halves of an s16x2 word */
-          const uint4 t = tnext;
-          tnext = lds128(crow0 + 512 * (cr + 1 < 8 / VS ? cr + 1 : cr));
+          const uint4 t = lds128(crow0 + 512 * cr);
           const uint32_t cs[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
           for (int i = 0; i < 4; i++) {
@@ -572,13 +560,13 @@ k_mcu(const __grid_constant__ CUtensorMap tm_rows,   /* (64, rows), boxes of 16 
           if (k < vis_rows) {
             uint32_t ya[4], yb[4], w[12];
             if (C::kStageBytes) {   /* A01 B01 | A23 B23 | A45 B45 | A67 B67 */
-              const uint4 t = ty[sub][0];
+              const uint4 t = lds128(g.mine + C::kOffStage + C::kStageRow * k);
               ya[0] = __byte_perm(t.x, 0u, 0x4140); yb[0] = __byte_perm(t.x, 0u, 0x4342);
               ya[1] = __byte_perm(t.y, 0u, 0x4140); yb[1] = __byte_perm(t.y, 0u, 0x4342);
               ya[2] = __byte_perm(t.z, 0u, 0x4140); yb[2] = __byte_perm(t.z, 0u, 0x4342);
               ya[3] = __byte_perm(t.w, 0u, 0x4140); yb[3] = __byte_perm(t.w, 0u, 0x4342);
             } else {                /* a0 b0 a1 b1 | a2 b2 a3 b3 */
-              const uint4 t0 = ty[sub][0], t1 = ty[sub][1];
+              const uint4 t0 = lds128(g.mine + C::kOffStage + C::kStageRow * k), t1 = lds128(g.mine + C::kOffStage + C::kStageRow * k + 512);
               ya[0] = t0.x; ya[1] = t0.z; ya[2] = t1.x; ya[3] = t1.z;
               yb[0] = t0.y; yb[1] = t0.w; yb[2] = t1.y; yb[3] = t1.w;
             }
