@@ -1,11 +1,12 @@
 mkdir -p gpurun_out/r2
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
-for wl in 4k420_b256 4k422_b128 4kgray_b256 4k444_b64; do
-  python bench.py --workload $wl --no-e2e --no-cpu > gpurun_out/r2/bench_7_$wl.json 2> gpurun_out/r2/bench_7.err
-  python - <<PY
+python bench.py > gpurun_out/r2/bench_8.json 2> gpurun_out/r2/bench_8.err; tail -5 gpurun_out/r2/bench_8.err
+python - <<'PY'
 import json
-try:
-    d=json.load(open("gpurun_out/r2/bench_7_$wl.json")); print("$wl",round(d["ms_per_step"],4),"ms frac",round(d["roofline"]["frac"],4), d.get("parity"))
-except Exception as e: print("$wl","failed",e)
+d=json.load(open("gpurun_out/r2/bench_8.json"))
+print("value",round(d["value"]),"ms",round(d["ms_per_step"],4),"frac",round(d["roofline"]["frac"],4),"parity",d["parity"])
+print("e2e",d["e2e"]and round(d["e2e"]["value"]),"pack",d["e2e_pack"] and round(d["e2e_pack"]["value"]))
+print("jpeg",{k:(round(v) if isinstance(v,float) else v) for k,v in (d["e2e_jpeg"] or {}).items() if "value" in k})
+for k,v in (d["extra"] or {}).items(): print(k, round(v["value"]), "frac", round(v["roofline"]["frac"],4), v["parity"]["checked"], v["parity"]["mismatching_images"])
+print("cpu",d["cpu_baseline"])
 PY
-done
+python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/r2/bench_8_ref.json 2>gpurun_out/r2/bench_8_ref.err; cat gpurun_out/r2/bench_8_ref.json | head -c 900; tail -3 gpurun_out/r2/bench_8_ref.err
