@@ -13,7 +13,7 @@
  *   jpeg_decode_out, the five function
  *   typedefs, jpeg_decode_ctx_vtbl             <- src/jpeg_wrap.h:22-54
  *
- * tests/test_abi_layout.py compiles one probe against this header and one
+ * tests/test_abi.py compiles one probe against this header and one
  * against the reference's headers and compares sizeof/offsetof of every
  * member.  The include guards below are deliberately the reference's own, so
  * that including both sets in one translation unit cannot redeclare a type.

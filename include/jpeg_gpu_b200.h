@@ -61,12 +61,29 @@ extern const jpeg_decode_ctx_vtbl CUDA_DECODE_CTX_VTBL;
  * CUDA_DECODE_CTX_VTBL when the library is used outside the reference tree. */
 extern const jpeg_decode_ctx_vtbl JFRONT_DECODE_CTX_VTBL;
 
+/* Options of a CUDA decoder context.  The reference's five-slot table has no room for them
+ * (decode_alloc takes the file only, src/jpeg_wrap.h:35), so the slot reads the CALLING THREAD's
+ * current options -- set with the cuda_decode_set_* functions below, each thread its own copy, no
+ * process-wide state -- and the context keeps what it read for its lifetime.  Callers outside the
+ * table's shape can pass them explicitly: cuda_decode_alloc_ex. */
+typedef struct cuda_decode_options {
+  const jpeg_decode_ctx_vtbl *frontend; /* NULL: JFRONT_DECODE_CTX_VTBL */
+  int device;                           /* CUDA ordinal; < 0: $JGPU_DEVICE, else 0 */
+  jpeg_decode_out upload;               /* JPEG_DECODE_QUANT or JPEG_DECODE_PACK */
+  int entropy_on_device;                /* 0 / 1; < 0: $JGPU_ENTROPY=gpu turns it on */
+} cuda_decode_options;
+/* Fills *opt with the calling thread's current options. */
+void cuda_decode_get_options(cuda_decode_options *opt);
+/* decode_alloc with explicit options (the other four slots of CUDA_DECODE_CTX_VTBL apply to the
+ * result).  NULL on a bad option (message in jgpu_last_error()) or out of memory. */
+jpeg_decode_ctx *cuda_decode_alloc_ex(jpeg_info *info, const cuda_decode_options *opt);
+
 /* Inside the reference tree: make CUDA_DECODE_CTX_VTBL pull its coefficient
  * planes from the reference's own reader, e.g.
  *     cuda_decode_set_frontend(&XJPEG_DECODE_CTX_VTBL);
- * NULL restores JFRONT_DECODE_CTX_VTBL.  Affects contexts allocated later. */
+ * NULL restores JFRONT_DECODE_CTX_VTBL.  Affects contexts this thread allocates later. */
 void cuda_decode_set_frontend(const jpeg_decode_ctx_vtbl *frontend);
-/* CUDA device ordinal used by contexts allocated later (default 0, or
+/* CUDA device ordinal used by contexts this thread allocates later (default 0, or
  * $JGPU_DEVICE). */
 void cuda_decode_set_device(int device);
 
@@ -92,10 +109,16 @@ int cuda_decode_set_entropy(int on_device);
  * jpeg_info_init / jpeg_info_clear (src/jpeg_info.c:31-61), for callers that
  * do not link the reference objects.  Buffers are 16-byte aligned. */
 int jgpu_image_init(image *img, jpeg_header *header);
-/* on != 0: surfaces initialised afterwards get page-locked `pixels` (cudaHostAlloc; ordinary
- * memory when that fails), which the backend reads back into a millisecond faster per 4K frame.
- * Off by default.  jgpu_image_clear frees either kind. */
+/* JGPU_IMAGE_PINNED: page-locked `pixels` (cudaHostAlloc; ordinary memory when that fails), which
+ * the backend reads back into a millisecond faster per 4K frame.  jgpu_image_clear frees either
+ * kind (it asks the CUDA runtime what the pointer is). */
+#define JGPU_IMAGE_PINNED 1u
+int jgpu_image_init_ex(image *img, jpeg_header *header, unsigned flags);
+/* For callers that keep the two-argument shape: on != 0 makes the surfaces THIS THREAD initialises
+ * afterwards with jgpu_image_init page-locked.  Off by default. */
 void jgpu_image_set_pinned(int on);
+/* 1 when p points into page-locked host memory known to the CUDA runtime, else 0. */
+int jgpu_host_is_pinned(const void *p);
 void jgpu_image_zero(image *img);
 void jgpu_image_clear(image *img);
 int jgpu_info_init(jpeg_info *info, const char *name);

@@ -22,6 +22,11 @@ OUT_NAMES = {"pack": 0, "quant": 1, "dct": 2, "yuv": 3, "rgb": 4}
 SUBSAMP_NAMES = ["Unknown", "4:4:4", "4:2:2", "4:2:0", "4:4:0", "4:1:1", "Mono"]
 
 JGPU_OUT_RGB, JGPU_OUT_YUV, JGPU_FORCE_GENERIC = 1, 2, 4
+JGPU_IMAGE_PINNED = 1
+
+
+class cuda_decode_options(C.Structure):
+    _fields_ = [("frontend", C.c_void_p), ("device", C.c_int), ("upload", C.c_int), ("entropy_on_device", C.c_int)]
 
 
 # ---- include/jgpu_ref_abi.h --------------------------------------------------
@@ -106,7 +111,11 @@ EXPORTS = [
     ("cuda_decode_set_device", None, [C.c_int]),
     ("cuda_decode_set_upload", C.c_int, [C.c_int]),
     ("cuda_decode_set_entropy", C.c_int, [C.c_int]),
+    ("cuda_decode_get_options", None, [C.c_void_p]),
+    ("cuda_decode_alloc_ex", C.c_void_p, [C.POINTER(jpeg_info), C.c_void_p]),
     ("jgpu_image_set_pinned", None, [C.c_int]),
+    ("jgpu_image_init_ex", C.c_int, [C.POINTER(image), C.POINTER(jpeg_header), C.c_uint]),
+    ("jgpu_host_is_pinned", C.c_int, [C.c_void_p]),
     ("jgpu_decode_image_packed", C.c_int, [C.c_void_p, C.POINTER(jpeg_header), C.POINTER(image), C.c_int64, C.c_int]),
     ("jgpu_image_init", C.c_int, [C.POINTER(image), C.POINTER(jpeg_header)]),
     ("jgpu_image_zero", None, [C.POINTER(image)]),

@@ -57,6 +57,12 @@ int jgpu_layout_query(const jgpu_image_desc *d, jgpu_layout *out) {
     return jgpu_fail("Unsupported sampling: component 0 must have the largest "
                      "horizontal factor (coefficient layout, src/xjpeg.c:558)");
   }
+  if (d->vsamp[0] != out->vmax) {
+    /* the reference's colour pass reads luma row t of plane 0 for output row t
+     * (res/unyuv.fs.glsl:29-31, res/yuv.fs.glsl:17-19): a vertically decimated plane 0 has no
+     * defined rendering there either */
+    return jgpu_fail("Unsupported sampling: component 0 must have the largest vertical factor");
+  }
   out->nhmb = (d->width + 8 * out->hmax - 1) / (8 * out->hmax);
   out->nvmb = (d->height + 8 * out->vmax - 1) / (8 * out->vmax);
   for (i = 0; i < d->ncomps; i++) {
@@ -126,52 +132,32 @@ void jgpu_aligned_free(void *p) { free(p); }
 
 /* Page-locked `pixels` for surfaces of callers that decode through the CUDA backend: the
  * read-back of a 4K frame into pageable memory costs 0.95 ms more than into pinned memory
- * (2.68 vs 1.73 ms per frame).  Off by default (jgpu_image_init then behaves like the
- * reference's image_init); which pointers are pinned is remembered here because the `image`
- * struct is the reference's and has no room for a flag. */
-#include <pthread.h>
-static int g_pinned_surfaces = 0;
-static pthread_mutex_t g_pinned_lock = PTHREAD_MUTEX_INITIALIZER;
-static void *g_pinned[64];
+ * (2.68 vs 1.73 ms per frame).  Asked for per surface (jgpu_image_init_ex) or, for callers that
+ * keep the reference's two-argument image_init shape, per THREAD (jgpu_image_set_pinned): no
+ * process-wide switch.  Which kind of memory a surface got is asked of the CUDA runtime when it is
+ * freed (jgpu_host_is_pinned), so nothing is remembered beside the reference's `image` struct. */
+static __thread int t_pinned_surfaces = 0;
 
-void jgpu_image_set_pinned(int on) { g_pinned_surfaces = on != 0; }
+void jgpu_image_set_pinned(int on) { t_pinned_surfaces = on != 0; }
 
-static void *surface_alloc(size_t bytes) {
-  if (g_pinned_surfaces) {
+static void *surface_alloc(size_t bytes, int pinned) {
+  if (pinned) {
     void *p = jgpu_host_alloc(bytes);
-    if (p != NULL) {
-      int i, kept = 0;
-      pthread_mutex_lock(&g_pinned_lock);
-      for (i = 0; i < (int)(sizeof(g_pinned) / sizeof(g_pinned[0])) && !kept; i++) {
-        if (g_pinned[i] == NULL) {
-          g_pinned[i] = p;
-          kept = 1;
-        }
-      }
-      pthread_mutex_unlock(&g_pinned_lock);
-      if (kept) return p;
-      jgpu_host_free(p);   /* registry full: fall back to ordinary memory */
-    }
+    if (p != NULL) return p;   /* else: ordinary memory, the copy is merely slower */
   }
   return jgpu_aligned_malloc(bytes);
 }
 
 static void surface_free(void *p) {
-  int i, pinned = 0;
   if (p == NULL) return;
-  pthread_mutex_lock(&g_pinned_lock);
-  for (i = 0; i < (int)(sizeof(g_pinned) / sizeof(g_pinned[0])); i++) {
-    if (g_pinned[i] == p) {
-      g_pinned[i] = NULL;
-      pinned = 1;
-      break;
-    }
-  }
-  pthread_mutex_unlock(&g_pinned_lock);
-  if (pinned) jgpu_host_free(p); else jgpu_aligned_free(p);
+  if (jgpu_host_is_pinned(p)) jgpu_host_free(p); else jgpu_aligned_free(p);
 }
 
 int jgpu_image_init(image *img, jpeg_header *header) {
+  return jgpu_image_init_ex(img, header, t_pinned_surfaces ? JGPU_IMAGE_PINNED : 0u);
+}
+
+int jgpu_image_init_ex(image *img, jpeg_header *header, unsigned flags) {
   jgpu_image_desc d;
   jgpu_layout lay;
   int i;
@@ -216,7 +202,7 @@ int jgpu_image_init(image *img, jpeg_header *header) {
     }
     blocks += ((int64_t)c->hblocks << p->xdec) * p->cstride;
   }
-  img->pixels = (unsigned char *)surface_alloc((size_t)img->width * img->height * 3);
+  img->pixels = (unsigned char *)surface_alloc((size_t)img->width * img->height * 3, (flags & JGPU_IMAGE_PINNED) != 0);
   img->coef = (short *)jgpu_aligned_malloc((size_t)blocks * 64 * sizeof(short));
   img->index = (int *)jgpu_aligned_malloc((size_t)blocks * sizeof(int));
   if (img->pixels == NULL || img->coef == NULL || img->index == NULL) {

@@ -37,7 +37,7 @@ namespace jgpu {
 
 /* Constants of src/dct.c:51,62-65,89-98 after the double->float conversion the
  * reference performs, as exact bit patterns (printed from the oracle, see
- * tests/test_constants.py). */
+ * tests/test_host_core.py::test_constants_are_the_references). */
 #if defined(__CUDACC__)
 #define JGPU_CONSTEXPR_HD __host__ __device__ constexpr
 #else

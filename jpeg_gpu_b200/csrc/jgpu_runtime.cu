@@ -484,6 +484,15 @@ extern "C" int jgpu_plan_run(jgpu_plan *plan, const int16_t *d_coef, const uint1
 /* -------------------------------------------------------------------------- */
 /* host-buffer entry point                                                    */
 
+extern "C" int jgpu_host_is_pinned(const void *p) {
+  cudaPointerAttributes a;
+  if (p == nullptr || cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return a.type == cudaMemoryTypeHost;
+}
+
 static bool is_pinned(const void *p) {
   cudaPointerAttributes a;
   if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
@@ -1370,7 +1379,8 @@ static int decode_jpegs_gpu_entropy(jgpu_ctx *ctx, const jgpu_jpeg *files, int n
       int i1 = i0;
       int64_t acc = 0;
       if (chunk > 0 && chunk_bytes < (192ll << 20)) chunk_bytes *= 2;
-      while (i1 < m && (i1 == i0 || acc + plan->layouts[i1].coef_len * 2 <= chunk_bytes)) {
+      /* (a group's file count is gridDim.y of the entropy kernels: at most 65535) */
+      while (i1 < m && i1 - i0 < 65535 && (i1 == i0 || acc + plan->layouts[i1].coef_len * 2 <= chunk_bytes)) {
         acc += plan->layouts[i1].coef_len * 2;
         i1++;
       }
@@ -1465,14 +1475,12 @@ static int decode_jpegs_gpu_entropy(jgpu_ctx *ctx, const jgpu_jpeg *files, int n
   }
 
   /* ---- files the GPU decoder left to the sequential reader ---------------------------- */
+  auto leftovers = [&]() -> int {   /* returns through CU_TRY on a CUDA failure; the caller cleans up */
   for (int k = 0; k < m; k++) {
     if (on_gpu[k] && h_status[k] == 0) continue;
     JpegItem &it = items[ok[k]];
     info[ok[k]].tasks = 1;
-    if (ctx->hz_coef.reserve((size_t)it.lay.coef_len * 2 + 256)) {
-      release_fronts();
-      return EXIT_FAILURE;
-    }
+    if (ctx->hz_coef.reserve((size_t)it.lay.coef_len * 2 + 256)) return EXIT_FAILURE;
     int16_t *h_coef = (int16_t *)ctx->hz_coef.ptr;
     memset(h_coef, 0, (size_t)it.lay.coef_len * 2);
     image img;
@@ -1500,7 +1508,6 @@ static int decode_jpegs_gpu_entropy(jgpu_ctx *ctx, const jgpu_jpeg *files, int n
     cudaStream_t st = ctx->streams[0];
     CU_TRY(cudaMemcpyAsync(d_coef + it.desc.coef_off, h_coef, (size_t)it.lay.coef_len * 2, cudaMemcpyHostToDevice, st));
     if (plan_run_range(plan, k, k + 1, d_coef, d_qtabs, m, yuv_out ? nullptr : d_rgb, yuv_out ? d_rgb : nullptr, st)) {
-      release_fronts();
       return EXIT_FAILURE;
     }
     if (!device_out) {
@@ -1508,6 +1515,12 @@ static int decode_jpegs_gpu_entropy(jgpu_ctx *ctx, const jgpu_jpeg *files, int n
                              cudaMemcpyDeviceToHost, st));
     }
     CU_TRY(cudaStreamSynchronize(st));
+  }
+  return EXIT_SUCCESS;
+  };
+  if (leftovers() != EXIT_SUCCESS) {
+    release_fronts();
+    return EXIT_FAILURE;
   }
   if (m != n) rc = EXIT_FAILURE;
   release_fronts();

@@ -18,31 +18,33 @@
 #include <stdint.h>
 #include "jgpu_internal.h"
 
-static const jpeg_decode_ctx_vtbl *g_frontend = NULL;
-static int g_device = -1;
+/* The calling thread's options (include/jpeg_gpu_b200.h, cuda_decode_options): thread-local, so
+ * two threads configuring and allocating contexts do not see each other's settings. */
+static __thread cuda_decode_options t_opt = {NULL, -1, JPEG_DECODE_QUANT, -1};
 
-void cuda_decode_set_frontend(const jpeg_decode_ctx_vtbl *frontend) { g_frontend = frontend; }
-void cuda_decode_set_device(int device) { g_device = device; }
+void cuda_decode_get_options(cuda_decode_options *opt) {
+  if (opt != NULL) *opt = t_opt;
+}
+void cuda_decode_set_frontend(const jpeg_decode_ctx_vtbl *frontend) { t_opt.frontend = frontend; }
+void cuda_decode_set_device(int device) { t_opt.device = device; }
 
-static jpeg_decode_out g_upload = JPEG_DECODE_QUANT;
 int cuda_decode_set_upload(jpeg_decode_out format) {
   if (format != JPEG_DECODE_QUANT && format != JPEG_DECODE_PACK) {
     fprintf(stderr, "Unsupported upload format %i for cuda wrapper.\n", (int)format);
     return EXIT_FAILURE;
   }
-  g_upload = format;
+  t_opt.upload = format;
   return EXIT_SUCCESS;
 }
 
-/* Where RGB decodes do their Huffman decoding: 0 = the CPU front end (default: it is the
+/* Where RGB / YUV decodes do their Huffman decoding: 0 = the CPU front end (default: it is the
  * pluggable part), 1 = on the device (jgpu_huff.cu), for the built-in front end only. */
-static int g_entropy_on_device = -1;   /* -1: not set, $JGPU_ENTROPY=gpu turns it on */
 int cuda_decode_set_entropy(int on_device) {
   if (on_device != 0 && on_device != 1) {
     fprintf(stderr, "Unsupported entropy decoder %i for cuda wrapper.\n", on_device);
     return EXIT_FAILURE;
   }
-  g_entropy_on_device = on_device;
+  t_opt.entropy_on_device = on_device;
   return EXIT_SUCCESS;
 }
 
@@ -61,19 +63,28 @@ typedef struct cuda_decode_ctx {
   jpeg_header header;   /* copy taken in decode_header; decode_image needs the tables */
 } cuda_decode_ctx;
 
-static cuda_decode_ctx *cuda_decode_alloc(jpeg_info *info) {
-  cuda_decode_ctx *ctx = (cuda_decode_ctx *)calloc(1, sizeof(cuda_decode_ctx));
+jpeg_decode_ctx *cuda_decode_alloc_ex(jpeg_info *info, const cuda_decode_options *opt) {
+  cuda_decode_ctx *ctx;
+  if (info == NULL || opt == NULL) {
+    jgpu_fail("cuda_decode_alloc_ex: NULL argument");
+    return NULL;
+  }
+  if (opt->upload != JPEG_DECODE_QUANT && opt->upload != JPEG_DECODE_PACK) {
+    jgpu_fail("cuda_decode_alloc_ex: unsupported upload format %i", (int)opt->upload);
+    return NULL;
+  }
+  ctx = (cuda_decode_ctx *)calloc(1, sizeof(cuda_decode_ctx));
   if (ctx == NULL) return NULL;
-  ctx->front = g_frontend ? *g_frontend : JFRONT_DECODE_CTX_VTBL;
-  ctx->device = g_device;
-  ctx->upload = g_upload;
+  ctx->front = opt->frontend ? *opt->frontend : JFRONT_DECODE_CTX_VTBL;
+  ctx->device = opt->device;
+  ctx->upload = opt->upload;
   {
-    int on = g_entropy_on_device;
+    int on = opt->entropy_on_device;
     if (on < 0) {
       const char *env = getenv("JGPU_ENTROPY");
       on = env != NULL && strcmp(env, "gpu") == 0;
     }
-    ctx->entropy_on_device = on && g_frontend == NULL;
+    ctx->entropy_on_device = on && opt->frontend == NULL;
   }
   ctx->buf = info->buf;
   ctx->size = info->size;
@@ -86,7 +97,12 @@ static cuda_decode_ctx *cuda_decode_alloc(jpeg_info *info) {
     free(ctx);
     return NULL;
   }
-  return ctx;
+  return (jpeg_decode_ctx *)ctx;
+}
+
+/* The table's slot: the calling thread's options. */
+static cuda_decode_ctx *cuda_decode_alloc(jpeg_info *info) {
+  return (cuda_decode_ctx *)cuda_decode_alloc_ex(info, &t_opt);
 }
 
 static int cuda_decode_header(cuda_decode_ctx *ctx, jpeg_header *header) {

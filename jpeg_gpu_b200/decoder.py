@@ -84,9 +84,8 @@ class Decoder:
         if self._img is None:
             self._img = _capi.image()
             # the CUDA backend reads pixels back into the surface: page-locked memory for it
-            _capi.lib().jgpu_image_set_pinned(1 if self._impl == "cuda" else 0)
-            rc = _capi.lib().jgpu_image_init(C.byref(self._img), C.byref(self._hdr))
-            _capi.lib().jgpu_image_set_pinned(0)
+            rc = _capi.lib().jgpu_image_init_ex(C.byref(self._img), C.byref(self._hdr),
+                                                _capi.JGPU_IMAGE_PINNED if self._impl == "cuda" else 0)
             if rc != 0:
                 self._img = None
                 raise DecodeError("Error initializing image")

@@ -12,7 +12,7 @@
  * file keeps the exact operation order and operand order of the reference and
  * MUST be built with -ffp-contract=off and without -ffast-math; see
  * oracle/Makefile.  Parity of this restatement is pinned against the compiled
- * reference (oracle/_ref) in tests/test_oracle_vs_reference.py and against the
+ * reference (oracle/_ref) in tests/test_oracle_golden.py and against the
  * reference's own IEEE-1180 tolerances (test/dct.c:229-261) in
  * tests/test_ieee1180.py.
  */

@@ -17,6 +17,7 @@
 // jgpu_host.c can ask the CUDA runtime glue for page-locked memory; this host-only build has none
 extern "C" void *jgpu_host_alloc(size_t) { return nullptr; }
 extern "C" void jgpu_host_free(void *) {}
+extern "C" int jgpu_host_is_pinned(const void *) { return 0; }
 
 namespace {
 

@@ -150,3 +150,50 @@ def test_grey_one_block_per_thread_variant(checker, monkeypatch):
         ctx.close()
         monkeypatch.delenv("JGPU_GRAY_TPB")
         J.Context(0).close()     # back to the product configuration for the tests that follow
+
+
+def test_sixteen_bit_tables_through_the_chunked_host_path(gpu_ctx, checker):
+    """16-bit DQT entries AND a batch of several 48 MB chunks: jgpu_decode_batch_host runs the chunks
+    of one cached plan on three streams.  The table preparation of a later chunk used to zero the
+    16-bit flag under an earlier chunk's kernels (both instantiations then returned at once and the
+    chunk's pixels were never written); it now only ever WRITES the flag's value."""
+    import torch
+    shapes = [(1920, 1080, "420")] * 40          # 40 x 6.3 MB of coefficients = 5 chunks
+    descs, coef_len, rgb_len, _ = make_batch(shapes, want_yuv=False)
+    q = synth.quality_tables(60).astype(np.uint16)
+    q[0, 9] = 300; q[1, 2] = 700; q[1, 63] = 4000
+    one = synth.image_coefficients(descs[0], synth.quality_tables(60), synth.SEED_BASE)
+    lay = descs[0].query_layout()
+    coef = torch.zeros(coef_len, dtype=torch.int16).pin_memory()
+    for d in descs:
+        coef[d.coef_off:d.coef_off + lay.coef_len] = torch.from_numpy(one)
+    one_desc, c_len, r_len, _ = make_batch(shapes[:1], want_yuv=False)
+    exp, _ = oracle_batch(checker, one_desc, one, q, r_len, 0, nthreads=8)
+    for rep in range(3):
+        rgb = torch.full((rgb_len,), 0x5A, dtype=torch.uint8).pin_memory()
+        gpu_ctx.decode_batch_host(descs, coef, q, rgb, None)
+        got = rgb.numpy()
+        for i, d in enumerate(descs):
+            assert np.array_equal(got[d.rgb_off:d.rgb_off + lay.rgb_len], exp[:lay.rgb_len]), (rep, i)
+
+
+@pytest.mark.parametrize("ss", ["gray", "444", "422", "420", "440"])
+def test_planes_out_of_the_fused_kernel(gpu_ctx, checker, ss):
+    """JGPU_OUT_YUV plans run the fused kernel too: the padded planes of xjpeg's YUV output
+    (src/xjpeg.c:565-584), every byte of them, for sizes that leave half-tasks, half units and
+    invisible MCU rows at the edges."""
+    shapes = [(1920, 1080, ss), (520, 40, ss), (70, 50, ss), (8, 8, ss), (1000, 563, ss), (264, 16, ss)]
+    q = synth.quality_tables(85)
+    descs, coef_len, rgb_len, yuv_len = make_batch(shapes, want_yuv=True)
+    coef = synth.batch_coefficients(descs, coef_len, q, kinds=["natural", "dense", "int16"])
+    _, exp_yuv = oracle_batch(checker, descs, coef, q, rgb_len, yuv_len, nthreads=8)
+    plan = gpu_ctx.plan(descs, rgb=False, yuv=True)
+    assert plan.launches <= 3, "planes-only plans must take the fused path (prep + two instantiations per mode)"
+    plan.close()
+    _, got_yuv = gpu_batch(gpu_ctx, descs, coef, q, rgb_len, yuv_len, want_rgb=False)
+    compare_batch(descs, None, got_yuv, None, exp_yuv)
+    # bytes between the images' planes stay untouched (0xCD fill of gpu_batch)
+    for d in descs:
+        end = d.yuv_off + d.query_layout().data_len
+        if end < yuv_len:
+            assert got_yuv[end] == 0xCD

@@ -90,3 +90,26 @@ def test_reference_reader_errors_keep_the_convention(ref, plugged):
     with Session(plugged, jpg, ref.lib.image_init, ref.lib.image_zero, ref.lib.image_clear) as s:
         assert s.header() == 0
         assert s.vt.decode_image(s.dec, C.byref(s.img), 9) == 1
+
+
+def test_explicit_options_instead_of_the_thread_knobs(ref):
+    """cuda_decode_alloc_ex: the reference's reader and the PACK upload chosen per context, nothing
+    set on the thread; the other four slots are the table's."""
+    jpg, want = expected("c420_rst_80x48")
+    L = _capi.lib()
+    vt = _capi.vtbl("CUDA_DECODE_CTX_VTBL")
+    opt = _capi.cuda_decode_options(ref.xjpeg_address, 0, _capi.JPEG_DECODE_PACK, 0)
+
+    class Explicit:   # a table whose alloc slot passes the options
+        decode_header, decode_image, decode_reset, decode_free = vt.decode_header, vt.decode_image, vt.decode_reset, vt.decode_free
+
+        @staticmethod
+        def decode_alloc(info):
+            return L.cuda_decode_alloc_ex(info, C.byref(opt))
+
+    with Session(Explicit, jpg, ref.lib.image_init, ref.lib.image_zero, ref.lib.image_clear) as s:
+        assert s.header() == 0 and s.image("rgb") == 0
+        assert sha(s.pixels()) == want["rgb"]
+        s.reset()
+        assert s.header() == 0 and s.image("yuv") == 0
+        assert sha(s.planes()) == want["yuv"]
