@@ -61,6 +61,14 @@ int jgo_unpack_image(const jgo_geom *g, const unsigned short *pack, long long pa
 long long jgo_pack_image(const jgo_geom *g, const short *coef, unsigned short *pack,
                          long long pack_cap, int *index, int *packed);
 
+/* the reference's OpenGL float path, emulated (oracle_glsl.c): a comparator, not the ground truth */
+void jgo_glsl_scales2d(float out[64]);
+int jgo_glsl_decode_image(const jgo_geom *g, const short *coef, const unsigned short *qtabs, const int *tq,
+                          int floor_mode, unsigned char *rgb, int *samples);
+int jgo_glsl_decode_image_flat(int width, int height, int ncomps, const int *hsamp, const int *vsamp,
+                               const short *coef, const unsigned short *qtabs, const int *tq, int floor_mode,
+                               unsigned char *rgb, int *samples);
+
 /* whole path over a batch; the CPU baseline */
 int jgo_decode_batch(int n, const long long *desc, const short *coef,
                      const unsigned short *qtabs, unsigned char *rgb,
