@@ -9,8 +9,9 @@ product is bit-exact with it -- so these tests state the measured distance betwe
   * samples (the integer texture of pass 2, clamped for the comparison): never more than 1 apart;
     with the shader's truncation about half of them are +1 (every sample below the +128 bias,
     SURVEY F5), with floor() in its place a few in 100 000;
-  * pixels whose Y, Cb and Cr are all inside 0..255 in the GL texture: within 1 of ours with floor(),
-    within 3 with the truncation as written (+1 on Y and on Cr gives +2.4 on R);
+  * pixels whose Y, Cb and Cr are all inside 0..255 in the GL texture: with floor() within 1 of ours,
+    except the few in 100 000 where a chroma sample itself is one off (1.772 * 1 rounds to 2 on B):
+    never more than 2; within 3 with the truncation as written (+1 on Y and on Cr gives +2.4 on R);
   * pixels fed by an out-of-range sample: unbounded -- the GL path multiplies the unclamped value by
     the colour matrix (res/unyuv.fs.glsl:48), xjpeg clamps first (src/xjpeg.c:578).
 """
@@ -72,7 +73,9 @@ def test_distance_between_the_gl_path_and_the_ground_truth(port, ss, kind):
         ok = in_range_mask(g, samples)
         dist = pixel_distance(g, grgb, rgb.reshape(-1))
         if ok.any():
-            assert dist[ok].max() <= pixel_bound, (floor_mode, int(dist[ok].max()))
+            assert dist[ok].max() <= pixel_bound + (1 if floor_mode else 0), (floor_mode, int(dist[ok].max()))
+            if floor_mode:
+                assert (dist[ok] > 1).mean() < 1e-4
 
 
 @pytest.mark.parametrize("name", NAMES)
@@ -88,8 +91,9 @@ def test_reference_files_through_the_gl_path(port, name):
 
 @pytest.mark.gpu
 def test_cuda_pixels_against_the_gl_path(gpu_ctx, port):
-    """The CUDA kernel's pixels vs the emulated GL float path at 1080p 4:2:0: +-1 LSB per channel (floor in
-    place of ivec4) on every pixel the GL path computes from in-range samples."""
+    """The CUDA kernel's pixels vs the emulated GL float path at 1080p 4:2:0 (floor in place of ivec4), on
+    every pixel the GL path computes from in-range samples: +-1 LSB per channel but for fewer than one
+    pixel in 10 000 (a chroma sample one off), never more than 2."""
     from util import gpu_batch, make_batch
     shapes = [(1920, 1080, "420")]
     q = synth.quality_tables(85)
@@ -100,4 +104,4 @@ def test_cuda_pixels_against_the_gl_path(gpu_ctx, port):
     grgb, samples = port.glsl_decode_image(g, coef[:g.coef_len], q, descs[0].tq, True)
     ok = in_range_mask(g, samples)
     dist = pixel_distance(g, grgb, got[:g.rgb_len])
-    assert ok.mean() > 0.95 and dist[ok].max() <= 1
+    assert ok.mean() > 0.95 and dist[ok].max() <= 2 and (dist[ok] > 1).mean() < 1e-4
