@@ -593,6 +593,521 @@ k_mcu(const __grid_constant__ CUtensorMap tm_rows,   /* (64, rows), boxes of 16 
   }
 }
 
+/* ==== k_tk: the same work with the warps split by what they do ==================================
+ *
+ * ncu on k_mcu (profiles/r2_notes.md): issue slots 59 % busy, FMA pipe 50 %, ALU pipe 44 %, XU 27 % --
+ * nothing saturated, yet "no eligible warp" in 41 % of the cycles.  A warp of k_mcu alternates between
+ * the transform (dequantise, prescale, two 8-point passes: packed binary32 on the FMA pipe, which takes
+ * two cycles per instruction) and the colour stage (PRMT / VIADDMNMX on the ALU pipe, two cycles each
+ * as well); with three warps per scheduler the phases of the three coincide more often than not and
+ * queue for one pipe while the other idles.
+ *
+ * k_tk fixes who does what.  A CTA is 8 PAIRS of warps; a pair works through tasks as a k_mcu warp does.
+ *   T warp (warps 0-7, 192 registers after setmaxnreg.inc): loads, dequantise, both passes, clamp; the
+ *     clamped samples of every step go into a 4 KB STRIP of shared memory (chroma: (Cb-128, Cr-128)
+ *     bytes; luma: bytes in staging order), one of a ring of four per pair.
+ *   K warp (warps 8-15, 64 registers after setmaxnreg.dec): waits for strips, derives the colour
+ *     offsets, adds, packs and stores the pixel rows (or copies the strips to the planes), hands the
+ *     strips back; it also claims the pair's tasks from the launch's counter and fetches their
+ *     descriptors, four tasks ahead.
+ * Every scheduler then holds two T warps and two K warps: the FMA pipe is fed by warps that want
+ * nothing else and the ALU pipe by the others.  Hand-over is one mbarrier pair (full / empty) per strip,
+ * touched by the two warps of the pair only; there is still no CTA-wide synchronisation after start-up.
+ */
+constexpr int kTkPairs = 8;
+constexpr int kTkStrips = 4;
+constexpr int kTkRing = 8;          /* task descriptors per pair */
+constexpr int kTkAhead = 4;         /* K fetches the descriptor of task n + 4 while it works on task n */
+constexpr int kStripBytes = 8 * 32 * 16;
+#ifndef JGPU_TK_REGS_T
+#define JGPU_TK_REGS_T 192
+#endif
+#ifndef JGPU_TK_REGS_K
+#define JGPU_TK_REGS_K 64
+#endif
+static_assert(kTkPairs * 32 * (JGPU_TK_REGS_T + JGPU_TK_REGS_K) <= 65536, "register file");
+
+template <int HS, int VS, bool GRAY, bool WIDE>
+struct TkCfg {
+  static constexpr int kChromaSteps = GRAY ? 0 : (HS == 2 ? 1 : 2);
+  static constexpr int kLumaSteps = GRAY ? 1 : VS;
+  static constexpr int kSteps = kChromaSteps + kLumaSteps;
+  static constexpr int kChannels = GRAY ? 1 : 3;
+  static constexpr int kTabBytes = WIDE ? kQtabBytes : kQtabBytes / 2;
+  static constexpr int kOffTab = 0;
+  static constexpr int kOffStrip = 2 * kTabBytes;
+  static constexpr int kOffRing = kOffStrip + kTkStrips * kStripBytes;
+  static constexpr int kOffBar = kOffRing + kTkRing * (int)sizeof(WarpTask);   /* data, ring[8], full[4], empty[4] */
+  static constexpr int kOffLoop = kOffBar + 8 * (1 + kTkRing + 2 * kTkStrips);  /* T's step counter */
+  static constexpr int kOffIdx = kOffLoop + 8;                                  /* task index of each ring slot */
+  static constexpr int kPairMisc = (kOffIdx + 4 * kTkRing + 15) / 16 * 16;
+  static constexpr int kThreads = 2 * 32 * kTkPairs;
+  static constexpr int kSmemBytes = kTkPairs * (kZoneBytes + kPairMisc);
+  static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
+  static_assert(kOffStrip % 16 == 0 && kOffBar % 8 == 0, "alignment");
+};
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+/* ---- the colour stage of one pixel row (K warps) ---------------------------------------------- */
+
+/* one staged luma row (bytes A01 B01 | A23 B23 | A45 B45 | A67 B67) -> s16x2 words: ya[0..3] = the pixel
+ * pairs of block A, yb[0..3] = of block B */
+__device__ __forceinline__ void tk_staged_row(uint32_t row, uint32_t (&ya)[4], uint32_t (&yb)[4]) {
+  const uint4 t = lds128(row);
+  ya[0] = __byte_perm(t.x, 0u, 0x4140); yb[0] = __byte_perm(t.x, 0u, 0x4342);
+  ya[1] = __byte_perm(t.y, 0u, 0x4140); yb[1] = __byte_perm(t.y, 0u, 0x4342);
+  ya[2] = __byte_perm(t.z, 0u, 0x4140); yb[2] = __byte_perm(t.z, 0u, 0x4342);
+  ya[3] = __byte_perm(t.w, 0u, 0x4140); yb[3] = __byte_perm(t.w, 0u, 0x4342);
+}
+/* ... and as 16 bytes in pixel order */
+__device__ __forceinline__ uint4 tk_staged_row_bytes(uint32_t row) {
+  const uint4 t = lds128(row);
+  return make_uint4(__byte_perm(t.x, t.y, 0x5410), __byte_perm(t.z, t.w, 0x5410),
+                    __byte_perm(t.x, t.y, 0x7632), __byte_perm(t.z, t.w, 0x7632));
+}
+/* colour offsets of one chroma row for block A / block B: 4 pixel pairs x (R,G,B) as s16x2 words.
+ * crow: this lane's 16 bytes of the strip row; crow_b: the same in the odd MCUs' strip (1x luma modes) */
+template <int HS>
+__device__ __forceinline__ void tk_row_offsets(uint32_t crow, uint32_t crow_b, uint32_t (&ca)[12], uint32_t (&cb)[12]) {
+  if (HS == 2) {
+    /* 8 chroma samples, each serving one horizontal pixel pair: offsets replicated into both halves */
+    const uint4 t = lds128(crow);
+    const uint32_t cs[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      uint32_t *o = i < 2 ? ca : cb;
+      const int p = 6 * (i & 1);
+      uint32_t r[2], gg[2], b[2];
+      chroma_offsets_bits2(cs[i], r, gg, b);
+      o[p + 0] = __byte_perm(r[0], r[0], kSelRep);
+      o[p + 1] = __byte_perm(gg[0], gg[0], kSelRep);
+      o[p + 2] = __byte_perm(b[0], b[0], kSelRep);
+      o[p + 3] = __byte_perm(r[1], r[1], kSelRep);
+      o[p + 4] = __byte_perm(gg[1], gg[1], kSelRep);
+      o[p + 5] = __byte_perm(b[1], b[1], kSelRep);
+    }
+  } else {
+    /* block A = even MCU, block B = odd MCU: 8 samples each, one per pixel */
+#pragma unroll
+    for (int blk = 0; blk < 2; blk++) {
+      const uint4 t = lds128(blk ? crow_b : crow);
+      const uint32_t cs[4] = {t.x, t.y, t.z, t.w};
+      uint32_t *o = blk == 0 ? ca : cb;
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        uint32_t r[2], gg[2], b[2];
+        chroma_offsets_bits2(cs[i], r, gg, b);
+        o[3 * i + 0] = __byte_perm(r[0], r[1], kSelPair);
+        o[3 * i + 1] = __byte_perm(gg[0], gg[1], kSelPair);
+        o[3 * i + 2] = __byte_perm(b[0], b[1], kSelPair);
+      }
+    }
+  }
+}
+/* 16 staged samples + the offsets -> 48 bytes of RGB as 12 words */
+__device__ __forceinline__ void tk_row_words(const uint32_t (&ya)[4], const uint32_t (&yb)[4], const uint32_t (&ca)[12],
+                                             const uint32_t (&cb)[12], uint32_t (&w)[12]) {
+  rgb4(ya[0], ya[1], ca[0], ca[1], ca[2], ca[3], ca[4], ca[5], w[0], w[1], w[2]);
+  rgb4(ya[2], ya[3], ca[6], ca[7], ca[8], ca[9], ca[10], ca[11], w[3], w[4], w[5]);
+  rgb4(yb[0], yb[1], cb[0], cb[1], cb[2], cb[3], cb[4], cb[5], w[6], w[7], w[8]);
+  rgb4(yb[2], yb[3], cb[6], cb[7], cb[8], cb[9], cb[10], cb[11], w[9], w[10], w[11]);
+}
+/* The first nbytes (<= 48) of w[0..11] to dst, whatever its alignment: byte stores up to the first
+ * 4-byte boundary, funnel-shifted 32-bit stores from there, byte stores for what is left. */
+__device__ __forceinline__ void tk_store_any(uint8_t *dst, const uint32_t (&w)[12], int nbytes) {
+  const int head = (int)((4u - (uint32_t)(uintptr_t)dst) & 3u);   /* bytes before the boundary */
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    if (i < head && i < nbytes) dst[i] = (uint8_t)(w[0] >> (8 * i));
+  }
+  uint8_t *p = dst + head;
+  const int left = nbytes - head;
+  const uint32_t sh = 8u * (uint32_t)head;
+#pragma unroll
+  for (int i = 0; i < 12; i++) {
+    /* the four bytes that follow byte head + 4 i of the row */
+    const uint32_t v = __funnelshift_r(w[i], i + 1 < 12 ? w[i + 1] : 0u, sh);
+    if (4 * i + 4 <= left) {
+      *reinterpret_cast<uint32_t *>(p + 4 * i) = v;
+    } else {
+#pragma unroll
+      for (int b = 0; b < 3; b++) {
+        if (4 * i + b < left) p[4 * i + b] = (uint8_t)(v >> (8 * b));
+      }
+    }
+  }
+}
+
+template <int HS, int VS, bool GRAY, bool WIDE, int OUT>
+__global__ void __launch_bounds__(TkCfg<HS, VS, GRAY, WIDE>::kThreads, 1)
+k_tk(const __grid_constant__ CUtensorMap tm_rows,   /* (64, rows), boxes of 16 rows            */
+     const __grid_constant__ CUtensorMap tm_pairs,  /* (64, parity, pairs), boxes of 16 pairs  */
+     const WarpTask *__restrict__ tasks, int n_tasks, const uint32_t *__restrict__ qint,
+     const uint32_t *__restrict__ wide_flag, uint8_t *__restrict__ rgb, int rgb_aligned,
+     uint8_t *__restrict__ yuv, int *__restrict__ claim) {
+  using C = TkCfg<HS, VS, GRAY, WIDE>;
+  if ((*wide_flag != 0) != WIDE) return;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem0 = smem_u32(smem_raw);
+  if (smem0 & 1023u) __trap();   /* the 128-byte swizzle needs the boxes 1 KB aligned */
+
+  /* Where this thread's things live; re-derived from %tid.x at every point of use (see k_mcu). */
+  struct Geo {
+    int lane;
+    uint32_t pair;
+    uint32_t zone;      /* the pair's landing zone: box A, box B */
+    uint32_t misc;      /* the pair's area behind the zones */
+    uint32_t mine;      /* misc + 16*lane: this lane's column of every [row][lane] array */
+  };
+  auto geo = [&]() -> Geo {
+    uint32_t tid;
+    asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
+    Geo g;
+    g.lane = (int)(tid & 31);
+    g.pair = (tid >> 5) & (kTkPairs - 1);
+    g.zone = smem0 + g.pair * kZoneBytes;
+    g.misc = smem0 + kTkPairs * kZoneBytes + g.pair * C::kPairMisc;
+    g.mine = g.misc + 16u * (uint32_t)g.lane;
+    return g;
+  };
+  auto bar_data = [&](const Geo &g) { return g.misc + C::kOffBar; };
+  auto bar_ring = [&](const Geo &g, uint32_t slot) { return g.misc + C::kOffBar + 8 + 8 * slot; };
+  auto bar_full = [&](const Geo &g, uint32_t slot) { return g.misc + C::kOffBar + 8 * (1 + kTkRing) + 8 * slot; };
+  auto bar_empty = [&](const Geo &g, uint32_t slot) { return g.misc + C::kOffBar + 8 * (1 + kTkRing + kTkStrips) + 8 * slot; };
+  auto strip_addr = [&](const Geo &g, uint32_t slot) { return g.mine + C::kOffStrip + slot * kStripBytes; };
+  auto desc_addr = [&](const Geo &g, int n) { return g.misc + C::kOffRing + ((uint32_t)n % kTkRing) * (uint32_t)sizeof(WarpTask); };
+  auto half_addr = [&](const Geo &g, int n) { return desc_addr(g, n) + (uint32_t)(g.lane >> 4) * (uint32_t)sizeof(McuHalf); };
+  auto idx_addr = [&](const Geo &g, int n) { return g.misc + C::kOffIdx + 4u * ((uint32_t)n % kTkRing); };
+  /* Local task n of the pair lives in ring slot n % 8.  The K warp announces every local task, whether
+   * it exists or not: its index (>= n_tasks: the pair's work ends here) and, if it exists, its
+   * descriptor; the slot's mbarrier completes either way. */
+  auto announce = [&](const Geo &g, int n, int idx) {   /* K lane 0 only */
+    const uint32_t slot = (uint32_t)n % kTkRing;
+    sts32(idx_addr(g, n), (uint32_t)idx);
+    if (idx < n_tasks) {
+      mbar_expect_tx(bar_ring(g, slot), (uint32_t)sizeof(WarpTask));
+      bulk_load(desc_addr(g, n), tasks + idx, (uint32_t)sizeof(WarpTask), bar_ring(g, slot));
+    } else {
+      mbar_arrive(bar_ring(g, slot));
+    }
+  };
+  auto wait_desc = [&](const Geo &g, int n) {
+    mbar_wait_hint<JGPU_MCU_WAIT_NS>(bar_ring(g, (uint32_t)n % kTkRing), ((uint32_t)n / kTkRing) & 1u);
+  };
+
+  const bool is_t = threadIdx.x < 32 * kTkPairs;
+  {
+    const Geo g = geo();
+    if (is_t && g.lane == 0) {
+      for (int i = 0; i < 1 + kTkRing + 2 * kTkStrips; i++) mbar_init(bar_data(g) + 8 * i, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+  }
+  __syncthreads();
+  const int gw = (int)blockIdx.x * kTkPairs + (int)((threadIdx.x >> 5) & (kTkPairs - 1));
+  const int nw = (int)gridDim.x * kTkPairs;
+
+  if (is_t) {
+    /* ================================ T: coefficients -> strips ================================ */
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(JGPU_TK_REGS_T));
+    if (gw >= n_tasks) return;
+    /* Start the loads of step s of local task n (lane 0 only; its descriptor must have landed): per
+     * half-task 16 rows of box A and 16 rows of box B (a half-task that does not exist repeats the
+     * other one's blocks, see mcu_plan_build), and the step's table(s). */
+    auto fire = [&](const Geo &g, int n, int s) {
+      const uint32_t d = desc_addr(g, n), bar = bar_data(g), tab = g.misc + C::kOffTab;
+      const bool chroma = s < C::kChromaSteps;
+      mbar_expect_tx(bar, 2 * kBoxBytes + (chroma ? 2 : 1) * C::kTabBytes);
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        const uint32_t hd = d + h * (uint32_t)sizeof(McuHalf);
+        const uint32_t dst = g.zone + h * kHalfBoxBytes;
+        if (chroma) {
+          int f0 = (int)lds32(hd + offsetof(McuHalf, cfirst));
+          int f1 = (int)lds32(hd + offsetof(McuHalf, cfirst) + 4);
+          if (HS == 2) {
+            tma_load_2d(dst, &tm_rows, 0, f0, bar);
+            tma_load_2d(dst + kBoxBytes, &tm_rows, 0, f1, bar);
+          } else {
+            f0 += s;
+            f1 += s;
+            tma_load_3d(dst, &tm_pairs, 0, f0 & 1, f0 >> 1, bar);
+            tma_load_3d(dst + kBoxBytes, &tm_pairs, 0, f1 & 1, f1 >> 1, bar);
+          }
+        } else {
+          const int first = (int)lds32(hd + offsetof(McuHalf, yfirst) + 4 * (s - C::kChromaSteps));
+          tma_load_3d(dst, &tm_pairs, 0, first & 1, first >> 1, bar);
+          tma_load_3d(dst + kBoxBytes, &tm_pairs, 0, (first + 1) & 1, (first + 1) >> 1, bar);
+        }
+      }
+      if (chroma) {
+        bulk_load(tab, qint + (size_t)lds32(d + offsetof(WarpTask, qidx) + 4) * 64, C::kTabBytes, bar);
+        bulk_load(tab + C::kTabBytes, qint + (size_t)lds32(d + offsetof(WarpTask, qidx) + 8) * 64, C::kTabBytes, bar);
+      } else {
+        bulk_load(tab, qint + (size_t)lds32(d + offsetof(WarpTask, qidx)) * 64, C::kTabBytes, bar);
+      }
+    };
+    {
+      const Geo g = geo();
+      sts32(g.misc + C::kOffLoop, 0u);   /* every lane, same value */
+      if (g.lane == 0) {
+        wait_desc(g, 0);   /* (gw < n_tasks: it exists) */
+        fire(g, 0, 0);
+      }
+      __syncwarp();
+    }
+#pragma unroll 1
+    for (;;) {
+      bool is_c, active;   /* a chroma step?  does this lane's unit exist / show in this step? */
+      {
+        const Geo g = geo();
+        const int step = (int)lds32(g.misc + C::kOffLoop);
+        const int n = step / C::kSteps, s = step - n * C::kSteps;
+        wait_desc(g, n);
+        if ((int)lds32(idx_addr(g, n)) >= n_tasks) break;
+        __syncwarp();
+        sts32(g.misc + C::kOffLoop, (uint32_t)step + 1u);
+        is_c = s < C::kChromaSteps;
+        const uint32_t ha = half_addr(g, n);
+        const int u = g.lane & 15;
+        if (OUT == kOutYuv) {
+          active = 2 * u + ((HS == 1 && is_c) ? s : 0) < (int)lds32(ha + offsetof(McuHalf, blocks_left));
+        } else {
+          const uint2 wr = lds64(ha + offsetof(McuHalf, width_left));   /* width_left, rows_left */
+          active = 16 * u + ((HS == 1 && is_c) ? 8 * s : 0) < (int)wr.x && (is_c || 8 * (s - C::kChromaSteps) < (int)wr.y);
+        }
+        mbar_wait_hint<JGPU_MCU_WAIT_NS>(bar_data(g), (uint32_t)step & 1u);
+      }
+      {
+        pair32 m[8][8];
+        if (active) {
+          const Geo g = geo();
+          const uint32_t qa = g.misc + C::kOffTab;
+          const uint32_t qb = is_c ? qa + C::kTabBytes : qa;   /* chroma: Cb table, then Cr table */
+          mcu_row_pass<WIDE, false>(m, g.zone, g.lane, qa, qb, 0u);
+        }
+        /* the boxes are in registers: start the loads of the pair's next step */
+        __syncwarp();
+        uint32_t strip;
+        {
+          const Geo g = geo();
+          const int next = (int)lds32(g.misc + C::kOffLoop);   /* this step + 1 */
+          if (g.lane == 0) {
+            const int n = next / C::kSteps, s = next - n * C::kSteps;
+            if (s != 0) {
+              fire(g, n, s);
+            } else {
+              wait_desc(g, n);
+              if ((int)lds32(idx_addr(g, n)) < n_tasks) fire(g, n, 0);
+            }
+          }
+          /* this step's strip: free once the K warp has handed back its previous contents */
+          const uint32_t cur = (uint32_t)next - 1u, slot = cur % kTkStrips;
+          mbar_wait_hint<JGPU_MCU_WAIT_NS>(bar_empty(g, slot), ((cur / kTkStrips) & 1u) ^ 1u);
+          strip = strip_addr(g, slot);
+        }
+        if (active) {
+          const pair32 magic = p_make_bits(kMagicBits, kMagicBits);
+          uint32_t keep_a[8];   /* the even column step's words, until the odd one completes them */
+          auto sink = [&](int j, pair32 (&u)[8], pair32 (&v)[8]) {
+            if (is_c) {
+              /* chroma: clamped samples of columns 2j, 2j+1 as four signed bytes (Cb, Cr, Cb, Cr);
+               * two column steps make 8 bytes of the strip's row */
+#pragma unroll
+              for (int k = 0; k < 8; k++) {
+                const uint32_t w = __byte_perm(chroma_clamped(u[k]), chroma_clamped(v[k]), 0x6420);
+                if ((j & 1) == 0) keep_a[k] = w;
+                else sts64(strip + 512 * k + 8 * (j >> 1), make_uint2(keep_a[k], w));
+              }
+            } else {
+              /* luma: (short)floor + 128, clamp: pixels 2j, 2j+1 of row k of block A and of block B, as
+               * bytes (A2j A2j+1 B2j B2j+1); two column steps make 8 bytes of the strip's row */
+#pragma unroll
+              for (int k = 0; k < 8; k++) {
+                uint32_t ulo, uhi, vlo, vhi;
+                p_split_bits(p_add_rm(u[k], magic), ulo, uhi);
+                p_split_bits(p_add_rm(v[k], magic), vlo, vhi);
+                const uint32_t wa = clamp_pair_u8(ulo, vlo), wb = clamp_pair_u8(uhi, vhi);
+                const uint32_t w = __byte_perm(wa, wb, 0x6420);
+                if ((j & 1) == 0) keep_a[k] = w;
+                else sts64(strip + 512 * k + 8 * (j >> 1), make_uint2(keep_a[k], w));
+              }
+            }
+          };
+          column_pass_by_pairs(m, sink);
+        }
+      }
+      __syncwarp();
+      {
+        const Geo g = geo();
+        if (g.lane == 0) mbar_arrive(bar_full(g, ((uint32_t)lds32(g.misc + C::kOffLoop) - 1u) % kTkStrips));
+      }
+    }
+    return;
+  }
+
+  /* ================================ K: strips -> pixels / planes ================================ */
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(JGPU_TK_REGS_K));
+  if (gw >= n_tasks) return;
+  const Geo g = geo();
+  if (g.lane == 0) {
+    for (int i = 0; i < kTkAhead; i++) announce(g, i, gw + i * nw);
+  }
+  const int u = g.lane & 15;   /* this lane's unit inside its half-task */
+  auto wait_full = [&](uint32_t st) { mbar_wait_hint<JGPU_MCU_WAIT_NS>(bar_full(g, st % kTkStrips), (st / kTkStrips) & 1u); };
+  auto hand_back = [&](uint32_t st) {   /* after __syncwarp(): every lane has read what it needs of the strip */
+    if (g.lane == 0) mbar_arrive(bar_empty(g, st % kTkStrips));
+  };
+  uint32_t step = 0;
+#pragma unroll 1
+  for (int n = 0;; n++, step += C::kSteps) {
+    wait_desc(g, n);
+    if ((int)lds32(idx_addr(g, n)) >= n_tasks) break;
+    /* claim the task four further on now, pick the answer up when this task's first rows are out */
+    int claimed = 0;
+    if (g.lane == 0) asm volatile("atom.global.add.u32 %0, [%1], 1;" : "=r"(claimed) : "l"(claim) : "memory");
+    const uint32_t da = desc_addr(g, n), ha = half_addr(g, n);
+    const uint2 b0 = lds64(ha + offsetof(McuHalf, base0));
+    const long long base0 = (long long)(((unsigned long long)b0.y << 32) | b0.x);
+    const int pitch = (int)lds32(da + offsetof(WarpTask, pitch0));
+
+    if (OUT == kOutYuv) {
+      const int blocks_left = (int)lds32(ha + offsetof(McuHalf, blocks_left));
+#pragma unroll 1
+      for (int s = 0; s < C::kSteps; s++) {
+        const uint32_t st = step + (uint32_t)s;
+        wait_full(st);
+        const uint32_t strip = strip_addr(g, st % kTkStrips);
+        if (s < C::kChromaSteps) {
+          /* 8 Cb bytes and 8 Cr bytes per row */
+          if (2 * u + (HS == 1 ? s : 0) < blocks_left) {
+            const uint2 b1 = lds64(ha + offsetof(McuHalf, base1));
+            const uint2 dl = lds64(da + offsetof(WarpTask, cr_delta));
+            const int cpitch = (int)lds32(da + offsetof(WarpTask, pitch1));
+            const long long col = HS == 2 ? 8 * u : 16 * u + 8 * s;
+            uint8_t *pb = yuv + (long long)(((unsigned long long)b1.y << 32) | b1.x) + col;
+            uint8_t *pr = pb + (long long)(((unsigned long long)dl.y << 32) | dl.x);
+#pragma unroll 2
+            for (int k = 0; k < 8; k++) {
+              const uint4 t = lds128(strip + 512 * k);
+              uint2 vb, vr;
+              vb.x = __byte_perm(t.x, t.y, 0x6420) ^ 0x80808080u;
+              vb.y = __byte_perm(t.z, t.w, 0x6420) ^ 0x80808080u;
+              vr.x = __byte_perm(t.x, t.y, 0x7531) ^ 0x80808080u;
+              vr.y = __byte_perm(t.z, t.w, 0x7531) ^ 0x80808080u;
+              stg64_stream(pb, vb);
+              stg64_stream(pr, vr);
+              pb += cpitch;
+              pr += cpitch;
+            }
+          }
+        } else if (2 * u < blocks_left) {
+          /* 16 Y bytes per row (8 when the unit's second block lies beyond the padded plane) */
+          const int yr = s - C::kChromaSteps;
+          const bool whole = 2 * u + 1 < blocks_left;
+          const bool wide16 = whole && (pitch & 8) == 0;   /* an odd number of blocks per row: rows are only 8-byte aligned */
+          uint8_t *py = yuv + base0 + (long long)(8 * yr) * pitch + 16 * u;
+#pragma unroll 2
+          for (int k = 0; k < 8; k++) {
+            const uint4 v = tk_staged_row_bytes(strip + 512 * k);
+            if (wide16) {
+              stg128_stream(py, v);
+            } else {
+              stg64_stream(py, make_uint2(v.x, v.y));
+              if (whole) stg64_stream(py + 8, make_uint2(v.z, v.w));
+            }
+            py += pitch;
+          }
+        }
+        __syncwarp();
+        hand_back(st);
+        if (s == 0 && g.lane == 0) announce(g, n + kTkAhead, kTkAhead * nw + claimed);
+      }
+      continue;
+    }
+
+    /* ---- pixels: colour offsets, pack, store ------------------------------------------------- */
+    const uint2 wr = lds64(ha + offsetof(McuHalf, width_left));   /* width_left, rows_left */
+    const int vis_px = min(16, (int)wr.x - 16 * u);
+    const bool fast = (lds32(da + offsetof(WarpTask, flags)) & (uint32_t)rgb_aligned & 1u) != 0 && vis_px == 16;
+    const int nbytes = C::kChannels * vis_px;
+#pragma unroll 1
+    for (int s = 0; s < C::kChromaSteps; s++) wait_full(step + (uint32_t)s);
+    const uint32_t cstrip = GRAY ? 0u : strip_addr(g, step % kTkStrips);                       /* HS == 2: the unit's chroma; else the even MCU's */
+    const uint32_t cstrip_b = HS == 2 ? cstrip : strip_addr(g, (step + 1u) % kTkStrips);        /* the odd MCU's */
+#pragma unroll 1
+    for (int yr = 0; yr < C::kLumaSteps; yr++) {
+      const uint32_t st = step + (uint32_t)(C::kChromaSteps + yr);
+      wait_full(st);
+      const uint32_t lstrip = strip_addr(g, st % kTkStrips);
+      const int vis_rows = min(8, (int)wr.y - 8 * yr);
+      uint8_t *dst = rgb + base0 + (long long)(8 * yr) * pitch + (long long)(16 * u) * C::kChannels;
+      /* chroma rows this luma block row uses, one per VS pixel rows */
+      const uint32_t crow0 = cstrip + (VS == 2 ? 4u * 512u * (uint32_t)yr : 0u);
+      const uint32_t crow0_b = cstrip_b + (VS == 2 ? 4u * 512u * (uint32_t)yr : 0u);
+      if (vis_px > 0 && vis_rows > 0) {
+        if (fast && vis_rows == 8) {
+          /* the whole 16 x 8 tile shows and its rows are 16-byte aligned: no per-row tests */
+          if (GRAY) {
+#pragma unroll 2
+            for (int k = 0; k < 8; k++, dst += pitch) stg128_stream(dst, tk_staged_row_bytes(lstrip + 512 * k));
+          } else {
+#pragma unroll 1
+            for (int cr = 0; cr < 8 / VS; cr++) {
+              uint32_t ca[12], cb[12];
+              tk_row_offsets<HS>(crow0 + 512u * (uint32_t)cr, crow0_b + 512u * (uint32_t)cr, ca, cb);
+#pragma unroll
+              for (int sub = 0; sub < VS; sub++) {
+                uint32_t ya[4], yb[4], w[12];
+                tk_staged_row(lstrip + 512u * (uint32_t)(cr * VS + sub), ya, yb);
+                tk_row_words(ya, yb, ca, cb, w);
+                stg128_stream(dst, make_uint4(w[0], w[1], w[2], w[3]));
+                stg128_stream(dst + 16, make_uint4(w[4], w[5], w[6], w[7]));
+                stg128_stream(dst + 32, make_uint4(w[8], w[9], w[10], w[11]));
+                dst += pitch;
+              }
+            }
+          }
+        } else {
+          /* edge tiles: cropped by the image's right or bottom edge, or rows that are not 16-byte aligned
+           * (any width that is not a multiple of 16 pixels): the same arithmetic, stores of whatever
+           * alignment the row has */
+          if (GRAY) {
+#pragma unroll 1
+            for (int k = 0; k < vis_rows; k++, dst += pitch) {
+              const uint4 v = tk_staged_row_bytes(lstrip + 512 * k);
+              const uint32_t w[12] = {v.x, v.y, v.z, v.w, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+              tk_store_any(dst, w, nbytes);
+            }
+          } else {
+#pragma unroll 1
+            for (int cr = 0; cr * VS < vis_rows; cr++) {
+              uint32_t ca[12], cb[12];
+              tk_row_offsets<HS>(crow0 + 512u * (uint32_t)cr, crow0_b + 512u * (uint32_t)cr, ca, cb);
+#pragma unroll 1
+              for (int k = cr * VS; k < cr * VS + VS && k < vis_rows; k++, dst += pitch) {
+                uint32_t ya[4], yb[4], w[12];
+                tk_staged_row(lstrip + 512u * (uint32_t)k, ya, yb);
+                tk_row_words(ya, yb, ca, cb, w);
+                tk_store_any(dst, w, nbytes);
+              }
+            }
+          }
+        }
+      }
+      __syncwarp();
+      hand_back(st);
+      if (yr == 0 && g.lane == 0) announce(g, n + kTkAhead, kTkAhead * nw + claimed);
+    }
+    /* (the __syncwarp() before the last hand_back covers the chroma strips too) */
+#pragma unroll 1
+    for (int s = 0; s < C::kChromaSteps; s++) hand_back(step + (uint32_t)s);
+  }
+}
+
 /* ---- host side ------------------------------------------------------------- */
 
 namespace {
@@ -621,7 +1136,17 @@ struct McuMode {
   size_t smem;
   int threads_wide, warps_wide;   /* the kernel for 16-bit tables (more table bytes per warp) */
   size_t smem_wide;
+  size_t tk_smem, tk_smem_wide;   /* k_tk: 8 warp pairs per CTA either way */
 };
+/* which kernel runs: k_tk unless JGPU_KERNEL=mcu (kept for A/B runs, profiles/r2_notes.md) */
+bool mcu_use_tk() {
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("JGPU_KERNEL");
+    v = (e && strcmp(e, "mcu") == 0) ? 0 : 1;
+  }
+  return v != 0;
+}
 McuMode g_mcu[kNumFusedModes];
 bool g_mcu_configured = false;
 
@@ -638,6 +1163,12 @@ cudaError_t mcu_configure_mode(int mode) {
   if ((e = cudaFuncSetAttribute(&k_mcu<HS, VS, GRAY, true, kOutRgb>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mi.smem_wide)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(&k_mcu<HS, VS, GRAY, false, kOutYuv>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mi.smem)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(&k_mcu<HS, VS, GRAY, true, kOutYuv>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mi.smem_wide)) != cudaSuccess) return e;
+  mi.tk_smem = TkCfg<HS, VS, GRAY, false>::kSmemBytes;
+  mi.tk_smem_wide = TkCfg<HS, VS, GRAY, true>::kSmemBytes;
+  if ((e = cudaFuncSetAttribute(&k_tk<HS, VS, GRAY, false, kOutRgb>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mi.tk_smem)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(&k_tk<HS, VS, GRAY, true, kOutRgb>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mi.tk_smem_wide)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(&k_tk<HS, VS, GRAY, false, kOutYuv>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mi.tk_smem)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(&k_tk<HS, VS, GRAY, true, kOutYuv>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mi.tk_smem_wide)) != cudaSuccess) return e;
   return cudaSuccess;
 }
 
@@ -645,6 +1176,18 @@ template <int HS, int VS, bool GRAY>
 cudaError_t mcu_launch_mode(bool planes, int sm_count, const McuMode &mi, cudaStream_t stream, const CUtensorMap &tm_rows,
                             const CUtensorMap &tm_pairs, const WarpTask *tasks, int n_tasks, const uint32_t *qint,
                             const uint32_t *wide_flag, uint8_t *rgb, int rgb_aligned, uint8_t *yuv, int *claim) {
+  if (mcu_use_tk()) {
+    const int grid = std::min((n_tasks + kTkPairs - 1) / kTkPairs, sm_count);
+    const int threads = 2 * 32 * kTkPairs;
+    if (planes) {
+      k_tk<HS, VS, GRAY, false, kOutYuv><<<grid, threads, mi.tk_smem, stream>>>(tm_rows, tm_pairs, tasks, n_tasks, qint, wide_flag, rgb, rgb_aligned, yuv, claim);
+      k_tk<HS, VS, GRAY, true, kOutYuv><<<grid, threads, mi.tk_smem_wide, stream>>>(tm_rows, tm_pairs, tasks, n_tasks, qint, wide_flag, rgb, rgb_aligned, yuv, claim);
+    } else {
+      k_tk<HS, VS, GRAY, false, kOutRgb><<<grid, threads, mi.tk_smem, stream>>>(tm_rows, tm_pairs, tasks, n_tasks, qint, wide_flag, rgb, rgb_aligned, yuv, claim);
+      k_tk<HS, VS, GRAY, true, kOutRgb><<<grid, threads, mi.tk_smem_wide, stream>>>(tm_rows, tm_pairs, tasks, n_tasks, qint, wide_flag, rgb, rgb_aligned, yuv, claim);
+    }
+    return cudaGetLastError();
+  }
   const int grid = std::min((n_tasks + mi.warps - 1) / mi.warps, sm_count);
   const int grid_w = std::min((n_tasks + mi.warps_wide - 1) / mi.warps_wide, sm_count);
   if (planes) {
