@@ -622,6 +622,21 @@ constexpr int kStripBytes = 8 * 32 * 16;
 #ifndef JGPU_TK_REGS_T
 #define JGPU_TK_REGS_T 192
 #endif
+#ifndef JGPU_TK_EXPERIMENT
+#define JGPU_TK_EXPERIMENT 0  /* timing experiments only (wrong output): 1: K warps skip their work, 2: T warps skip theirs */
+#endif
+#ifndef JGPU_TK_PARK
+#define JGPU_TK_PARK 1        /* 1: row 0 of the register tile waits in shared memory between the passes (as k_mcu at 12 warps) */
+#endif
+#ifndef JGPU_TK_STS32
+#define JGPU_TK_STS32 0       /* 1: T stores every finished word at once (32-bit stores) instead of pairing two column steps */
+#endif
+#ifndef JGPU_TK_T_HIGH
+#define JGPU_TK_T_HIGH 1      /* 1: the T warps are warps 8-15 (the schedulers favour high warp ids), 0: warps 0-7 */
+#endif
+#ifndef JGPU_TK_SPIN_NS
+#define JGPU_TK_SPIN_NS 0     /* K warps: nanosleep between two looks at a strip that is not full yet (0: none) */
+#endif
 #ifndef JGPU_TK_REGS_K
 #define JGPU_TK_REGS_K 64
 #endif
@@ -636,7 +651,9 @@ struct TkCfg {
   static constexpr int kTabBytes = WIDE ? kQtabBytes : kQtabBytes / 2;
   static constexpr int kOffTab = 0;
   static constexpr int kOffStrip = 2 * kTabBytes;
-  static constexpr int kOffRing = kOffStrip + kTkStrips * kStripBytes;
+  static constexpr bool kPark = JGPU_TK_PARK != 0;
+  static constexpr int kOffPark = kOffStrip + kTkStrips * kStripBytes;
+  static constexpr int kOffRing = kOffPark + (kPark ? 4 * 32 * 16 : 0);
   static constexpr int kOffBar = kOffRing + kTkRing * (int)sizeof(WarpTask);   /* data, ring[8], full[4], empty[4] */
   static constexpr int kOffLoop = kOffBar + 8 * (1 + kTkRing + 2 * kTkStrips);  /* T's step counter */
   static constexpr int kOffIdx = kOffLoop + 8;                                  /* task index of each ring slot */
@@ -798,7 +815,7 @@ k_tk(const __grid_constant__ CUtensorMap tm_rows,   /* (64, rows), boxes of 16 r
     mbar_wait_hint<JGPU_MCU_WAIT_NS>(bar_ring(g, (uint32_t)n % kTkRing), ((uint32_t)n / kTkRing) & 1u);
   };
 
-  const bool is_t = threadIdx.x < 32 * kTkPairs;
+  const bool is_t = JGPU_TK_T_HIGH ? threadIdx.x >= 32 * kTkPairs : threadIdx.x < 32 * kTkPairs;
   {
     const Geo g = geo();
     if (is_t && g.lane == 0) {
@@ -883,11 +900,12 @@ k_tk(const __grid_constant__ CUtensorMap tm_rows,   /* (64, rows), boxes of 16 r
       }
       {
         pair32 m[8][8];
+        if (JGPU_TK_EXPERIMENT == 2) active = false;
         if (active) {
           const Geo g = geo();
           const uint32_t qa = g.misc + C::kOffTab;
           const uint32_t qb = is_c ? qa + C::kTabBytes : qa;   /* chroma: Cb table, then Cr table */
-          mcu_row_pass<WIDE, false>(m, g.zone, g.lane, qa, qb, 0u);
+          mcu_row_pass<WIDE, C::kPark>(m, g.zone, g.lane, qa, qb, g.mine + C::kOffPark);
         }
         /* the boxes are in registers: start the loads of the pair's next step */
         __syncwarp();
@@ -910,34 +928,44 @@ k_tk(const __grid_constant__ CUtensorMap tm_rows,   /* (64, rows), boxes of 16 r
           strip = strip_addr(g, slot);
         }
         if (active) {
+          /* One sink for both kinds of step, without a branch, so that the whole column pass is one
+           * basic block and the clamping / packing of a column pair (ALU pipe) is scheduled between
+           * the butterflies of the next one (FMA pipe); ptxas does interleave them when it can.
+           *   luma:   (short)floor, +128, clamp to 0..255; bytes (A2j A2j+1 B2j B2j+1)
+           *   chroma: (short)floor, clamp to -128..127 (= clamp(v+128, 0, 255) - 128, src/xjpeg.c:578);
+           *           bytes (Cb2j Cr2j Cb2j+1 Cr2j+1): Cb rides in the low lanes, Cr in the high ones
+           * Two column steps make 8 bytes of the strip's row. */
           const pair32 magic = p_make_bits(kMagicBits, kMagicBits);
+          const uint32_t add2 = is_c ? 0u : 0x00800080u, lim2 = is_c ? 0xff80ff80u : 0u, sel = is_c ? 0x6240u : 0x6420u;
           uint32_t keep_a[8];   /* the even column step's words, until the odd one completes them */
           auto sink = [&](int j, pair32 (&u)[8], pair32 (&v)[8]) {
-            if (is_c) {
-              /* chroma: clamped samples of columns 2j, 2j+1 as four signed bytes (Cb, Cr, Cb, Cr);
-               * two column steps make 8 bytes of the strip's row */
 #pragma unroll
-              for (int k = 0; k < 8; k++) {
-                const uint32_t w = __byte_perm(chroma_clamped(u[k]), chroma_clamped(v[k]), 0x6420);
-                if ((j & 1) == 0) keep_a[k] = w;
-                else sts64(strip + 512 * k + 8 * (j >> 1), make_uint2(keep_a[k], w));
-              }
-            } else {
-              /* luma: (short)floor + 128, clamp: pixels 2j, 2j+1 of row k of block A and of block B, as
-               * bytes (A2j A2j+1 B2j B2j+1); two column steps make 8 bytes of the strip's row */
-#pragma unroll
-              for (int k = 0; k < 8; k++) {
-                uint32_t ulo, uhi, vlo, vhi;
-                p_split_bits(p_add_rm(u[k], magic), ulo, uhi);
-                p_split_bits(p_add_rm(v[k], magic), vlo, vhi);
-                const uint32_t wa = clamp_pair_u8(ulo, vlo), wb = clamp_pair_u8(uhi, vhi);
-                const uint32_t w = __byte_perm(wa, wb, 0x6420);
-                if ((j & 1) == 0) keep_a[k] = w;
-                else sts64(strip + 512 * k + 8 * (j >> 1), make_uint2(keep_a[k], w));
-              }
+            for (int k = 0; k < 8; k++) {
+              uint32_t ulo, uhi, vlo, vhi;
+              p_split_bits(p_add_rm(u[k], magic), ulo, uhi);
+              p_split_bits(p_add_rm(v[k], magic), vlo, vhi);
+              uint32_t wa = __byte_perm(ulo, vlo, 0x5410), wb = __byte_perm(uhi, vhi, 0x5410);   /* (short)floor, x2 */
+              wa = __viaddmin_s16x2(wa, 0u, 0x007f007fu);
+              wb = __viaddmin_s16x2(wb, 0u, 0x007f007fu);
+              wa = __viaddmax_s16x2(wa, add2, lim2);
+              wb = __viaddmax_s16x2(wb, add2, lim2);
+              const uint32_t w = __byte_perm(wa, wb, sel);
+              if (JGPU_TK_STS32) sts32(strip + 512 * k + 4 * j, w);
+              else if ((j & 1) == 0) keep_a[k] = w;
+              else sts64(strip + 512 * k + 8 * (j >> 1), make_uint2(keep_a[k], w));
             }
           };
-          column_pass_by_pairs(m, sink);
+          if (C::kPark) {
+            const uint32_t park = geo().mine + C::kOffPark;   /* (this lane's column) */
+            auto row0 = [&](int j, pair32 &a, pair32 &b) {
+              const uint4 c = lds128(park + 512 * j);
+              a = p_make_bits(c.x, c.y);
+              b = p_make_bits(c.z, c.w);
+            };
+            column_pass_by_pairs_parked(m, row0, sink);
+          } else {
+            column_pass_by_pairs(m, sink);
+          }
         }
       }
       __syncwarp();
@@ -957,7 +985,13 @@ k_tk(const __grid_constant__ CUtensorMap tm_rows,   /* (64, rows), boxes of 16 r
     for (int i = 0; i < kTkAhead; i++) announce(g, i, gw + i * nw);
   }
   const int u = g.lane & 15;   /* this lane's unit inside its half-task */
-  auto wait_full = [&](uint32_t st) { mbar_wait_hint<JGPU_MCU_WAIT_NS>(bar_full(g, st % kTkStrips), (st / kTkStrips) & 1u); };
+  auto wait_full = [&](uint32_t st) {
+    const uint32_t bar = bar_full(g, st % kTkStrips), parity = (st / kTkStrips) & 1u;
+    for (uint32_t spins = 0; !mbar_try_wait_hint<0>(bar, parity); spins++) {
+      if (JGPU_TK_SPIN_NS) __nanosleep(JGPU_TK_SPIN_NS);
+      if (spins > (1u << 26)) __trap();
+    }
+  };
   auto hand_back = [&](uint32_t st) {   /* after __syncwarp(): every lane has read what it needs of the strip */
     if (g.lane == 0) mbar_arrive(bar_empty(g, st % kTkStrips));
   };
@@ -1048,7 +1082,7 @@ k_tk(const __grid_constant__ CUtensorMap tm_rows,   /* (64, rows), boxes of 16 r
       /* chroma rows this luma block row uses, one per VS pixel rows */
       const uint32_t crow0 = cstrip + (VS == 2 ? 4u * 512u * (uint32_t)yr : 0u);
       const uint32_t crow0_b = cstrip_b + (VS == 2 ? 4u * 512u * (uint32_t)yr : 0u);
-      if (vis_px > 0 && vis_rows > 0) {
+      if (vis_px > 0 && vis_rows > 0 && JGPU_TK_EXPERIMENT != 1) {
         if (fast && vis_rows == 8) {
           /* the whole 16 x 8 tile shows and its rows are 16-byte aligned: no per-row tests */
           if (GRAY) {
