@@ -649,14 +649,15 @@ struct TkCfg {
   static constexpr int kSteps = kChromaSteps + kLumaSteps;
   static constexpr int kChannels = GRAY ? 1 : 3;
   static constexpr int kTabBytes = WIDE ? kQtabBytes : kQtabBytes / 2;
-  static constexpr int kOffTab = 0;
-  static constexpr int kOffStrip = 2 * kTabBytes;
+  static constexpr int kOffTab = 0;                /* three resident tables: luma, Cb, Cr */
+  static constexpr int kOffStrip = 3 * kTabBytes + (WIDE ? 0 : 128);
   static constexpr bool kPark = JGPU_TK_PARK != 0;
   static constexpr int kOffPark = kOffStrip + kTkStrips * kStripBytes;
   static constexpr int kOffRing = kOffPark + (kPark ? 4 * 32 * 16 : 0);
   static constexpr int kOffBar = kOffRing + kTkRing * (int)sizeof(WarpTask);   /* data, ring[8], full[4], empty[4] */
-  static constexpr int kOffLoop = kOffBar + 8 * (1 + kTkRing + 2 * kTkStrips);  /* T's step counter */
-  static constexpr int kOffIdx = kOffLoop + 8;                                  /* task index of each ring slot */
+  static constexpr int kOffLoop = (kOffBar + 8 * (1 + kTkRing + 2 * kTkStrips) + 15) / 16 * 16;  /* T's place: step, local task, step in it */
+  static constexpr int kOffQ = kOffLoop + 16;                                   /* which table each of the three slots holds */
+  static constexpr int kOffIdx = kOffQ + 16;                                    /* task index of each ring slot */
   static constexpr int kPairMisc = (kOffIdx + 4 * kTkRing + 15) / 16 * 16;
   static constexpr int kThreads = 2 * 32 * kTkPairs;
   static constexpr int kSmemBytes = kTkPairs * (kZoneBytes + kPairMisc);
@@ -760,8 +761,10 @@ __device__ __forceinline__ void tk_store_any(uint8_t *dst, const uint32_t (&w)[1
 
 template <int HS, int VS, bool GRAY, bool WIDE, int OUT>
 __global__ void __launch_bounds__(TkCfg<HS, VS, GRAY, WIDE>::kThreads, 1)
-k_tk(const __grid_constant__ CUtensorMap tm_rows,   /* (64, rows), boxes of 16 rows            */
-     const __grid_constant__ CUtensorMap tm_pairs,  /* (64, parity, pairs), boxes of 16 pairs  */
+k_tk(const __grid_constant__ CUtensorMap tm_rows,     /* (64, rows), boxes of 16 rows            */
+     const __grid_constant__ CUtensorMap tm_pairs,    /* (64, parity, pairs), boxes of 16 pairs  */
+     const __grid_constant__ CUtensorMap tm_rows32,   /* the same views with boxes of 32: a task whose two  */
+     const __grid_constant__ CUtensorMap tm_pairs32,  /* half-tasks follow each other in the block order    */
      const WarpTask *__restrict__ tasks, int n_tasks, const uint32_t *__restrict__ qint,
      const uint32_t *__restrict__ wide_flag, uint8_t *__restrict__ rgb, int rgb_aligned,
      uint8_t *__restrict__ yuv, int *__restrict__ claim) {
@@ -835,41 +838,75 @@ k_tk(const __grid_constant__ CUtensorMap tm_rows,   /* (64, rows), boxes of 16 r
      * half-task 16 rows of box A and 16 rows of box B (a half-task that does not exist repeats the
      * other one's blocks, see mcu_plan_build), and the step's table(s). */
     auto fire = [&](const Geo &g, int n, int s) {
-      const uint32_t d = desc_addr(g, n), bar = bar_data(g), tab = g.misc + C::kOffTab;
+      const uint32_t d = desc_addr(g, n), bar = bar_data(g), tab = g.misc + C::kOffTab, held = g.misc + C::kOffQ;
       const bool chroma = s < C::kChromaSteps;
-      mbar_expect_tx(bar, 2 * kBoxBytes + (chroma ? 2 : 1) * C::kTabBytes);
-#pragma unroll
-      for (int h = 0; h < 2; h++) {
-        const uint32_t hd = d + h * (uint32_t)sizeof(McuHalf);
-        const uint32_t dst = g.zone + h * kHalfBoxBytes;
+      /* the tables stay: slot 0 luma, 1 Cb, 2 Cr; a slot is fetched again only when the task asks for
+       * another table than it holds (never, in a batch with one table set).  The slot is free: its
+       * last readers were row passes that have completed. */
+      const uint32_t c0 = chroma ? 1u : 0u;
+      const uint32_t q0 = lds32(d + offsetof(WarpTask, qidx) + 4 * c0), q1 = lds32(d + offsetof(WarpTask, qidx) + 8);
+      const bool get0 = lds32(held + 4 * c0) != q0, get1 = chroma && lds32(held + 8) != q1;
+      mbar_expect_tx(bar, 2 * kBoxBytes + ((get0 ? 1 : 0) + (get1 ? 1 : 0)) * C::kTabBytes);
+      const bool joined = (lds32(d + offsetof(WarpTask, flags)) & 2u) != 0;
+      if (joined) {
+        /* one box of 32 rows for block A, one for block B */
         if (chroma) {
-          int f0 = (int)lds32(hd + offsetof(McuHalf, cfirst));
-          int f1 = (int)lds32(hd + offsetof(McuHalf, cfirst) + 4);
+          int f0 = (int)lds32(d + offsetof(McuHalf, cfirst));
+          int f1 = (int)lds32(d + offsetof(McuHalf, cfirst) + 4);
           if (HS == 2) {
-            tma_load_2d(dst, &tm_rows, 0, f0, bar);
-            tma_load_2d(dst + kBoxBytes, &tm_rows, 0, f1, bar);
+            tma_load_2d(g.zone, &tm_rows32, 0, f0, bar);
+            tma_load_2d(g.zone + kBoxBytes, &tm_rows32, 0, f1, bar);
           } else {
             f0 += s;
             f1 += s;
-            tma_load_3d(dst, &tm_pairs, 0, f0 & 1, f0 >> 1, bar);
-            tma_load_3d(dst + kBoxBytes, &tm_pairs, 0, f1 & 1, f1 >> 1, bar);
+            tma_load_3d(g.zone, &tm_pairs32, 0, f0 & 1, f0 >> 1, bar);
+            tma_load_3d(g.zone + kBoxBytes, &tm_pairs32, 0, f1 & 1, f1 >> 1, bar);
           }
         } else {
-          const int first = (int)lds32(hd + offsetof(McuHalf, yfirst) + 4 * (s - C::kChromaSteps));
-          tma_load_3d(dst, &tm_pairs, 0, first & 1, first >> 1, bar);
-          tma_load_3d(dst + kBoxBytes, &tm_pairs, 0, (first + 1) & 1, (first + 1) >> 1, bar);
+          const int first = (int)lds32(d + offsetof(McuHalf, yfirst) + 4 * (s - C::kChromaSteps));
+          tma_load_3d(g.zone, &tm_pairs32, 0, first & 1, first >> 1, bar);
+          tma_load_3d(g.zone + kBoxBytes, &tm_pairs32, 0, (first + 1) & 1, (first + 1) >> 1, bar);
+        }
+      } else {
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          const uint32_t hd = d + h * (uint32_t)sizeof(McuHalf);
+          const uint32_t dst = g.zone + h * kHalfBoxBytes;
+          if (chroma) {
+            int f0 = (int)lds32(hd + offsetof(McuHalf, cfirst));
+            int f1 = (int)lds32(hd + offsetof(McuHalf, cfirst) + 4);
+            if (HS == 2) {
+              tma_load_2d(dst, &tm_rows, 0, f0, bar);
+              tma_load_2d(dst + kBoxBytes, &tm_rows, 0, f1, bar);
+            } else {
+              f0 += s;
+              f1 += s;
+              tma_load_3d(dst, &tm_pairs, 0, f0 & 1, f0 >> 1, bar);
+              tma_load_3d(dst + kBoxBytes, &tm_pairs, 0, f1 & 1, f1 >> 1, bar);
+            }
+          } else {
+            const int first = (int)lds32(hd + offsetof(McuHalf, yfirst) + 4 * (s - C::kChromaSteps));
+            tma_load_3d(dst, &tm_pairs, 0, first & 1, first >> 1, bar);
+            tma_load_3d(dst + kBoxBytes, &tm_pairs, 0, (first + 1) & 1, (first + 1) >> 1, bar);
+          }
         }
       }
-      if (chroma) {
-        bulk_load(tab, qint + (size_t)lds32(d + offsetof(WarpTask, qidx) + 4) * 64, C::kTabBytes, bar);
-        bulk_load(tab + C::kTabBytes, qint + (size_t)lds32(d + offsetof(WarpTask, qidx) + 8) * 64, C::kTabBytes, bar);
-      } else {
-        bulk_load(tab, qint + (size_t)lds32(d + offsetof(WarpTask, qidx)) * 64, C::kTabBytes, bar);
+      if (get0) {
+        bulk_load(tab + c0 * C::kTabBytes, qint + (size_t)q0 * 64, C::kTabBytes, bar);
+        sts32(held + 4 * c0, q0);
+      }
+      if (get1) {
+        bulk_load(tab + 2 * C::kTabBytes, qint + (size_t)q1 * 64, C::kTabBytes, bar);
+        sts32(held + 8, q1);
       }
     };
     {
       const Geo g = geo();
-      sts32(g.misc + C::kOffLoop, 0u);   /* every lane, same value */
+      /* the pair's place in its work, kept in shared memory, not in registers: (steps so far, local task,
+       * step inside it); every lane writes the same values */
+      sts128(g.misc + C::kOffLoop, make_uint4(0u, 0u, 0u, 0u));
+      sts128(g.misc + C::kOffQ, make_uint4(~0u, ~0u, ~0u, ~0u));
+      __syncwarp();
       if (g.lane == 0) {
         wait_desc(g, 0);   /* (gw < n_tasks: it exists) */
         fire(g, 0, 0);
@@ -881,12 +918,12 @@ k_tk(const __grid_constant__ CUtensorMap tm_rows,   /* (64, rows), boxes of 16 r
       bool is_c, active;   /* a chroma step?  does this lane's unit exist / show in this step? */
       {
         const Geo g = geo();
-        const int step = (int)lds32(g.misc + C::kOffLoop);
-        const int n = step / C::kSteps, s = step - n * C::kSteps;
-        wait_desc(g, n);
-        if ((int)lds32(idx_addr(g, n)) >= n_tasks) break;
-        __syncwarp();
-        sts32(g.misc + C::kOffLoop, (uint32_t)step + 1u);
+        const uint4 at = lds128(g.misc + C::kOffLoop);
+        const int step = (int)at.x, n = (int)at.y, s = (int)at.z;
+        if (s == 0) {
+          wait_desc(g, n);
+          if ((int)lds32(idx_addr(g, n)) >= n_tasks) break;
+        }
         is_c = s < C::kChromaSteps;
         const uint32_t ha = half_addr(g, n);
         const int u = g.lane & 15;
@@ -903,8 +940,8 @@ k_tk(const __grid_constant__ CUtensorMap tm_rows,   /* (64, rows), boxes of 16 r
         if (JGPU_TK_EXPERIMENT == 2) active = false;
         if (active) {
           const Geo g = geo();
-          const uint32_t qa = g.misc + C::kOffTab;
-          const uint32_t qb = is_c ? qa + C::kTabBytes : qa;   /* chroma: Cb table, then Cr table */
+          const uint32_t qa = g.misc + C::kOffTab + (is_c ? C::kTabBytes : 0);   /* luma / Cb */
+          const uint32_t qb = is_c ? qa + C::kTabBytes : qa;                       /* luma / Cr */
           mcu_row_pass<WIDE, C::kPark>(m, g.zone, g.lane, qa, qb, g.mine + C::kOffPark);
         }
         /* the boxes are in registers: start the loads of the pair's next step */
@@ -912,18 +949,18 @@ k_tk(const __grid_constant__ CUtensorMap tm_rows,   /* (64, rows), boxes of 16 r
         uint32_t strip;
         {
           const Geo g = geo();
-          const int next = (int)lds32(g.misc + C::kOffLoop);   /* this step + 1 */
+          const uint4 at = lds128(g.misc + C::kOffLoop);
           if (g.lane == 0) {
-            const int n = next / C::kSteps, s = next - n * C::kSteps;
-            if (s != 0) {
-              fire(g, n, s);
+            if ((int)at.z + 1 < C::kSteps) {
+              fire(g, (int)at.y, (int)at.z + 1);
             } else {
+              const int n = (int)at.y + 1;
               wait_desc(g, n);
               if ((int)lds32(idx_addr(g, n)) < n_tasks) fire(g, n, 0);
             }
           }
           /* this step's strip: free once the K warp has handed back its previous contents */
-          const uint32_t cur = (uint32_t)next - 1u, slot = cur % kTkStrips;
+          const uint32_t cur = at.x, slot = cur % kTkStrips;
           mbar_wait_hint<JGPU_MCU_WAIT_NS>(bar_empty(g, slot), ((cur / kTkStrips) & 1u) ^ 1u);
           strip = strip_addr(g, slot);
         }
@@ -971,7 +1008,11 @@ k_tk(const __grid_constant__ CUtensorMap tm_rows,   /* (64, rows), boxes of 16 r
       __syncwarp();
       {
         const Geo g = geo();
-        if (g.lane == 0) mbar_arrive(bar_full(g, ((uint32_t)lds32(g.misc + C::kOffLoop) - 1u) % kTkStrips));
+        const uint4 at = lds128(g.misc + C::kOffLoop);
+        if (g.lane == 0) mbar_arrive(bar_full(g, at.x % kTkStrips));
+        __syncwarp();
+        const bool last = (int)at.z + 1 == C::kSteps;
+        sts128(g.misc + C::kOffLoop, make_uint4(at.x + 1u, last ? at.y + 1u : at.y, last ? 0u : at.z + 1u, 0u));
       }
     }
     return;
@@ -1208,17 +1249,17 @@ cudaError_t mcu_configure_mode(int mode) {
 
 template <int HS, int VS, bool GRAY>
 cudaError_t mcu_launch_mode(bool planes, int sm_count, const McuMode &mi, cudaStream_t stream, const CUtensorMap &tm_rows,
-                            const CUtensorMap &tm_pairs, const WarpTask *tasks, int n_tasks, const uint32_t *qint,
+                            const CUtensorMap &tm_pairs, const CUtensorMap &tm_rows32, const CUtensorMap &tm_pairs32, const WarpTask *tasks, int n_tasks, const uint32_t *qint,
                             const uint32_t *wide_flag, uint8_t *rgb, int rgb_aligned, uint8_t *yuv, int *claim) {
   if (mcu_use_tk()) {
     const int grid = std::min((n_tasks + kTkPairs - 1) / kTkPairs, sm_count);
     const int threads = 2 * 32 * kTkPairs;
     if (planes) {
-      k_tk<HS, VS, GRAY, false, kOutYuv><<<grid, threads, mi.tk_smem, stream>>>(tm_rows, tm_pairs, tasks, n_tasks, qint, wide_flag, rgb, rgb_aligned, yuv, claim);
-      k_tk<HS, VS, GRAY, true, kOutYuv><<<grid, threads, mi.tk_smem_wide, stream>>>(tm_rows, tm_pairs, tasks, n_tasks, qint, wide_flag, rgb, rgb_aligned, yuv, claim);
+      k_tk<HS, VS, GRAY, false, kOutYuv><<<grid, threads, mi.tk_smem, stream>>>(tm_rows, tm_pairs, tm_rows32, tm_pairs32, tasks, n_tasks, qint, wide_flag, rgb, rgb_aligned, yuv, claim);
+      k_tk<HS, VS, GRAY, true, kOutYuv><<<grid, threads, mi.tk_smem_wide, stream>>>(tm_rows, tm_pairs, tm_rows32, tm_pairs32, tasks, n_tasks, qint, wide_flag, rgb, rgb_aligned, yuv, claim);
     } else {
-      k_tk<HS, VS, GRAY, false, kOutRgb><<<grid, threads, mi.tk_smem, stream>>>(tm_rows, tm_pairs, tasks, n_tasks, qint, wide_flag, rgb, rgb_aligned, yuv, claim);
-      k_tk<HS, VS, GRAY, true, kOutRgb><<<grid, threads, mi.tk_smem_wide, stream>>>(tm_rows, tm_pairs, tasks, n_tasks, qint, wide_flag, rgb, rgb_aligned, yuv, claim);
+      k_tk<HS, VS, GRAY, false, kOutRgb><<<grid, threads, mi.tk_smem, stream>>>(tm_rows, tm_pairs, tm_rows32, tm_pairs32, tasks, n_tasks, qint, wide_flag, rgb, rgb_aligned, yuv, claim);
+      k_tk<HS, VS, GRAY, true, kOutRgb><<<grid, threads, mi.tk_smem_wide, stream>>>(tm_rows, tm_pairs, tm_rows32, tm_pairs32, tasks, n_tasks, qint, wide_flag, rgb, rgb_aligned, yuv, claim);
     }
     return cudaGetLastError();
   }
@@ -1270,7 +1311,8 @@ struct McuPlanImpl {
   unsigned claim_next = 0;
   long long coef_rows = 0; /* 128-byte rows the batch touches */
   const void *map_ptr = nullptr;
-  CUtensorMap tm_rows, tm_pairs;
+  CUtensorMap tm_rows, tm_pairs;       /* boxes of 16 rows / pairs */
+  CUtensorMap tm_rows32, tm_pairs32;   /* boxes of 32 */
   cudaStream_t side[kNumFusedModes] = {};
   cudaEvent_t fork = nullptr, join[kNumFusedModes] = {};
 };
@@ -1353,6 +1395,15 @@ int mcu_plan_build(FusedPlan &fp, const jgpu_image_desc *descs, const jgpu_layou
         /* every half-task starts at a multiple of 256 pixels of a row: aligned iff the image is */
         t.flags = ((d.rgb_off & 15) == 0 && (t.pitch0 & 15) == 0) ? 1 : 0;
       }
+      /* bit 1: the second half-task follows the first in the block order of every plane (the next 16
+       * units of the same MCU row): k_tk fetches one box of 32 rows instead of two of 16 */
+      if (k + 1 < halves.size()) {
+        const McuHalf &a = t.half[0], &b = t.half[1];
+        bool joined = true;
+        for (int v = 0; v < lrows; v++) joined = joined && b.yfirst[v] == a.yfirst[v] + 32;
+        if (!mi.gray) joined = joined && b.cfirst[0] == a.cfirst[0] + cper && b.cfirst[1] == a.cfirst[1] + cper;
+        if (joined) t.flags |= 2;
+      }
       for (int c = 0; c < d.ncomps; c++) t.qidx[c] = d.qtab_set * 4 + d.tq[c];
       tasks[modes[i]].push_back(t);
     }
@@ -1399,25 +1450,28 @@ static int mcu_build_maps(McuPlanImpl *p, const int16_t *coef) {
   }
   EncodeTiledFn enc = mcu_encode_fn();
   const cuuint64_t rows = (cuuint64_t)((p->coef_rows + 1) & ~1ll);
-  {
-    cuuint64_t dims[2] = {64, rows};
-    cuuint64_t strides[1] = {128};
-    cuuint32_t box[2] = {64, kHalfRows};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(&p->tm_rows, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<int16_t *>(coef), dims,
-                     strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return jgpu_fail("cuTensorMapEncodeTiled(rows) failed (%d)", (int)r);
-  }
-  {
-    cuuint64_t dims[3] = {64, 2, rows / 2};
-    cuuint64_t strides[2] = {128, 256};
-    cuuint32_t box[3] = {64, 1, kHalfRows};
-    cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = enc(&p->tm_pairs, CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, const_cast<int16_t *>(coef), dims,
-                     strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return jgpu_fail("cuTensorMapEncodeTiled(pairs) failed (%d)", (int)r);
+  for (int big = 0; big < 2; big++) {
+    const cuuint32_t box_rows = big ? 2 * kHalfRows : kHalfRows;
+    {
+      cuuint64_t dims[2] = {64, rows};
+      cuuint64_t strides[1] = {128};
+      cuuint32_t box[2] = {64, box_rows};
+      cuuint32_t estr[2] = {1, 1};
+      CUresult r = enc(big ? &p->tm_rows32 : &p->tm_rows, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<int16_t *>(coef), dims,
+                       strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return jgpu_fail("cuTensorMapEncodeTiled(rows) failed (%d)", (int)r);
+    }
+    {
+      cuuint64_t dims[3] = {64, 2, rows / 2};
+      cuuint64_t strides[2] = {128, 256};
+      cuuint32_t box[3] = {64, 1, box_rows};
+      cuuint32_t estr[3] = {1, 1, 1};
+      CUresult r = enc(big ? &p->tm_pairs32 : &p->tm_pairs, CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, const_cast<int16_t *>(coef), dims,
+                       strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return jgpu_fail("cuTensorMapEncodeTiled(pairs) failed (%d)", (int)r);
+    }
   }
   p->map_ptr = coef;
   return 0;
@@ -1476,11 +1530,11 @@ int mcu_plan_launch(FusedPlan &fp, int i0, int i1, const int16_t *coef, const ui
     const WarpTask *tasks = static_cast<const WarpTask *>(p->d_tasks[m]) + t0;
     const uint32_t *qint = static_cast<const uint32_t *>(p->d_qint);
     switch (m) {
-      case kModeGray: e = mcu_launch_mode<1, 1, true>(p->planes, grid, mi, stream, p->tm_rows, p->tm_pairs, tasks, t1 - t0, qint, wide_flag, rgb, rgb_aligned, yuv, claim); break;
-      case kMode444: e = mcu_launch_mode<1, 1, false>(p->planes, grid, mi, stream, p->tm_rows, p->tm_pairs, tasks, t1 - t0, qint, wide_flag, rgb, rgb_aligned, yuv, claim); break;
-      case kMode422: e = mcu_launch_mode<2, 1, false>(p->planes, grid, mi, stream, p->tm_rows, p->tm_pairs, tasks, t1 - t0, qint, wide_flag, rgb, rgb_aligned, yuv, claim); break;
-      case kMode420: e = mcu_launch_mode<2, 2, false>(p->planes, grid, mi, stream, p->tm_rows, p->tm_pairs, tasks, t1 - t0, qint, wide_flag, rgb, rgb_aligned, yuv, claim); break;
-      case kMode440: e = mcu_launch_mode<1, 2, false>(p->planes, grid, mi, stream, p->tm_rows, p->tm_pairs, tasks, t1 - t0, qint, wide_flag, rgb, rgb_aligned, yuv, claim); break;
+      case kModeGray: e = mcu_launch_mode<1, 1, true>(p->planes, grid, mi, stream, p->tm_rows, p->tm_pairs, p->tm_rows32, p->tm_pairs32, tasks, t1 - t0, qint, wide_flag, rgb, rgb_aligned, yuv, claim); break;
+      case kMode444: e = mcu_launch_mode<1, 1, false>(p->planes, grid, mi, stream, p->tm_rows, p->tm_pairs, p->tm_rows32, p->tm_pairs32, tasks, t1 - t0, qint, wide_flag, rgb, rgb_aligned, yuv, claim); break;
+      case kMode422: e = mcu_launch_mode<2, 1, false>(p->planes, grid, mi, stream, p->tm_rows, p->tm_pairs, p->tm_rows32, p->tm_pairs32, tasks, t1 - t0, qint, wide_flag, rgb, rgb_aligned, yuv, claim); break;
+      case kMode420: e = mcu_launch_mode<2, 2, false>(p->planes, grid, mi, stream, p->tm_rows, p->tm_pairs, p->tm_rows32, p->tm_pairs32, tasks, t1 - t0, qint, wide_flag, rgb, rgb_aligned, yuv, claim); break;
+      case kMode440: e = mcu_launch_mode<1, 2, false>(p->planes, grid, mi, stream, p->tm_rows, p->tm_pairs, p->tm_rows32, p->tm_pairs32, tasks, t1 - t0, qint, wide_flag, rgb, rgb_aligned, yuv, claim); break;
     }
     if (e != cudaSuccess) return jgpu_fail("fused kernel launch failed (%s)", cudaGetErrorString(e));
     if (stream != caller) {
