@@ -619,8 +619,11 @@ constexpr int kTkStrips = 4;
 constexpr int kTkRing = 8;          /* task descriptors per pair */
 constexpr int kTkAhead = 4;         /* K fetches the descriptor of task n + 4 while it works on task n */
 constexpr int kStripBytes = 8 * 32 * 16;
+/* Registers per thread after setmaxnreg (8 pairs x 32 x (T + K) <= 65536).  Measured (profiles/r2_notes.md):
+ * 192/64 leaves the K warps spilling loop state, 184/72 is 3 % faster for 4:2:0 (2.48 -> 2.41 ms); the 1x luma
+ * modes, whose colour stage reads two chroma strips, do best at 176/80.  JGPU_TK_REGS_T / _K override both. */
 #ifndef JGPU_TK_REGS_T
-#define JGPU_TK_REGS_T 192
+#define JGPU_TK_REGS_T 0
 #endif
 #ifndef JGPU_TK_EXPERIMENT
 #define JGPU_TK_EXPERIMENT 0  /* timing experiments only (wrong output): 1: K warps skip their work, 2: T warps skip theirs */
@@ -638,9 +641,8 @@ constexpr int kStripBytes = 8 * 32 * 16;
 #define JGPU_TK_SPIN_NS 0     /* K warps: nanosleep between two looks at a strip that is not full yet (0: none) */
 #endif
 #ifndef JGPU_TK_REGS_K
-#define JGPU_TK_REGS_K 64
+#define JGPU_TK_REGS_K 0
 #endif
-static_assert(kTkPairs * 32 * (JGPU_TK_REGS_T + JGPU_TK_REGS_K) <= 65536, "register file");
 
 template <int HS, int VS, bool GRAY, bool WIDE>
 struct TkCfg {
@@ -648,6 +650,9 @@ struct TkCfg {
   static constexpr int kLumaSteps = GRAY ? 1 : VS;
   static constexpr int kSteps = kChromaSteps + kLumaSteps;
   static constexpr int kChannels = GRAY ? 1 : 3;
+  static constexpr int kRegsT = JGPU_TK_REGS_T ? JGPU_TK_REGS_T : ((!GRAY && HS == 1) ? 176 : 184);
+  static constexpr int kRegsK = JGPU_TK_REGS_K ? JGPU_TK_REGS_K : ((!GRAY && HS == 1) ? 80 : 72);
+  static_assert(kTkPairs * 32 * (kRegsT + kRegsK) <= 65536, "register file");
   static constexpr int kTabBytes = WIDE ? kQtabBytes : kQtabBytes / 2;
   static constexpr int kOffTab = 0;                /* three resident tables: luma, Cb, Cr */
   static constexpr int kOffStrip = 3 * kTabBytes + (WIDE ? 0 : 128);
@@ -832,7 +837,7 @@ k_tk(const __grid_constant__ CUtensorMap tm_rows,     /* (64, rows), boxes of 16
 
   if (is_t) {
     /* ================================ T: coefficients -> strips ================================ */
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(JGPU_TK_REGS_T));
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(C::kRegsT));
     if (gw >= n_tasks) return;
     /* Start the loads of step s of local task n (lane 0 only; its descriptor must have landed): per
      * half-task 16 rows of box A and 16 rows of box B (a half-task that does not exist repeats the
@@ -1019,7 +1024,7 @@ k_tk(const __grid_constant__ CUtensorMap tm_rows,     /* (64, rows), boxes of 16
   }
 
   /* ================================ K: strips -> pixels / planes ================================ */
-  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(JGPU_TK_REGS_K));
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(C::kRegsK));
   if (gw >= n_tasks) return;
   const Geo g = geo();
   if (g.lane == 0) {
