@@ -625,6 +625,10 @@ constexpr int kStripBytes = 8 * 32 * 16;
 #ifndef JGPU_TK_REGS_T
 #define JGPU_TK_REGS_T 0
 #endif
+#ifndef JGPU_TK_ARRIVE_ALL
+#define JGPU_TK_ARRIVE_ALL 1  /* 1: every lane arrives at a strip's full / empty barrier itself (count 32): each writer is ordered
+                                 before each reader directly; 0: __syncwarp(), then lane 0 arrives for the warp (count 1) */
+#endif
 #ifndef JGPU_TK_EXPERIMENT
 #define JGPU_TK_EXPERIMENT 0  /* timing experiments only (wrong output): 1: K warps skip their work, 2: T warps skip theirs */
 #endif
@@ -827,7 +831,7 @@ k_tk(const __grid_constant__ CUtensorMap tm_rows,     /* (64, rows), boxes of 16
   {
     const Geo g = geo();
     if (is_t && g.lane == 0) {
-      for (int i = 0; i < 1 + kTkRing + 2 * kTkStrips; i++) mbar_init(bar_data(g) + 8 * i, 1);
+      for (int i = 0; i < 1 + kTkRing + 2 * kTkStrips; i++) mbar_init(bar_data(g) + 8 * i, (JGPU_TK_ARRIVE_ALL && i >= 1 + kTkRing) ? 32 : 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
   }
@@ -923,6 +927,7 @@ k_tk(const __grid_constant__ CUtensorMap tm_rows,     /* (64, rows), boxes of 16
       bool is_c, active;   /* a chroma step?  does this lane's unit exist / show in this step? */
       {
         const Geo g = geo();
+        __syncwarp();   /* (the record below was written by every lane, with the same values) */
         const uint4 at = lds128(g.misc + C::kOffLoop);
         const int step = (int)at.x, n = (int)at.y, s = (int)at.z;
         if (s == 0) {
@@ -1014,7 +1019,7 @@ k_tk(const __grid_constant__ CUtensorMap tm_rows,     /* (64, rows), boxes of 16
       {
         const Geo g = geo();
         const uint4 at = lds128(g.misc + C::kOffLoop);
-        if (g.lane == 0) mbar_arrive(bar_full(g, at.x % kTkStrips));
+        if (JGPU_TK_ARRIVE_ALL || g.lane == 0) mbar_arrive(bar_full(g, at.x % kTkStrips));
         __syncwarp();
         const bool last = (int)at.z + 1 == C::kSteps;
         sts128(g.misc + C::kOffLoop, make_uint4(at.x + 1u, last ? at.y + 1u : at.y, last ? 0u : at.z + 1u, 0u));
@@ -1039,7 +1044,7 @@ k_tk(const __grid_constant__ CUtensorMap tm_rows,     /* (64, rows), boxes of 16
     }
   };
   auto hand_back = [&](uint32_t st) {   /* after __syncwarp(): every lane has read what it needs of the strip */
-    if (g.lane == 0) mbar_arrive(bar_empty(g, st % kTkStrips));
+    if (JGPU_TK_ARRIVE_ALL || g.lane == 0) mbar_arrive(bar_empty(g, st % kTkStrips));
   };
   uint32_t step = 0;
 #pragma unroll 1

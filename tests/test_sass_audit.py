@@ -40,8 +40,12 @@ def test_only_sm100a_code(sass):
 
 
 def test_idct_has_no_contracted_multiply_add(sass):
-    kernels = {n: body for n, body in sass.items() if "k_fused" in n or "k_coef_to_planes" in n}
-    assert len(kernels) >= 11      # generic + 5 fused modes x {8-bit, 16-bit tables}
+    kernels = {n: body for n, body in sass.items()
+               if "k_fused" in n or "k_coef_to_planes" in n or "k_mcu" in n or "k_tk" in n}
+    # generic + 5 modes x {8-bit, 16-bit tables} of k_fused, + 5 modes x 2 x {pixels, planes} of k_mcu and of
+    # k_tk (the product path)
+    assert len(kernels) >= 11 + 20 + 20
+    assert sum("k_tk" in n for n in kernels) == 20
     for name, body in kernels.items():
         text = "\n".join(body)
         assert "FMUL2" not in text, name
@@ -71,8 +75,20 @@ def test_colour_stage_has_no_fma(sass):
             assert not any(re.search(r"\bFFMA\b", l) for l in body), name
 
 
+def test_product_kernel_splits_registers_between_its_warp_roles(sass):
+    """k_tk: transform warps raise their register allowance, colour warps give theirs back."""
+    tk = {n: "\n".join(body) for n, body in sass.items() if "k_tk" in n}
+    assert tk
+    for name, text in tk.items():
+        assert "USETMAXREG.TRY_ALLOC" in text and "USETMAXREG.DEALLOC" in text, name
+        t_part = text.split("USETMAXREG.DEALLOC")[0]
+        # the transform keeps its 64 sample pairs in registers: no spills to speak of (4:4:0 at 176 registers: 6)
+        assert len(re.findall(r"\b(STL|LDL)\b", t_part.split("USETMAXREG.TRY_ALLOC")[1])) <= 8, name
+
+
 def test_fused_kernel_uses_tma_and_mbarriers(sass):
-    fused = [body for n, body in sass.items() if "k_fused" in n]
+    fused = [body for n, body in sass.items() if "k_fused" in n or "k_mcu" in n or "k_tk" in n]
+    assert len(fused) >= 50
     for body in fused:
         text = "\n".join(body)
         assert "UTMALDG" in text          # cp.async.bulk.tensor

@@ -1,4 +1,4 @@
 mkdir -p gpurun_out/r2
-timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-TAG=22 VARIANTS="default" WLS="4k420_b256 4k422_b128 4kgray_b256 4k444_b64 4k440_b128 mixed_stress 1080p420_b512" bash tools/ab.sh
-python bench.py > gpurun_out/r2/bench_22_full.json 2> gpurun_out/r2/bench_22_full.err; tail -c 3000 gpurun_out/r2/bench_22_full.json
+timeout 900 compute-sanitizer --tool racecheck python -m pytest tests/test_gpu_parity.py -q -x -k "test_parity_by_subsampling or test_planes_out or test_parity_mixed_batch or test_sixteen_bit_quant" > gpurun_out/r2/sanitize_tk_racecheck2.log 2>&1
+tail -3 gpurun_out/r2/sanitize_tk_racecheck2.log
+TAG=23 VARIANTS="default arr1" WLS="4k420_b256 4k444_b64 4kgray_b256" bash tools/ab.sh
