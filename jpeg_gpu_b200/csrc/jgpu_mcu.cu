@@ -104,6 +104,13 @@ static_assert(sizeof(McuHalf) == 48 && sizeof(WarpTask) == 128, "WarpTask is cop
 #ifndef JGPU_MCU_WARPS
 #define JGPU_MCU_WARPS 12
 #endif
+/* A/B knob (profiles/r2_notes.md section 6): 1 = skip the dequantisation and the row pass of a coefficient row that
+ * is all zero in every block the warp holds (SURVEY 7 lever ii).  Exact: the pass maps zeros to zeros, and the sign of
+ * a zero never reaches the floored samples.  Off: it has to be warp-uniform to save anything, and the test costs 9
+ * instructions per row. */
+#ifndef JGPU_SKIP_ZERO_ROWS
+#define JGPU_SKIP_ZERO_ROWS 0
+#endif
 #ifndef JGPU_MCU_STAGE_BYTES
 #define JGPU_MCU_STAGE_BYTES (JGPU_MCU_WARPS >= 12)
 #endif
@@ -168,6 +175,14 @@ __device__ __forceinline__ void mcu_row_pass(pair32 (&m)[8][8], uint32_t zone, i
     const uint4 a = lds128(ra + off);
     const uint4 b = lds128(rb + off);
     const uint4 z = make_uint4(0, 0, 0, 0);
+    if (JGPU_SKIP_ZERO_ROWS && r > 0) {
+      const uint32_t any = a.x | a.y | a.z | a.w | b.x | b.y | b.z | b.w;
+      if (!__any_sync(__activemask(), any != 0u)) {
+#pragma unroll
+        for (int c = 0; c < 8; c++) m[r][c] = p_make_bits(0u, 0u);
+        continue;
+      }
+    }
     load_row_pair_packed<WIDE>(m[r], a, b, lds128(tab + 16 * r), lds128(tab_b + 16 * r),
                                WIDE ? lds128(tab + kHi + 16 * r) : z, WIDE ? lds128(tab_b + kHi + 16 * r) : z, r);
     inv_pass8(m[r]);
