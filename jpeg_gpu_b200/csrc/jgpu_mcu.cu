@@ -758,8 +758,9 @@ __device__ __forceinline__ void tk_row_words(const uint32_t (&ya)[4], const uint
   rgb4(yb[2], yb[3], cb[6], cb[7], cb[8], cb[9], cb[10], cb[11], w[9], w[10], w[11]);
 }
 /* The first nbytes (<= 48) of w[0..11] to dst, whatever its alignment: byte stores up to the first
- * 4-byte boundary, funnel-shifted 32-bit stores from there, byte stores for what is left. */
-__device__ __forceinline__ void tk_store_any(uint8_t *dst, const uint32_t (&w)[12], int nbytes) {
+ * 4-byte boundary, funnel-shifted 32-bit stores from there, byte stores for what is left.  (The form the
+ * K warps' main loop carries inline for its cropped tiles: anything cleverer costs that loop registers.) */
+__device__ __forceinline__ void tk_store_any_short(uint8_t *dst, const uint32_t (&w)[12], int nbytes) {
   const int head = (int)((4u - (uint32_t)(uintptr_t)dst) & 3u);   /* bytes before the boundary */
 #pragma unroll
   for (int i = 0; i < 3; i++) {
@@ -783,7 +784,120 @@ __device__ __forceinline__ void tk_store_any(uint8_t *dst, const uint32_t (&w)[1
   }
 }
 
-template <int HS, int VS, bool GRAY, bool WIDE, int OUT>
+/* The first nbytes (< 48: a unit cropped by the image's right edge) of w[0..11] to dst, whatever its
+ * alignment: byte stores up to the first 4-byte boundary, funnel-shifted 32-bit stores from there, byte
+ * stores for what is left of the last word. */
+__device__ __forceinline__ void tk_store_any(uint8_t *dst, const uint32_t (&w)[12], int nbytes) {
+  const int head = (int)((4u - (uint32_t)(uintptr_t)dst) & 3u);   /* bytes before the boundary */
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    if (i < head && i < nbytes) dst[i] = (uint8_t)(w[0] >> (8 * i));
+  }
+  uint8_t *p = dst + head;
+  const int left = nbytes - head;
+  const uint32_t sh = 8u * (uint32_t)head;
+  uint32_t last = 0u;   /* the word the row ends in */
+#pragma unroll
+  for (int i = 0; i < 12; i++) {
+    /* the four bytes that follow byte head + 4 i of the row */
+    const uint32_t v = __funnelshift_r(w[i], i + 1 < 12 ? w[i + 1] : 0u, sh);
+    if (4 * i + 4 <= left) *reinterpret_cast<uint32_t *>(p + 4 * i) = v;
+    if (i == (left >> 2)) last = v;
+  }
+  if (left > 0) {
+    uint8_t *t = p + (left & ~3);
+#pragma unroll
+    for (int b = 0; b < 3; b++) {
+      if (b < (left & 3)) t[b] = (uint8_t)(last >> (8 * b));
+    }
+  }
+}
+
+__device__ __forceinline__ void stg32_stream(uint8_t *p, uint32_t v) {
+  asm volatile("st.global.cs.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+/* All 48 bytes of w[0..11] to dst, whatever its alignment, with the widest stores the address allows: bytes
+ * up to the first 4-byte boundary (hb of them), single words up to the first 16-byte boundary (nh of them),
+ * two aligned 128-bit stores, then the words and bytes that are left.  x[i] = the four bytes that follow
+ * byte hb + 4 i of the row; which of them start the 128-bit stores depends on nh, hence the switch (all
+ * lanes of a half-task share hb and nh: a lane's 48 bytes keep the alignment of the run's first byte). */
+__device__ __forceinline__ void tk_store48(uint8_t *dst, const uint32_t (&w)[12]) {
+  const uint32_t a = (uint32_t)(uintptr_t)dst & 15u;
+  if (a == 0u) {
+    stg128_stream(dst, make_uint4(w[0], w[1], w[2], w[3]));
+    stg128_stream(dst + 16, make_uint4(w[4], w[5], w[6], w[7]));
+    stg128_stream(dst + 32, make_uint4(w[8], w[9], w[10], w[11]));
+    return;
+  }
+  const uint32_t hb = (4u - a) & 3u;
+  if (hb & 1u) dst[0] = (uint8_t)w[0];
+  if (hb & 2u) *reinterpret_cast<uint16_t *>(dst + (hb & 1u)) = (uint16_t)(w[0] >> (8u * (hb & 1u)));
+  uint8_t *p = dst + hb;                                             /* 4-byte aligned */
+  const uint32_t nh = ((16u - ((uint32_t)(uintptr_t)p & 15u)) & 15u) >> 2;   /* 0..3 */
+  uint32_t x[12];
+#pragma unroll
+  for (int i = 0; i < 12; i++) x[i] = __funnelshift_r(w[i], i + 1 < 12 ? w[i + 1] : 0u, 8u * hb);
+  /* full words in x: 12 (hb == 0) or 11, then 4 - hb bytes in x[11] */
+  const bool whole = hb == 0u;
+#define JGPU_TK_STORE48_CASE(NH)                                                                        \
+  {                                                                                                      \
+    _Pragma("unroll") for (int i = 0; i < NH; i++) stg32_stream(p + 4 * i, x[i]);                        \
+    stg128_stream(p + 4 * NH, make_uint4(x[NH], x[NH + 1], x[NH + 2], x[NH + 3]));                       \
+    stg128_stream(p + 4 * NH + 16, make_uint4(x[NH + 4], x[NH + 5], x[NH + 6], x[NH + 7]));              \
+    _Pragma("unroll") for (int i = NH + 8; i < 11; i++) stg32_stream(p + 4 * i, x[i]);                   \
+    if (NH + 8 <= 11 && whole) stg32_stream(p + 44, x[11]);                                              \
+  }
+  switch (nh) {
+    case 0: JGPU_TK_STORE48_CASE(0) break;
+    case 1: JGPU_TK_STORE48_CASE(1) break;
+    case 2: JGPU_TK_STORE48_CASE(2) break;
+    default: JGPU_TK_STORE48_CASE(3) break;
+  }
+#undef JGPU_TK_STORE48_CASE
+  if (!whole) {
+    /* 4 - hb bytes of x[11] at p + 44 */
+    const uint32_t tb = 4u - hb;
+    if (tb & 2u) *reinterpret_cast<uint16_t *>(p + 44) = (uint16_t)x[11];
+    if (tb & 1u) p[44 + (tb & 2u)] = (uint8_t)(x[11] >> (8u * (tb & 2u)));
+  }
+}
+
+/* The colour / store stage of a tile that is cropped by the image's right or bottom edge, or whose rows are not
+ * 16-byte aligned (any width that is not a multiple of 16 pixels): the same arithmetic, stores of whatever
+ * alignment each row has.  Only the EDGE instantiations of k_tk carry it (plans with such rows): in the others its
+ * registers would weigh on the K warps' main loop. */
+template <int HS, int VS, bool GRAY>
+__device__ __forceinline__ void tk_edge_rows(uint32_t lstrip, uint32_t crow0, uint32_t crow0_b, uint8_t *dst, int pitch,
+                                                 int vis_rows, int nbytes) {
+  if (GRAY) {
+#pragma unroll 1
+    for (int k = 0; k < vis_rows; k++, dst += pitch) {
+      const uint4 v = tk_staged_row_bytes(lstrip + 512 * k);
+      if (nbytes == 16 && ((uintptr_t)dst & 15) == 0) {
+        stg128_stream(dst, v);
+      } else {
+        const uint32_t w[12] = {v.x, v.y, v.z, v.w, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+        tk_store_any(dst, w, nbytes);
+      }
+    }
+  } else {
+#pragma unroll 1
+    for (int cr = 0; cr * VS < vis_rows; cr++) {
+      uint32_t ca[12], cb[12];
+      tk_row_offsets<HS>(crow0 + 512u * (uint32_t)cr, crow0_b + 512u * (uint32_t)cr, ca, cb);
+#pragma unroll 1
+      for (int k = cr * VS; k < cr * VS + VS && k < vis_rows; k++, dst += pitch) {
+        uint32_t ya[4], yb[4], w[12];
+        tk_staged_row(lstrip + 512u * (uint32_t)k, ya, yb);
+        tk_row_words(ya, yb, ca, cb, w);
+        if (nbytes == 48) tk_store48(dst, w);
+        else tk_store_any(dst, w, nbytes);
+      }
+    }
+  }
+}
+
+template <int HS, int VS, bool GRAY, bool WIDE, int OUT, bool EDGE>
 __global__ void __launch_bounds__(TkCfg<HS, VS, GRAY, WIDE>::kThreads, 1)
 k_tk(const __grid_constant__ CUtensorMap tm_rows,     /* (64, rows), boxes of 16 rows            */
      const __grid_constant__ CUtensorMap tm_pairs,    /* (64, parity, pairs), boxes of 16 pairs  */
@@ -1175,12 +1289,17 @@ k_tk(const __grid_constant__ CUtensorMap tm_rows,     /* (64, rows), boxes of 16
           /* edge tiles: cropped by the image's right or bottom edge, or rows that are not 16-byte aligned
            * (any width that is not a multiple of 16 pixels): the same arithmetic, stores of whatever
            * alignment the row has */
-          if (GRAY) {
+          if (EDGE) {
+            /* the instantiation for plans with rows of any alignment: widest stores each row allows */
+            tk_edge_rows<HS, VS, GRAY>(lstrip, crow0, crow0_b, dst, pitch, vis_rows, nbytes);
+          } else if (GRAY) {
+            /* (plans whose rows are all 16-byte aligned get here for cropped tiles only: the short form,
+             * which leaves the K warps' main loop its registers; 2.3 % on the 4K 4:2:0 batch) */
 #pragma unroll 1
             for (int k = 0; k < vis_rows; k++, dst += pitch) {
               const uint4 v = tk_staged_row_bytes(lstrip + 512 * k);
               const uint32_t w[12] = {v.x, v.y, v.z, v.w, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
-              tk_store_any(dst, w, nbytes);
+              tk_store_any_short(dst, w, nbytes);
             }
           } else {
 #pragma unroll 1
@@ -1192,7 +1311,7 @@ k_tk(const __grid_constant__ CUtensorMap tm_rows,     /* (64, rows), boxes of 16
                 uint32_t ya[4], yb[4], w[12];
                 tk_staged_row(lstrip + 512u * (uint32_t)k, ya, yb);
                 tk_row_words(ya, yb, ca, cb, w);
-                tk_store_any(dst, w, nbytes);
+                tk_store_any_short(dst, w, nbytes);
               }
             }
           }
@@ -1265,26 +1384,31 @@ cudaError_t mcu_configure_mode(int mode) {
   if ((e = cudaFuncSetAttribute(&k_mcu<HS, VS, GRAY, true, kOutYuv>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mi.smem_wide)) != cudaSuccess) return e;
   mi.tk_smem = TkCfg<HS, VS, GRAY, false>::kSmemBytes;
   mi.tk_smem_wide = TkCfg<HS, VS, GRAY, true>::kSmemBytes;
-  if ((e = cudaFuncSetAttribute(&k_tk<HS, VS, GRAY, false, kOutRgb>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mi.tk_smem)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(&k_tk<HS, VS, GRAY, true, kOutRgb>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mi.tk_smem_wide)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(&k_tk<HS, VS, GRAY, false, kOutYuv>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mi.tk_smem)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(&k_tk<HS, VS, GRAY, true, kOutYuv>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mi.tk_smem_wide)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(&k_tk<HS, VS, GRAY, false, kOutRgb, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mi.tk_smem)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(&k_tk<HS, VS, GRAY, true, kOutRgb, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mi.tk_smem_wide)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(&k_tk<HS, VS, GRAY, false, kOutRgb, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mi.tk_smem)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(&k_tk<HS, VS, GRAY, true, kOutRgb, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mi.tk_smem_wide)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(&k_tk<HS, VS, GRAY, false, kOutYuv, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mi.tk_smem)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(&k_tk<HS, VS, GRAY, true, kOutYuv, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mi.tk_smem_wide)) != cudaSuccess) return e;
   return cudaSuccess;
 }
 
 template <int HS, int VS, bool GRAY>
-cudaError_t mcu_launch_mode(bool planes, int sm_count, const McuMode &mi, cudaStream_t stream, const CUtensorMap &tm_rows,
+cudaError_t mcu_launch_mode(bool planes, bool edge, int sm_count, const McuMode &mi, cudaStream_t stream, const CUtensorMap &tm_rows,
                             const CUtensorMap &tm_pairs, const CUtensorMap &tm_rows32, const CUtensorMap &tm_pairs32, const WarpTask *tasks, int n_tasks, const uint32_t *qint,
                             const uint32_t *wide_flag, uint8_t *rgb, int rgb_aligned, uint8_t *yuv, int *claim) {
   if (mcu_use_tk()) {
     const int grid = std::min((n_tasks + kTkPairs - 1) / kTkPairs, sm_count);
     const int threads = 2 * 32 * kTkPairs;
     if (planes) {
-      k_tk<HS, VS, GRAY, false, kOutYuv><<<grid, threads, mi.tk_smem, stream>>>(tm_rows, tm_pairs, tm_rows32, tm_pairs32, tasks, n_tasks, qint, wide_flag, rgb, rgb_aligned, yuv, claim);
-      k_tk<HS, VS, GRAY, true, kOutYuv><<<grid, threads, mi.tk_smem_wide, stream>>>(tm_rows, tm_pairs, tm_rows32, tm_pairs32, tasks, n_tasks, qint, wide_flag, rgb, rgb_aligned, yuv, claim);
+      k_tk<HS, VS, GRAY, false, kOutYuv, false><<<grid, threads, mi.tk_smem, stream>>>(tm_rows, tm_pairs, tm_rows32, tm_pairs32, tasks, n_tasks, qint, wide_flag, rgb, rgb_aligned, yuv, claim);
+      k_tk<HS, VS, GRAY, true, kOutYuv, false><<<grid, threads, mi.tk_smem_wide, stream>>>(tm_rows, tm_pairs, tm_rows32, tm_pairs32, tasks, n_tasks, qint, wide_flag, rgb, rgb_aligned, yuv, claim);
+    } else if (edge) {
+      k_tk<HS, VS, GRAY, false, kOutRgb, true><<<grid, threads, mi.tk_smem, stream>>>(tm_rows, tm_pairs, tm_rows32, tm_pairs32, tasks, n_tasks, qint, wide_flag, rgb, rgb_aligned, yuv, claim);
+      k_tk<HS, VS, GRAY, true, kOutRgb, true><<<grid, threads, mi.tk_smem_wide, stream>>>(tm_rows, tm_pairs, tm_rows32, tm_pairs32, tasks, n_tasks, qint, wide_flag, rgb, rgb_aligned, yuv, claim);
     } else {
-      k_tk<HS, VS, GRAY, false, kOutRgb><<<grid, threads, mi.tk_smem, stream>>>(tm_rows, tm_pairs, tm_rows32, tm_pairs32, tasks, n_tasks, qint, wide_flag, rgb, rgb_aligned, yuv, claim);
-      k_tk<HS, VS, GRAY, true, kOutRgb><<<grid, threads, mi.tk_smem_wide, stream>>>(tm_rows, tm_pairs, tm_rows32, tm_pairs32, tasks, n_tasks, qint, wide_flag, rgb, rgb_aligned, yuv, claim);
+      k_tk<HS, VS, GRAY, false, kOutRgb, false><<<grid, threads, mi.tk_smem, stream>>>(tm_rows, tm_pairs, tm_rows32, tm_pairs32, tasks, n_tasks, qint, wide_flag, rgb, rgb_aligned, yuv, claim);
+      k_tk<HS, VS, GRAY, true, kOutRgb, false><<<grid, threads, mi.tk_smem_wide, stream>>>(tm_rows, tm_pairs, tm_rows32, tm_pairs32, tasks, n_tasks, qint, wide_flag, rgb, rgb_aligned, yuv, claim);
     }
     return cudaGetLastError();
   }
@@ -1326,6 +1450,7 @@ struct McuPlanImpl {
   bool planes = false;   /* tasks cover the padded planes (YUV output) instead of the visible pixels */
   void *d_tasks[kNumFusedModes] = {};
   int n_tasks[kNumFusedModes] = {};
+  bool any_unaligned[kNumFusedModes] = {};   /* the mode has images whose pixel rows are not all 16-byte aligned */
   std::vector<int> first_task[kNumFusedModes]; /* per mode, n+1 entries */
   void *d_qint = nullptr;
   int qint_cap = 0; /* tables */
@@ -1419,6 +1544,7 @@ int mcu_plan_build(FusedPlan &fp, const jgpu_image_desc *descs, const jgpu_layou
         t.pitch0 = d.width * mi.channels;
         /* every half-task starts at a multiple of 256 pixels of a row: aligned iff the image is */
         t.flags = ((d.rgb_off & 15) == 0 && (t.pitch0 & 15) == 0) ? 1 : 0;
+        if (!t.flags) p->any_unaligned[modes[i]] = true;
       }
       /* bit 1: the second half-task follows the first in the block order of every plane (the next 16
        * units of the same MCU row): k_tk fetches one box of 32 rows instead of two of 16 */
@@ -1555,11 +1681,11 @@ int mcu_plan_launch(FusedPlan &fp, int i0, int i1, const int16_t *coef, const ui
     const WarpTask *tasks = static_cast<const WarpTask *>(p->d_tasks[m]) + t0;
     const uint32_t *qint = static_cast<const uint32_t *>(p->d_qint);
     switch (m) {
-      case kModeGray: e = mcu_launch_mode<1, 1, true>(p->planes, grid, mi, stream, p->tm_rows, p->tm_pairs, p->tm_rows32, p->tm_pairs32, tasks, t1 - t0, qint, wide_flag, rgb, rgb_aligned, yuv, claim); break;
-      case kMode444: e = mcu_launch_mode<1, 1, false>(p->planes, grid, mi, stream, p->tm_rows, p->tm_pairs, p->tm_rows32, p->tm_pairs32, tasks, t1 - t0, qint, wide_flag, rgb, rgb_aligned, yuv, claim); break;
-      case kMode422: e = mcu_launch_mode<2, 1, false>(p->planes, grid, mi, stream, p->tm_rows, p->tm_pairs, p->tm_rows32, p->tm_pairs32, tasks, t1 - t0, qint, wide_flag, rgb, rgb_aligned, yuv, claim); break;
-      case kMode420: e = mcu_launch_mode<2, 2, false>(p->planes, grid, mi, stream, p->tm_rows, p->tm_pairs, p->tm_rows32, p->tm_pairs32, tasks, t1 - t0, qint, wide_flag, rgb, rgb_aligned, yuv, claim); break;
-      case kMode440: e = mcu_launch_mode<1, 2, false>(p->planes, grid, mi, stream, p->tm_rows, p->tm_pairs, p->tm_rows32, p->tm_pairs32, tasks, t1 - t0, qint, wide_flag, rgb, rgb_aligned, yuv, claim); break;
+      case kModeGray: e = mcu_launch_mode<1, 1, true>(p->planes, p->any_unaligned[m] || !rgb_aligned, grid, mi, stream, p->tm_rows, p->tm_pairs, p->tm_rows32, p->tm_pairs32, tasks, t1 - t0, qint, wide_flag, rgb, rgb_aligned, yuv, claim); break;
+      case kMode444: e = mcu_launch_mode<1, 1, false>(p->planes, p->any_unaligned[m] || !rgb_aligned, grid, mi, stream, p->tm_rows, p->tm_pairs, p->tm_rows32, p->tm_pairs32, tasks, t1 - t0, qint, wide_flag, rgb, rgb_aligned, yuv, claim); break;
+      case kMode422: e = mcu_launch_mode<2, 1, false>(p->planes, p->any_unaligned[m] || !rgb_aligned, grid, mi, stream, p->tm_rows, p->tm_pairs, p->tm_rows32, p->tm_pairs32, tasks, t1 - t0, qint, wide_flag, rgb, rgb_aligned, yuv, claim); break;
+      case kMode420: e = mcu_launch_mode<2, 2, false>(p->planes, p->any_unaligned[m] || !rgb_aligned, grid, mi, stream, p->tm_rows, p->tm_pairs, p->tm_rows32, p->tm_pairs32, tasks, t1 - t0, qint, wide_flag, rgb, rgb_aligned, yuv, claim); break;
+      case kMode440: e = mcu_launch_mode<1, 2, false>(p->planes, p->any_unaligned[m] || !rgb_aligned, grid, mi, stream, p->tm_rows, p->tm_pairs, p->tm_rows32, p->tm_pairs32, tasks, t1 - t0, qint, wide_flag, rgb, rgb_aligned, yuv, claim); break;
     }
     if (e != cudaSuccess) return jgpu_fail("fused kernel launch failed (%s)", cudaGetErrorString(e));
     if (stream != caller) {
