@@ -1357,15 +1357,10 @@ struct McuMode {
   size_t smem_wide;
   size_t tk_smem, tk_smem_wide;   /* k_tk: 8 warp pairs per CTA either way */
 };
-/* which kernel runs: k_tk unless JGPU_KERNEL=mcu (kept for A/B runs, profiles/r2_notes.md) */
-bool mcu_use_tk() {
-  static int v = -1;
-  if (v < 0) {
-    const char *e = getenv("JGPU_KERNEL");
-    v = (e && strcmp(e, "mcu") == 0) ? 0 : 1;
-  }
-  return v != 0;
-}
+/* which kernel runs: k_tk unless JGPU_KERNEL=mcu (kept for A/B runs, profiles/r2_notes.md); read when a
+ * context is created (mcu_configure) */
+bool g_use_tk = true;
+bool mcu_use_tk() { return g_use_tk; }
 McuMode g_mcu[kNumFusedModes];
 bool g_mcu_configured = false;
 
@@ -1434,6 +1429,10 @@ extern "C" int jgpu_mcu_trace_read(unsigned long long *out, int n_words) {
 
 cudaError_t mcu_configure(int device) {
   (void)device;
+  {
+    const char *k = getenv("JGPU_KERNEL");
+    g_use_tk = !(k && strcmp(k, "mcu") == 0);
+  }
   cudaError_t e;
   if ((e = mcu_configure_mode<1, 1, true>(kModeGray)) != cudaSuccess) return e;
   if ((e = mcu_configure_mode<1, 1, false>(kMode444)) != cudaSuccess) return e;

@@ -198,3 +198,60 @@ def test_planes_out_of_the_fused_kernel(gpu_ctx, checker, ss):
         end = d.yuv_off + d.query_layout().data_len
         if end < yuv_len and end not in starts:
             assert got_yuv[end] == 0xCD
+
+
+@pytest.mark.parametrize("ss", ["gray", "444", "422", "420", "440"])
+def test_rows_of_every_alignment(gpu_ctx, checker, ss):
+    """Widths 257..272 (and a few narrow ones): tight pixel rows of 3 x width bytes start at every 16-byte
+    phase, so every case of the any-alignment store path (head bytes, head words, two 128-bit words, tail)
+    runs, next to units cropped by the right edge and tiles cropped by the bottom edge; the bytes between
+    the images must stay untouched."""
+    shapes = [(256 + r, 17 + r % 9, ss) for r in range(1, 17)] + [(33 + r, 9, ss) for r in range(0, 16, 5)]
+    descs, coef_len, rgb_len, _ = make_batch(shapes, want_yuv=False)
+    q = synth.quality_tables(85)
+    coef = synth.batch_coefficients(descs, coef_len, q, kinds=KINDS)
+    exp_rgb, _ = oracle_batch(checker, descs, coef, q, rgb_len, 0, nthreads=8)
+    got_rgb, _ = gpu_batch(gpu_ctx, descs, coef, q, rgb_len, 0)
+    compare_batch(descs, got_rgb, None, exp_rgb, None)
+    starts = {d.rgb_off for d in descs}
+    for d in descs:
+        end = d.rgb_off + d.query_layout().rgb_len
+        if end < rgb_len and end not in starts:
+            assert (got_rgb[end:min(rgb_len, (end + 255) // 256 * 256)] == 0xAB).all(), (d.width, d.height)
+
+
+@pytest.mark.parametrize("n_images", [1, 2, 7, 9, 150])
+def test_task_counts_around_the_static_share(gpu_ctx, checker, n_images):
+    """k_tk hands every warp pair its first four tasks statically and the rest from a counter: batches with
+    fewer tasks than pairs, with a handful, and with a few more than the static share of one SM."""
+    shapes = [(520, 40, "420"), (300, 24, "422"), (260, 8, "444"), (70, 50, "gray")]
+    shapes = [shapes[i % len(shapes)] for i in range(n_images)]
+    descs, coef_len, rgb_len, _ = make_batch(shapes, want_yuv=False)
+    q = synth.quality_tables(85)
+    coef = synth.batch_coefficients(descs, coef_len, q, kinds=["natural", "dense"])
+    exp_rgb, _ = oracle_batch(checker, descs, coef, q, rgb_len, 0, nthreads=8)
+    for _ in range(2):   # twice: the second run reuses the plan's task counters
+        got_rgb, _ = gpu_batch(gpu_ctx, descs, coef, q, rgb_len, 0)
+        compare_batch(descs, got_rgb, None, exp_rgb, None)
+
+
+def test_previous_kernel_still_matches(checker, monkeypatch):
+    """JGPU_KERNEL=mcu (A/B reference, profiles/r2_notes.md): k_mcu, one warp doing both halves of k_tk's
+    pairs, same bits."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    monkeypatch.setenv("JGPU_KERNEL", "mcu")
+    ctx = J.Context(0)           # the kernel choice is read per context creation
+    try:
+        shapes = [(w, h, ss) for ss in ("gray", "444", "422", "420", "440") for (w, h) in [(70, 50), (1000, 563), (1920, 1080)]]
+        descs, coef_len, rgb_len, yuv_len = make_batch(shapes, want_yuv=False)
+        q = synth.quality_tables(85)
+        coef = synth.batch_coefficients(descs, coef_len, q, kinds=KINDS)
+        exp_rgb, _ = oracle_batch(checker, descs, coef, q, rgb_len, 0, nthreads=8)
+        got_rgb, _ = gpu_batch(ctx, descs, coef, q, rgb_len, 0)
+        compare_batch(descs, got_rgb, None, exp_rgb, None)
+    finally:
+        ctx.close()
+        monkeypatch.delenv("JGPU_KERNEL")
+        J.Context(0).close()     # back to the product kernel for the tests that follow
