@@ -21,6 +21,7 @@ SUBSAMPLINGS = {
     "420": ((2, 1, 1), (2, 1, 1)),
     "440": ((1, 1, 1), (2, 1, 1)),
     "411": ((4, 1, 1), (1, 1, 1)),
+    "410": ((4, 1, 1), (2, 1, 1)),
 }
 
 

@@ -72,7 +72,8 @@ enum FusedMode : int32_t {
   kMode422 = 2,  /* luma 2x1                    MCU 16x8,  4 blocks */
   kMode420 = 3,  /* luma 2x2                    MCU 16x16, 6 blocks */
   kMode440 = 4,  /* luma 1x2                    MCU  8x16, 4 blocks */
-  kNumFusedModes = 5
+  kMode411 = 5,  /* luma 4x1                    MCU 32x8,  6 blocks (k_tk only) */
+  kNumFusedModes = 6
 };
 
 /* One image for the fused kernel.  block0[] are GLOBAL block indices: the

@@ -77,7 +77,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 template <uint32_t HINT_NS>
 __device__ __forceinline__ void mbar_wait_hint(uint32_t bar, uint32_t parity) {
   for (uint32_t spins = 0; !mbar_try_wait_hint<HINT_NS>(bar, parity); spins++) {
-    if (spins > (HINT_NS ? (1u << 22) : (1u << 26))) __trap();
+    if (spins > (HINT_NS ? (1u << 22) : (1u << 23))) __trap();   /* (a few seconds: a protocol bug must trap, not hang the box) */
   }
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *tm, int c0, int c1,

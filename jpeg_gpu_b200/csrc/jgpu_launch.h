@@ -51,6 +51,8 @@ cudaError_t launch_prep_qtabs(const uint16_t *qtabs, uint32_t *qint, int n_table
 /* ---- fused path, one MCU column per thread (jgpu_mcu.cu) -------------------- */
 /* Same plan interface; `flags` selects pixels (JGPU_OUT_RGB) or planes (JGPU_OUT_YUV), not both. */
 cudaError_t mcu_configure(int device);
+/* whether the kernel in use (k_tk, or k_mcu with JGPU_KERNEL=mcu) has this FusedMode */
+bool mcu_has_mode(int mode);
 int mcu_plan_build(FusedPlan &fp, const jgpu_image_desc *descs, const jgpu_layout *layouts,
                    const int *modes, int n, unsigned flags, int sm_count);
 void mcu_plan_release(FusedPlan &fp);

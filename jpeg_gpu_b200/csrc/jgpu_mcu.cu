@@ -665,10 +665,15 @@ constexpr int kStripBytes = 8 * 32 * 16;
 
 template <int HS, int VS, bool GRAY, bool WIDE>
 struct TkCfg {
-  static constexpr int kChromaSteps = GRAY ? 0 : (HS == 2 ? 1 : 2);
-  static constexpr int kLumaSteps = GRAY ? 1 : VS;
+  /* HS == 4 (4:1:1): the unit is one MCU of 32 pixels; its chroma pair comes first, then the two halves (blocks
+   * 0-1, blocks 2-3) of its luma block row.  (4:1:0 would be five strips per unit with the chroma strip held to
+   * the end: more than the ring of four holds, so it stays on the generic path.) */
+  static_assert(!(HS == 4 && VS != 1), "4x luma modes: one luma block row per MCU only");
+  static constexpr int kChromaSteps = GRAY ? 0 : (HS == 1 ? 2 : 1);
+  static constexpr int kLumaSteps = GRAY ? 1 : (HS == 4 ? 2 * VS : VS);
   static constexpr int kSteps = kChromaSteps + kLumaSteps;
   static constexpr int kChannels = GRAY ? 1 : 3;
+  static constexpr int kUnitPx = HS == 4 ? 32 : 16;
   static constexpr int kRegsT = JGPU_TK_REGS_T ? JGPU_TK_REGS_T : ((!GRAY && HS == 1) ? 176 : 184);
   static constexpr int kRegsK = JGPU_TK_REGS_K ? JGPU_TK_REGS_K : ((!GRAY && HS == 1) ? 80 : 72);
   static_assert(kTkPairs * 32 * (kRegsT + kRegsK) <= 65536, "register file");
@@ -714,7 +719,23 @@ __device__ __forceinline__ uint4 tk_staged_row_bytes(uint32_t row) {
  * crow: this lane's 16 bytes of the strip row; crow_b: the same in the odd MCUs' strip (1x luma modes) */
 template <int HS>
 __device__ __forceinline__ void tk_row_offsets(uint32_t crow, uint32_t crow_b, uint32_t (&ca)[12], uint32_t (&cb)[12]) {
-  if (HS == 2) {
+  if (HS == 4) {
+    /* crow: the 8 bytes of this half of the MCU: 4 chroma samples, each serving two horizontal pixel pairs */
+    const uint2 t = lds64(crow);
+    const uint32_t cs[2] = {t.x, t.y};
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+      uint32_t *o = i == 0 ? ca : cb;
+      uint32_t r[2], gg[2], b[2];
+      chroma_offsets_bits2(cs[i], r, gg, b);
+      o[0] = o[3] = __byte_perm(r[0], r[0], kSelRep);
+      o[1] = o[4] = __byte_perm(gg[0], gg[0], kSelRep);
+      o[2] = o[5] = __byte_perm(b[0], b[0], kSelRep);
+      o[6] = o[9] = __byte_perm(r[1], r[1], kSelRep);
+      o[7] = o[10] = __byte_perm(gg[1], gg[1], kSelRep);
+      o[8] = o[11] = __byte_perm(b[1], b[1], kSelRep);
+    }
+  } else if (HS == 2) {
     /* 8 chroma samples, each serving one horizontal pixel pair: offsets replicated into both halves */
     const uint4 t = lds128(crow);
     const uint32_t cs[4] = {t.x, t.y, t.z, t.w};
@@ -903,6 +924,8 @@ k_tk(const __grid_constant__ CUtensorMap tm_rows,     /* (64, rows), boxes of 16
      const __grid_constant__ CUtensorMap tm_pairs,    /* (64, parity, pairs), boxes of 16 pairs  */
      const __grid_constant__ CUtensorMap tm_rows32,   /* the same views with boxes of 32: a task whose two  */
      const __grid_constant__ CUtensorMap tm_pairs32,  /* half-tasks follow each other in the block order    */
+     const __grid_constant__ CUtensorMap tm_quads,    /* (64, 4, quads): every fourth block (HS == 4), boxes of 16 */
+     const __grid_constant__ CUtensorMap tm_quads32,  /* ... and of 32                                              */
      const WarpTask *__restrict__ tasks, int n_tasks, const uint32_t *__restrict__ qint,
      const uint32_t *__restrict__ wide_flag, uint8_t *__restrict__ rgb, int rgb_aligned,
      uint8_t *__restrict__ yuv, int *__restrict__ claim) {
@@ -991,7 +1014,7 @@ k_tk(const __grid_constant__ CUtensorMap tm_rows,     /* (64, rows), boxes of 16
         if (chroma) {
           int f0 = (int)lds32(d + offsetof(McuHalf, cfirst));
           int f1 = (int)lds32(d + offsetof(McuHalf, cfirst) + 4);
-          if (HS == 2) {
+          if (HS != 1) {
             tma_load_2d(g.zone, &tm_rows32, 0, f0, bar);
             tma_load_2d(g.zone + kBoxBytes, &tm_rows32, 0, f1, bar);
           } else {
@@ -1000,6 +1023,12 @@ k_tk(const __grid_constant__ CUtensorMap tm_rows,     /* (64, rows), boxes of 16
             tma_load_3d(g.zone, &tm_pairs32, 0, f0 & 1, f0 >> 1, bar);
             tma_load_3d(g.zone + kBoxBytes, &tm_pairs32, 0, f1 & 1, f1 >> 1, bar);
           }
+        } else if (HS == 4) {
+          /* lane L owns blocks 4 L + 2 h and 4 L + 2 h + 1 of a 128-block run: every fourth block */
+          const int ls = s - C::kChromaSteps;
+          const int first = (int)lds32(d + offsetof(McuHalf, yfirst) + 4 * (ls >> 1)) + 2 * (ls & 1);
+          tma_load_3d(g.zone, &tm_quads32, 0, first & 3, first >> 2, bar);
+          tma_load_3d(g.zone + kBoxBytes, &tm_quads32, 0, (first + 1) & 3, (first + 1) >> 2, bar);
         } else {
           const int first = (int)lds32(d + offsetof(McuHalf, yfirst) + 4 * (s - C::kChromaSteps));
           tma_load_3d(g.zone, &tm_pairs32, 0, first & 1, first >> 1, bar);
@@ -1013,7 +1042,7 @@ k_tk(const __grid_constant__ CUtensorMap tm_rows,     /* (64, rows), boxes of 16
           if (chroma) {
             int f0 = (int)lds32(hd + offsetof(McuHalf, cfirst));
             int f1 = (int)lds32(hd + offsetof(McuHalf, cfirst) + 4);
-            if (HS == 2) {
+            if (HS != 1) {
               tma_load_2d(dst, &tm_rows, 0, f0, bar);
               tma_load_2d(dst + kBoxBytes, &tm_rows, 0, f1, bar);
             } else {
@@ -1022,6 +1051,11 @@ k_tk(const __grid_constant__ CUtensorMap tm_rows,     /* (64, rows), boxes of 16
               tma_load_3d(dst, &tm_pairs, 0, f0 & 1, f0 >> 1, bar);
               tma_load_3d(dst + kBoxBytes, &tm_pairs, 0, f1 & 1, f1 >> 1, bar);
             }
+          } else if (HS == 4) {
+            const int ls = s - C::kChromaSteps;
+            const int first = (int)lds32(hd + offsetof(McuHalf, yfirst) + 4 * (ls >> 1)) + 2 * (ls & 1);
+            tma_load_3d(dst, &tm_quads, 0, first & 3, first >> 2, bar);
+            tma_load_3d(dst + kBoxBytes, &tm_quads, 0, (first + 1) & 3, (first + 1) >> 2, bar);
           } else {
             const int first = (int)lds32(hd + offsetof(McuHalf, yfirst) + 4 * (s - C::kChromaSteps));
             tma_load_3d(dst, &tm_pairs, 0, first & 1, first >> 1, bar);
@@ -1066,7 +1100,15 @@ k_tk(const __grid_constant__ CUtensorMap tm_rows,     /* (64, rows), boxes of 16
         is_c = s < C::kChromaSteps;
         const uint32_t ha = half_addr(g, n);
         const int u = g.lane & 15;
-        if (OUT == kOutYuv) {
+        if (HS == 4) {
+          const int ls = s - C::kChromaSteps;   /* luma step: block row ls >> 1, half ls & 1 */
+          if (OUT == kOutYuv) {
+            active = 4 * u + (is_c ? 0 : 2 * (ls & 1)) < (int)lds32(ha + offsetof(McuHalf, blocks_left));
+          } else {
+            const uint2 wr = lds64(ha + offsetof(McuHalf, width_left));   /* width_left, rows_left */
+            active = 32 * u + (is_c ? 0 : 16 * (ls & 1)) < (int)wr.x && (is_c || 8 * (ls >> 1) < (int)wr.y);
+          }
+        } else if (OUT == kOutYuv) {
           active = 2 * u + ((HS == 1 && is_c) ? s : 0) < (int)lds32(ha + offsetof(McuHalf, blocks_left));
         } else {
           const uint2 wr = lds64(ha + offsetof(McuHalf, width_left));   /* width_left, rows_left */
@@ -1169,7 +1211,7 @@ k_tk(const __grid_constant__ CUtensorMap tm_rows,     /* (64, rows), boxes of 16
     const uint32_t bar = bar_full(g, st % kTkStrips), parity = (st / kTkStrips) & 1u;
     for (uint32_t spins = 0; !mbar_try_wait_hint<0>(bar, parity); spins++) {
       if (JGPU_TK_SPIN_NS) __nanosleep(JGPU_TK_SPIN_NS);
-      if (spins > (1u << 26)) __trap();
+      if (spins > (1u << 23)) __trap();
     }
   };
   auto hand_back = [&](uint32_t st) {   /* after __syncwarp(): every lane has read what it needs of the strip */
@@ -1197,11 +1239,11 @@ k_tk(const __grid_constant__ CUtensorMap tm_rows,     /* (64, rows), boxes of 16
         const uint32_t strip = strip_addr(g, st % kTkStrips);
         if (s < C::kChromaSteps) {
           /* 8 Cb bytes and 8 Cr bytes per row */
-          if (2 * u + (HS == 1 ? s : 0) < blocks_left) {
+          if ((HS == 4 ? 4 * u : 2 * u + (HS == 1 ? s : 0)) < blocks_left) {
             const uint2 b1 = lds64(ha + offsetof(McuHalf, base1));
             const uint2 dl = lds64(da + offsetof(WarpTask, cr_delta));
             const int cpitch = (int)lds32(da + offsetof(WarpTask, pitch1));
-            const long long col = HS == 2 ? 8 * u : 16 * u + 8 * s;
+            const long long col = HS != 1 ? 8 * u : 16 * u + 8 * s;
             uint8_t *pb = yuv + (long long)(((unsigned long long)b1.y << 32) | b1.x) + col;
             uint8_t *pr = pb + (long long)(((unsigned long long)dl.y << 32) | dl.x);
 #pragma unroll 2
@@ -1218,12 +1260,14 @@ k_tk(const __grid_constant__ CUtensorMap tm_rows,     /* (64, rows), boxes of 16
               pr += cpitch;
             }
           }
-        } else if (2 * u < blocks_left) {
+        } else if ((HS == 4 ? 4 * u + 2 * ((s - C::kChromaSteps) & 1) : 2 * u) < blocks_left) {
           /* 16 Y bytes per row (8 when the unit's second block lies beyond the padded plane) */
-          const int yr = s - C::kChromaSteps;
-          const bool whole = 2 * u + 1 < blocks_left;
+          const int ls = s - C::kChromaSteps;
+          const int yr = HS == 4 ? ls >> 1 : ls;
+          const int blk = HS == 4 ? 4 * u + 2 * (ls & 1) : 2 * u;   /* first of the two blocks, in the half-task */
+          const bool whole = blk + 1 < blocks_left;
           const bool wide16 = whole && (pitch & 8) == 0;   /* an odd number of blocks per row: rows are only 8-byte aligned */
-          uint8_t *py = yuv + base0 + (long long)(8 * yr) * pitch + 16 * u;
+          uint8_t *py = yuv + base0 + (long long)(8 * yr) * pitch + 8 * blk;
 #pragma unroll 2
           for (int k = 0; k < 8; k++) {
             const uint4 v = tk_staged_row_bytes(strip + 512 * k);
@@ -1245,22 +1289,30 @@ k_tk(const __grid_constant__ CUtensorMap tm_rows,     /* (64, rows), boxes of 16
 
     /* ---- pixels: colour offsets, pack, store ------------------------------------------------- */
     const uint2 wr = lds64(ha + offsetof(McuHalf, width_left));   /* width_left, rows_left */
-    const int vis_px = min(16, (int)wr.x - 16 * u);
-    const bool fast = (lds32(da + offsetof(WarpTask, flags)) & (uint32_t)rgb_aligned & 1u) != 0 && vis_px == 16;
-    const int nbytes = C::kChannels * vis_px;
+    const bool rows_aligned = (lds32(da + offsetof(WarpTask, flags)) & (uint32_t)rgb_aligned & 1u) != 0;
+    int vis_px = min(16, (int)wr.x - 16 * u);   /* (HS == 4: per luma step, below) */
+    bool fast = rows_aligned && vis_px == 16;
+    int nbytes = C::kChannels * vis_px;
 #pragma unroll 1
     for (int s = 0; s < C::kChromaSteps; s++) wait_full(step + (uint32_t)s);
     const uint32_t cstrip = GRAY ? 0u : strip_addr(g, step % kTkStrips);                       /* HS == 2: the unit's chroma; else the even MCU's */
-    const uint32_t cstrip_b = HS == 2 ? cstrip : strip_addr(g, (step + 1u) % kTkStrips);        /* the odd MCU's */
+    const uint32_t cstrip_b = HS != 1 ? cstrip : strip_addr(g, (step + 1u) % kTkStrips);        /* the odd MCU's */
 #pragma unroll 1
-    for (int yr = 0; yr < C::kLumaSteps; yr++) {
-      const uint32_t st = step + (uint32_t)(C::kChromaSteps + yr);
+    for (int ls = 0; ls < C::kLumaSteps; ls++) {
+      const uint32_t st = step + (uint32_t)(C::kChromaSteps + ls);
       wait_full(st);
       const uint32_t lstrip = strip_addr(g, st % kTkStrips);
+      const int yr = HS == 4 ? ls >> 1 : ls;          /* luma block row of the MCU row */
+      const int xoff = HS == 4 ? 16 * (ls & 1) : 0;   /* HS == 4: which half of the 32-pixel unit */
+      if (HS == 4) {
+        vis_px = min(16, (int)wr.x - 32 * u - xoff);
+        fast = rows_aligned && vis_px == 16;
+        nbytes = C::kChannels * vis_px;
+      }
       const int vis_rows = min(8, (int)wr.y - 8 * yr);
-      uint8_t *dst = rgb + base0 + (long long)(8 * yr) * pitch + (long long)(16 * u) * C::kChannels;
-      /* chroma rows this luma block row uses, one per VS pixel rows */
-      const uint32_t crow0 = cstrip + (VS == 2 ? 4u * 512u * (uint32_t)yr : 0u);
+      uint8_t *dst = rgb + base0 + (long long)(8 * yr) * pitch + (long long)(C::kUnitPx * u + xoff) * C::kChannels;
+      /* chroma rows this luma block row uses, one per VS pixel rows (HS == 4: the half's 8 bytes of each) */
+      const uint32_t crow0 = cstrip + (VS == 2 ? 4u * 512u * (uint32_t)yr : 0u) + (HS == 4 ? (uint32_t)xoff / 2u : 0u);
       const uint32_t crow0_b = cstrip_b + (VS == 2 ? 4u * 512u * (uint32_t)yr : 0u);
       if (vis_px > 0 && vis_rows > 0 && JGPU_TK_EXPERIMENT != 1) {
         if (fast && vis_rows == 8) {
@@ -1319,7 +1371,7 @@ k_tk(const __grid_constant__ CUtensorMap tm_rows,     /* (64, rows), boxes of 16
       }
       __syncwarp();
       hand_back(st);
-      if (yr == 0 && g.lane == 0) announce(g, n + kTkAhead, kTkAhead * nw + claimed);
+      if (ls == 0 && g.lane == 0) announce(g, n + kTkAhead, kTkAhead * nw + claimed);
     }
     /* (the __syncwarp() before the last hand_back covers the chroma strips too) */
 #pragma unroll 1
@@ -1366,17 +1418,19 @@ bool g_mcu_configured = false;
 
 template <int HS, int VS, bool GRAY>
 cudaError_t mcu_configure_mode(int mode) {
-  using C = McuCfg<HS, VS, GRAY, false>;
-  using CW = McuCfg<HS, VS, GRAY, true>;
   McuMode &mi = g_mcu[mode];
-  mi.hs = HS; mi.vs = VS; mi.gray = GRAY; mi.channels = C::kChannels;
-  mi.threads = C::kThreads; mi.warps = C::kWarps; mi.smem = C::kSmemBytes;
-  mi.threads_wide = CW::kThreads; mi.warps_wide = CW::kWarps; mi.smem_wide = CW::kSmemBytes;
+  mi.hs = HS; mi.vs = VS; mi.gray = GRAY; mi.channels = GRAY ? 1 : 3;
   cudaError_t e;
-  if ((e = cudaFuncSetAttribute(&k_mcu<HS, VS, GRAY, false, kOutRgb>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mi.smem)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(&k_mcu<HS, VS, GRAY, true, kOutRgb>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mi.smem_wide)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(&k_mcu<HS, VS, GRAY, false, kOutYuv>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mi.smem)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(&k_mcu<HS, VS, GRAY, true, kOutYuv>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mi.smem_wide)) != cudaSuccess) return e;
+  if constexpr (HS != 4) {   /* (k_mcu has no 4x luma modes: they came with k_tk) */
+    using C = McuCfg<HS, VS, GRAY, false>;
+    using CW = McuCfg<HS, VS, GRAY, true>;
+    mi.threads = C::kThreads; mi.warps = C::kWarps; mi.smem = C::kSmemBytes;
+    mi.threads_wide = CW::kThreads; mi.warps_wide = CW::kWarps; mi.smem_wide = CW::kSmemBytes;
+    if ((e = cudaFuncSetAttribute(&k_mcu<HS, VS, GRAY, false, kOutRgb>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mi.smem)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(&k_mcu<HS, VS, GRAY, true, kOutRgb>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mi.smem_wide)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(&k_mcu<HS, VS, GRAY, false, kOutYuv>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mi.smem)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(&k_mcu<HS, VS, GRAY, true, kOutYuv>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mi.smem_wide)) != cudaSuccess) return e;
+  }
   mi.tk_smem = TkCfg<HS, VS, GRAY, false>::kSmemBytes;
   mi.tk_smem_wide = TkCfg<HS, VS, GRAY, true>::kSmemBytes;
   if ((e = cudaFuncSetAttribute(&k_tk<HS, VS, GRAY, false, kOutRgb, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mi.tk_smem)) != cudaSuccess) return e;
@@ -1390,33 +1444,37 @@ cudaError_t mcu_configure_mode(int mode) {
 
 template <int HS, int VS, bool GRAY>
 cudaError_t mcu_launch_mode(bool planes, bool edge, int sm_count, const McuMode &mi, cudaStream_t stream, const CUtensorMap &tm_rows,
-                            const CUtensorMap &tm_pairs, const CUtensorMap &tm_rows32, const CUtensorMap &tm_pairs32, const WarpTask *tasks, int n_tasks, const uint32_t *qint,
+                            const CUtensorMap &tm_pairs, const CUtensorMap &tm_rows32, const CUtensorMap &tm_pairs32, const CUtensorMap &tm_quads,
+                            const CUtensorMap &tm_quads32, const WarpTask *tasks, int n_tasks, const uint32_t *qint,
                             const uint32_t *wide_flag, uint8_t *rgb, int rgb_aligned, uint8_t *yuv, int *claim) {
   if (mcu_use_tk()) {
     const int grid = std::min((n_tasks + kTkPairs - 1) / kTkPairs, sm_count);
     const int threads = 2 * 32 * kTkPairs;
     if (planes) {
-      k_tk<HS, VS, GRAY, false, kOutYuv, false><<<grid, threads, mi.tk_smem, stream>>>(tm_rows, tm_pairs, tm_rows32, tm_pairs32, tasks, n_tasks, qint, wide_flag, rgb, rgb_aligned, yuv, claim);
-      k_tk<HS, VS, GRAY, true, kOutYuv, false><<<grid, threads, mi.tk_smem_wide, stream>>>(tm_rows, tm_pairs, tm_rows32, tm_pairs32, tasks, n_tasks, qint, wide_flag, rgb, rgb_aligned, yuv, claim);
+      k_tk<HS, VS, GRAY, false, kOutYuv, false><<<grid, threads, mi.tk_smem, stream>>>(tm_rows, tm_pairs, tm_rows32, tm_pairs32, tm_quads, tm_quads32, tasks, n_tasks, qint, wide_flag, rgb, rgb_aligned, yuv, claim);
+      k_tk<HS, VS, GRAY, true, kOutYuv, false><<<grid, threads, mi.tk_smem_wide, stream>>>(tm_rows, tm_pairs, tm_rows32, tm_pairs32, tm_quads, tm_quads32, tasks, n_tasks, qint, wide_flag, rgb, rgb_aligned, yuv, claim);
     } else if (edge) {
-      k_tk<HS, VS, GRAY, false, kOutRgb, true><<<grid, threads, mi.tk_smem, stream>>>(tm_rows, tm_pairs, tm_rows32, tm_pairs32, tasks, n_tasks, qint, wide_flag, rgb, rgb_aligned, yuv, claim);
-      k_tk<HS, VS, GRAY, true, kOutRgb, true><<<grid, threads, mi.tk_smem_wide, stream>>>(tm_rows, tm_pairs, tm_rows32, tm_pairs32, tasks, n_tasks, qint, wide_flag, rgb, rgb_aligned, yuv, claim);
+      k_tk<HS, VS, GRAY, false, kOutRgb, true><<<grid, threads, mi.tk_smem, stream>>>(tm_rows, tm_pairs, tm_rows32, tm_pairs32, tm_quads, tm_quads32, tasks, n_tasks, qint, wide_flag, rgb, rgb_aligned, yuv, claim);
+      k_tk<HS, VS, GRAY, true, kOutRgb, true><<<grid, threads, mi.tk_smem_wide, stream>>>(tm_rows, tm_pairs, tm_rows32, tm_pairs32, tm_quads, tm_quads32, tasks, n_tasks, qint, wide_flag, rgb, rgb_aligned, yuv, claim);
     } else {
-      k_tk<HS, VS, GRAY, false, kOutRgb, false><<<grid, threads, mi.tk_smem, stream>>>(tm_rows, tm_pairs, tm_rows32, tm_pairs32, tasks, n_tasks, qint, wide_flag, rgb, rgb_aligned, yuv, claim);
-      k_tk<HS, VS, GRAY, true, kOutRgb, false><<<grid, threads, mi.tk_smem_wide, stream>>>(tm_rows, tm_pairs, tm_rows32, tm_pairs32, tasks, n_tasks, qint, wide_flag, rgb, rgb_aligned, yuv, claim);
+      k_tk<HS, VS, GRAY, false, kOutRgb, false><<<grid, threads, mi.tk_smem, stream>>>(tm_rows, tm_pairs, tm_rows32, tm_pairs32, tm_quads, tm_quads32, tasks, n_tasks, qint, wide_flag, rgb, rgb_aligned, yuv, claim);
+      k_tk<HS, VS, GRAY, true, kOutRgb, false><<<grid, threads, mi.tk_smem_wide, stream>>>(tm_rows, tm_pairs, tm_rows32, tm_pairs32, tm_quads, tm_quads32, tasks, n_tasks, qint, wide_flag, rgb, rgb_aligned, yuv, claim);
     }
     return cudaGetLastError();
   }
-  const int grid = std::min((n_tasks + mi.warps - 1) / mi.warps, sm_count);
-  const int grid_w = std::min((n_tasks + mi.warps_wide - 1) / mi.warps_wide, sm_count);
-  if (planes) {
-    k_mcu<HS, VS, GRAY, false, kOutYuv><<<grid, mi.threads, mi.smem, stream>>>(tm_rows, tm_pairs, tasks, n_tasks, qint, wide_flag, rgb, rgb_aligned, yuv, claim);
-    k_mcu<HS, VS, GRAY, true, kOutYuv><<<grid_w, mi.threads_wide, mi.smem_wide, stream>>>(tm_rows, tm_pairs, tasks, n_tasks, qint, wide_flag, rgb, rgb_aligned, yuv, claim);
-  } else {
-    k_mcu<HS, VS, GRAY, false, kOutRgb><<<grid, mi.threads, mi.smem, stream>>>(tm_rows, tm_pairs, tasks, n_tasks, qint, wide_flag, rgb, rgb_aligned, yuv, claim);
-    k_mcu<HS, VS, GRAY, true, kOutRgb><<<grid_w, mi.threads_wide, mi.smem_wide, stream>>>(tm_rows, tm_pairs, tasks, n_tasks, qint, wide_flag, rgb, rgb_aligned, yuv, claim);
+  if constexpr (HS != 4) {
+    const int grid = std::min((n_tasks + mi.warps - 1) / mi.warps, sm_count);
+    const int grid_w = std::min((n_tasks + mi.warps_wide - 1) / mi.warps_wide, sm_count);
+    if (planes) {
+      k_mcu<HS, VS, GRAY, false, kOutYuv><<<grid, mi.threads, mi.smem, stream>>>(tm_rows, tm_pairs, tasks, n_tasks, qint, wide_flag, rgb, rgb_aligned, yuv, claim);
+      k_mcu<HS, VS, GRAY, true, kOutYuv><<<grid_w, mi.threads_wide, mi.smem_wide, stream>>>(tm_rows, tm_pairs, tasks, n_tasks, qint, wide_flag, rgb, rgb_aligned, yuv, claim);
+    } else {
+      k_mcu<HS, VS, GRAY, false, kOutRgb><<<grid, mi.threads, mi.smem, stream>>>(tm_rows, tm_pairs, tasks, n_tasks, qint, wide_flag, rgb, rgb_aligned, yuv, claim);
+      k_mcu<HS, VS, GRAY, true, kOutRgb><<<grid_w, mi.threads_wide, mi.smem_wide, stream>>>(tm_rows, tm_pairs, tasks, n_tasks, qint, wide_flag, rgb, rgb_aligned, yuv, claim);
+    }
+    return cudaGetLastError();
   }
-  return cudaGetLastError();
+  return cudaErrorInvalidValue;
 }
 
 }  // namespace
@@ -1426,6 +1484,8 @@ extern "C" int jgpu_mcu_trace_read(unsigned long long *out, int n_words) {
   return cudaMemcpyFromSymbol(out, g_mcu_trace, sizeof(unsigned long long) * (size_t)n_words) == cudaSuccess ? 0 : 1;
 }
 #endif
+
+bool mcu_has_mode(int mode) { return mode < kMode411 || g_use_tk; }
 
 cudaError_t mcu_configure(int device) {
   (void)device;
@@ -1439,6 +1499,7 @@ cudaError_t mcu_configure(int device) {
   if ((e = mcu_configure_mode<2, 1, false>(kMode422)) != cudaSuccess) return e;
   if ((e = mcu_configure_mode<2, 2, false>(kMode420)) != cudaSuccess) return e;
   if ((e = mcu_configure_mode<1, 2, false>(kMode440)) != cudaSuccess) return e;
+  if ((e = mcu_configure_mode<4, 1, false>(kMode411)) != cudaSuccess) return e;
   g_mcu_configured = true;
   return cudaSuccess;
 }
@@ -1462,6 +1523,7 @@ struct McuPlanImpl {
   const void *map_ptr = nullptr;
   CUtensorMap tm_rows, tm_pairs;       /* boxes of 16 rows / pairs */
   CUtensorMap tm_rows32, tm_pairs32;   /* boxes of 32 */
+  CUtensorMap tm_quads, tm_quads32;    /* (64, 4, quads): every fourth block (4x luma modes) */
   cudaStream_t side[kNumFusedModes] = {};
   cudaEvent_t fork = nullptr, join[kNumFusedModes] = {};
 };
@@ -1493,10 +1555,11 @@ int mcu_plan_build(FusedPlan &fp, const jgpu_image_desc *descs, const jgpu_layou
     const int nv = mi.gray ? lay.plane[0].vblocks : lay.nvmb;
     const int lrows = mi.gray ? 1 : mi.vs;                /* luma block rows per MCU row */
     const int lblocks = hblocks[0];                       /* luma blocks per block row */
-    const int cper = mi.gray ? 0 : (mi.hs == 2 ? 16 : 32);  /* chroma blocks a half-task spans */
+    const int cper = mi.gray ? 0 : (mi.hs == 1 ? 32 : 16);  /* chroma blocks a half-task spans */
+    const int lper = mi.hs == 4 ? 64 : 32;                  /* luma blocks a half-task spans: 16 units */
     std::vector<McuHalf> halves;
     for (int r = 0; r < nv; r++) {
-      for (int b = 0; b < lblocks; b += 32) {
+      for (int b = 0; b < lblocks; b += lper) {
         const int x0 = b * 8, y0 = r * mcu_h;
         /* half-tasks wholly to the right of / below the visible image carry no pixels */
         if (!p->planes && (x0 >= d.width || y0 >= d.height)) continue;
@@ -1507,14 +1570,14 @@ int mcu_plan_build(FusedPlan &fp, const jgpu_image_desc *descs, const jgpu_layou
         h.blocks_left = lblocks - b;
         for (int v = 0; v < lrows; v++) h.yfirst[v] = block0[0] + (r * lrows + v) * lblocks + b;
         if (!mi.gray) {
-          const int cx = b / 32 * cper;
+          const int cx = b / lper * cper;
           h.cfirst[0] = block0[1] + r * hblocks[1] + cx;
           h.cfirst[1] = block0[2] + r * hblocks[2] + cx;
         }
         if (p->planes) {
           h.base0 = d.yuv_off + lay.plane[0].data_off + (long long)y0 * lay.plane[0].width + x0;
           if (!mi.gray) {
-            h.base1 = d.yuv_off + lay.plane[1].data_off + (long long)(r * 8) * lay.plane[1].width + (b / 32) * cper * 8;
+            h.base1 = d.yuv_off + lay.plane[1].data_off + (long long)(r * 8) * lay.plane[1].width + (b / lper) * cper * 8;
           }
         } else {
           h.base0 = d.rgb_off + ((long long)y0 * d.width + x0) * mi.channels;
@@ -1550,7 +1613,7 @@ int mcu_plan_build(FusedPlan &fp, const jgpu_image_desc *descs, const jgpu_layou
       if (k + 1 < halves.size()) {
         const McuHalf &a = t.half[0], &b = t.half[1];
         bool joined = true;
-        for (int v = 0; v < lrows; v++) joined = joined && b.yfirst[v] == a.yfirst[v] + 32;
+        for (int v = 0; v < lrows; v++) joined = joined && b.yfirst[v] == a.yfirst[v] + lper;
         if (!mi.gray) joined = joined && b.cfirst[0] == a.cfirst[0] + cper && b.cfirst[1] == a.cfirst[1] + cper;
         if (joined) t.flags |= 2;
       }
@@ -1599,7 +1662,7 @@ static int mcu_build_maps(McuPlanImpl *p, const int16_t *coef) {
     return jgpu_fail("fused path: the coefficient buffer must be 256-byte aligned");
   }
   EncodeTiledFn enc = mcu_encode_fn();
-  const cuuint64_t rows = (cuuint64_t)((p->coef_rows + 1) & ~1ll);
+  const cuuint64_t rows = (cuuint64_t)((p->coef_rows + 3) & ~3ll);
   for (int big = 0; big < 2; big++) {
     const cuuint32_t box_rows = big ? 2 * kHalfRows : kHalfRows;
     {
@@ -1621,6 +1684,16 @@ static int mcu_build_maps(McuPlanImpl *p, const int16_t *coef) {
                        strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r != CUDA_SUCCESS) return jgpu_fail("cuTensorMapEncodeTiled(pairs) failed (%d)", (int)r);
+    }
+    {
+      cuuint64_t dims[3] = {64, 4, rows / 4};
+      cuuint64_t strides[2] = {128, 512};
+      cuuint32_t box[3] = {64, 1, box_rows};
+      cuuint32_t estr[3] = {1, 1, 1};
+      CUresult r = enc(big ? &p->tm_quads32 : &p->tm_quads, CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, const_cast<int16_t *>(coef), dims,
+                       strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return jgpu_fail("cuTensorMapEncodeTiled(quads) failed (%d)", (int)r);
     }
   }
   p->map_ptr = coef;
@@ -1680,11 +1753,12 @@ int mcu_plan_launch(FusedPlan &fp, int i0, int i1, const int16_t *coef, const ui
     const WarpTask *tasks = static_cast<const WarpTask *>(p->d_tasks[m]) + t0;
     const uint32_t *qint = static_cast<const uint32_t *>(p->d_qint);
     switch (m) {
-      case kModeGray: e = mcu_launch_mode<1, 1, true>(p->planes, p->any_unaligned[m] || !rgb_aligned, grid, mi, stream, p->tm_rows, p->tm_pairs, p->tm_rows32, p->tm_pairs32, tasks, t1 - t0, qint, wide_flag, rgb, rgb_aligned, yuv, claim); break;
-      case kMode444: e = mcu_launch_mode<1, 1, false>(p->planes, p->any_unaligned[m] || !rgb_aligned, grid, mi, stream, p->tm_rows, p->tm_pairs, p->tm_rows32, p->tm_pairs32, tasks, t1 - t0, qint, wide_flag, rgb, rgb_aligned, yuv, claim); break;
-      case kMode422: e = mcu_launch_mode<2, 1, false>(p->planes, p->any_unaligned[m] || !rgb_aligned, grid, mi, stream, p->tm_rows, p->tm_pairs, p->tm_rows32, p->tm_pairs32, tasks, t1 - t0, qint, wide_flag, rgb, rgb_aligned, yuv, claim); break;
-      case kMode420: e = mcu_launch_mode<2, 2, false>(p->planes, p->any_unaligned[m] || !rgb_aligned, grid, mi, stream, p->tm_rows, p->tm_pairs, p->tm_rows32, p->tm_pairs32, tasks, t1 - t0, qint, wide_flag, rgb, rgb_aligned, yuv, claim); break;
-      case kMode440: e = mcu_launch_mode<1, 2, false>(p->planes, p->any_unaligned[m] || !rgb_aligned, grid, mi, stream, p->tm_rows, p->tm_pairs, p->tm_rows32, p->tm_pairs32, tasks, t1 - t0, qint, wide_flag, rgb, rgb_aligned, yuv, claim); break;
+      case kModeGray: e = mcu_launch_mode<1, 1, true>(p->planes, p->any_unaligned[m] || !rgb_aligned, grid, mi, stream, p->tm_rows, p->tm_pairs, p->tm_rows32, p->tm_pairs32, p->tm_quads, p->tm_quads32, tasks, t1 - t0, qint, wide_flag, rgb, rgb_aligned, yuv, claim); break;
+      case kMode444: e = mcu_launch_mode<1, 1, false>(p->planes, p->any_unaligned[m] || !rgb_aligned, grid, mi, stream, p->tm_rows, p->tm_pairs, p->tm_rows32, p->tm_pairs32, p->tm_quads, p->tm_quads32, tasks, t1 - t0, qint, wide_flag, rgb, rgb_aligned, yuv, claim); break;
+      case kMode422: e = mcu_launch_mode<2, 1, false>(p->planes, p->any_unaligned[m] || !rgb_aligned, grid, mi, stream, p->tm_rows, p->tm_pairs, p->tm_rows32, p->tm_pairs32, p->tm_quads, p->tm_quads32, tasks, t1 - t0, qint, wide_flag, rgb, rgb_aligned, yuv, claim); break;
+      case kMode420: e = mcu_launch_mode<2, 2, false>(p->planes, p->any_unaligned[m] || !rgb_aligned, grid, mi, stream, p->tm_rows, p->tm_pairs, p->tm_rows32, p->tm_pairs32, p->tm_quads, p->tm_quads32, tasks, t1 - t0, qint, wide_flag, rgb, rgb_aligned, yuv, claim); break;
+      case kMode440: e = mcu_launch_mode<1, 2, false>(p->planes, p->any_unaligned[m] || !rgb_aligned, grid, mi, stream, p->tm_rows, p->tm_pairs, p->tm_rows32, p->tm_pairs32, p->tm_quads, p->tm_quads32, tasks, t1 - t0, qint, wide_flag, rgb, rgb_aligned, yuv, claim); break;
+      case kMode411: e = mcu_launch_mode<4, 1, false>(p->planes, p->any_unaligned[m] || !rgb_aligned, grid, mi, stream, p->tm_rows, p->tm_pairs, p->tm_rows32, p->tm_pairs32, p->tm_quads, p->tm_quads32, tasks, t1 - t0, qint, wide_flag, rgb, rgb_aligned, yuv, claim); break;
     }
     if (e != cudaSuccess) return jgpu_fail("fused kernel launch failed (%s)", cudaGetErrorString(e));
     if (stream != caller) {

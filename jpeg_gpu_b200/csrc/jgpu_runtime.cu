@@ -240,7 +240,9 @@ static bool fused_eligible(const jgpu_image_desc &d, const jgpu_layout &lay, uns
     else if (d.hsamp[0] == 2 && d.vsamp[0] == 1) *mode = kMode422;
     else if (d.hsamp[0] == 2 && d.vsamp[0] == 2) *mode = kMode420;
     else if (d.hsamp[0] == 1 && d.vsamp[0] == 2) *mode = kMode440;
+    else if (d.hsamp[0] == 4 && d.vsamp[0] == 1) *mode = kMode411;
     else return false;
+    if (*mode >= kMode411 && (use_v9() || !mcu_has_mode(*mode))) return false;
   }
   /* the fused kernels write pixels OR planes and address coefficients by 128-byte row */
   const unsigned out = flags & (JGPU_OUT_RGB | JGPU_OUT_YUV);

@@ -17,14 +17,14 @@ SIZES = [(8, 8), (16, 16), (70, 50), (64, 48), (129, 65), (512, 512), (1000, 563
 KINDS = ["natural", "dense", "dc", "zero", "impulse"]
 
 
-# (force_generic, want_yuv): RGB-only plans take the fused kernel for gray/444/422/420/440,
-# plans that also want the planes (or 411, or force_generic) take the two-kernel generic path
+# (force_generic, want_yuv): RGB-only plans take the fused kernel (gray/444/422/420/440/411),
+# plans that also want the planes (or 410, or force_generic) take the two-kernel generic path
 PATHS = [(False, False), (False, True), (True, False), (True, True)]
 PATH_IDS = ["fused-rgb", "auto-rgb+yuv", "generic-rgb", "generic-rgb+yuv"]
 
 
 @pytest.mark.parametrize("force_generic,want_yuv", PATHS, ids=PATH_IDS)
-@pytest.mark.parametrize("ss", ["gray", "444", "422", "420", "440", "411"])
+@pytest.mark.parametrize("ss", ["gray", "444", "422", "420", "440", "411", "410"])
 def test_parity_by_subsampling(gpu_ctx, checker, ss, force_generic, want_yuv):
     shapes = [(w, h, ss) for (w, h) in SIZES]
     descs, coef_len, rgb_len, yuv_len = make_batch(shapes, want_yuv=want_yuv)
@@ -177,12 +177,12 @@ def test_sixteen_bit_tables_through_the_chunked_host_path(gpu_ctx, checker):
             assert np.array_equal(got[d.rgb_off:d.rgb_off + lay.rgb_len], exp[:lay.rgb_len]), (rep, i)
 
 
-@pytest.mark.parametrize("ss", ["gray", "444", "422", "420", "440"])
+@pytest.mark.parametrize("ss", ["gray", "444", "422", "420", "440", "411"])
 def test_planes_out_of_the_fused_kernel(gpu_ctx, checker, ss):
     """JGPU_OUT_YUV plans run the fused kernel too: the padded planes of xjpeg's YUV output
     (src/xjpeg.c:565-584), every byte of them, for sizes that leave half-tasks, half units and
     invisible MCU rows at the edges."""
-    shapes = [(1920, 1080, ss), (520, 40, ss), (70, 50, ss), (8, 8, ss), (1000, 563, ss), (264, 16, ss)]
+    shapes = [(1920, 1080, ss), (520, 40, ss), (70, 50, ss), (8, 8, ss), (1000, 563, ss), (264, 16, ss), (2100, 24, ss)]
     q = synth.quality_tables(85)
     descs, coef_len, rgb_len, yuv_len = make_batch(shapes, want_yuv=True)
     coef = synth.batch_coefficients(descs, coef_len, q, kinds=["natural", "dense", "int16"])
@@ -200,7 +200,7 @@ def test_planes_out_of_the_fused_kernel(gpu_ctx, checker, ss):
             assert got_yuv[end] == 0xCD
 
 
-@pytest.mark.parametrize("ss", ["gray", "444", "422", "420", "440"])
+@pytest.mark.parametrize("ss", ["gray", "444", "422", "420", "440", "411", "410"])
 def test_rows_of_every_alignment(gpu_ctx, checker, ss):
     """Widths 257..272 (and a few narrow ones): tight pixel rows of 3 x width bytes start at every 16-byte
     phase, so every case of the any-alignment store path (head bytes, head words, two 128-bit words, tail)
@@ -224,7 +224,7 @@ def test_rows_of_every_alignment(gpu_ctx, checker, ss):
 def test_task_counts_around_the_static_share(gpu_ctx, checker, n_images):
     """k_tk hands every warp pair its first four tasks statically and the rest from a counter: batches with
     fewer tasks than pairs, with a handful, and with a few more than the static share of one SM."""
-    shapes = [(520, 40, "420"), (300, 24, "422"), (260, 8, "444"), (70, 50, "gray")]
+    shapes = [(520, 40, "420"), (300, 24, "422"), (260, 8, "444"), (70, 50, "gray"), (530, 20, "411"), (100, 33, "410")]
     shapes = [shapes[i % len(shapes)] for i in range(n_images)]
     descs, coef_len, rgb_len, _ = make_batch(shapes, want_yuv=False)
     q = synth.quality_tables(85)

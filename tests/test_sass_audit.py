@@ -42,10 +42,10 @@ def test_only_sm100a_code(sass):
 def test_idct_has_no_contracted_multiply_add(sass):
     kernels = {n: body for n, body in sass.items()
                if "k_fused" in n or "k_coef_to_planes" in n or "k_mcu" in n or "k_tk" in n}
-    # generic + 5 modes x {8-bit, 16-bit tables} of k_fused, + 5 modes x 2 x {pixels, planes} of k_mcu and of
-    # k_tk (the product path)
-    assert len(kernels) >= 11 + 20 + 20
-    assert sum("k_tk" in n for n in kernels) == 20
+    # generic + 5 modes x {8-bit, 16-bit tables} of k_fused, + 5 modes x 2 x {pixels, planes} of k_mcu, + 6 modes
+    # x 2 x {pixels, pixels with rows of any alignment, planes} of k_tk (the product path)
+    assert len(kernels) >= 11 + 20 + 36
+    assert sum("k_tk" in n for n in kernels) == 36
     for name, body in kernels.items():
         text = "\n".join(body)
         assert "FMUL2" not in text, name
