@@ -1,39 +1,44 @@
-/* jgpu_mcu.cu — the fused coefficient -> pixels kernel, one MCU column per thread (sm_100a).
+/* jgpu_mcu.cu — the fused coefficient -> pixels / planes kernels, one MCU column per thread (sm_100a).
  *
  * Same work as the reference's three render passes (res/horz_quant_*.fs.glsl ->
  * res/vert.fs.glsl -> res/unyuv.fs.glsl / ungrey.fs.glsl, driven by
- * src/jpeg_gpu.c:1341-1363) and the same arithmetic as jgpu_fused.cu (its
- * predecessor, kept as an A/B reference): dequantise, both IDCT passes, bias / clamp,
- * nearest-neighbour chroma upsample, colour, crop, RGB8 store -- or the clamped planes
- * themselves (src/xjpeg.c:565-584) when the plan asks for YUV.
+ * src/jpeg_gpu.c:1341-1363) and the same arithmetic as jgpu_fused.cu (round 1's kernel, kept as
+ * an A/B reference): dequantise, both IDCT passes, bias / clamp, nearest-neighbour chroma
+ * upsample, colour, crop, RGB8 store -- or the clamped planes themselves
+ * (src/xjpeg.c:565-584) when the plan asks for YUV.
  *
- * What is different: there are no warp roles and nothing is shared between warps.
+ * Two kernels over the same task descriptors and the same data movement:
+ *   k_tk   (second half of the file) THE PRODUCT KERNEL: the work of a task is split between a
+ *          transform warp and a colour warp with different register budgets (setmaxnreg), 8 such
+ *          pairs per CTA, samples handed over in 4 KB strips of shared memory; see the comment
+ *          above it.  gray, 4:4:4, 4:2:2, 4:2:0, 4:4:0, 4:1:1.
+ *   k_mcu  (first half) its predecessor, JGPU_KERNEL=mcu: one warp does both halves.  What follows
+ *          describes it; unit, task, steps and the TMA views are k_tk's too.
+ *
  *   unit   = a 16-pixel-wide column of one MCU row: one MCU for the 2x luma modes (4:2:0,
  *            4:2:2), two MCUs for the 1x modes (4:4:4, 4:4:0), two blocks for grey.
  *   thread = one unit, start to finish.  It runs the block-PAIR transform of
- *            jgpu_idct_core.cuh once per "step": first the chroma pair(s) of its unit
- *            (Cb and Cr of one MCU ride in the two packed lanes), whose clamped samples it
- *            parks in a private strip of shared memory, then one luma pair per luma block
- *            row (two horizontally adjacent blocks = 16 pixels), whose clamped samples stay
- *            in registers while the colour offsets are added and the 48 bytes of each
- *            pixel row are stored.
- *   warp   = 32 consecutive units = 512 pixels of one MCU row: a "task".  Warps take tasks
- *            round-robin and never wait for one another: each has its own TMA landing
- *            zone (two 4 KB boxes, 128-byte swizzle), its own tables, its own mbarrier and
- *            its own ring of task descriptors.
+ *            jgpu_idct_core.cuh once per "step": first the chroma pair(s) of its unit (Cb and Cr
+ *            of one MCU ride in the two packed lanes), whose clamped samples it parks in a
+ *            private strip of shared memory, then one luma pair per luma block row (two
+ *            horizontally adjacent blocks = 16 pixels), whose clamped samples are staged while
+ *            the colour offsets are added and the 48 bytes of each pixel row are stored.
+ *   warp   = 32 consecutive units = 512 pixels of one MCU row: a "task".  Warps take tasks from a
+ *            counter and never wait for one another: each has its own TMA landing zone (two
+ *            4 KB boxes, 128-byte swizzle), its own tables, its own mbarrier and its own ring of
+ *            task descriptors.
  * In jgpu_fused.cu four luma warps and two chroma warps of a CTA met at named barriers once
  * per tile; ncu showed the chroma warps asleep half of the time and the luma warps a tenth
- * of theirs at the barrier (profiles/r2_notes.md).  Here every resident warp carries the
- * same mix of work and the only waits left are on a warp's own loads.
+ * of theirs at the barrier (profiles/r2_notes.md).
  *
  * Data movement
- *   HBM -> smem: cp.async.bulk.tensor boxes of 32 blocks x 128 B, as in jgpu_fused.cu: a 2-D
- *     view (64, rows) for runs of consecutive blocks and a 3-D view (64, parity, pairs) that
- *     gathers every second block, so that lane L owns blocks 2L and 2L+1 of a 64-block run.
- *     A warp starts the loads of its next step as soon as the row pass has pulled the
- *     current boxes into registers.
- *   task descriptors: 128 bytes per task, built on the host, fetched two tasks ahead into a
- *     per-warp 4-slot ring with cp.async.bulk.
+ *   HBM -> smem: cp.async.bulk.tensor boxes of 16 or 32 blocks x 128 B: a 2-D view (64, rows) for
+ *     runs of consecutive blocks, a 3-D view (64, parity, pairs) that gathers every second block
+ *     (lane L owns blocks 2L and 2L+1 of a 64-block run) and, for 4:1:1, (64, 4, quads).  A warp
+ *     starts the loads of its next step as soon as the row pass has pulled the current boxes
+ *     into registers.
+ *   task descriptors: 128 bytes per task, built on the host, fetched ahead into a per-warp ring
+ *     with cp.async.bulk.
  *   regs -> HBM: per pixel row three 128-bit streaming stores per thread (a warp covers 1536
  *     contiguous bytes); planes: 16 bytes of Y / 8 bytes of Cb and of Cr per thread and row.
  */
