@@ -592,15 +592,39 @@ k_gray_tpb(const __grid_constant__ CUtensorMap tm_rows, const TileDesc *__restri
  * somebody must zero first: chunks of one batch run this on several streams at once with the same
  * tables (jgpu_decode_batch_host), and every such launch stores the same bytes -- a zeroing memset
  * from a later chunk could otherwise land between an earlier chunk's two kernel instantiations. */
-__global__ void __launch_bounds__(256) k_prep_qtabs(const uint16_t *__restrict__ q, uint32_t *__restrict__ out,
-                                                    int n_words, uint32_t *__restrict__ wide_flag) {
+__global__ void __launch_bounds__(1024) k_prep_qtabs(const uint16_t *__restrict__ q, uint32_t *__restrict__ out,
+                                                     int n_words, uint32_t *__restrict__ wide_flag, int vec) {
   int wide = 0;
-  for (int i = threadIdx.x; i < n_words; i += blockDim.x) {
-    const int table = i >> 6, w = i & 63, hi = w >> 5, idx = (w & 31) * 2;
-    const uint32_t q0 = q[table * 64 + idx], q1 = q[table * 64 + idx + 1];
-    const uint32_t v = hi ? ((q0 >> 8) | ((q1 >> 8) << 24)) : ((q0 & 255u) | ((q1 & 255u) << 24));
-    out[i] = v;
-    wide |= (hi && v);
+  if (vec) {
+    /* eight entries per thread and step (one 128-bit load): four low-byte words, four high-byte words.  One CTA on
+     * purpose -- the flag is the OR over all tables and is only ever written whole -- so it has to be quick: a batch
+     * of JPEG files brings a table set per file and every group of files converts them (512 tables: 65 us with one
+     * entry per thread and step, 6 us this way) */
+    const int n_vec = n_words / 8;   /* 64 entries = 8 vectors per table */
+    for (int i = threadIdx.x; i < n_vec; i += blockDim.x) {
+      const int table = i >> 3, k = i & 7;
+      const uint4 v = reinterpret_cast<const uint4 *>(q)[i];
+      const uint32_t e[4] = {v.x, v.y, v.z, v.w};   /* e[j] = entries 8k+2j (low half), 8k+2j+1 (high half) */
+      uint32_t lo[4], hi[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const uint32_t q0 = e[j] & 0xffffu, q1 = e[j] >> 16;
+        lo[j] = (q0 & 255u) | ((q1 & 255u) << 24);
+        hi[j] = (q0 >> 8) | ((q1 >> 8) << 24);
+        wide |= hi[j] != 0u;
+      }
+      uint4 *o = reinterpret_cast<uint4 *>(out + table * 64);
+      o[k] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      o[8 + k] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    }
+  } else {
+    for (int i = threadIdx.x; i < n_words; i += blockDim.x) {
+      const int table = i >> 6, w = i & 63, hi = w >> 5, idx = (w & 31) * 2;
+      const uint32_t q0 = q[table * 64 + idx], q1 = q[table * 64 + idx + 1];
+      const uint32_t v = hi ? ((q0 >> 8) | ((q1 >> 8) << 24)) : ((q0 & 255u) | ((q1 & 255u) << 24));
+      out[i] = v;
+      wide |= (hi && v);
+    }
   }
   wide = __syncthreads_or(wide);
   if (threadIdx.x == 0) *wide_flag = wide ? 1u : 0u;
@@ -611,7 +635,8 @@ __global__ void __launch_bounds__(256) k_prep_qtabs(const uint16_t *__restrict__
 /* u16 tables -> packed tables + the 16-bit flag, on `stream` (shared with jgpu_mcu.cu). */
 cudaError_t launch_prep_qtabs(const uint16_t *qtabs, uint32_t *qint, int n_tables, uint32_t *wide_flag,
                               cudaStream_t stream) {
-  k_prep_qtabs<<<1, 256, 0, stream>>>(qtabs, qint, n_tables * 64, wide_flag);
+  const int vec = ((reinterpret_cast<uintptr_t>(qtabs) | reinterpret_cast<uintptr_t>(qint)) & 15) == 0 ? 1 : 0;
+  k_prep_qtabs<<<1, 1024, 0, stream>>>(qtabs, qint, n_tables * 64, wide_flag, vec);
   return cudaGetLastError();
 }
 

@@ -166,7 +166,7 @@ __device__ __forceinline__ void stage(SyncSmem<S> &sm, const jgpu_huff_file *fil
 }
 
 template <int S>
-__global__ void __launch_bounds__(kCta, JGPU_HUFF_S >= 64 ? 2 : 4)
+__global__ void __launch_bounds__(kCta, JGPU_HUFF_S >= 64 ? 2 : (1024 / kCta))
 k_huff_sync(const jgpu_huff_file *__restrict__ files, const uint32_t *__restrict__ stream,
             const jgpu_huff_table *__restrict__ tables, const uint32_t *__restrict__ seg_first,
             uint32_t *__restrict__ state, uint32_t *__restrict__ nslots, uint32_t *__restrict__ segid,
@@ -333,7 +333,7 @@ k_huff_scan(const jgpu_huff_file *__restrict__ files, const uint32_t *__restrict
 }
 
 template <int S>
-__global__ void __launch_bounds__(kCta, JGPU_HUFF_S >= 64 ? 2 : 4)
+__global__ void __launch_bounds__(kCta, JGPU_HUFF_S >= 64 ? 2 : (1024 / kCta))
 k_huff_write(const jgpu_huff_file *__restrict__ files, const uint32_t *__restrict__ stream,
              const jgpu_huff_table *__restrict__ tables, const uint32_t *__restrict__ seg_first,
              const uint32_t *__restrict__ state, const uint32_t *__restrict__ nslots,

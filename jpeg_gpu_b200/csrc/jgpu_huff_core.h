@@ -40,7 +40,9 @@
 #endif
 #define JGPU_HUFF_MAX_BLOCKS 10   /* blocks per MCU, T.81 B.2.3 */
 #define JGPU_HUFF_TABLES 6        /* per file: (DC, AC) of each of up to 3 scan components */
-#define JGPU_HUFF_CTA 256         /* subsequences per CTA of the sync / write kernels */
+#ifndef JGPU_HUFF_CTA
+#define JGPU_HUFF_CTA 256         /* subsequences per CTA of the sync / write kernels (128 measured: profiles/r2_notes.md) */
+#endif
 /* Sync kernel: the first JGPU_HUFF_WARM threads of a CTA re-decode the last subsequences of the
  * CTA before it, only to hand the first subsequence the CTA OWNS a start state that has already
  * fallen into step (the chance that eight pieces in a row do not is about 0.1 % on 4:2:0 files).
