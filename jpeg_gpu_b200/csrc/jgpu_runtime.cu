@@ -1373,17 +1373,30 @@ static int decode_jpegs_gpu_entropy(jgpu_ctx *ctx, const jgpu_jpeg *files, int n
     CU_TRY(cudaMemcpyAsync(d_qtabs, qtabs.data(), qtabs.size() * 2, cudaMemcpyHostToDevice, ctx->streams[0]));
     CU_TRY(cudaEventRecord(ctx->events[0], ctx->streams[0]));
     for (int s = 1; s < kHostStreams; s++) CU_TRY(cudaStreamWaitEvent(ctx->streams[s], ctx->events[0], 0));
-    /* groups grow from 48 MB to 192 MB of coefficients: a small first group gets the read-back
-     * (the slowest stage) going early, large later ones keep the kernels' grids full */
-    int64_t chunk_bytes = 48ll << 20;
+    /* Groups of files.  The first one is small (48 MB of coefficients: one 4K file) so that the read-back, the
+     * slowest stage, gets going early.  The later ones are sized by the entropy kernels' grids: those CTAs run
+     * rounds of a serial chain and take about as long whatever their number, so a grid of 1.5 waves costs two;
+     * and every launch pays the slowest CTA's rounds (about 0.4 ms) before throughput counts.  A group takes as
+     * many files as fill one wave of resident CTAs (second group), then two (4K files: groups of 4, then 9;
+     * the groups of 7 = 1.5 waves that 192 MB of coefficients gave were 12 % slower on 128 files, groups of three
+     * waves no faster there and slower on 32 files, profiles/r2_notes.md), within 512 MB of coefficients. */
+    const int64_t first_bytes = 48ll << 20, max_bytes = 512ll << 20;
+    const long wave = (long)ctx->sm_count * (1024 / JGPU_HUFF_CTA);   /* CTAs of k_huff_sync / k_huff_write resident at once */
     int i0 = 0, chunk = 0;
     while (i0 < m) {
       int i1 = i0;
       int64_t acc = 0;
-      if (chunk > 0 && chunk_bytes < (192ll << 20)) chunk_bytes *= 2;
+      long ctas = 0;
+      const long target = (chunk < 2 ? chunk : 2) * wave;
       /* (a group's file count is gridDim.y of the entropy kernels: at most 65535) */
-      while (i1 < m && i1 - i0 < 65535 && (i1 == i0 || acc + plan->layouts[i1].coef_len * 2 <= chunk_bytes)) {
-        acc += plan->layouts[i1].coef_len * 2;
+      while (i1 < m && i1 - i0 < 65535) {
+        JpegItem &it = items[ok[i1]];
+        while (it.tasks_left.load(std::memory_order_acquire) > 0) std::this_thread::yield();
+        const int64_t bytes = plan->layouts[i1].coef_len * 2;
+        const long c = on_gpu[i1] ? (long)((h_files[i1].n_subseq + JGPU_HUFF_OWN - 1) / JGPU_HUFF_OWN) : 0;
+        if (i1 > i0 && (acc + bytes > max_bytes || (target > 0 ? ctas + c > target : acc + bytes > first_bytes))) break;
+        acc += bytes;
+        ctas += c;
         i1++;
       }
       HuffLaunch l;
