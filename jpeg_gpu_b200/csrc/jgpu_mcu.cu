@@ -1414,10 +1414,18 @@ struct McuMode {
   size_t smem_wide;
   size_t tk_smem, tk_smem_wide;   /* k_tk: 8 warp pairs per CTA either way */
 };
-/* which kernel runs: k_tk unless JGPU_KERNEL=mcu (kept for A/B runs, profiles/r2_notes.md); read when a
- * context is created (mcu_configure) */
-bool g_use_tk = true;
-bool mcu_use_tk() { return g_use_tk; }
+/* Which kernel runs.  k_tk, except where the colour warps have next to nothing to do and k_mcu's twelve
+ * do-everything warps are faster (measured, profiles/r2_notes.md section 11): grey pixels (when the rows are 16-byte
+ * aligned: k_mcu stores other rows byte by byte) and the planes of grey, 4:2:0 and 4:2:2.  JGPU_KERNEL=mcu / tk
+ * forces one of them (A/B runs; 4:1:1 exists in k_tk only); read when a context is created (mcu_configure). */
+int g_kernel_choice = 0;   /* 0: as above, 1: k_tk, 2: k_mcu */
+bool mcu_use_tk(int mode, bool planes, bool edge) {
+  if (mode >= kMode411 || g_kernel_choice == 1) return true;
+  if (g_kernel_choice == 2) return false;
+  if (mode == kModeGray) return planes ? false : edge;
+  if (planes) return !(mode == kMode420 || mode == kMode422);
+  return true;
+}
 McuMode g_mcu[kNumFusedModes];
 bool g_mcu_configured = false;
 
@@ -1448,11 +1456,11 @@ cudaError_t mcu_configure_mode(int mode) {
 }
 
 template <int HS, int VS, bool GRAY>
-cudaError_t mcu_launch_mode(bool planes, bool edge, int sm_count, const McuMode &mi, cudaStream_t stream, const CUtensorMap &tm_rows,
+cudaError_t mcu_launch_mode(bool use_tk, bool planes, bool edge, int sm_count, const McuMode &mi, cudaStream_t stream, const CUtensorMap &tm_rows,
                             const CUtensorMap &tm_pairs, const CUtensorMap &tm_rows32, const CUtensorMap &tm_pairs32, const CUtensorMap &tm_quads,
                             const CUtensorMap &tm_quads32, const WarpTask *tasks, int n_tasks, const uint32_t *qint,
                             const uint32_t *wide_flag, uint8_t *rgb, int rgb_aligned, uint8_t *yuv, int *claim) {
-  if (mcu_use_tk()) {
+  if (use_tk) {
     const int grid = std::min((n_tasks + kTkPairs - 1) / kTkPairs, sm_count);
     const int threads = 2 * 32 * kTkPairs;
     if (planes) {
@@ -1490,13 +1498,13 @@ extern "C" int jgpu_mcu_trace_read(unsigned long long *out, int n_words) {
 }
 #endif
 
-bool mcu_has_mode(int mode) { return mode < kMode411 || g_use_tk; }
+bool mcu_has_mode(int mode) { return mode < kMode411 || g_kernel_choice != 2; }
 
 cudaError_t mcu_configure(int device) {
   (void)device;
   {
     const char *k = getenv("JGPU_KERNEL");
-    g_use_tk = !(k && strcmp(k, "mcu") == 0);
+    g_kernel_choice = !k ? 0 : strcmp(k, "tk") == 0 ? 1 : strcmp(k, "mcu") == 0 ? 2 : 0;
   }
   cudaError_t e;
   if ((e = mcu_configure_mode<1, 1, true>(kModeGray)) != cudaSuccess) return e;
@@ -1758,12 +1766,12 @@ int mcu_plan_launch(FusedPlan &fp, int i0, int i1, const int16_t *coef, const ui
     const WarpTask *tasks = static_cast<const WarpTask *>(p->d_tasks[m]) + t0;
     const uint32_t *qint = static_cast<const uint32_t *>(p->d_qint);
     switch (m) {
-      case kModeGray: e = mcu_launch_mode<1, 1, true>(p->planes, p->any_unaligned[m] || !rgb_aligned, grid, mi, stream, p->tm_rows, p->tm_pairs, p->tm_rows32, p->tm_pairs32, p->tm_quads, p->tm_quads32, tasks, t1 - t0, qint, wide_flag, rgb, rgb_aligned, yuv, claim); break;
-      case kMode444: e = mcu_launch_mode<1, 1, false>(p->planes, p->any_unaligned[m] || !rgb_aligned, grid, mi, stream, p->tm_rows, p->tm_pairs, p->tm_rows32, p->tm_pairs32, p->tm_quads, p->tm_quads32, tasks, t1 - t0, qint, wide_flag, rgb, rgb_aligned, yuv, claim); break;
-      case kMode422: e = mcu_launch_mode<2, 1, false>(p->planes, p->any_unaligned[m] || !rgb_aligned, grid, mi, stream, p->tm_rows, p->tm_pairs, p->tm_rows32, p->tm_pairs32, p->tm_quads, p->tm_quads32, tasks, t1 - t0, qint, wide_flag, rgb, rgb_aligned, yuv, claim); break;
-      case kMode420: e = mcu_launch_mode<2, 2, false>(p->planes, p->any_unaligned[m] || !rgb_aligned, grid, mi, stream, p->tm_rows, p->tm_pairs, p->tm_rows32, p->tm_pairs32, p->tm_quads, p->tm_quads32, tasks, t1 - t0, qint, wide_flag, rgb, rgb_aligned, yuv, claim); break;
-      case kMode440: e = mcu_launch_mode<1, 2, false>(p->planes, p->any_unaligned[m] || !rgb_aligned, grid, mi, stream, p->tm_rows, p->tm_pairs, p->tm_rows32, p->tm_pairs32, p->tm_quads, p->tm_quads32, tasks, t1 - t0, qint, wide_flag, rgb, rgb_aligned, yuv, claim); break;
-      case kMode411: e = mcu_launch_mode<4, 1, false>(p->planes, p->any_unaligned[m] || !rgb_aligned, grid, mi, stream, p->tm_rows, p->tm_pairs, p->tm_rows32, p->tm_pairs32, p->tm_quads, p->tm_quads32, tasks, t1 - t0, qint, wide_flag, rgb, rgb_aligned, yuv, claim); break;
+      case kModeGray: e = mcu_launch_mode<1, 1, true>(mcu_use_tk(m, p->planes, p->any_unaligned[m] || !rgb_aligned), p->planes, p->any_unaligned[m] || !rgb_aligned, grid, mi, stream, p->tm_rows, p->tm_pairs, p->tm_rows32, p->tm_pairs32, p->tm_quads, p->tm_quads32, tasks, t1 - t0, qint, wide_flag, rgb, rgb_aligned, yuv, claim); break;
+      case kMode444: e = mcu_launch_mode<1, 1, false>(mcu_use_tk(m, p->planes, p->any_unaligned[m] || !rgb_aligned), p->planes, p->any_unaligned[m] || !rgb_aligned, grid, mi, stream, p->tm_rows, p->tm_pairs, p->tm_rows32, p->tm_pairs32, p->tm_quads, p->tm_quads32, tasks, t1 - t0, qint, wide_flag, rgb, rgb_aligned, yuv, claim); break;
+      case kMode422: e = mcu_launch_mode<2, 1, false>(mcu_use_tk(m, p->planes, p->any_unaligned[m] || !rgb_aligned), p->planes, p->any_unaligned[m] || !rgb_aligned, grid, mi, stream, p->tm_rows, p->tm_pairs, p->tm_rows32, p->tm_pairs32, p->tm_quads, p->tm_quads32, tasks, t1 - t0, qint, wide_flag, rgb, rgb_aligned, yuv, claim); break;
+      case kMode420: e = mcu_launch_mode<2, 2, false>(mcu_use_tk(m, p->planes, p->any_unaligned[m] || !rgb_aligned), p->planes, p->any_unaligned[m] || !rgb_aligned, grid, mi, stream, p->tm_rows, p->tm_pairs, p->tm_rows32, p->tm_pairs32, p->tm_quads, p->tm_quads32, tasks, t1 - t0, qint, wide_flag, rgb, rgb_aligned, yuv, claim); break;
+      case kMode440: e = mcu_launch_mode<1, 2, false>(mcu_use_tk(m, p->planes, p->any_unaligned[m] || !rgb_aligned), p->planes, p->any_unaligned[m] || !rgb_aligned, grid, mi, stream, p->tm_rows, p->tm_pairs, p->tm_rows32, p->tm_pairs32, p->tm_quads, p->tm_quads32, tasks, t1 - t0, qint, wide_flag, rgb, rgb_aligned, yuv, claim); break;
+      case kMode411: e = mcu_launch_mode<4, 1, false>(mcu_use_tk(m, p->planes, p->any_unaligned[m] || !rgb_aligned), p->planes, p->any_unaligned[m] || !rgb_aligned, grid, mi, stream, p->tm_rows, p->tm_pairs, p->tm_rows32, p->tm_pairs32, p->tm_quads, p->tm_quads32, tasks, t1 - t0, qint, wide_flag, rgb, rgb_aligned, yuv, claim); break;
     }
     if (e != cudaSuccess) return jgpu_fail("fused kernel launch failed (%s)", cudaGetErrorString(e));
     if (stream != caller) {

@@ -235,13 +235,15 @@ def test_task_counts_around_the_static_share(gpu_ctx, checker, n_images):
         compare_batch(descs, got_rgb, None, exp_rgb, None)
 
 
-def test_previous_kernel_still_matches(checker, monkeypatch):
-    """JGPU_KERNEL=mcu (A/B reference, profiles/r2_notes.md): k_mcu, one warp doing both halves of k_tk's
-    pairs, same bits."""
+@pytest.mark.parametrize("kernel", ["mcu", "tk"])
+def test_either_kernel_everywhere(checker, monkeypatch, kernel):
+    """By default grey pixels and the planes of grey / 4:2:0 / 4:2:2 run k_mcu (one warp doing both halves of
+    k_tk's pairs; faster where the colour warps have nothing to do, profiles/r2_notes.md) and everything else
+    k_tk; JGPU_KERNEL forces one of them for every mode it has: same bits, pixels and planes."""
     import torch
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
-    monkeypatch.setenv("JGPU_KERNEL", "mcu")
+    monkeypatch.setenv("JGPU_KERNEL", kernel)
     ctx = J.Context(0)           # the kernel choice is read per context creation
     try:
         shapes = [(w, h, ss) for ss in ("gray", "444", "422", "420", "440") for (w, h) in [(70, 50), (1000, 563), (1920, 1080)]]
@@ -251,7 +253,14 @@ def test_previous_kernel_still_matches(checker, monkeypatch):
         exp_rgb, _ = oracle_batch(checker, descs, coef, q, rgb_len, 0, nthreads=8)
         got_rgb, _ = gpu_batch(ctx, descs, coef, q, rgb_len, 0)
         compare_batch(descs, got_rgb, None, exp_rgb, None)
+        descs, coef_len, rgb_len, yuv_len = make_batch(shapes, want_yuv=True)
+        _, exp_yuv = oracle_batch(checker, descs, coef, q, rgb_len, yuv_len, nthreads=8)
+        plan = ctx.plan(descs, rgb=False, yuv=True)
+        assert plan.launches <= 1 + 2 * 5, "planes-only plans take the fused path"
+        plan.close()
+        _, got_yuv = gpu_batch(ctx, descs, coef, q, rgb_len, yuv_len, want_rgb=False)
+        compare_batch(descs, None, got_yuv, None, exp_yuv)
     finally:
         ctx.close()
         monkeypatch.delenv("JGPU_KERNEL")
-        J.Context(0).close()     # back to the product kernel for the tests that follow
+        J.Context(0).close()     # back to the product's choice for the tests that follow

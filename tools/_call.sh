@@ -1,5 +1,3 @@
-mkdir -p gpurun_out/r2
-for tool in memcheck racecheck synccheck; do
-  timeout 1200 compute-sanitizer --tool $tool python -m pytest tests/test_gpu_parity.py -q -x -k "test_rows_of_every_alignment or test_task_counts or test_planes_out or (test_parity_by_subsampling and fused) or test_parity_mixed_batch" > gpurun_out/r2/sanitize_tk2_$tool.log 2>&1
-  tail -3 gpurun_out/r2/sanitize_tk2_$tool.log
-done
+timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+TAG=34 VARIANTS="default" WLS="4k420_b256 4kgray_b256 mixed_stress" bash tools/ab.sh
+for wl in 4k420_b256 4kgray_b256; do python bench.py --workload $wl --yuv --no-e2e --no-cpu --no-extra 2>/dev/null | python -c "import json,sys; d=json.load(sys.stdin); print('planes $wl', round(d['ms_per_step'],4), round(d['roofline']['frac'],4), d['parity']['mismatching_images'])"; done
