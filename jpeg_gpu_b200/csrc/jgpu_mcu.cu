@@ -813,7 +813,8 @@ __device__ __forceinline__ void tk_store_any_short(uint8_t *dst, const uint32_t 
 /* The first nbytes (< 48: a unit cropped by the image's right edge) of w[0..11] to dst, whatever its
  * alignment: byte stores up to the first 4-byte boundary, funnel-shifted 32-bit stores from there, byte
  * stores for what is left of the last word. */
-__device__ __forceinline__ void tk_store_any(uint8_t *dst, const uint32_t (&w)[12], int nbytes) {
+template <int NW>
+__device__ __forceinline__ void tk_store_any(uint8_t *dst, const uint32_t (&w)[NW], int nbytes) {
   const int head = (int)((4u - (uint32_t)(uintptr_t)dst) & 3u);   /* bytes before the boundary */
 #pragma unroll
   for (int i = 0; i < 3; i++) {
@@ -824,9 +825,9 @@ __device__ __forceinline__ void tk_store_any(uint8_t *dst, const uint32_t (&w)[1
   const uint32_t sh = 8u * (uint32_t)head;
   uint32_t last = 0u;   /* the word the row ends in */
 #pragma unroll
-  for (int i = 0; i < 12; i++) {
+  for (int i = 0; i < NW; i++) {
     /* the four bytes that follow byte head + 4 i of the row */
-    const uint32_t v = __funnelshift_r(w[i], i + 1 < 12 ? w[i + 1] : 0u, sh);
+    const uint32_t v = __funnelshift_r(w[i], i + 1 < NW ? w[i + 1] : 0u, sh);
     if (4 * i + 4 <= left) *reinterpret_cast<uint32_t *>(p + 4 * i) = v;
     if (i == (left >> 2)) last = v;
   }
@@ -902,8 +903,8 @@ __device__ __forceinline__ void tk_edge_rows(uint32_t lstrip, uint32_t crow0, ui
       if (nbytes == 16 && ((uintptr_t)dst & 15) == 0) {
         stg128_stream(dst, v);
       } else {
-        const uint32_t w[12] = {v.x, v.y, v.z, v.w, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
-        tk_store_any(dst, w, nbytes);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        tk_store_any<4>(dst, w, nbytes);
       }
     }
   } else {
@@ -917,7 +918,7 @@ __device__ __forceinline__ void tk_edge_rows(uint32_t lstrip, uint32_t crow0, ui
         tk_staged_row(lstrip + 512u * (uint32_t)k, ya, yb);
         tk_row_words(ya, yb, ca, cb, w);
         if (nbytes == 48) tk_store48(dst, w);
-        else tk_store_any(dst, w, nbytes);
+        else tk_store_any<12>(dst, w, nbytes);
       }
     }
   }

@@ -1,3 +1,3 @@
-timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-TAG=34 VARIANTS="default" WLS="4k420_b256 4kgray_b256 mixed_stress" bash tools/ab.sh
-for wl in 4k420_b256 4kgray_b256; do python bench.py --workload $wl --yuv --no-e2e --no-cpu --no-extra 2>/dev/null | python -c "import json,sys; d=json.load(sys.stdin); print('planes $wl', round(d['ms_per_step'],4), round(d['roofline']['frac'],4), d['parity']['mismatching_images'])"; done
+timeout 900 python -m pytest tests/test_gpu_parity.py -x -q 2>&1 | tail -2
+python tools/kind_bench.py 2>&1 | grep -E "gray"
+TAG=35 VARIANTS="default" WLS="mixed_stress" bash tools/ab.sh
