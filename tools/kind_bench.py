@@ -11,8 +11,11 @@ ctx = J.Context(0)
 q = synth.quality_tables(85)
 d_q = torch.from_numpy(q.astype(np.int16).reshape(-1)).to(dev)
 peak = 6447.8
-for (w, h) in [(512, 512), (1920, 1080), (3840, 2160), (70, 50), (1000, 563), (1537, 771), (1008, 563), (1536, 771)]:
-    for ss in ["gray", "444", "420", "422"]:
+import os
+SIZES = [tuple(int(v) for v in s.split("x")) for s in os.environ.get("KIND_SIZES", "512x512,1920x1080,3840x2160,70x50,1000x563,1537x771,1008x563,1536x771").split(",")]
+MODES = os.environ.get("KIND_MODES", "gray,444,420,422").split(",")
+for (w, h) in SIZES:
+    for ss in MODES:
         n = max(4, int(600e6 / (w * h)))       # ~600 Mpx per batch
         n = min(n, 4096)
         hs, vs = J.SUBSAMPLINGS[ss]
