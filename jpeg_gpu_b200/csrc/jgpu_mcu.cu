@@ -57,6 +57,9 @@
 
 namespace jgpu {
 
+#ifndef JGPU_TMA_L2_PROMOTION
+#define JGPU_TMA_L2_PROMOTION CU_TENSOR_MAP_L2_PROMOTION_L2_128B   /* (256B and NONE measured: profiles/r2_notes.md) */
+#endif
 #ifndef JGPU_MCU_WAIT_NS
 #define JGPU_MCU_WAIT_NS 0       /* suspend-time hint of the mbarrier waits; 0: plain try_wait (see mbar_try_wait_hint) */
 #endif
@@ -1686,7 +1689,7 @@ static int mcu_build_maps(McuPlanImpl *p, const int16_t *coef) {
       cuuint32_t estr[2] = {1, 1};
       CUresult r = enc(big ? &p->tm_rows32 : &p->tm_rows, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<int16_t *>(coef), dims,
                        strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                       JGPU_TMA_L2_PROMOTION, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r != CUDA_SUCCESS) return jgpu_fail("cuTensorMapEncodeTiled(rows) failed (%d)", (int)r);
     }
     {
@@ -1696,7 +1699,7 @@ static int mcu_build_maps(McuPlanImpl *p, const int16_t *coef) {
       cuuint32_t estr[3] = {1, 1, 1};
       CUresult r = enc(big ? &p->tm_pairs32 : &p->tm_pairs, CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, const_cast<int16_t *>(coef), dims,
                        strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                       JGPU_TMA_L2_PROMOTION, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r != CUDA_SUCCESS) return jgpu_fail("cuTensorMapEncodeTiled(pairs) failed (%d)", (int)r);
     }
     {
@@ -1706,7 +1709,7 @@ static int mcu_build_maps(McuPlanImpl *p, const int16_t *coef) {
       cuuint32_t estr[3] = {1, 1, 1};
       CUresult r = enc(big ? &p->tm_quads32 : &p->tm_quads, CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, const_cast<int16_t *>(coef), dims,
                        strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                       JGPU_TMA_L2_PROMOTION, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r != CUDA_SUCCESS) return jgpu_fail("cuTensorMapEncodeTiled(quads) failed (%d)", (int)r);
     }
   }
