@@ -105,9 +105,12 @@ JGPU_DEV void load_row_pair_packed(pair32 (&row)[8], uint4 a, uint4 b, uint4 qa,
       b0 += dp2a_lo_s16_u8(wb[i], hb[i]) << 8;
       b1 += dp2a_hi_s16_u8(wb[i], hb[i]) << 8;
     }
-#if JGPU_DEQ_MAGIC
+#if JGPU_DEQ_MAGIC == 1
     row[2 * i] = prescale(s16_pair_to_float(a0, b0), r, 2 * i);
     row[2 * i + 1] = prescale(s16_pair_to_float(a1, b1), r, 2 * i + 1);
+#elif JGPU_DEQ_MAGIC == 2   /* every fourth pair without the conversion unit (A/B, profiles/r2_notes.md) */
+    row[2 * i] = prescale((i & 1) ? s16_pair_to_float(a0, b0) : p_make((float)(short)a0, (float)(short)b0), r, 2 * i);
+    row[2 * i + 1] = prescale(p_make((float)(short)a1, (float)(short)b1), r, 2 * i + 1);
 #else
     row[2 * i] = prescale(p_make((float)(short)a0, (float)(short)b0), r, 2 * i);
     row[2 * i + 1] = prescale(p_make((float)(short)a1, (float)(short)b1), r, 2 * i + 1);
