@@ -18,6 +18,8 @@
 #include <cuda_runtime.h>
 #include <stddef.h>
 #include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
 #include <algorithm>
 
 #include "jgpu_huff.h"
@@ -32,10 +34,21 @@ constexpr int kGuardWords = 4;
 
 __constant__ unsigned char c_zigzag[64] = JGPU_HUFF_ZIGZAG_NATURAL;
 
+/* JGPU_HUFF_GW=1: the sync kernel reads the scan words from global memory through L1 instead of
+ * staging them in shared memory: 19 KB instead of 51 KB per CTA, so more CTAs are resident while
+ * the ones in their late rounds (one or two warps busy, the rest at the barrier) hold their place. */
+#ifndef JGPU_HUFF_GW
+#define JGPU_HUFF_GW 1
+#endif
+#ifndef JGPU_HUFF_SYNC_CTAS
+#define JGPU_HUFF_SYNC_CTAS (JGPU_HUFF_GW ? 6 : 4)
+#endif
+constexpr bool kGlobalWords = JGPU_HUFF_GW != 0;
+
 template <int S>
 struct SyncSmem {
   jgpu_huff_table tabs[JGPU_HUFF_TABLES];
-  uint32_t words[(kCta + 1) * S];
+  uint32_t words[kGlobalWords ? 4 : (kCta + 1) * S];
   uint32_t s_out[kCta + 1];   /* s_out[i + 1]: state subsequence i ends in */
   uint32_t s_in[kCta];        /* state subsequence i starts from (current estimate) */
   uint32_t n[kCta];           /* slots it advances when decoded from s_in */
@@ -75,7 +88,9 @@ struct DevMem {
   uint32_t base_word;  /* file-relative index of the CTA's first word */
   uint32_t tabs, file, zz;
   uint32_t comps;      /* huff::comp_pack of the file */
+  const uint32_t *gwords;   /* kGlobalWords: the file's scan in global memory, as stored */
   __device__ __forceinline__ uint32_t word(uint32_t i) const {
+    if (kGlobalWords) return __byte_perm(__ldg(gwords + i), 0, 0x0123);
     const uint32_t l = i - base_word, row = l / S;
     return lds_u32(words + 4u * ((l & ~(uint32_t)(S - 1)) | ((l ^ row) & (S - 1))));
   }
@@ -114,8 +129,9 @@ __device__ __forceinline__ uint32_t pinned(uint32_t v) {
 }
 
 template <int S>
-__device__ __forceinline__ DevMem<S> dev_mem(const SyncSmem<S> &sm, int first) {
+__device__ __forceinline__ DevMem<S> dev_mem(const SyncSmem<S> &sm, int first, const uint32_t *stream) {
   DevMem<S> m;
+  m.gwords = stream + sm.file.word0;
   m.words = pinned((uint32_t)__cvta_generic_to_shared(sm.words));
   m.base_word = pinned((uint32_t)first * S);
   m.tabs = pinned((uint32_t)__cvta_generic_to_shared(sm.tabs));
@@ -149,7 +165,7 @@ __device__ __forceinline__ void stage(SyncSmem<S> &sm, const jgpu_huff_file *fil
     uint4 *dst = reinterpret_cast<uint4 *>(sm.tabs);
     for (int i = t; i < (int)(sizeof(jgpu_huff_table) * JGPU_HUFF_TABLES / 16); i += kCta) dst[i] = src[i];
   }
-  {
+  if (!kGlobalWords) {
     const uint4 *src = reinterpret_cast<const uint4 *>(stream + sm.file.word0 + (size_t)first * S);
     const int nvec = (count * S + kGuardWords) / 4;
     for (int i = t; i < nvec; i += kCta) {
@@ -166,7 +182,7 @@ __device__ __forceinline__ void stage(SyncSmem<S> &sm, const jgpu_huff_file *fil
 }
 
 template <int S>
-__global__ void __launch_bounds__(kCta, JGPU_HUFF_S >= 64 ? 2 : (1024 / kCta))
+__global__ void __launch_bounds__(kCta, JGPU_HUFF_S >= 64 ? 2 : (JGPU_HUFF_SYNC_CTAS * 256 / kCta))
 k_huff_sync(const jgpu_huff_file *__restrict__ files, const uint32_t *__restrict__ stream,
             const jgpu_huff_table *__restrict__ tables, const uint32_t *__restrict__ seg_first,
             uint32_t *__restrict__ state, uint32_t *__restrict__ nslots, uint32_t *__restrict__ segid,
@@ -236,7 +252,7 @@ k_huff_sync(const jgpu_huff_file *__restrict__ files, const uint32_t *__restrict
   }
   __syncthreads();
 
-  const DevMem<S> mem = dev_mem<S>(sm, first);
+  const DevMem<S> mem = dev_mem<S>(sm, first, stream);
   const int bpm = sm.file.bpm;
   /* Rounds.  In the first two nearly every subsequence is decoded (from the guess, then from
    * what its left neighbour ended in); after that the ones whose input still moves thin out
@@ -359,7 +375,7 @@ k_huff_write(const jgpu_huff_file *__restrict__ files, const uint32_t *__restric
   if ((slot0 & 63u) != JGPU_HUFF_STATE_Z(st) || (uint32_t)(g0 % f.bpm) != JGPU_HUFF_STATE_C(st)) {
     flags = JGPU_HUFF_ERR_SYNC;
   } else if (g0 < seg_blocks) {
-    const DevMem<S> mem = dev_mem<S>(sm, first);
+    const DevMem<S> mem = dev_mem<S>(sm, first, stream);
     huff::StoreSink<DevMem<S>> sink;
     sink.start(&mem, f.bpm, f.nhmb, coef, seg_mcu0, g0, seg_blocks);
     uint32_t n = 0, err = 0;
@@ -376,6 +392,238 @@ k_huff_write(const jgpu_huff_file *__restrict__ files, const uint32_t *__restric
     }
     if (sink.g < seg_blocks) {
       /* the interval goes on: into the next subsequence, which must start where this one ended */
+      if (i + 1 == seg_first[f.seg0 + seg + 1]) flags |= JGPU_HUFF_ERR_SHORT;
+      else if (out != state[gi + 1] || n != (nslots[gi] & 0x7fffffffu)) flags |= JGPU_HUFF_ERR_SYNC;
+    }
+  }
+  if (flags) atomicOr(status + f.status_slot, flags);
+}
+
+/* ---- write pass, staged -------------------------------------------------------------------
+ * The write pass above stores every non-zero coefficient where it belongs the moment it is
+ * decoded: 2-byte stores from 32 lanes into 32 different 128-byte lines, 28.6 L1 tag requests per
+ * store instruction, and the table look-ups of the decoding loop queue behind them in the same
+ * load/store unit (profiles/r1_ncu_summary.md: the kernel runs twice as fast without its stores).
+ * Here every thread owns a 128-byte block buffer in shared memory, stores coefficients there, and
+ * when a lane completes a block the WARP writes it out: lane r moves word r, one full line per
+ * block.  Blocks a thread only sees a part of (the one its subsequence starts in the middle of,
+ * the one it ends in the middle of) are written as their non-zero halves only, like before, so
+ * two threads sharing a block never overwrite each other; the coefficient range is zero before
+ * the kernel either way.  The scan words come straight from global memory through L1 (one load
+ * per 32 bits consumed, fetched one refill ahead), which leaves the shared memory to the block
+ * buffers: 47.6 KB per CTA, four CTAs per SM as before.
+ *
+ * Buffer layout: word w of lane l's block sits at word (w + l) & 31 of its 128 bytes, so that
+ * lanes storing the same coefficient index hit different banks and the cooperative read of one
+ * block (lane r reads physical word r) is conflict-free. */
+template <int S>
+struct WriteSmem {
+  jgpu_huff_table tabs[JGPU_HUFF_TABLES];
+  uint32_t blocks[kCta * 32];
+  jgpu_huff_file file;
+  unsigned char zz[64];
+};
+
+__device__ __forceinline__ void sts_u16(uint32_t a, uint32_t v) {
+  asm volatile("{\n\t.reg .u16 t;\n\tcvt.u16.u32 t, %1;\n\tst.shared.u16 [%0], t;\n\t}" ::"r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) {
+  asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t lds_u32_v(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
+
+/* The warp writes out the blocks of the lanes in `m`; `pm`: lanes whose block is a partial one.
+ * blk = the lane's current block, in blocks from the coefficient buffer's start. */
+__device__ __forceinline__ void flush_blocks(uint32_t m, uint32_t pm, uint32_t blk, uint32_t warpbuf, int lane,
+                                             int16_t *__restrict__ coef) {
+  __syncwarp();
+  do {
+    const int l = __ffs((int)m) - 1;
+    m &= m - 1;
+    const uint32_t b = __shfl_sync(0xffffffffu, blk, l);
+    const uint32_t a = warpbuf + (uint32_t)l * 128u + (uint32_t)lane * 4u;
+    const uint32_t v = lds_u32_v(a);
+    sts_u32(a, 0u);
+    int16_t *dst = coef + (size_t)b * 64 + 2u * ((uint32_t)(lane - l) & 31u);
+    if (!((pm >> l) & 1u)) {
+      *reinterpret_cast<uint32_t *>(dst) = v;
+    } else {
+      if (v & 0xffffu) dst[0] = (int16_t)(v & 0xffffu);
+      if (v >> 16) dst[1] = (int16_t)(v >> 16);
+    }
+  } while (m);
+  __syncwarp();
+}
+
+template <int S>
+__global__ void __launch_bounds__(kCta, 1024 / kCta)
+k_huff_write_staged(const jgpu_huff_file *__restrict__ files, const uint32_t *__restrict__ stream,
+                    const jgpu_huff_table *__restrict__ tables, const uint32_t *__restrict__ seg_first,
+                    const uint32_t *__restrict__ state, const uint32_t *__restrict__ nslots,
+                    const uint32_t *__restrict__ slots, const uint32_t *__restrict__ segid,
+                    int16_t *__restrict__ coef, uint32_t *__restrict__ status) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  WriteSmem<S> &sm = *reinterpret_cast<WriteSmem<S> *>(smem_raw);
+  const jgpu_huff_file &gf = files[blockIdx.y];
+  const int first = cta_x() * kCta;
+  if (first >= (int)gf.n_subseq) return;
+  const int count = min(kCta, (int)gf.n_subseq - first);
+  const int t = threadIdx.x, lane = t & 31;
+  {
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(files + blockIdx.y);
+    uint32_t *dst = reinterpret_cast<uint32_t *>(&sm.file);
+    for (int i = t; i < (int)(sizeof(jgpu_huff_file) / 4); i += kCta) dst[i] = src[i];
+    if (t < 64) sm.zz[t] = c_zigzag[t];
+    uint4 *z = reinterpret_cast<uint4 *>(sm.blocks);
+    for (int i = t; i < kCta * 8; i += kCta) z[i] = make_uint4(0u, 0u, 0u, 0u);
+  }
+  __syncthreads();
+  {
+    const uint4 *src = reinterpret_cast<const uint4 *>(tables + sm.file.table0);
+    uint4 *dst = reinterpret_cast<uint4 *>(sm.tabs);
+    for (int i = t; i < (int)(sizeof(jgpu_huff_table) * JGPU_HUFF_TABLES / 16); i += kCta) dst[i] = src[i];
+  }
+  __syncthreads();
+  const jgpu_huff_file &f = sm.file;
+  DevMem<S> mem;
+  mem.words = 0;
+  mem.base_word = 0;
+  mem.gwords = stream + sm.file.word0;
+  mem.tabs = pinned((uint32_t)__cvta_generic_to_shared(sm.tabs));
+  mem.file = pinned((uint32_t)__cvta_generic_to_shared(&sm.file));
+  mem.zz = pinned((uint32_t)__cvta_generic_to_shared(sm.zz));
+  mem.comps = pinned(huff::comp_pack(sm.file));
+  const uint32_t mybuf = pinned((uint32_t)__cvta_generic_to_shared(sm.blocks) + (uint32_t)t * 128u);
+  const uint32_t warpbuf = mybuf - (uint32_t)lane * 128u;
+  const int bpm = f.bpm, nhmb = f.nhmb;
+  const uint32_t *wp = stream + f.word0;
+
+  /* what the thread is about */
+  bool active = false;
+  uint32_t flags = 0;
+  const uint32_t i = (uint32_t)(first + min(t, count - 1)), gi = f.subseq0 + i;
+  const uint32_t seg = segid[gi];
+  const int seg_mcu0 = (int)seg * f.mcus_per_seg;
+  const int64_t seg_blocks = (int64_t)min(f.mcus_per_seg, f.total_mcus - seg_mcu0) * bpm;
+  const uint32_t st = state[gi];
+  int64_t g = 0;
+  if (t < count) {
+    const uint32_t slot0 = slots[gi];
+    g = slot0 >> 6;
+    if ((slot0 & 63u) != JGPU_HUFF_STATE_Z(st) || (uint32_t)(g % bpm) != JGPU_HUFF_STATE_C(st)) {
+      flags = JGPU_HUFF_ERR_SYNC;
+    } else if (g < seg_blocks) {
+      active = true;
+    }
+  }
+  const bool decoded = active;
+
+  /* decoder state (jgpu_huff_core.h decode_subsequence, same arithmetic) */
+  int pos = (int)JGPU_HUFF_STATE_P(st);
+  uint32_t c = JGPU_HUFF_STATE_C(st), z = JGPU_HUFF_STATE_Z(st);
+  constexpr int end = 32 * S;
+  uint32_t n = 0, bad = 0;
+  uint32_t next = i * S + (uint32_t)(pos >> 5);
+  uint64_t buf = 0;
+  uint32_t ahead = 0;
+  int avail = 64 - (pos & 31);
+  int mbx = 0, mby = 0;
+  uint32_t blk = 0;
+  auto locate = [&]() {
+    blk = (uint32_t)((mem.blk_base((int)c) + (int64_t)mbx * mem.blk_xs((int)c) + (int64_t)mby * mem.blk_ys((int)c)) >> 6);
+  };
+  if (active) {
+    buf = ((uint64_t)__byte_perm(__ldg(wp + next), 0, 0x0123) << 32) | __byte_perm(__ldg(wp + next + 1), 0, 0x0123);
+    next += 2;
+    buf <<= (pos & 31);
+    ahead = __byte_perm(__ldg(wp + next), 0, 0x0123);
+    const int mcu = seg_mcu0 + (int)(g / bpm);
+    mbx = mcu % nhmb;
+    mby = mcu / nhmb;
+    locate();
+  }
+  uint32_t tdc = mem.blk_table(c);
+  bool partial = z != 0;   /* the block this subsequence starts inside belongs to two threads */
+
+  for (;;) {
+    bool fin = false;
+    if (active) {
+      if (avail < 32) {
+        buf |= (uint64_t)ahead << (32 - avail);
+        avail += 32;
+        ahead = __byte_perm(__ldg(wp + (++next)), 0, 0x0123);
+      }
+      const uint32_t ac = z != 0;
+      const uint32_t look = (uint32_t)(buf >> 48);
+      uint32_t e = mem.lut(tdc + ac, look >> (16 - JGPU_HUFF_LUT_BITS));
+      if (e == 0) {
+        e = huff::lookup_long(mem, tdc + ac, look);
+        if (e == 0) {
+          bad = 1;
+          e = 16u << 8;
+        }
+      }
+      const int len = (int)(e >> 8);
+      const uint32_t sym = e & 0xffu;
+      const int s = (int)(sym & 15u);
+      const uint32_t hi = (uint32_t)((buf << len) >> 32);
+      const uint32_t bits = (hi >> 1) >> (31 - s);
+      const uint32_t half = (1u << s) >> 1;
+      const int v = bits < half ? (int)bits - (1 << s) + 1 : (int)bits;
+      buf <<= (len + s);
+      avail -= len + s;
+      pos += len + s;
+      const uint32_t k = z + (ac ? sym >> 4 : 0u);
+      const uint32_t over = k > 63u;
+      const uint32_t stop = (ac & (uint32_t)(sym == 0)) | over;
+      bad |= over;
+      if (v != 0 && !stop) {
+        const uint32_t p = mem.zigzag((int)k);
+        sts_u16(mybuf + 4u * (((p >> 1) + (uint32_t)lane) & 31u) + 2u * (p & 1u), (uint32_t)v);
+      }
+      const uint32_t znew = stop ? 64u : k + 1;
+      n += znew - z;
+      z = znew;
+      fin = z == 64;
+    }
+    const uint32_t m = __ballot_sync(0xffffffffu, fin);
+    if (m) flush_blocks(m, __ballot_sync(0xffffffffu, partial), blk, warpbuf, lane, coef);
+    if (fin) {
+      z = 0;
+      partial = false;
+      g++;
+      if (++c == (uint32_t)bpm) {
+        c = 0;
+        if (++mbx == nhmb) {
+          mbx = 0;
+          mby++;
+        }
+      }
+      tdc = mem.blk_table(c);
+      if (g >= seg_blocks) active = false;
+      else locate();
+    }
+    if (pos >= end) active = false;
+    if (!__any_sync(0xffffffffu, active)) break;
+  }
+  /* blocks left unfinished: the next subsequence carries on with them */
+  {
+    const uint32_t m = __ballot_sync(0xffffffffu, decoded && z != 0);
+    if (m) flush_blocks(m, 0xffffffffu, blk, warpbuf, lane, coef);
+  }
+  if (decoded) {
+    const uint32_t out = JGPU_HUFF_STATE(pos > end ? pos - end : 0, c, z);
+    if (bad) flags |= JGPU_HUFF_ERR_CODE;
+    if (g >= seg_blocks) {
+      const uint32_t *sf = seg_first + f.seg0;
+      const uint32_t bits = sf[f.n_seg + 1 + seg];
+      const long long used = (long long)(i - sf[seg]) * (32 * S) + pos;
+      if (bits != 0xffffffffu && (long long)bits - used >= 8) flags |= JGPU_HUFF_ERR_TRAIL;
+    } else {
       if (i + 1 == seg_first[f.seg0 + seg + 1]) flags |= JGPU_HUFF_ERR_SHORT;
       else if (out != state[gi + 1] || n != (nslots[gi] & 0x7fffffffu)) flags |= JGPU_HUFF_ERR_SYNC;
     }
@@ -447,13 +695,22 @@ cudaError_t configure_kernels() {
   cudaError_t e = cudaFuncSetAttribute(k_huff_sync<S>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)sizeof(SyncSmem<S>));
   if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(k_huff_write<S>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              (int)sizeof(SyncSmem<S>));
+  e = cudaFuncSetAttribute(k_huff_write<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SyncSmem<S>));
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(k_huff_write_staged<S>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)sizeof(WriteSmem<S>));
 }
 
 }  // namespace
 
-cudaError_t huff_configure() { return configure_kernels<kHuffSubseqWords>(); }
+/* JGPU_HUFF_WRITE=scatter: the write pass that stores coefficient by coefficient (A/B, profiles/r2_notes.md) */
+static bool g_staged_write = true;
+
+cudaError_t huff_configure() {
+  const char *w = getenv("JGPU_HUFF_WRITE");
+  g_staged_write = !(w && strcmp(w, "scatter") == 0);
+  return configure_kernels<kHuffSubseqWords>();
+}
 
 int huff_launches(const HuffLaunch &l) { return l.sync_passes + 3 + (l.max_dc_chain > kDcPiece ? 1 : 0); }
 
@@ -481,8 +738,14 @@ int huff_launch(const HuffLaunch &l, cudaStream_t st) {
                                              l.d_carry[pass & 1], pass);
   }
   k_huff_scan<<<l.n_files, 1024, 0, st>>>(l.d_files, l.d_nslots, l.d_slots);
-  k_huff_write<S><<<grid, kCta, smem, st>>>(l.d_files, l.d_stream, l.d_tables, l.d_seg_first, l.d_state,
-                                            l.d_nslots, l.d_slots, l.d_segid, l.d_coef, l.d_status);
+  if (g_staged_write) {
+    k_huff_write_staged<S><<<grid, kCta, sizeof(WriteSmem<S>), st>>>(l.d_files, l.d_stream, l.d_tables, l.d_seg_first,
+                                                                    l.d_state, l.d_nslots, l.d_slots, l.d_segid,
+                                                                    l.d_coef, l.d_status);
+  } else {
+    k_huff_write<S><<<grid, kCta, smem, st>>>(l.d_files, l.d_stream, l.d_tables, l.d_seg_first, l.d_state,
+                                              l.d_nslots, l.d_slots, l.d_segid, l.d_coef, l.d_status);
+  }
   const int pieces = std::max(1, (l.max_dc_chain + kDcPiece - 1) / kDcPiece);
   const dim3 dc_grid((unsigned)(std::max(1, l.max_dc_jobs) * pieces), (unsigned)l.n_files);
   if (pieces > 1) {

@@ -73,6 +73,11 @@ struct jgpu_ctx {
   int sm_count = 0;
   cudaStream_t streams[kHostStreams] = {};
   cudaEvent_t events[kHostStreams] = {};
+  /* jgpu_decode_jpegs_ex, entropy decoding on the device: the compressed scans go up on a stream of
+   * their own, one event per group of files, so that a group's kernels never wait behind the copy
+   * of a later group (created on first use) */
+  cudaStream_t up_stream = nullptr;
+  std::vector<cudaEvent_t> up_events;
   /* device mirrors used by the host-buffer entry points (grow-only) */
   Buffer d_coef, d_qtabs, d_rgb, d_yuv;
   Buffer d_pack, d_index, d_pack_off; /* jgpu_decode_batch_host_packed */
@@ -184,6 +189,8 @@ extern "C" void jgpu_destroy(jgpu_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->cached_plan) jgpu_plan_destroy(ctx->cached_plan);
+  if (ctx->up_stream) cudaStreamDestroy(ctx->up_stream);
+  for (cudaEvent_t e : ctx->up_events) cudaEventDestroy(e);
   for (int i = 0; i < kHostStreams; i++) {
     if (ctx->streams[i]) cudaStreamDestroy(ctx->streams[i]);
     if (ctx->events[i]) cudaEventDestroy(ctx->events[i]);
@@ -1383,11 +1390,23 @@ static int decode_jpegs_gpu_entropy(jgpu_ctx *ctx, const jgpu_jpeg *files, int n
     const int64_t first_bytes = 48ll << 20, max_bytes = 512ll << 20;
     const long wave = (long)ctx->sm_count * (1024 / JGPU_HUFF_CTA);   /* CTAs of k_huff_sync / k_huff_write resident at once */
     int i0 = 0, chunk = 0;
+    /* JGPU_HUFF_WAVES: experiment knob, waves of entropy CTAs per group */
+    const int max_waves = getenv("JGPU_HUFF_WAVES") ? std::max(1, atoi(getenv("JGPU_HUFF_WAVES"))) : 2;
+    /* JGPU_TRACE: device-side times of every group (events on its stream) */
+    std::vector<cudaEvent_t> tev;
+    std::vector<int> tfiles;
+    auto mark = [&](cudaStream_t s) {
+      if (!trace) return;
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      cudaEventRecord(e, s);
+      tev.push_back(e);
+    };
     while (i0 < m) {
       int i1 = i0;
       int64_t acc = 0;
       long ctas = 0;
-      const long target = (chunk < 2 ? chunk : 2) * wave;
+      const long target = (chunk < max_waves ? chunk : max_waves) * wave;
       /* (a group's file count is gridDim.y of the entropy kernels: at most 65535) */
       while (i1 < m && i1 - i0 < 65535) {
         JpegItem &it = items[ok[i1]];
@@ -1409,27 +1428,43 @@ static int decode_jpegs_gpu_entropy(jgpu_ctx *ctx, const jgpu_jpeg *files, int n
         info[ok[k]].tasks = on_gpu[k] ? (int32_t)h_files[k].n_subseq : 1;
       }
       cudaStream_t st = ctx->streams[chunk % kHostStreams];
+      mark(st);
+      tfiles.push_back(i1 - i0);
+      /* The group's input goes up on the upload stream; its kernels wait for that copy alone.  (With the
+       * copies on the groups' own streams the three streams fell into step -- all copying, then all
+       * computing -- and the SMs sat idle a third of the time, profiles/r2_notes.md 14.) */
+      if (!ctx->up_stream) CU_TRY(cudaStreamCreateWithFlags(&ctx->up_stream, cudaStreamNonBlocking));
+      while ((int)ctx->up_events.size() <= chunk) {
+        cudaEvent_t e;
+        CU_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->up_events.push_back(e);
+      }
+      cudaStream_t up = ctx->up_stream;
       /* each file's stream is a little shorter than its slot (headers, stuffing and markers are
        * gone): large files are copied slot by slot, many small ones in one go, gaps included */
       if (i1 - i0 > 16) {
         CU_TRY(cudaMemcpyAsync((unsigned char *)ctx->dz_stream.ptr + slot[i0].stream_off, h_stream + slot[i0].stream_off,
-                               (size_t)(slot[i1].stream_off - slot[i0].stream_off), cudaMemcpyHostToDevice, st));
+                               (size_t)(slot[i1].stream_off - slot[i0].stream_off), cudaMemcpyHostToDevice, up));
       } else {
         for (int k = i0; k < i1; k++) {
           if (!on_gpu[k]) continue;
           const size_t bytes = (size_t)h_files[k].n_subseq * 4 * S + 16;
           CU_TRY(cudaMemcpyAsync((unsigned char *)ctx->dz_stream.ptr + slot[k].stream_off, h_stream + slot[k].stream_off,
-                                 bytes, cudaMemcpyHostToDevice, st));
+                                 bytes, cudaMemcpyHostToDevice, up));
         }
       }
       CU_TRY(cudaMemcpyAsync((jgpu_huff_file *)ctx->dz_files.ptr + i0, h_files + i0, sizeof(jgpu_huff_file) * (i1 - i0),
-                             cudaMemcpyHostToDevice, st));
+                             cudaMemcpyHostToDevice, up));
       CU_TRY(cudaMemcpyAsync((jgpu_huff_table *)ctx->dz_tables.ptr + (size_t)JGPU_HUFF_TABLES * i0,
                              h_tables + (size_t)JGPU_HUFF_TABLES * i0,
-                             sizeof(jgpu_huff_table) * JGPU_HUFF_TABLES * (i1 - i0), cudaMemcpyHostToDevice, st));
+                             sizeof(jgpu_huff_table) * JGPU_HUFF_TABLES * (i1 - i0), cudaMemcpyHostToDevice, up));
       CU_TRY(cudaMemcpyAsync((uint32_t *)ctx->dz_segs.ptr + slot[i0].seg0, h_segs + slot[i0].seg0,
-                             4 * (size_t)(slot[i1].seg0 - slot[i0].seg0), cudaMemcpyHostToDevice, st));
+                             4 * (size_t)(slot[i1].seg0 - slot[i0].seg0), cudaMemcpyHostToDevice, up));
+      CU_TRY(cudaEventRecord(ctx->up_events[chunk], up));
+      CU_TRY(cudaStreamWaitEvent(st, ctx->up_events[chunk], 0));
+      mark(st);
       CU_TRY(cudaMemsetAsync(d_coef + descs[i0].coef_off, 0, (size_t)acc, st));
+      mark(st);
       {
         /* scratch of the DC pass, one buffer per stream (groups on one stream run in order) */
         Buffer &dc = ctx->dz_dc[chunk % kHostStreams];
@@ -1458,9 +1493,11 @@ static int decode_jpegs_gpu_entropy(jgpu_ctx *ctx, const jgpu_jpeg *files, int n
       l.d_status = (uint32_t *)ctx->dz_status.ptr;
       l.d_coef = d_coef;
       if (huff_launch(l, st)) return EXIT_FAILURE;
+      mark(st);
       if (plan_run_range(plan, i0, i1, d_coef, d_qtabs, m, yuv_out ? nullptr : d_rgb, yuv_out ? d_rgb : nullptr, st)) {
         return EXIT_FAILURE;
       }
+      mark(st);
       CU_TRY(cudaMemcpyAsync(h_status + i0, (uint32_t *)ctx->dz_status.ptr + i0, 4 * (size_t)(i1 - i0),
                              cudaMemcpyDeviceToHost, st));
       if (!device_out) {
@@ -1474,7 +1511,19 @@ static int decode_jpegs_gpu_entropy(jgpu_ctx *ctx, const jgpu_jpeg *files, int n
     }
     t_enqueued = since();
     for (int s = 0; s < kHostStreams; s++) CU_TRY(cudaStreamSynchronize(ctx->streams[s]));
+    CU_TRY(cudaStreamSynchronize(ctx->up_stream));
     t_synced = since();
+    for (size_t g = 0; g + 4 < tev.size() + 1 && g / 5 < tfiles.size(); g += 5) {
+      float a = 0, b = 0, c = 0, d = 0, e = 0;
+      cudaEventElapsedTime(&a, tev[0], tev[g]);
+      cudaEventElapsedTime(&b, tev[g], tev[g + 1]);
+      cudaEventElapsedTime(&c, tev[g + 1], tev[g + 2]);
+      cudaEventElapsedTime(&d, tev[g + 2], tev[g + 3]);
+      cudaEventElapsedTime(&e, tev[g + 3], tev[g + 4]);
+      fprintf(stderr, "  group %2d (%2d files, stream %d): starts %.2f ms, copy in %.2f, zero %.2f, entropy %.2f, blocks %.2f\n",
+              (int)(g / 5), tfiles[g / 5], (int)((g / 5) % kHostStreams), a, b, c, d, e);
+    }
+    for (cudaEvent_t e : tev) cudaEventDestroy(e);
     return EXIT_SUCCESS;
   };
   int rc = gpu_part();

@@ -1,9 +1,8 @@
 mkdir -p gpurun_out/r2
-python bench.py > gpurun_out/r2/bench_final2.json 2> gpurun_out/r2/bench_final2.err
-ncu --metrics gpu__time_duration.sum --clock-control none -k regex:k_ -c 60 --csv --log-file gpurun_out/r2/launches_final2.csv python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu --no-extra > /dev/null 2>&1
-python - <<PY
-import json
-d=json.load(open("gpurun_out/r2/bench_final2.json"))
-print("value",round(d["value"]),"ms",round(d["ms_per_step"],4),"frac",round(d["roofline"]["frac"],4),"e2e",round(d["e2e"]["value"]),"pack",round(d["e2e_pack"]["value"]),"jpeg",round(d["e2e_jpeg"]["value"]),round(d["e2e_jpeg"]["device_out_value"]),round(d["e2e_jpeg"]["yuv_out_value"]), "cpu", round(d["cpu_baseline"]["value"]))
-for k,v in d["extra"].items(): print(k, round(v["value"]), round(v["ms_per_step"],4), round(v["roofline"]["frac"],4), v["parity"]["mismatching_images"])
-PY
+PROFILE_DEVICE_OUT=1 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_huff_sync --launch-skip 6 --launch-count 1 -o /tmp/sync_gw python tools/profile_jpegs.py 16 gpu 240 1 > /dev/null 2>&1
+PROFILE_DEVICE_OUT=1 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_huff_write --launch-skip 2 --launch-count 1 -o /tmp/write_st python tools/profile_jpegs.py 16 gpu 240 1 > /dev/null 2>&1
+ncu -i /tmp/sync_gw.ncu-rep --page raw --csv > gpurun_out/r2/ncu_sync_gw_raw.csv
+ncu -i /tmp/write_st.ncu-rep --page raw --csv > gpurun_out/r2/ncu_write_staged_raw.csv
+ncu -i /tmp/sync_gw.ncu-rep --page source --csv > gpurun_out/r2/ncu_sync_gw_source.csv 2>/dev/null
+ncu -i /tmp/write_st.ncu-rep --page source --csv > gpurun_out/r2/ncu_write_staged_source.csv 2>/dev/null
+ls -la gpurun_out/r2/ncu_*
