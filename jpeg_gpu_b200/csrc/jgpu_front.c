@@ -640,8 +640,8 @@ long long jfront_huff_prepare(jpeg_decode_ctx *ctx, int subseq_words, unsigned c
   for (i = 0; i < ns; i++) {
     const int plane = (int)(sc[i].fc - w.comp);
     int dx, dy;
-    if (jgpu_huff_build_table(&tables[2 * plane], sc[i].dc->counts, sc[i].dc->symbols) ||
-        jgpu_huff_build_table(&tables[2 * plane + 1], sc[i].ac->counts, sc[i].ac->symbols)) {
+    if (jgpu_huff_build_table(&tables[2 * plane], sc[i].dc->counts, sc[i].dc->symbols, 0) ||
+        jgpu_huff_build_table(&tables[2 * plane + 1], sc[i].ac->counts, sc[i].ac->symbols, 1)) {
       *why = "Error invalid DHT.";
       return -1;
     }

@@ -97,6 +97,8 @@ struct DevMem {
   __device__ __forceinline__ uint32_t lut(uint32_t t, uint32_t i) const {
     return lds_u16(tabs + t * (uint32_t)sizeof(jgpu_huff_table) + 2u * i);
   }
+  __device__ __forceinline__ uint32_t table_ref(uint32_t t) const { return tabs + t * (uint32_t)sizeof(jgpu_huff_table); }
+  __device__ __forceinline__ uint32_t lut_at(uint32_t ref, uint32_t i) const { return lds_u16(ref + 2u * i); }
   __device__ __forceinline__ uint32_t limit(uint32_t t, int len) const {
     return lds_u32(tabs + t * (uint32_t)sizeof(jgpu_huff_table) + (uint32_t)offsetof(jgpu_huff_table, limit) + 4u * len);
   }
@@ -500,7 +502,6 @@ k_huff_write_staged(const jgpu_huff_file *__restrict__ files, const uint32_t *__
   const uint32_t mybuf = pinned((uint32_t)__cvta_generic_to_shared(sm.blocks) + (uint32_t)t * 128u);
   const uint32_t warpbuf = mybuf - (uint32_t)lane * 128u;
   const int bpm = f.bpm, nhmb = f.nhmb;
-  const uint32_t *wp = stream + f.word0;
 
   /* what the thread is about */
   bool active = false;
@@ -523,77 +524,72 @@ k_huff_write_staged(const jgpu_huff_file *__restrict__ files, const uint32_t *__
   const bool decoded = active;
 
   /* decoder state (jgpu_huff_core.h decode_subsequence, same arithmetic) */
-  int pos = (int)JGPU_HUFF_STATE_P(st);
   uint32_t c = JGPU_HUFF_STATE_C(st), z = JGPU_HUFF_STATE_Z(st);
-  constexpr int end = 32 * S;
-  uint32_t n = 0, bad = 0;
-  uint32_t next = i * S + (uint32_t)(pos >> 5);
-  uint64_t buf = 0;
-  uint32_t ahead = 0;
-  int avail = 64 - (pos & 31);
+  const uint32_t z0 = z;
+  uint32_t nblk = 0, bad = 0;
+  uint32_t bp = JGPU_HUFF_STATE_P(st) & 31u;
+  uint32_t wi = i * S + (JGPU_HUFF_STATE_P(st) >> 5);
+  const uint32_t wend = (i + 1) * S;
+  uint32_t wa = 0, wb = 0, ahead = 0;
   int mbx = 0, mby = 0;
   uint32_t blk = 0;
+  const uint32_t *gw = mem.gwords;
+  auto gword = [&](uint32_t idx) { return __byte_perm(__ldg(gw + idx), 0, 0x0123); };
   auto locate = [&]() {
     blk = (uint32_t)((mem.blk_base((int)c) + (int64_t)mbx * mem.blk_xs((int)c) + (int64_t)mby * mem.blk_ys((int)c)) >> 6);
   };
   if (active) {
-    buf = ((uint64_t)__byte_perm(__ldg(wp + next), 0, 0x0123) << 32) | __byte_perm(__ldg(wp + next + 1), 0, 0x0123);
-    next += 2;
-    buf <<= (pos & 31);
-    ahead = __byte_perm(__ldg(wp + next), 0, 0x0123);
+    wa = gword(wi);
+    wb = gword(wi + 1);
+    ahead = gword(wi + 2);
     const int mcu = seg_mcu0 + (int)(g / bpm);
     mbx = mcu % nhmb;
     mby = mcu / nhmb;
     locate();
   }
-  uint32_t tdc = mem.blk_table(c);
+  uint32_t tdc = mem.table_ref(mem.blk_table(c)), tac = mem.table_ref(mem.blk_table(c) + 1);
+  uint32_t tab = z ? tac : tdc;
   bool partial = z != 0;   /* the block this subsequence starts inside belongs to two threads */
 
   for (;;) {
     bool fin = false;
     if (active) {
-      if (avail < 32) {
-        buf |= (uint64_t)ahead << (32 - avail);
-        avail += 32;
-        ahead = __byte_perm(__ldg(wp + (++next)), 0, 0x0123);
-      }
-      const uint32_t ac = z != 0;
-      const uint32_t look = (uint32_t)(buf >> 48);
-      uint32_t e = mem.lut(tdc + ac, look >> (16 - JGPU_HUFF_LUT_BITS));
+      const uint32_t look = huff::window32(wa, wb, bp);
+      uint32_t e = mem.lut_at(tab, look >> (32 - JGPU_HUFF_LUT_BITS));
       if (e == 0) {
-        e = huff::lookup_long(mem, tdc + ac, look);
-        if (e == 0) {
-          bad = 1;
-          e = 16u << 8;
+        const uint32_t l = huff::lookup_long(mem, mem.blk_table(c) + (z != 0), look >> 16);
+        e = l ? JGPU_HUFF_ENTRY(l >> 8, l & 0xffu, z != 0) : JGPU_HUFF_ENTRY(16u, 0u, z != 0);
+        bad |= (uint32_t)(l == 0);
+      }
+      const uint32_t total = JGPU_HUFF_ENTRY_T(e);
+      const uint32_t za = z + JGPU_HUFF_ENTRY_A(e);
+      if (za <= 64u) {
+        const uint32_t s = JGPU_HUFF_ENTRY_S(e);
+        const uint32_t bits = ((look << (total - s)) >> 1) >> (31u - s);
+        const uint32_t half = (1u << s) >> 1;
+        const int v = bits < half ? (int)bits - (int)(1u << s) + 1 : (int)bits;
+        if (v != 0) {
+          const uint32_t p = mem.zigzag((int)za - 1);
+          sts_u16(mybuf + 4u * (((p >> 1) + (uint32_t)lane) & 31u) + 2u * (p & 1u), (uint32_t)v);
         }
       }
-      const int len = (int)(e >> 8);
-      const uint32_t sym = e & 0xffu;
-      const int s = (int)(sym & 15u);
-      const uint32_t hi = (uint32_t)((buf << len) >> 32);
-      const uint32_t bits = (hi >> 1) >> (31 - s);
-      const uint32_t half = (1u << s) >> 1;
-      const int v = bits < half ? (int)bits - (1 << s) + 1 : (int)bits;
-      buf <<= (len + s);
-      avail -= len + s;
-      pos += len + s;
-      const uint32_t k = z + (ac ? sym >> 4 : 0u);
-      const uint32_t over = k > 63u;
-      const uint32_t stop = (ac & (uint32_t)(sym == 0)) | over;
-      bad |= over;
-      if (v != 0 && !stop) {
-        const uint32_t p = mem.zigzag((int)k);
-        sts_u16(mybuf + 4u * (((p >> 1) + (uint32_t)lane) & 31u) + 2u * (p & 1u), (uint32_t)v);
+      bp += total;
+      if (bp >= 32u) {
+        bp -= 32u;
+        wa = wb;
+        wb = ahead;
+        ahead = gword(++wi + 2);
       }
-      const uint32_t znew = stop ? 64u : k + 1;
-      n += znew - z;
-      z = znew;
-      fin = z == 64;
+      z = za;
+      tab = tac;
+      fin = za >= 64u;
     }
     const uint32_t m = __ballot_sync(0xffffffffu, fin);
     if (m) flush_blocks(m, __ballot_sync(0xffffffffu, partial), blk, warpbuf, lane, coef);
     if (fin) {
+      bad |= (uint32_t)(z > 64u && z <= JGPU_HUFF_EOB);
       z = 0;
+      nblk++;
       partial = false;
       g++;
       if (++c == (uint32_t)bpm) {
@@ -603,13 +599,18 @@ k_huff_write_staged(const jgpu_huff_file *__restrict__ files, const uint32_t *__
           mby++;
         }
       }
-      tdc = mem.blk_table(c);
+      tdc = mem.table_ref(mem.blk_table(c));
+      tac = mem.table_ref(mem.blk_table(c) + 1);
+      tab = tdc;
       if (g >= seg_blocks) active = false;
       else locate();
     }
-    if (pos >= end) active = false;
+    if (wi >= wend) active = false;
     if (!__any_sync(0xffffffffu, active)) break;
   }
+  const int end = 32 * S;
+  const int pos = (int)(32u * (wi - i * S) + bp);
+  const uint32_t n = 64u * nblk + z - z0;
   /* blocks left unfinished: the next subsequence carries on with them */
   {
     const uint32_t m = __ballot_sync(0xffffffffu, decoded && z != 0);

@@ -51,10 +51,29 @@
 #define JGPU_HUFF_WARM 8
 #define JGPU_HUFF_OWN (JGPU_HUFF_CTA - JGPU_HUFF_WARM)   /* subsequences a sync CTA owns */
 
+/* What the decoding loop needs to know about a symbol, packed so that the loop spends no
+ * arithmetic on taking the symbol apart (the loop is bound by the integer pipe, profiles/r2_notes.md 14):
+ *   bits 0-4   T = code length + number of extra bits: what the symbol consumes
+ *   bits 5-8   s = number of extra bits (T.81 F.1.2.1.1 SSSS)
+ *   bits 9-15  A = how far the zig-zag index moves: 1 in a DC table; run + 1 in an AC table, and
+ *              JGPU_HUFF_EOB for the end-of-block symbol 0x00, which lands every index (1..63)
+ *              beyond anything a run can reach (63 + 16), so that
+ *                  index + A == 64  the block's last coefficient,
+ *                  index + A  > 64  the block ends without one (end of block, or a run past 63:
+ *                                   an error, and below JGPU_HUFF_EOB + 1 by construction).
+ * 0 is no entry (T >= 1 otherwise). */
+#define JGPU_HUFF_EOB 96u
+#define JGPU_HUFF_ENTRY(len, sym, ac)                                                             \
+  ((uint32_t)((len) + ((sym) & 15u)) | (((uint32_t)(sym) & 15u) << 5) |                           \
+   ((uint32_t)((ac) ? (((sym) & 0xffu) == 0 ? JGPU_HUFF_EOB : (((uint32_t)(sym) >> 4) & 15u) + 1u) : 1u) << 9))
+#define JGPU_HUFF_ENTRY_T(e) ((e) & 31u)
+#define JGPU_HUFF_ENTRY_S(e) (((e) >> 5) & 15u)
+#define JGPU_HUFF_ENTRY_A(e) ((e) >> 9)
+
 /* One Huffman table prepared for the decoder. */
 typedef struct jgpu_huff_table {
-  /* (length << 8) | symbol for every JGPU_HUFF_LUT_BITS-bit window whose leading bits are a
-   * code of at most that many bits; 0 otherwise */
+  /* JGPU_HUFF_ENTRY of the symbol for every JGPU_HUFF_LUT_BITS-bit window whose leading bits are
+   * a code of at most that many bits; 0 otherwise */
   uint16_t lut[1 << JGPU_HUFF_LUT_BITS];
   /* canonical decoding of the longer codes (T.81 F.2.2.3) on a 16-bit window W:
    * the code has length L for the smallest L with W < limit[L]; its symbol is
@@ -123,6 +142,9 @@ namespace huff {
  * re-derive inside the loop) while the host emulation hands it plain pointers:
  *   word(i)            big-endian 32-bit word i of the file's unstuffed scan (16 guard bytes follow it)
  *   lut(t, i)          jgpu_huff_table[t].lut[i]          t = 2 * component + (AC ? 1 : 0)
+ *   table_ref(t), lut_at(ref, i)   the same in two steps: the loop keeps the reference (on the
+ *                      device the table's shared-memory address) of the table the next symbol
+ *                      is read with, instead of rebuilding it for every symbol
  *   limit(t, L), delta(t, L), symbol(t, i)                the canonical part of table t
  *   blk_table(c)       2 * component of block c of the MCU
  *   blk_base(c), blk_xs(c), blk_ys(c), zigzag(k)          write pass only */
@@ -140,6 +162,8 @@ struct HostMem {
   const unsigned char *zz;
   uint32_t word(uint32_t i) const { return __builtin_bswap32(words[i]); }
   uint32_t lut(uint32_t t, uint32_t i) const { return tabs[t].lut[i]; }
+  uint32_t table_ref(uint32_t t) const { return t; }
+  uint32_t lut_at(uint32_t ref, uint32_t i) const { return tabs[ref].lut[i]; }
   uint32_t limit(uint32_t t, int len) const { return tabs[t].limit[len]; }
   int32_t delta(uint32_t t, int len) const { return tabs[t].delta[len]; }
   uint32_t symbol(uint32_t t, int i) const { return tabs[t].symbols[i]; }
@@ -150,9 +174,8 @@ struct HostMem {
   uint32_t zigzag(int k) const { return zz[k]; }
 };
 
-/* Symbol at the head of the 16-bit window `look`: (length << 8) | symbol, or 0 for a bit
- * pattern that is no code of the table. */
-/* Codes longer than the look-up table covers: canonical search by length. */
+/* Codes longer than the look-up table covers: canonical search by length on the 16-bit window
+ * `look`; (length << 8) | symbol, or 0 for a bit pattern that is no code of the table. */
 template <typename Mem>
 JGPU_HUFF_HD uint32_t lookup_long(const Mem &mem, uint32_t t, uint32_t look) {
 #if defined(__CUDA_ARCH__)
@@ -166,10 +189,14 @@ JGPU_HUFF_HD uint32_t lookup_long(const Mem &mem, uint32_t t, uint32_t look) {
   return 0;
 }
 
+/* JGPU_HUFF_ENTRY of the symbol at the head of the 16-bit window `look`, or 0 for a bit pattern
+ * that is no code of table t (an AC table if `ac`). */
 template <typename Mem>
-JGPU_HUFF_HD uint32_t lookup(const Mem &mem, uint32_t t, uint32_t look) {
+JGPU_HUFF_HD uint32_t lookup(const Mem &mem, uint32_t t, uint32_t look, uint32_t ac) {
   const uint32_t e = mem.lut(t, look >> (16 - JGPU_HUFF_LUT_BITS));
-  return e ? e : lookup_long(mem, t, look);
+  if (e) return e;
+  const uint32_t l = lookup_long(mem, t, look);
+  return l ? JGPU_HUFF_ENTRY(l >> 8, l & 0xffu, ac) : 0u;
 }
 
 /* Decodes the symbols that START inside one subsequence.
@@ -185,70 +212,78 @@ JGPU_HUFF_HD uint32_t lookup(const Mem &mem, uint32_t t, uint32_t look) {
  * from the start of the subsequence when decoding stopped; *err is raised on a bit
  * pattern that is no code and on a run past coefficient 63 (the reference's reader does not
  * check either, src/xjpeg.c:67-78; ours fails on both, jgpu_front.c decode_symbol/decode_mcu). */
+/* 32 bits of the stream starting `bp` bits (0..31) into word a, which word b follows */
+JGPU_HUFF_HD uint32_t window32(uint32_t a, uint32_t b, uint32_t bp) {
+#if defined(__CUDA_ARCH__)
+  return __funnelshift_l(b, a, bp);
+#else
+  return bp ? (a << bp) | (b >> (32u - bp)) : a;
+#endif
+}
+
 template <typename Mem, typename Sink>
 JGPU_HUFF_HD uint32_t decode_subsequence(const Mem &mem, int bpm, uint32_t w0, int nwords, uint32_t state,
                                          Sink &sink, uint32_t *n_out, uint32_t *err, int *pos_out = nullptr) {
-  int pos = (int)JGPU_HUFF_STATE_P(state);
   uint32_t c = JGPU_HUFF_STATE_C(state), z = JGPU_HUFF_STATE_Z(state);
-  const int end = 32 * nwords;
-  uint32_t n = 0, bad = 0;
-  /* 64-bit window, MSB first: `avail` valid bits */
-  uint32_t next = w0 + (uint32_t)(pos >> 5);
-  uint64_t buf = ((uint64_t)mem.word(next) << 32) | mem.word(next + 1);
-  next += 2;
-  buf <<= (pos & 31);
-  int avail = 64 - (pos & 31);
-  uint32_t ahead = mem.word(next);   /* the word the next refill needs, fetched one refill early */
-  uint32_t tdc = mem.blk_table(c);   /* DC table of the current block; its AC table follows */
-  /* The body is written without branches on the kind of symbol (DC / AC / end of block): the
-   * threads of a warp sit at unrelated places of their blocks, and every divergent branch
-   * would be paid by all of them. */
-  while (pos < end) {
-    if (avail < 32) {
-      buf |= (uint64_t)ahead << (32 - avail);
-      avail += 32;
-      ahead = mem.word(++next);
-    }
-    const uint32_t ac = z != 0;
-    const uint32_t look = (uint32_t)(buf >> 48);
-    uint32_t e = mem.lut(tdc + ac, look >> (16 - JGPU_HUFF_LUT_BITS));
+  const uint32_t z0 = z;
+  uint32_t nblk = 0, bad = 0;
+  /* the window: 32 bits from bit bp of word wi; a symbol takes at most 16 + 15 of them */
+  uint32_t bp = JGPU_HUFF_STATE_P(state) & 31u;
+  uint32_t wi = w0 + (JGPU_HUFF_STATE_P(state) >> 5);
+  const uint32_t wend = w0 + (uint32_t)nwords;
+  uint32_t wa = mem.word(wi), wb = mem.word(wi + 1);
+  uint32_t ahead = mem.word(wi + 2);   /* the word the next step forward needs, fetched one step early */
+  /* the tables of the current block, and the one the next symbol is read with */
+  uint32_t tdc = mem.table_ref(mem.blk_table(c)), tac = mem.table_ref(mem.blk_table(c) + 1);
+  uint32_t tab = z ? tac : tdc;
+  /* The body has no branch on the kind of symbol (DC / AC / end of block) except where a block
+   * ends: the threads of a warp sit at unrelated places of their blocks, and every divergent
+   * branch would be paid by all of them. */
+  while (wi < wend) {
+    const uint32_t look = window32(wa, wb, bp);
+    uint32_t e = mem.lut_at(tab, look >> (32 - JGPU_HUFF_LUT_BITS));
     if (e == 0) {   /* rare per thread: everything about long and invalid codes stays off the main path */
-      e = lookup_long(mem, tdc + ac, look);
-      if (e == 0) {
-        bad = 1;
-        e = 16u << 8;   /* no code: skip the window like jgpu_front.c decode_symbol; symbol 0 */
-      }
+      const uint32_t l = lookup_long(mem, mem.blk_table(c) + (z != 0), look >> 16);
+      /* no code: skip the window like jgpu_front.c decode_symbol; symbol 0 */
+      e = l ? JGPU_HUFF_ENTRY(l >> 8, l & 0xffu, z != 0) : JGPU_HUFF_ENTRY(16u, 0u, z != 0);
+      bad |= (uint32_t)(l == 0);
     }
-    const int len = (int)(e >> 8);
-    const uint32_t sym = e & 0xffu;
-    const int s = (int)(sym & 15u);
-    /* T.81 F.2.2.1 EXTEND on the s bits after the code (s = 0 gives 0) */
-    const uint32_t hi = (uint32_t)((buf << len) >> 32);
-    const uint32_t bits = (hi >> 1) >> (31 - s);
-    const uint32_t half = (1u << s) >> 1;
-    const int v = bits < half ? (int)bits - (1 << s) + 1 : (int)bits;
-    buf <<= (len + s);
-    avail -= len + s;
-    pos += len + s;
-    /* where the coefficient goes and where the block stands afterwards */
-    const uint32_t k = z + (ac ? sym >> 4 : 0u);       /* DC: z = 0, k = 0 */
-    const uint32_t over = k > 63u;                     /* run past the block: jgpu_front.c fails */
-    const uint32_t stop = (ac & (uint32_t)(sym == 0)) | over;   /* end of block */
-    bad |= over;
-    if (v != 0 && !stop) sink.coef((int)k, v);
-    const uint32_t znew = stop ? 64u : k + 1;
-    n += znew - z;
-    z = znew;
-    if (z == 64) {
+    const uint32_t total = JGPU_HUFF_ENTRY_T(e);
+    const uint32_t za = z + JGPU_HUFF_ENTRY_A(e);   /* index of the coefficient + 1, if there is one */
+    if (za <= 64u) {
+      /* T.81 F.2.2.1 EXTEND on the s bits after the code (s = 0 gives 0); never taken apart by a
+       * sink that stores nothing */
+      const uint32_t s = JGPU_HUFF_ENTRY_S(e);
+      const uint32_t bits = ((look << (total - s)) >> 1) >> (31u - s);
+      const uint32_t half = (1u << s) >> 1;
+      const int v = bits < half ? (int)bits - (int)(1u << s) + 1 : (int)bits;
+      if (v != 0) sink.coef((int)za - 1, v);
+    }
+    bp += total;
+    if (bp >= 32u) {
+      bp -= 32u;
+      wa = wb;
+      wb = ahead;
+      ahead = mem.word(++wi + 2);
+    }
+    z = za;
+    tab = tac;
+    if (za >= 64u) {   /* the block ends: last coefficient, end-of-block symbol, or a run past it */
+      bad |= (uint32_t)(za > 64u && za <= JGPU_HUFF_EOB);   /* jgpu_front.c fails on the run */
       z = 0;
+      nblk++;
       c = c + 1 == (uint32_t)bpm ? 0 : c + 1;
-      tdc = mem.blk_table(c);
+      tdc = mem.table_ref(mem.blk_table(c));
+      tac = mem.table_ref(mem.blk_table(c) + 1);
+      tab = tdc;
       if (sink.block_done()) break;
     }
   }
-  *n_out = n;
+  *n_out = 64u * nblk + z - z0;
   if (bad) *err = 1;
-  if (pos_out) *pos_out = pos;   /* bits from the start of the subsequence to where decoding stopped */
+  const int pos = (int)(32u * (wi - w0) + bp);   /* bits from the start of the subsequence to where decoding stopped */
+  if (pos_out) *pos_out = pos;
+  const int end = 32 * nwords;
   return JGPU_HUFF_STATE(pos > end ? pos - end : 0, c, z);
 }
 
@@ -341,9 +376,10 @@ extern "C" {
 /* ---- host-side preparation (jgpu_huff_prep.c) -------------------------------------------- */
 
 /* Builds one decoder table from the canonical description a DHT segment gives (T.81 C.2):
- * counts[L-1] codes of length L, their symbols in code order.  Returns 0, or 1 when the
- * counts over-subscribe the code space. */
-int jgpu_huff_build_table(jgpu_huff_table *t, const unsigned char counts[16], const unsigned char *symbols);
+ * counts[L-1] codes of length L, their symbols in code order; `ac`: an AC table (the entries of
+ * the look-up table differ, JGPU_HUFF_ENTRY).  Returns 0, or 1 when the counts over-subscribe the
+ * code space. */
+int jgpu_huff_build_table(jgpu_huff_table *t, const unsigned char counts[16], const unsigned char *symbols, int ac);
 
 /* Derives blk_base / blk_xs / blk_ys once hs, vs, blk_*, hblocks and plane_off are set. */
 void jgpu_huff_file_finish(jgpu_huff_file *f);

@@ -6,7 +6,7 @@
 /* T.81 C.2 (code generation) and F.2.2.3 (decoding by code length), laid out for a decoder
  * that looks at a left-aligned 16-bit window: the reference builds its own lookahead table
  * from the same description, src/xjpeg.c:311-336. */
-int jgpu_huff_build_table(jgpu_huff_table *t, const unsigned char counts[16], const unsigned char *symbols) {
+int jgpu_huff_build_table(jgpu_huff_table *t, const unsigned char counts[16], const unsigned char *symbols, int ac) {
   int code = 0, k = 0, len, i;
   memset(t, 0, sizeof(*t));
   for (len = 1; len <= 16; len++) {
@@ -18,7 +18,7 @@ int jgpu_huff_build_table(jgpu_huff_table *t, const unsigned char counts[16], co
         const int first = (code + i) << (JGPU_HUFF_LUT_BITS - len);
         const int span = 1 << (JGPU_HUFF_LUT_BITS - len);
         int s;
-        for (s = 0; s < span; s++) t->lut[first + s] = (uint16_t)((len << 8) | symbols[k + i]);
+        for (s = 0; s < span; s++) t->lut[first + s] = (uint16_t)JGPU_HUFF_ENTRY((unsigned)len, (unsigned)symbols[k + i], ac);
       }
     }
     k += n;

@@ -26,7 +26,10 @@ using namespace jgpu;
 
 namespace {
 
-constexpr int kHostStreams = 3;
+#ifndef JGPU_HOST_STREAMS
+#define JGPU_HOST_STREAMS 3
+#endif
+constexpr int kHostStreams = JGPU_HOST_STREAMS;
 
 /* A grow-only device or pinned-host buffer. */
 struct Buffer {
@@ -206,10 +209,11 @@ extern "C" void jgpu_destroy(jgpu_ctx *ctx) {
   ctx->d_pack_off.release();
   for (Buffer *b : {&ctx->hz_stream, &ctx->hz_files, &ctx->hz_tables, &ctx->hz_segs, &ctx->hz_status, &ctx->hz_coef,
                     &ctx->dz_stream, &ctx->dz_files, &ctx->dz_tables, &ctx->dz_segs, &ctx->dz_status,
-                    &ctx->dz_sub[0], &ctx->dz_sub[1], &ctx->dz_sub[2], &ctx->dz_sub[3], &ctx->dz_carry[0],
-                    &ctx->dz_carry[1], &ctx->dz_dc[0], &ctx->dz_dc[1], &ctx->dz_dc[2]}) {
+                    &ctx->dz_sub[0], &ctx->dz_sub[1], &ctx->dz_sub[2], &ctx->dz_sub[3],
+                    &ctx->dz_carry[0], &ctx->dz_carry[1]}) {
     b->release();
   }
+  for (int i = 0; i < kHostStreams; i++) ctx->dz_dc[i].release();
   delete ctx;
 }
 

@@ -225,9 +225,10 @@ extern "C" long long huff_emulate(const unsigned char *jpeg, int size, short *co
 
 // jgpu_huff_build_table against a bit-by-bit canonical decoder: every 16-bit window.
 extern "C" int huff_table_selfcheck(const unsigned char *counts, const unsigned char *symbols) {
-  jgpu_huff_table t;
-  if (jgpu_huff_build_table(&t, counts, symbols)) return -1;
   int mismatches = 0;
+  for (int ac = 0; ac < 2; ac++) {
+  jgpu_huff_table t;
+  if (jgpu_huff_build_table(&t, counts, symbols, ac)) return -1;
   for (uint32_t look = 0; look < 65536; look++) {
     // T.81 F.2.2.3 DECODE
     int code = 0, k = 0, want = 0, first = 0;
@@ -235,14 +236,15 @@ extern "C" int huff_table_selfcheck(const unsigned char *counts, const unsigned 
       code = (int)(look >> (16 - len));
       const int cnt = counts[len - 1];
       if (code - first < cnt) {
-        want = (len << 8) | symbols[k + code - first];
+        want = (int)JGPU_HUFF_ENTRY((unsigned)len, (unsigned)symbols[k + code - first], ac);
         break;
       }
       k += cnt;
       first = (first + cnt) << 1;
     }
     const jgpu::huff::HostMem mem = {nullptr, &t, nullptr, nullptr};
-    if ((int)jgpu::huff::lookup(mem, 0, look) != want) mismatches++;
+    if ((int)jgpu::huff::lookup(mem, 0, look, (uint32_t)ac) != want) mismatches++;
+  }
   }
   return mismatches;
 }
