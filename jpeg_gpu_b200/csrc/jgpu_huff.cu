@@ -56,6 +56,7 @@ struct SyncSmem {
   int n_list;
   jgpu_huff_file file;
   unsigned char zz[64];
+  uint4 brec[JGPU_HUFF_MAX_BLOCKS + 2];   /* block_records() */
 };
 
 __device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
@@ -71,6 +72,11 @@ __device__ __forceinline__ uint32_t lds_u16(uint32_t a) {
 __device__ __forceinline__ uint32_t lds_u8(uint32_t a) {
   uint32_t v;
   asm volatile("{\n\t.reg .u16 t;\n\tld.shared.u8 t, [%1];\n\tcvt.u32.u16 %0, t;\n\t}" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint4 lds_u128(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
   return v;
 }
 __device__ __forceinline__ unsigned long long lds_u64(uint32_t a) {
@@ -89,6 +95,29 @@ struct DevMem {
   uint32_t tabs, file, zz;
   uint32_t comps;      /* huff::comp_pack of the file */
   const uint32_t *gwords;   /* kGlobalWords: the file's scan in global memory, as stored */
+  uint32_t brec;            /* shared address of the block records */
+  /* what the decoding loop needs when a block ends, one load: the block after block c and the
+   * shared-memory addresses of its tables */
+  __device__ __forceinline__ uint32_t next_block(uint32_t c, uint32_t *tdc, uint32_t *tac) const {
+    const uint32_t r = lds_u32(brec + 16u * c);
+    *tdc = r & 0xffffffu;
+    *tac = (r & 0xffffffu) + (uint32_t)sizeof(jgpu_huff_table);
+    return r >> 24;
+  }
+  struct Cursor {
+    const uint32_t *p;
+    uint32_t i;
+  };
+  __device__ __forceinline__ Cursor cursor(uint32_t i) const {
+    Cursor cur;
+    cur.p = gwords + i;
+    cur.i = i;
+    return cur;
+  }
+  __device__ __forceinline__ uint32_t next_word(Cursor &cur) const {
+    if (kGlobalWords) return __byte_perm(__ldg(++cur.p), 0, 0x0123);
+    return word(++cur.i);
+  }
   __device__ __forceinline__ uint32_t word(uint32_t i) const {
     if (kGlobalWords) return __byte_perm(__ldg(gwords + i), 0, 0x0123);
     const uint32_t l = i - base_word, row = l / S;
@@ -130,6 +159,24 @@ __device__ __forceinline__ uint32_t pinned(uint32_t v) {
   return r;
 }
 
+/* Record c describes the block that FOLLOWS block c of the MCU: x = shared address of its DC table
+ * | its index << 24; y, z, w = where it lies, in blocks: y + MCU column * z + MCU row * w
+ * (jgpu_huff_file_finish, every term a whole number of blocks).  Written by the first threads of
+ * the CTA once the file descriptor is in shared memory; a __syncthreads() follows. */
+__device__ __forceinline__ void block_records(uint4 *brec, const jgpu_huff_file &f, const jgpu_huff_table *tabs) {
+  const int c = threadIdx.x;
+  if (c < f.bpm && c < JGPU_HUFF_MAX_BLOCKS) {
+    const int nc = c + 1 == f.bpm ? 0 : c + 1;
+    const uint32_t t = 2u * (f.blk_comp[nc] & 3u);
+    uint4 r;
+    r.x = ((uint32_t)__cvta_generic_to_shared(tabs) + t * (uint32_t)sizeof(jgpu_huff_table)) | ((uint32_t)nc << 24);
+    r.y = (uint32_t)(f.blk_base[nc] >> 6);
+    r.z = (uint32_t)(f.blk_xs[nc] >> 6);
+    r.w = (uint32_t)(f.blk_ys[nc] >> 6);
+    brec[c] = r;
+  }
+}
+
 template <int S>
 __device__ __forceinline__ DevMem<S> dev_mem(const SyncSmem<S> &sm, int first, const uint32_t *stream) {
   DevMem<S> m;
@@ -140,6 +187,7 @@ __device__ __forceinline__ DevMem<S> dev_mem(const SyncSmem<S> &sm, int first, c
   m.file = pinned((uint32_t)__cvta_generic_to_shared(&sm.file));
   m.zz = pinned((uint32_t)__cvta_generic_to_shared(sm.zz));
   m.comps = pinned(huff::comp_pack(sm.file));
+  m.brec = pinned((uint32_t)__cvta_generic_to_shared(sm.brec));
   return m;
 }
 
@@ -162,6 +210,7 @@ __device__ __forceinline__ void stage(SyncSmem<S> &sm, const jgpu_huff_file *fil
     if (t < 64) sm.zz[t] = c_zigzag[t];
   }
   __syncthreads();
+  block_records(sm.brec, sm.file, sm.tabs);
   {
     const uint4 *src = reinterpret_cast<const uint4 *>(tables + sm.file.table0);
     uint4 *dst = reinterpret_cast<uint4 *>(sm.tabs);
@@ -424,6 +473,7 @@ struct WriteSmem {
   uint32_t blocks[kCta * 32];
   jgpu_huff_file file;
   unsigned char zz[64];
+  uint4 brec[JGPU_HUFF_MAX_BLOCKS + 2];   /* block_records() */
 };
 
 __device__ __forceinline__ void sts_u16(uint32_t a, uint32_t v) {
@@ -484,6 +534,7 @@ k_huff_write_staged(const jgpu_huff_file *__restrict__ files, const uint32_t *__
     for (int i = t; i < kCta * 8; i += kCta) z[i] = make_uint4(0u, 0u, 0u, 0u);
   }
   __syncthreads();
+  block_records(sm.brec, sm.file, sm.tabs);
   {
     const uint4 *src = reinterpret_cast<const uint4 *>(tables + sm.file.table0);
     uint4 *dst = reinterpret_cast<uint4 *>(sm.tabs);
@@ -499,6 +550,7 @@ k_huff_write_staged(const jgpu_huff_file *__restrict__ files, const uint32_t *__
   mem.file = pinned((uint32_t)__cvta_generic_to_shared(&sm.file));
   mem.zz = pinned((uint32_t)__cvta_generic_to_shared(sm.zz));
   mem.comps = pinned(huff::comp_pack(sm.file));
+  mem.brec = pinned((uint32_t)__cvta_generic_to_shared(sm.brec));
   const uint32_t mybuf = pinned((uint32_t)__cvta_generic_to_shared(sm.blocks) + (uint32_t)t * 128u);
   const uint32_t warpbuf = mybuf - (uint32_t)lane * 128u;
   const int bpm = f.bpm, nhmb = f.nhmb;
@@ -528,24 +580,23 @@ k_huff_write_staged(const jgpu_huff_file *__restrict__ files, const uint32_t *__
   const uint32_t z0 = z;
   uint32_t nblk = 0, bad = 0;
   uint32_t bp = JGPU_HUFF_STATE_P(st) & 31u;
-  uint32_t wi = i * S + (JGPU_HUFF_STATE_P(st) >> 5);
-  const uint32_t wend = (i + 1) * S;
+  int left = S - (int)(JGPU_HUFF_STATE_P(st) >> 5);
   uint32_t wa = 0, wb = 0, ahead = 0;
+  const uint32_t *cur = mem.gwords + (i * S + (JGPU_HUFF_STATE_P(st) >> 5));
   int mbx = 0, mby = 0;
   uint32_t blk = 0;
-  const uint32_t *gw = mem.gwords;
-  auto gword = [&](uint32_t idx) { return __byte_perm(__ldg(gw + idx), 0, 0x0123); };
-  auto locate = [&]() {
-    blk = (uint32_t)((mem.blk_base((int)c) + (int64_t)mbx * mem.blk_xs((int)c) + (int64_t)mby * mem.blk_ys((int)c)) >> 6);
-  };
+  /* blocks of the restart interval from this thread's first one on (g counts up to it) */
+  const uint32_t blocks_left0 = active ? (uint32_t)(seg_blocks - g) : 0u;
+  uint32_t blocks_left = blocks_left0;
   if (active) {
-    wa = gword(wi);
-    wb = gword(wi + 1);
-    ahead = gword(wi + 2);
+    wa = __byte_perm(__ldg(cur), 0, 0x0123);
+    wb = __byte_perm(__ldg(cur + 1), 0, 0x0123);
+    ahead = __byte_perm(__ldg(cur + 2), 0, 0x0123);
+    cur += 2;
     const int mcu = seg_mcu0 + (int)(g / bpm);
     mbx = mcu % nhmb;
     mby = mcu / nhmb;
-    locate();
+    blk = (uint32_t)((mem.blk_base((int)c) + (int64_t)mbx * mem.blk_xs((int)c) + (int64_t)mby * mem.blk_ys((int)c)) >> 6);
   }
   uint32_t tdc = mem.table_ref(mem.blk_table(c)), tac = mem.table_ref(mem.blk_table(c) + 1);
   uint32_t tab = z ? tac : tdc;
@@ -576,9 +627,10 @@ k_huff_write_staged(const jgpu_huff_file *__restrict__ files, const uint32_t *__
       bp += total;
       if (bp >= 32u) {
         bp -= 32u;
+        left--;
         wa = wb;
         wb = ahead;
-        ahead = gword(++wi + 2);
+        ahead = __byte_perm(__ldg(++cur), 0, 0x0123);
       }
       z = za;
       tab = tac;
@@ -591,26 +643,26 @@ k_huff_write_staged(const jgpu_huff_file *__restrict__ files, const uint32_t *__
       z = 0;
       nblk++;
       partial = false;
-      g++;
-      if (++c == (uint32_t)bpm) {
-        c = 0;
-        if (++mbx == nhmb) {
-          mbx = 0;
-          mby++;
-        }
-      }
-      tdc = mem.table_ref(mem.blk_table(c));
-      tac = mem.table_ref(mem.blk_table(c) + 1);
+      /* the next block: its tables and where it lies, one load (block_records) */
+      const uint4 r = lds_u128(mem.brec + 16u * c);
+      c = r.x >> 24;
+      tdc = r.x & 0xffffffu;
+      tac = tdc + (uint32_t)sizeof(jgpu_huff_table);
       tab = tdc;
-      if (g >= seg_blocks) active = false;
-      else locate();
+      if (c == 0 && ++mbx == nhmb) {
+        mbx = 0;
+        mby++;
+      }
+      blk = r.y + (uint32_t)mbx * r.z + (uint32_t)mby * r.w;
+      if (--blocks_left == 0) active = false;
     }
-    if (wi >= wend) active = false;
+    if (left <= 0) active = false;
     if (!__any_sync(0xffffffffu, active)) break;
   }
   const int end = 32 * S;
-  const int pos = (int)(32u * (wi - i * S) + bp);
+  const int pos = 32 * (S - left) + (int)bp;
   const uint32_t n = 64u * nblk + z - z0;
+  g += nblk;
   /* blocks left unfinished: the next subsequence carries on with them */
   {
     const uint32_t m = __ballot_sync(0xffffffffu, decoded && z != 0);

@@ -145,6 +145,10 @@ namespace huff {
  *   table_ref(t), lut_at(ref, i)   the same in two steps: the loop keeps the reference (on the
  *                      device the table's shared-memory address) of the table the next symbol
  *                      is read with, instead of rebuilding it for every symbol
+ *   next_block(c, &tdc, &tac)      the block after block c of the MCU and the references of its
+ *                      two tables (one shared-memory load on the device)
+ *   cursor(i), next_word(cur)      a position in the scan that steps forward one word at a time
+ *                      (on the device a pointer: no address is rebuilt from an index)
  *   limit(t, L), delta(t, L), symbol(t, i)                the canonical part of table t
  *   blk_table(c)       2 * component of block c of the MCU
  *   blk_base(c), blk_xs(c), blk_ys(c), zigzag(k)          write pass only */
@@ -164,6 +168,15 @@ struct HostMem {
   uint32_t lut(uint32_t t, uint32_t i) const { return tabs[t].lut[i]; }
   uint32_t table_ref(uint32_t t) const { return t; }
   uint32_t lut_at(uint32_t ref, uint32_t i) const { return tabs[ref].lut[i]; }
+  uint32_t next_block(uint32_t c, uint32_t *tdc, uint32_t *tac) const {
+    c = c + 1 == (uint32_t)f->bpm ? 0 : c + 1;
+    *tdc = blk_table(c);
+    *tac = blk_table(c) + 1;
+    return c;
+  }
+  typedef uint32_t Cursor;
+  Cursor cursor(uint32_t i) const { return i; }
+  uint32_t next_word(Cursor &cur) const { return word(++cur); }
   uint32_t limit(uint32_t t, int len) const { return tabs[t].limit[len]; }
   int32_t delta(uint32_t t, int len) const { return tabs[t].delta[len]; }
   uint32_t symbol(uint32_t t, int i) const { return tabs[t].symbols[i]; }
@@ -227,11 +240,13 @@ JGPU_HUFF_HD uint32_t decode_subsequence(const Mem &mem, int bpm, uint32_t w0, i
   uint32_t c = JGPU_HUFF_STATE_C(state), z = JGPU_HUFF_STATE_Z(state);
   const uint32_t z0 = z;
   uint32_t nblk = 0, bad = 0;
-  /* the window: 32 bits from bit bp of word wi; a symbol takes at most 16 + 15 of them */
+  /* the window: 32 bits from bit bp of the current word; a symbol takes at most 16 + 15 of them.
+   * `left`: words of the subsequence from the current one on. */
   uint32_t bp = JGPU_HUFF_STATE_P(state) & 31u;
-  uint32_t wi = w0 + (JGPU_HUFF_STATE_P(state) >> 5);
-  const uint32_t wend = w0 + (uint32_t)nwords;
+  const uint32_t wi = w0 + (JGPU_HUFF_STATE_P(state) >> 5);
+  int left = nwords - (int)(JGPU_HUFF_STATE_P(state) >> 5);
   uint32_t wa = mem.word(wi), wb = mem.word(wi + 1);
+  typename Mem::Cursor cur = mem.cursor(wi + 2);
   uint32_t ahead = mem.word(wi + 2);   /* the word the next step forward needs, fetched one step early */
   /* the tables of the current block, and the one the next symbol is read with */
   uint32_t tdc = mem.table_ref(mem.blk_table(c)), tac = mem.table_ref(mem.blk_table(c) + 1);
@@ -239,7 +254,7 @@ JGPU_HUFF_HD uint32_t decode_subsequence(const Mem &mem, int bpm, uint32_t w0, i
   /* The body has no branch on the kind of symbol (DC / AC / end of block) except where a block
    * ends: the threads of a warp sit at unrelated places of their blocks, and every divergent
    * branch would be paid by all of them. */
-  while (wi < wend) {
+  while (left > 0) {
     const uint32_t look = window32(wa, wb, bp);
     uint32_t e = mem.lut_at(tab, look >> (32 - JGPU_HUFF_LUT_BITS));
     if (e == 0) {   /* rare per thread: everything about long and invalid codes stays off the main path */
@@ -262,9 +277,10 @@ JGPU_HUFF_HD uint32_t decode_subsequence(const Mem &mem, int bpm, uint32_t w0, i
     bp += total;
     if (bp >= 32u) {
       bp -= 32u;
+      left--;
       wa = wb;
       wb = ahead;
-      ahead = mem.word(++wi + 2);
+      ahead = mem.next_word(cur);
     }
     z = za;
     tab = tac;
@@ -272,16 +288,14 @@ JGPU_HUFF_HD uint32_t decode_subsequence(const Mem &mem, int bpm, uint32_t w0, i
       bad |= (uint32_t)(za > 64u && za <= JGPU_HUFF_EOB);   /* jgpu_front.c fails on the run */
       z = 0;
       nblk++;
-      c = c + 1 == (uint32_t)bpm ? 0 : c + 1;
-      tdc = mem.table_ref(mem.blk_table(c));
-      tac = mem.table_ref(mem.blk_table(c) + 1);
+      c = mem.next_block(c, &tdc, &tac);
       tab = tdc;
       if (sink.block_done()) break;
     }
   }
   *n_out = 64u * nblk + z - z0;
   if (bad) *err = 1;
-  const int pos = (int)(32u * (wi - w0) + bp);   /* bits from the start of the subsequence to where decoding stopped */
+  const int pos = 32 * (nwords - left) + (int)bp;   /* bits from the start of the subsequence to where decoding stopped */
   if (pos_out) *pos_out = pos;
   const int end = 32 * nwords;
   return JGPU_HUFF_STATE(pos > end ? pos - end : 0, c, z);

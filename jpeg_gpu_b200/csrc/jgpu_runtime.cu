@@ -1394,6 +1394,7 @@ static int decode_jpegs_gpu_entropy(jgpu_ctx *ctx, const jgpu_jpeg *files, int n
     const int64_t first_bytes = 48ll << 20, max_bytes = 512ll << 20;
     const long wave = (long)ctx->sm_count * (1024 / JGPU_HUFF_CTA);   /* CTAs of k_huff_sync / k_huff_write resident at once */
     int i0 = 0, chunk = 0;
+    const bool blocks_at_end = device_out && !getenv("JGPU_BLOCKS_PER_GROUP");
     /* JGPU_HUFF_WAVES: experiment knob, waves of entropy CTAs per group */
     const int max_waves = getenv("JGPU_HUFF_WAVES") ? std::max(1, atoi(getenv("JGPU_HUFF_WAVES"))) : 2;
     /* JGPU_TRACE: device-side times of every group (events on its stream) */
@@ -1498,7 +1499,13 @@ static int decode_jpegs_gpu_entropy(jgpu_ctx *ctx, const jgpu_jpeg *files, int n
       l.d_coef = d_coef;
       if (huff_launch(l, st)) return EXIT_FAILURE;
       mark(st);
-      if (plan_run_range(plan, i0, i1, d_coef, d_qtabs, m, yuv_out ? nullptr : d_rgb, yuv_out ? d_rgb : nullptr, st)) {
+      /* The block decoder takes whole SMs (one CTA of 227 KB each): launched between the entropy kernels of
+       * three streams it waits for SMs to drain and they wait for it (0.4-1.2 ms per group against 0.11 ms
+       * alone, profiles/r2_notes.md 14).  When the pixels stay on the device nothing waits for a group's
+       * pixels, so one launch at the end decodes the blocks of all groups; with the read-back in the
+       * pipeline every group is decoded as soon as its coefficients are there. */
+      if (!blocks_at_end &&
+          plan_run_range(plan, i0, i1, d_coef, d_qtabs, m, yuv_out ? nullptr : d_rgb, yuv_out ? d_rgb : nullptr, st)) {
         return EXIT_FAILURE;
       }
       mark(st);
@@ -1512,6 +1519,16 @@ static int decode_jpegs_gpu_entropy(jgpu_ctx *ctx, const jgpu_jpeg *files, int n
       i0 = i1;
       chunk++;
       if (i0 >= m) t_prepared = since();
+    }
+    if (blocks_at_end) {
+      for (int s = 1; s < kHostStreams; s++) {
+        CU_TRY(cudaEventRecord(ctx->events[s], ctx->streams[s]));
+        CU_TRY(cudaStreamWaitEvent(ctx->streams[0], ctx->events[s], 0));
+      }
+      if (plan_run_range(plan, 0, m, d_coef, d_qtabs, m, yuv_out ? nullptr : d_rgb, yuv_out ? d_rgb : nullptr,
+                         ctx->streams[0])) {
+        return EXIT_FAILURE;
+      }
     }
     t_enqueued = since();
     for (int s = 0; s < kHostStreams; s++) CU_TRY(cudaStreamSynchronize(ctx->streams[s]));

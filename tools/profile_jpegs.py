@@ -30,10 +30,11 @@ def main():
     device_out = os.environ.get("PROFILE_DEVICE_OUT") == "1"
     out = torch.zeros(total, dtype=torch.uint8, device="cuda:0") if device_out else torch.zeros(total, dtype=torch.uint8).pin_memory()
     ctx = J.Context(0)
-    ctx.decode_jpegs(files, out, entropy=entropy)
+    nthreads = int(os.environ.get("PROFILE_THREADS", "0"))
+    ctx.decode_jpegs(files, out, entropy=entropy, nthreads=nthreads)
     for _ in range(reps):
         t0 = time.perf_counter()
-        ctx.decode_jpegs(files, out, entropy=entropy)
+        ctx.decode_jpegs(files, out, entropy=entropy, nthreads=nthreads)
         dt = time.perf_counter() - t0
         print(f"{entropy}: {n} files of {len(files[0])} bytes in {dt * 1e3:.2f} ms = {n * w * h / 1e6 / dt:.0f} Mpx/s", flush=True)
     ctx.close()
