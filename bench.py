@@ -538,9 +538,21 @@ def main():
             if world == 1:
                 e2e_jpeg["cpu_entropy_value"] = timed(lambda: ctx.decode_jpegs(files, jpeg_rgb, nthreads=host_threads, entropy="cpu"))
             # the same with the pixels left in device memory (callers whose next stage runs on the GPU)
+            # (half the host threads: this call is as long as the chain of kernels, and the thread that feeds
+            # it must not be starved by the unstuffing workers -- the library's own default for this output)
             jpeg_dev = torch.empty(total, dtype=torch.uint8, device=dev)
-            e2e_jpeg["device_out_value"] = timed(lambda: ctx.decode_jpegs(files, jpeg_dev, nthreads=host_threads, entropy="gpu"))
+            dev_threads = max(1, host_threads // 2)
+            e2e_jpeg["device_out_value"] = timed(lambda: ctx.decode_jpegs(files, jpeg_dev, nthreads=dev_threads, entropy="gpu"))
+            e2e_jpeg["device_out_host_threads_per_rank"] = dev_threads
             del jpeg_dev
+            if world == 1:
+                # the same on 128 files (3.2 GB of pixels): the pipeline's steady state, not its ramp
+                files128 = files * 4
+                total128, _ = J.probe_jpegs(files128)
+                jpeg_dev = torch.empty(total128, dtype=torch.uint8, device=dev)
+                v = timed(lambda: ctx.decode_jpegs(files128, jpeg_dev, nthreads=dev_threads, entropy="gpu"))
+                e2e_jpeg["device_out_128_files_value"] = v * 4   # timed() counts len(files) files
+                del jpeg_dev, files128
             # planes instead of pixels (what the reference's xjpeg backend itself produces)
             yuv_total, _ = J.probe_jpegs(files, out="yuv")
             jpeg_yuv = torch.zeros(yuv_total, dtype=torch.uint8).pin_memory()

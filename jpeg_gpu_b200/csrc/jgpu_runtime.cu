@@ -1223,7 +1223,14 @@ static int decode_jpegs_gpu_entropy(jgpu_ctx *ctx, const jgpu_jpeg *files, int n
   const auto t_begin = std::chrono::steady_clock::now();
   auto since = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(); };
   double t_setup = 0, t_prepared = 0, t_enqueued = 0, t_synced = 0;
-  if (nthreads <= 0) nthreads = (int)std::thread::hardware_concurrency();
+  if (nthreads <= 0) {
+    nthreads = (int)std::thread::hardware_concurrency();
+    /* With the pixels staying on the device the call is as long as the chain of groups on the GPU, and this
+     * thread feeds that chain: workers on every core starve it (16-core box, 128 4K files: 19.9 ms with 16
+     * workers, 17.2 with 14, 15.9-17.4 with 8; profiles/r2_notes.md 14).  With the read-back in the pipeline
+     * the link is the limit and all cores are marginally better (66.2 against 67.9 ms). */
+    if (device_out && nthreads > 2) nthreads /= 2;
+  }
   if (nthreads <= 0) nthreads = 1;
 
   /* ---- headers, layout ------------------------------------------------------ */

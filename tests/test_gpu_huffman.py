@@ -171,3 +171,37 @@ def test_fuzzed_files_agree_with_the_host_thread_path(gpu_ctx, capfd):
             assert np.array_equal(got[a.rgb_off:a.rgb_off + a.rgb_len], ref[b.rgb_off:b.rgb_off + b.rgb_len]), k
     assert on_device > 100
     capfd.readouterr()
+
+
+@pytest.mark.parametrize("knob", ["JGPU_HUFF_WRITE=scatter", "JGPU_BLOCKS_PER_GROUP=1", "JGPU_HUFF_WAVES=1"])
+def test_a_b_knobs_give_the_same_bytes(gpu_ctx, monkeypatch, knob):
+    """The write pass that stages blocks in shared memory (product) against the one that stores coefficient
+    by coefficient (JGPU_HUFF_WRITE=scatter), the block decoder after every group against once at the end
+    (pixels on the device), small groups: same pixels, same planes, files with and without restart markers,
+    long codes (optimised tables) and blocks that straddle subsequences everywhere."""
+    pytest.importorskip("PIL")
+    import torch
+    files = [_jpeg(1920, 1080, 2, rst=120), _jpeg(1000, 563, 1, optimize=True, q=95), _jpeg(333, 222, "L", rst=5),
+             _jpeg(640, 480, 0, q=30), load("c444_40x24")[0], _jpeg(1280, 720, 2, q=98, noise=90)] * 3
+    total, _ = J.probe_jpegs(files)
+    ref, ri = gpu_ctx.decode_jpegs(files, entropy="gpu")
+    ref_yuv, ry = gpu_ctx.decode_jpegs(files, entropy="gpu", out="yuv")
+    name, value = knob.split("=")
+    monkeypatch.setenv(name, value)
+    ctx = J.Context(0)   # the knobs are read when a context is created / per call
+    try:
+        def same(got, gi, want, wi):   # image by image: the bytes between images belong to nobody
+            for a, b in zip(gi, wi):
+                assert a.status == 0 and (a.rgb_off, a.rgb_len) == (b.rgb_off, b.rgb_len)
+                assert np.array_equal(got[a.rgb_off:a.rgb_off + a.rgb_len], want[b.rgb_off:b.rgb_off + b.rgb_len])
+        dev = torch.zeros(total, dtype=torch.uint8, device="cuda:0")
+        out, gi = ctx.decode_jpegs(files, dev, entropy="gpu")
+        same(out.cpu().numpy(), gi, ref, ri)
+        got, gi = ctx.decode_jpegs(files, entropy="gpu")
+        same(got, gi, ref, ri)
+        got_yuv, gy = ctx.decode_jpegs(files, entropy="gpu", out="yuv")
+        same(got_yuv, gy, ref_yuv, ry)
+    finally:
+        ctx.close()
+        monkeypatch.delenv(name)
+        J.Context(0).close()

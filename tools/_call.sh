@@ -1,5 +1,10 @@
-nproc
-run() { PROFILE_DEVICE_OUT=1 timeout 300 python tools/profile_jpegs.py $1 gpu 240 4 2>&1 | tail -3 | awk '{print $(NF-4), $(NF-3)}' | tr '\n' ' '; echo; }
-for t in 0 4 8 16 32 64; do echo "--- threads $t: 128 files"; PROFILE_THREADS=$t run 128; done
-for t in 0 8 16; do echo "--- threads $t: 32 files"; PROFILE_THREADS=$t run 32; done
-PROFILE_THREADS=16 JGPU_TRACE=1 PROFILE_DEVICE_OUT=1 timeout 300 python tools/profile_jpegs.py 128 gpu 240 1 2>&1 | tail -19
+mkdir -p gpurun_out/r2
+timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -4
+timeout 600 python bench.py > gpurun_out/r2/bench_huff3.json 2> gpurun_out/r2/bench_huff3.err
+python - <<PY
+import json
+d=json.load(open("gpurun_out/r2/bench_huff3.json"))
+print("value",round(d["value"]),"ms",round(d["ms_per_step"],4),"frac",round(d["roofline"]["frac"],4),"e2e",round(d["e2e"]["value"]),"pack",round(d["e2e_pack"]["value"]))
+j=d["e2e_jpeg"]
+print({k:(round(v) if isinstance(v,float) else v) for k,v in j.items() if "value" in k or "threads" in k})
+PY
