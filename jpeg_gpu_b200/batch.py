@@ -156,21 +156,36 @@ class JpegInfo:
         return (self.height, self.width) if self.ncomps == 1 else (self.height, self.width, 3)
 
 
+_JPEG_DT = np.dtype([("data", "<u8"), ("size", "<i8")])
+_INFO_DT = np.dtype([("status", "<i4"), ("width", "<i4"), ("height", "<i4"), ("ncomps", "<i4"), ("hsamp0", "<i4"),
+                     ("vsamp0", "<i4"), ("restart_interval", "<i4"), ("tasks", "<i4"), ("rgb_off", "<i8"),
+                     ("rgb_len", "<i8"), ("message", "<u8")])
+assert _JPEG_DT.itemsize == C.sizeof(_capi.jgpu_jpeg) and _INFO_DT.itemsize == C.sizeof(_capi.jgpu_jpeg_info)
+
+
 def _jpeg_array(files: Sequence[bytes]):
-    arr = (_capi.jgpu_jpeg * len(files))()
-    keep = []
-    for i, f in enumerate(files):
-        # no copy: the C side reads the bytes object's own buffer (kept alive by `keep`)
-        f = bytes(f) if not isinstance(f, bytes) else f
-        keep.append(f)
-        arr[i].data = C.cast(C.c_char_p(f if len(f) else b"\0"), C.c_void_p).value
-        arr[i].size = len(f)
+    """The jgpu_jpeg array of a batch.  No copy: the C side reads the bytes objects' own buffers (kept
+    alive by `keep`).  Filled column-wise -- a batch is hundreds of files and the call is milliseconds."""
+    keep = [f if isinstance(f, bytes) else bytes(f) for f in files]
+    n = len(keep)
+    arr = (_capi.jgpu_jpeg * n)()
+    if n:
+        ptrs = (C.c_char_p * n)(*[f if f else b"\0" for f in keep])   # the buffers' addresses, taken in C
+        view = np.frombuffer(arr, dtype=_JPEG_DT)
+        view["data"] = np.frombuffer(ptrs, dtype=np.uint64)
+        view["size"] = np.fromiter(map(len, keep), dtype=np.int64, count=n)
     return arr, keep
 
 
 def _jpeg_infos(raw) -> List[JpegInfo]:
-    return [JpegInfo(r.status, r.width, r.height, r.ncomps, r.hsamp0, r.vsamp0, r.restart_interval, r.tasks,
-                     r.rgb_off, r.rgb_len, r.message.decode() if r.message else None) for r in raw]
+    if len(raw) == 0:
+        return []
+    v = np.frombuffer(raw, dtype=_INFO_DT)
+    msgs = [C.cast(int(m), C.c_char_p).value.decode() if m else None for m in v["message"].tolist()] \
+        if v["message"].any() else [None] * len(v)
+    cols = [v[k].tolist() for k in ("status", "width", "height", "ncomps", "hsamp0", "vsamp0", "restart_interval",
+                                   "tasks", "rgb_off", "rgb_len")]
+    return [JpegInfo(*row, msg) for row, msg in zip(zip(*cols), msgs)]
 
 
 def probe_jpegs(files: Sequence[bytes], out: str = "rgb"):

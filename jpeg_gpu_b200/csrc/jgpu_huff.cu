@@ -34,15 +34,6 @@ constexpr int kGuardWords = 4;
 
 __constant__ unsigned char c_zigzag[64] = JGPU_HUFF_ZIGZAG_NATURAL;
 
-/* JGPU_HUFF_GW=1: the sync kernel reads the scan words from global memory through L1 instead of
- * staging them in shared memory: 19 KB instead of 51 KB per CTA, so more CTAs are resident while
- * the ones in their late rounds (one or two warps busy, the rest at the barrier) hold their place. */
-#ifndef JGPU_HUFF_GW
-#define JGPU_HUFF_GW 1
-#endif
-#ifndef JGPU_HUFF_SYNC_CTAS
-#define JGPU_HUFF_SYNC_CTAS (JGPU_HUFF_GW ? 6 : 4)
-#endif
 constexpr bool kGlobalWords = JGPU_HUFF_GW != 0;
 
 template <int S>

@@ -11,6 +11,16 @@ namespace jgpu {
 #define JGPU_HUFF_S 32
 #endif
 constexpr int kHuffSubseqWords = JGPU_HUFF_S;   /* 1024 bits per subsequence (16 and 64 measured, profiles/r1_ab_notes.md) */
+/* JGPU_HUFF_GW=1: the sync kernel reads the scan words from global memory through L1 instead of
+ * staging them in shared memory: 19 KB instead of 51 KB per CTA, so more CTAs are resident while
+ * the ones in their late rounds (one or two warps busy, the rest at the barrier) hold their place. */
+#ifndef JGPU_HUFF_GW
+#define JGPU_HUFF_GW 1
+#endif
+#ifndef JGPU_HUFF_SYNC_CTAS
+#define JGPU_HUFF_SYNC_CTAS (JGPU_HUFF_GW ? 6 : 4)
+#endif
+constexpr int kHuffSyncCtasPerSm = JGPU_HUFF_SYNC_CTAS;   /* the runtime sizes its groups of files by this */
 constexpr int kHuffSyncPasses = 3;     /* launches of k_huff_sync (1 + hand-overs across CTAs) */
 
 /* One group of files, everything on the device.  Per-subsequence arrays are indexed by

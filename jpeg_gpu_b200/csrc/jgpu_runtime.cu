@@ -1391,19 +1391,21 @@ static int decode_jpegs_gpu_entropy(jgpu_ctx *ctx, const jgpu_jpeg *files, int n
     CU_TRY(cudaMemcpyAsync(d_qtabs, qtabs.data(), qtabs.size() * 2, cudaMemcpyHostToDevice, ctx->streams[0]));
     CU_TRY(cudaEventRecord(ctx->events[0], ctx->streams[0]));
     for (int s = 1; s < kHostStreams; s++) CU_TRY(cudaStreamWaitEvent(ctx->streams[s], ctx->events[0], 0));
-    /* Groups of files.  The first one is small (48 MB of coefficients: one 4K file) so that the read-back, the
-     * slowest stage, gets going early.  The later ones are sized by the entropy kernels' grids: those CTAs run
-     * rounds of a serial chain and take about as long whatever their number, so a grid of 1.5 waves costs two;
-     * and every launch pays the slowest CTA's rounds (about 0.4 ms) before throughput counts.  A group takes as
-     * many files as fill one wave of resident CTAs (second group), then two (4K files: groups of 4, then 9;
-     * the groups of 7 = 1.5 waves that 192 MB of coefficients gave were 12 % slower on 128 files, groups of three
-     * waves no faster there and slower on 32 files, profiles/r2_notes.md), within 512 MB of coefficients. */
+    /* Groups of files.  The first one is small (48 MB of coefficients: two 4K files) so that the GPU -- and with
+     * host output the read-back, the slowest stage -- gets going early.  The later ones are sized by the sync
+     * kernel's grid: its CTAs run rounds of a serial chain and take about as long whatever their number, so a
+     * grid of 1.3 waves costs two.  Groups two and three take the files that fill half a wave of resident CTAs,
+     * the rest one wave (4K files: 2, 3, 3, then 6 or 7 per group), within 512 MB of coefficients.  Measured on
+     * 128 / 32 4K files, pixels left on the device (profiles/r2_notes.md 14): one wave 15.2 / 6.0 ms, two waves
+     * 15.7 / 6.4, half waves throughout 17.5 / 5.65. */
     const int64_t first_bytes = 48ll << 20, max_bytes = 512ll << 20;
-    const long wave = (long)ctx->sm_count * (1024 / JGPU_HUFF_CTA);   /* CTAs of k_huff_sync / k_huff_write resident at once */
+    long wave = (long)ctx->sm_count * kHuffSyncCtasPerSm;   /* CTAs of k_huff_sync resident at once */
+    if (getenv("JGPU_HUFF_WAVE_PER_SM")) wave = (long)ctx->sm_count * std::max(1, atoi(getenv("JGPU_HUFF_WAVE_PER_SM")));
     int i0 = 0, chunk = 0;
     const bool blocks_at_end = device_out && !getenv("JGPU_BLOCKS_PER_GROUP");
-    /* JGPU_HUFF_WAVES: experiment knob, waves of entropy CTAs per group */
-    const int max_waves = getenv("JGPU_HUFF_WAVES") ? std::max(1, atoi(getenv("JGPU_HUFF_WAVES"))) : 2;
+
+    /* JGPU_HUFF_WAVES / JGPU_HUFF_WAVE_PER_SM: experiment knobs, waves of sync CTAs per group and CTAs per SM in a wave */
+    const int max_waves = getenv("JGPU_HUFF_WAVES") ? std::max(1, atoi(getenv("JGPU_HUFF_WAVES"))) : 1;
     /* JGPU_TRACE: device-side times of every group (events on its stream) */
     std::vector<cudaEvent_t> tev;
     std::vector<int> tfiles;
@@ -1418,7 +1420,7 @@ static int decode_jpegs_gpu_entropy(jgpu_ctx *ctx, const jgpu_jpeg *files, int n
       int i1 = i0;
       int64_t acc = 0;
       long ctas = 0;
-      const long target = (chunk < max_waves ? chunk : max_waves) * wave;
+      const long target = chunk == 0 ? 0 : chunk < 3 ? wave / 2 : max_waves * wave;
       /* (a group's file count is gridDim.y of the entropy kernels: at most 65535) */
       while (i1 < m && i1 - i0 < 65535) {
         JpegItem &it = items[ok[i1]];
@@ -1475,6 +1477,8 @@ static int decode_jpegs_gpu_entropy(jgpu_ctx *ctx, const jgpu_jpeg *files, int n
       CU_TRY(cudaEventRecord(ctx->up_events[chunk], up));
       CU_TRY(cudaStreamWaitEvent(st, ctx->up_events[chunk], 0));
       mark(st);
+      /* (zeroing on the upload stream instead, ahead of the group's turn, holds up the copies behind it:
+       * 16.4 against 15.8 ms for 128 files) */
       CU_TRY(cudaMemsetAsync(d_coef + descs[i0].coef_off, 0, (size_t)acc, st));
       mark(st);
       {

@@ -1,10 +1,7 @@
-mkdir -p gpurun_out/r2
-timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -4
-timeout 600 python bench.py > gpurun_out/r2/bench_huff3.json 2> gpurun_out/r2/bench_huff3.err
-python - <<PY
-import json
-d=json.load(open("gpurun_out/r2/bench_huff3.json"))
-print("value",round(d["value"]),"ms",round(d["ms_per_step"],4),"frac",round(d["roofline"]["frac"],4),"e2e",round(d["e2e"]["value"]),"pack",round(d["e2e_pack"]["value"]))
-j=d["e2e_jpeg"]
-print({k:(round(v) if isinstance(v,float) else v) for k,v in j.items() if "value" in k or "threads" in k})
-PY
+run() { PROFILE_DEVICE_OUT=1 timeout 300 python tools/profile_jpegs.py $1 gpu 240 5 2>&1 | tail -4 | awk '{print $(NF-4), $(NF-3)}' | tr '\n' ' '; echo; }
+echo "--- default 128"; run 128
+echo "--- default 32"; run 32
+echo "--- default 8"; run 8
+echo "--- 128 host out"; timeout 300 python tools/profile_jpegs.py 128 gpu 240 3 2>&1 | tail -2 | awk '{print $(NF-4), $(NF-3)}' | tr '\n' ' '; echo
+echo "--- 32 host out"; timeout 300 python tools/profile_jpegs.py 32 gpu 240 3 2>&1 | tail -2 | awk '{print $(NF-4), $(NF-3)}' | tr '\n' ' '; echo
+timeout 900 python -m pytest tests/test_gpu_huffman.py tests/test_gpu_jpegs.py -x -q -m gpu 2>&1 | tail -3
