@@ -116,6 +116,20 @@ def test_pixels_can_stay_on_the_device(gpu_ctx):
     for a, b in zip(gi, ri):
         assert a.status == 0 and (a.rgb_off, a.rgb_len) == (b.rgb_off, b.rgb_len)
         assert np.array_equal(got[a.rgb_off:a.rgb_off + a.rgb_len], ref[b.rgb_off:b.rgb_off + b.rgb_len])
+    # planes on the device, and a damaged file in the batch (it goes through the sequential reader after the
+    # one block-decoder launch that ends a device-output call)
+    bad = bytearray(files[0])
+    bad[len(bad) // 2] ^= 0x5a
+    files2 = files + [bytes(bad)]
+    ref, ri = gpu_ctx.decode_jpegs(files2, entropy="gpu", out="yuv", strict=False)   # host output: per-group launches
+    total, _ = J.probe_jpegs(files2, out="yuv")
+    dev = torch.zeros(total, dtype=torch.uint8, device="cuda:0")
+    out, gi = gpu_ctx.decode_jpegs(files2, dev, entropy="gpu", out="yuv", strict=False)
+    got = out.cpu().numpy()
+    for a, b in zip(gi, ri):
+        assert a.status == b.status and (a.rgb_off, a.rgb_len) == (b.rgb_off, b.rgb_len)
+        if a.status == 0:
+            assert np.array_equal(got[a.rgb_off:a.rgb_off + a.rgb_len], ref[b.rgb_off:b.rgb_off + b.rgb_len])
 
 
 def test_planes_instead_of_pixels(gpu_ctx):
