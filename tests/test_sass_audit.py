@@ -97,3 +97,24 @@ def test_fused_kernel_uses_tma_and_mbarriers(sass):
         assert "IDP.2A" in text           # packed-table dequantisation
         assert "VIADDMNMX" in text        # s16x2 add+clamp
         assert "STG.E.EF.128" in text or "STG.E.128" in text or re.search(r"STG\.E\.[A-Z.]*128", text)
+
+
+def test_entropy_kernels_keep_their_shape(sass):
+    """The entropy decoder's two hot kernels (jgpu_huff.cu): the sync pass must keep the register count
+    that lets six CTAs of 256 threads share an SM and must not stage scan words in shared memory (they come through
+    L1: LDG.E.CONSTANT in the loop); the write pass must flush finished blocks as whole words per lane after a vote
+    (VOTE + SHFL + one STG.E per lane and block), not as 2-byte stores from the decoding loop; neither may spill."""
+    sync = [body for n, body in sass.items() if "k_huff_sync" in n]
+    staged = [body for n, body in sass.items() if "k_huff_write_staged" in n]
+    assert len(sync) == 1 and len(staged) == 1
+    for body in sync + staged:
+        text = "\n".join(body)
+        assert not re.search(r"\b(STL|LDL)\b", text), "spills in an entropy kernel"
+    s = "\n".join(sync[0])
+    assert "LDG.E.CONSTANT" in s and "SHF.L.W.U32.HI" in s, "scan words through L1, funnel-shift window"
+    w = "\n".join(staged[0])
+    assert "VOTE.ANY" in w and "SHFL.IDX" in w and "STS.U16" in w
+    assert re.search(r"LDS\.128", w), "block record: one 16-byte shared load per block end"
+    # 32-bit stores of whole words (full blocks) and predicated 16-bit stores (partial blocks) exist; nothing wider
+    # than that goes to the coefficient planes from this kernel
+    assert re.search(r"STG\.E\s+desc", w) and "STG.E.U16" in w
