@@ -455,9 +455,10 @@ k_huff_write(const jgpu_huff_file *__restrict__ files, const uint32_t *__restric
  * per 32 bits consumed, fetched one refill ahead), which leaves the shared memory to the block
  * buffers: 47.6 KB per CTA, four CTAs per SM as before.
  *
- * Buffer layout: word w of lane l's block sits at word (w + l) & 31 of its 128 bytes, so that
- * lanes storing the same coefficient index hit different banks and the cooperative read of one
- * block (lane r reads physical word r) is conflict-free. */
+ * Buffer layout: word w of lane l's block sits at word w ^ l of its 128 bytes, so that lanes
+ * storing the same coefficient index hit different banks and the cooperative read of one block
+ * (lane r reads physical word r) is conflict-free; the zig-zag table of this kernel holds byte
+ * offsets (2 x natural index), so a coefficient's address is buffer + (offset ^ 4 * lane). */
 template <int S>
 struct WriteSmem {
   jgpu_huff_table tabs[JGPU_HUFF_TABLES];
@@ -480,25 +481,34 @@ __device__ __forceinline__ uint32_t lds_u32_v(uint32_t a) {
 }
 
 /* The warp writes out the blocks of the lanes in `m`; `pm`: lanes whose block is a partial one.
- * blk = the lane's current block, in blocks from the coefficient buffer's start. */
-__device__ __forceinline__ void flush_blocks(uint32_t m, uint32_t pm, uint32_t blk, uint32_t warpbuf, int lane,
+ * blk = the lane's current block, in blocks from the coefficient buffer's start; lane4 = 4 * lane.
+ * Lane r moves physical word r of the block's buffer = word r ^ l of lane l's block. */
+__device__ __forceinline__ void flush_blocks(uint32_t m, uint32_t pm, uint32_t blk, uint32_t warpbuf, uint32_t lane4,
                                              int16_t *__restrict__ coef) {
+  unsigned char *const base = reinterpret_cast<unsigned char *>(coef);
   __syncwarp();
-  do {
-    const int l = __ffs((int)m) - 1;
-    m &= m - 1;
+  uint32_t full = m & ~pm;
+  while (full) {   /* whole blocks: one line each */
+    const int l = __ffs((int)full) - 1;
+    full &= full - 1;
     const uint32_t b = __shfl_sync(0xffffffffu, blk, l);
-    const uint32_t a = warpbuf + (uint32_t)l * 128u + (uint32_t)lane * 4u;
+    const uint32_t a = warpbuf + (uint32_t)l * 128u + lane4;
     const uint32_t v = lds_u32_v(a);
     sts_u32(a, 0u);
-    int16_t *dst = coef + (size_t)b * 64 + 2u * ((uint32_t)(lane - l) & 31u);
-    if (!((pm >> l) & 1u)) {
-      *reinterpret_cast<uint32_t *>(dst) = v;
-    } else {
-      if (v & 0xffffu) dst[0] = (int16_t)(v & 0xffffu);
-      if (v >> 16) dst[1] = (int16_t)(v >> 16);
-    }
-  } while (m);
+    *reinterpret_cast<uint32_t *>(base + (size_t)b * 128 + (lane4 ^ ((uint32_t)l << 2))) = v;
+  }
+  uint32_t part = m & pm;
+  while (part) {   /* blocks shared with a neighbouring subsequence: the non-zero halves only */
+    const int l = __ffs((int)part) - 1;
+    part &= part - 1;
+    const uint32_t b = __shfl_sync(0xffffffffu, blk, l);
+    const uint32_t a = warpbuf + (uint32_t)l * 128u + lane4;
+    const uint32_t v = lds_u32_v(a);
+    sts_u32(a, 0u);
+    int16_t *dst = reinterpret_cast<int16_t *>(base + (size_t)b * 128 + (lane4 ^ ((uint32_t)l << 2)));
+    if (v & 0xffffu) dst[0] = (int16_t)(v & 0xffffu);
+    if (v >> 16) dst[1] = (int16_t)(v >> 16);
+  }
   __syncwarp();
 }
 
@@ -520,7 +530,7 @@ k_huff_write_staged(const jgpu_huff_file *__restrict__ files, const uint32_t *__
     const uint32_t *src = reinterpret_cast<const uint32_t *>(files + blockIdx.y);
     uint32_t *dst = reinterpret_cast<uint32_t *>(&sm.file);
     for (int i = t; i < (int)(sizeof(jgpu_huff_file) / 4); i += kCta) dst[i] = src[i];
-    if (t < 64) sm.zz[t] = c_zigzag[t];
+    if (t < 64) sm.zz[t] = (unsigned char)(2 * c_zigzag[t]);   /* byte offset inside the block */
     uint4 *z = reinterpret_cast<uint4 *>(sm.blocks);
     for (int i = t; i < kCta * 8; i += kCta) z[i] = make_uint4(0u, 0u, 0u, 0u);
   }
@@ -544,6 +554,7 @@ k_huff_write_staged(const jgpu_huff_file *__restrict__ files, const uint32_t *__
   mem.brec = pinned((uint32_t)__cvta_generic_to_shared(sm.brec));
   const uint32_t mybuf = pinned((uint32_t)__cvta_generic_to_shared(sm.blocks) + (uint32_t)t * 128u);
   const uint32_t warpbuf = mybuf - (uint32_t)lane * 128u;
+  const uint32_t lane4 = pinned((uint32_t)lane * 4u);
   const int bpm = f.bpm, nhmb = f.nhmb;
 
   /* what the thread is about */
@@ -594,7 +605,6 @@ k_huff_write_staged(const jgpu_huff_file *__restrict__ files, const uint32_t *__
   bool partial = z != 0;   /* the block this subsequence starts inside belongs to two threads */
 
   for (;;) {
-    bool fin = false;
     if (active) {
       const uint32_t look = huff::window32(wa, wb, bp);
       uint32_t e = mem.lut_at(tab, look >> (32 - JGPU_HUFF_LUT_BITS));
@@ -606,14 +616,12 @@ k_huff_write_staged(const jgpu_huff_file *__restrict__ files, const uint32_t *__
       const uint32_t total = JGPU_HUFF_ENTRY_T(e);
       const uint32_t za = z + JGPU_HUFF_ENTRY_A(e);
       if (za <= 64u) {
+        /* T.81 F.2.2.1 EXTEND: the s bits after the code, less 2^s - 1 when their first bit is 0 */
         const uint32_t s = JGPU_HUFF_ENTRY_S(e);
-        const uint32_t bits = ((look << (total - s)) >> 1) >> (31u - s);
-        const uint32_t half = (1u << s) >> 1;
-        const int v = bits < half ? (int)bits - (int)(1u << s) + 1 : (int)bits;
-        if (v != 0) {
-          const uint32_t p = mem.zigzag((int)za - 1);
-          sts_u16(mybuf + 4u * (((p >> 1) + (uint32_t)lane) & 31u) + 2u * (p & 1u), (uint32_t)v);
-        }
+        const uint32_t x = look << (total - s);
+        const uint32_t bits = (x >> 1) >> (31u - s);
+        const int v = (int)bits - (int)(~(uint32_t)((int)x >> 31) & ((1u << s) - 1u));
+        if (v != 0) sts_u16(mybuf + (mem.zigzag((int)za - 1) ^ lane4), (uint32_t)v);
       }
       bp += total;
       if (bp >= 32u) {
@@ -625,10 +633,10 @@ k_huff_write_staged(const jgpu_huff_file *__restrict__ files, const uint32_t *__
       }
       z = za;
       tab = tac;
-      fin = za >= 64u;
     }
+    const bool fin = z >= 64u;   /* (z is below 64 between symbols for a lane that has stopped, too) */
     const uint32_t m = __ballot_sync(0xffffffffu, fin);
-    if (m) flush_blocks(m, __ballot_sync(0xffffffffu, partial), blk, warpbuf, lane, coef);
+    if (m) flush_blocks(m, __ballot_sync(0xffffffffu, partial), blk, warpbuf, lane4, coef);
     if (fin) {
       bad |= (uint32_t)(z > 64u && z <= JGPU_HUFF_EOB);
       z = 0;
@@ -657,7 +665,7 @@ k_huff_write_staged(const jgpu_huff_file *__restrict__ files, const uint32_t *__
   /* blocks left unfinished: the next subsequence carries on with them */
   {
     const uint32_t m = __ballot_sync(0xffffffffu, decoded && z != 0);
-    if (m) flush_blocks(m, 0xffffffffu, blk, warpbuf, lane, coef);
+    if (m) flush_blocks(m, 0xffffffffu, blk, warpbuf, lane4, coef);
   }
   if (decoded) {
     const uint32_t out = JGPU_HUFF_STATE(pos > end ? pos - end : 0, c, z);
