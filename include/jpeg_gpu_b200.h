@@ -323,7 +323,8 @@ int jgpu_decode_jpegs(jgpu_ctx *ctx, const jgpu_jpeg *files, int n, int nthreads
  * returns only when the pixels are complete.  The call is then as long as the chain of kernels,
  * so nthreads <= 0 means HALF the host cores here (the thread that feeds the GPU must not be
  * starved by the unstuffing workers), and the block decoder runs once, after the last group of
- * files, instead of once per group. */
+ * files, instead of once per group.  (One process per GPU on a shared host: pass nthreads
+ * explicitly, cores / processes, or half of that here -- the default knows of one process only.) */
 #define JGPU_JPEGS_DEVICE_OUT 0x100u
 /* OR-ed into flags: the output is what the reference's xjpeg backend produces for JPEG_DECODE_YUV
  * (src/xjpeg.c:565-584) instead of pixels -- per file the padded u8 planes Y | Cb | Cr back to
