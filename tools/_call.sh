@@ -1,9 +1,14 @@
 mkdir -p gpurun_out/r2
-timeout 900 python -m pytest tests/test_gpu_huffman.py tests/test_gpu_jpegs.py -x -q -m gpu 2>&1 | tail -3
-run() { PROFILE_DEVICE_OUT=1 timeout 300 python tools/profile_jpegs.py $1 gpu $2 5 2>&1 | tail -4 | awk '{print $(NF-4), $(NF-3)}' | tr '\n' ' '; echo; }
-echo "--- 128"; run 128 240
-echo "--- 32"; run 32 240
-echo "--- 128 no restart markers"; run 128 0
-PROFILE_DEVICE_OUT=1 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:k_huff_scan -c 6 --csv --log-file gpurun_out/r2/launches_huff_scan.csv python tools/profile_jpegs.py 24 gpu 240 1 > /dev/null 2>&1
-grep -h "k_huff_scan" gpurun_out/r2/launches_huff_scan.csv | awk -F'","' '{print $(NF-6), $NF}'
-timeout 600 python tools/fuzz_jpegs_gpu.py 23 600 2>&1 | tail -2
+PROFILE_DEVICE_OUT=1 JGPU_HUFF_WAVES=2 JGPU_HUFF_WAVE_PER_SM=4 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_huff_write --launch-skip 3 --launch-count 1 -o /tmp/write_f python tools/profile_jpegs.py 24 gpu 240 1 > /dev/null 2>&1
+ncu -i /tmp/write_f.ncu-rep --page raw --csv > gpurun_out/r2/ncu_write_final2_raw.csv
+PROFILE_DEVICE_OUT=1 JGPU_HUFF_WAVES=2 JGPU_HUFF_WAVE_PER_SM=4 timeout 300 ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum,smsp__issue_active.avg.pct_of_peak_sustained_active,sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active --clock-control none -k regex:k_ --launch-skip 21 -c 9 --csv --log-file gpurun_out/r2/launches_jpeg_final_9files.csv python tools/profile_jpegs.py 24 gpu 240 1 > /dev/null 2>&1
+python - <<PY
+import csv
+rows=[r for r in csv.reader(open("gpurun_out/r2/launches_jpeg_final_9files.csv")) if len(r)>10]
+h=rows[0]
+acc={}
+for r in rows[1:]:
+    d=dict(zip(h,r))
+    acc.setdefault(d["ID"],[d["Kernel Name"][:60], d["Grid Size"]]).append(d["Metric Value"])
+for k,v in acc.items(): print(k, v)
+PY
