@@ -22,9 +22,18 @@ def main():
     rng = np.random.default_rng(20261017)
     yy, xx = np.mgrid[0:h, 0:w]
     base = np.stack([(xx * 5 + yy * 3) % 256, (yy * 7 + xx) % 256, (xx * 2 + yy * 9) % 256], -1)
-    pic = np.clip(base + rng.integers(-24, 25, size=base.shape), 0, 255).astype(np.uint8)
+    # PROFILE_NOISE / PROFILE_Q / PROFILE_SS (0: 4:4:4, 1: 4:2:2, 2: 4:2:0, L: grey) / PROFILE_SMOOTH=1 vary the picture
+    noise = int(os.environ.get("PROFILE_NOISE", "24"))
+    q = int(os.environ.get("PROFILE_Q", "85"))
+    ss = os.environ.get("PROFILE_SS", "2")
+    if os.environ.get("PROFILE_SMOOTH") == "1":
+        base = np.stack([(xx + yy) // 24 % 256, (yy * 2 + xx) // 32 % 256, (xx * 3) // 40 % 256], -1)
+    pic = np.clip(base + rng.integers(-noise, noise + 1, size=base.shape), 0, 255).astype(np.uint8)
     bio = io.BytesIO()
-    Image.fromarray(pic).save(bio, "JPEG", quality=85, subsampling=2, restart_marker_blocks=rst)
+    if ss == "L":
+        Image.fromarray(pic[..., 0]).save(bio, "JPEG", quality=q, restart_marker_blocks=rst)
+    else:
+        Image.fromarray(pic).save(bio, "JPEG", quality=q, subsampling=int(ss), restart_marker_blocks=rst)
     files = [bio.getvalue()] * n
     total, _ = J.probe_jpegs(files)
     device_out = os.environ.get("PROFILE_DEVICE_OUT") == "1"
