@@ -1,10 +1,9 @@
-run() { PROFILE_DEVICE_OUT=1 timeout 300 python tools/profile_jpegs.py 64 gpu ${RST:-240} 3 2>&1 | tail -2 | sed 's/gpu: //' | tr '\n' ';'; echo; }
-echo "--- bench picture"; run
-echo "--- smooth, no noise"; PROFILE_SMOOTH=1 PROFILE_NOISE=0 run
-echo "--- smooth, noise 2, q95"; PROFILE_SMOOTH=1 PROFILE_NOISE=2 PROFILE_Q=95 run
-echo "--- noise 60 q98"; PROFILE_NOISE=60 PROFILE_Q=98 run
-echo "--- q40"; PROFILE_Q=40 run
-echo "--- 4:4:4"; PROFILE_SS=0 run
-echo "--- 4:2:2"; PROFILE_SS=1 run
-echo "--- grey"; PROFILE_SS=L run
-echo "--- smooth no restart markers"; RST=0 PROFILE_SMOOTH=1 PROFILE_NOISE=1 run
+run() { PROFILE_DEVICE_OUT=1 timeout 300 python tools/profile_jpegs.py $1 gpu 240 4 2>&1 | tail -3 | awk '{print $(NF-4), $(NF-3)}' | tr '\n' ' '; echo; }
+for v in default loop; do
+  if [ "$v" = default ]; then unset JGPU_LIB_PATH; else export JGPU_LIB_PATH=$PWD/jpeg_gpu_b200/libjpeg_gpu_b200.$v.so; fi
+  echo "--- $v 128"; run 128
+  echo "--- $v q98 noise 60, 32 files"; PROFILE_NOISE=60 PROFILE_Q=98 run 32
+  echo "--- $v q95, 64 files"; PROFILE_Q=95 run 64
+done
+unset JGPU_LIB_PATH
+timeout 600 python -m pytest tests/test_gpu_huffman.py -x -q -m gpu 2>&1 | tail -2
