@@ -23,8 +23,70 @@ namespace {
 
 const unsigned char kZigzag[64] = JGPU_HUFF_ZIGZAG_NATURAL;
 
+// Write pass to emulate: 0 = k_huff_write (a store per coefficient), 1 = k_huff_write_staged (a block buffer per
+// thread; whole blocks written out zeros included, blocks shared with a neighbouring subsequence as their non-zero
+// coefficients only), 2 = the same with the threads run in descending order -- a block wrongly taken for a whole
+// one would wipe what its other owner stored, in one of the two orders.
+int g_write_mode = 0;
+
+// The rule of k_huff_write_staged in terms of the decoding loop's sink.
+struct StagedSink {
+  const jgpu::huff::HostMem *mem;
+  short *base;
+  int bpm, nhmb, mbx, mby, c;
+  int64_t g, seg_blocks;
+  short buf[64];
+  bool partial;
+  short *locate() const {
+    return base + mem->blk_base(c) + (int64_t)mbx * mem->blk_xs(c) + (int64_t)mby * mem->blk_ys(c);
+  }
+  void start(const jgpu::huff::HostMem *m, int blocks_per_mcu, int mcus_per_row, short *coef_base, int seg_mcu0,
+             int64_t g0, int64_t nblocks, bool starts_inside_a_block) {
+    mem = m;
+    bpm = blocks_per_mcu;
+    nhmb = mcus_per_row;
+    base = coef_base;
+    g = g0;
+    seg_blocks = nblocks;
+    const int mcu = seg_mcu0 + (int)(g0 / bpm);
+    c = (int)(g0 % bpm);
+    mbx = mcu % nhmb;
+    mby = mcu / nhmb;
+    memset(buf, 0, sizeof(buf));
+    partial = starts_inside_a_block;
+  }
+  void coef(int k, int v) { buf[mem->zigzag(k)] = (short)v; }
+  void flush(bool part) {
+    short *blk = locate();
+    if (!part) {
+      memcpy(blk, buf, sizeof(buf));
+    } else {
+      for (int i = 0; i < 64; i++) {
+        if (buf[i]) blk[i] = buf[i];
+      }
+    }
+    memset(buf, 0, sizeof(buf));
+  }
+  bool block_done() {
+    flush(partial);
+    partial = false;
+    g++;
+    if (g >= seg_blocks) return true;
+    if (++c == bpm) {
+      c = 0;
+      if (++mbx == nhmb) {
+        mbx = 0;
+        mby++;
+      }
+    }
+    return false;
+  }
+};
+
 
 }  // namespace
+
+extern "C" void huff_set_write_mode(int mode) { g_write_mode = mode; }
 
 // Decodes one JPEG file's scan into QUANT planes (reference layout) the way the kernels do.
 //   subseq_words, cta   the kernel's constants (32, 256), shrinkable so that small files still
@@ -174,7 +236,8 @@ extern "C" long long huff_emulate(const unsigned char *jpeg, int size, short *co
   }
   // ---- k_huff_write ----
   memset(coef, 0, sizeof(short) * (size_t)lay.coef_len);
-  for (int i = 0; i < n; i++) {
+  for (int step = 0; step < n; step++) {
+    const int i = g_write_mode == 2 ? n - 1 - step : step;
     const uint32_t seg = segid[i];
     const int seg_mcu0 = (int)seg * f.mcus_per_seg;
     const int64_t seg_blocks = (int64_t)std::min(f.mcus_per_seg, f.total_mcus - seg_mcu0) * f.bpm;
@@ -184,17 +247,27 @@ extern "C" long long huff_emulate(const unsigned char *jpeg, int size, short *co
       st_flags |= JGPU_HUFF_ERR_SYNC;
     } else if (g0 < seg_blocks) {
       StoreSink<HostMem> sink;
-      sink.start(&mem, f.bpm, f.nhmb, coef, seg_mcu0, g0, seg_blocks);
-      uint32_t nn = 0, err = 0;
+      StagedSink staged;
+      uint32_t nn = 0, err = 0, out;
       int pos = 0;
-      const uint32_t out = decode_subsequence(mem, f.bpm, (uint32_t)i * S, S, st, sink, &nn, &err, &pos);
+      int64_t g_end;
+      if (g_write_mode == 0) {
+        sink.start(&mem, f.bpm, f.nhmb, coef, seg_mcu0, g0, seg_blocks);
+        out = decode_subsequence(mem, f.bpm, (uint32_t)i * S, S, st, sink, &nn, &err, &pos);
+        g_end = sink.g;
+      } else {
+        staged.start(&mem, f.bpm, f.nhmb, coef, seg_mcu0, g0, seg_blocks, JGPU_HUFF_STATE_Z(st) != 0);
+        out = decode_subsequence(mem, f.bpm, (uint32_t)i * S, S, st, staged, &nn, &err, &pos);
+        if (JGPU_HUFF_STATE_Z(out) != 0) staged.flush(true);   // the block the next subsequence carries on with
+        g_end = staged.g;
+      }
       if (err) st_flags |= JGPU_HUFF_ERR_CODE;
-      if (sink.g >= seg_blocks) {
+      if (g_end >= seg_blocks) {
         const uint32_t bits = seg_first[f.n_seg + 1 + seg];
         const long long used = (long long)((uint32_t)i - seg_first[seg]) * (32 * S) + pos;
         if (bits != 0xffffffffu && (long long)bits - used >= 8) st_flags |= JGPU_HUFF_ERR_TRAIL;
       }
-      if (sink.g < seg_blocks) {
+      if (g_end < seg_blocks) {
         if ((uint32_t)i + 1 == seg_first[seg + 1]) st_flags |= JGPU_HUFF_ERR_SHORT;
         else if (out != state[i + 1] || nn != (nslots[i] & 0x7fffffffu)) st_flags |= JGPU_HUFF_ERR_SYNC;
       }

@@ -17,8 +17,14 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "jpeg_gpu_b200", "csrc")
 
 
-@pytest.fixture(scope="module")
-def emu(tmp_path_factory):
+WRITE_MODES = {"scatter": 0, "staged": 1, "staged_descending": 2}
+
+
+@pytest.fixture(scope="module", params=list(WRITE_MODES))
+def emu(tmp_path_factory, request):
+    """The emulation, once per write pass it can restate: k_huff_write (a store per coefficient) and
+    k_huff_write_staged (whole blocks from a buffer, shared blocks as their non-zero coefficients; threads in
+    ascending and in descending order, so that a shared block taken for a whole one cannot go unnoticed)."""
     d = tmp_path_factory.mktemp("huff_host")
     objs = []
     inc = ["-I", CSRC, "-I", os.path.join(ROOT, "include")]
@@ -34,6 +40,7 @@ def emu(tmp_path_factory):
     lib.huff_emulate.argtypes = [C.c_char_p, C.c_int, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int,
                                  C.POINTER(C.c_uint), C.POINTER(C.c_int)]
     lib.huff_table_selfcheck.argtypes = [C.c_char_p, C.c_char_p]
+    lib.huff_set_write_mode(WRITE_MODES[request.param])
     return lib
 
 
