@@ -48,7 +48,9 @@
  * fallen into step (the chance that eight pieces in a row do not is about 0.1 % on 4:2:0 files).
  * Without them every CTA's first state is a blind guess and nearly every CTA has to be redone
  * in the second launch. */
+#ifndef JGPU_HUFF_WARM
 #define JGPU_HUFF_WARM 8
+#endif
 #define JGPU_HUFF_OWN (JGPU_HUFF_CTA - JGPU_HUFF_WARM)   /* subsequences a sync CTA owns */
 
 /* What the decoding loop needs to know about a symbol, packed so that the loop spends no
