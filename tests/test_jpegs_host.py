@@ -95,3 +95,26 @@ def test_malformed_restart_markers_are_left_to_the_sequential_reader():
     jpg[pos[1] + 1] = 0xD5
     with pytest.raises(AssertionError):
         _segments_decode(bytes(jpg), lambda n: range(n))
+
+
+def test_batches_of_any_buffer_type_marshal_alike():
+    """The wrapper fills the jgpu_jpeg array column-wise (addresses taken in one C call, sizes through numpy):
+    bytes, bytearray and memoryview inputs, empty entries and a batch of hundreds give what one-by-one probing gives."""
+    base = [load(n)[0] for n in NAMES]
+    files = []
+    for i in range(300):
+        f = base[i % len(base)]
+        files.append(f if i % 3 == 0 else bytearray(f) if i % 3 == 1 else memoryview(f))
+    files[17] = b""
+    total, infos = J.probe_jpegs(files)
+    off = 0
+    for i, inf in enumerate(infos):
+        if i == 17:
+            assert inf.status == 1 and inf.message
+            continue
+        _, one = J.probe_jpegs([bytes(files[i])])
+        assert (inf.status, inf.width, inf.height, inf.ncomps, inf.rgb_len) == \
+               (0, one[0].width, one[0].height, one[0].ncomps, one[0].rgb_len)
+        assert inf.rgb_off == off
+        off += -(-inf.rgb_len // 256) * 256
+    assert total == off
