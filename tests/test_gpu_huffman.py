@@ -219,3 +219,19 @@ def test_a_b_knobs_give_the_same_bytes(gpu_ctx, monkeypatch, knob):
         ctx.close()
         monkeypatch.delenv(name)
         J.Context(0).close()
+
+
+def test_files_longer_than_one_sweep_of_the_scan_kernel(gpu_ctx):
+    """k_huff_scan takes 16 384 subsequences per sweep and carries the running count into the next one: 4K files
+    of 4 and 8 MB (two and four sweeps; with and without restart markers, where the carry matters for the whole
+    file) give the host-thread path's pixels, decoded on the device (tasks = subsequences)."""
+    pytest.importorskip("PIL")
+    files = [_jpeg(3840, 2160, 2, rst=240, q=85, noise=24), _jpeg(3840, 2160, 2, rst=0, q=85, noise=24),
+             _jpeg(3840, 2160, 2, rst=0, q=96, noise=40)]
+    got, gi = gpu_ctx.decode_jpegs(files, entropy="gpu")
+    ref, ri = gpu_ctx.decode_jpegs(files, entropy="cpu")
+    assert [i.status for i in gi] == [0, 0, 0]
+    assert all(i.tasks > 16384 for i in gi), [i.tasks for i in gi]
+    assert gi[2].tasks > 3 * 16384
+    for a, b in zip(gi, ri):
+        assert np.array_equal(got[a.rgb_off:a.rgb_off + a.rgb_len], ref[b.rgb_off:b.rgb_off + b.rgb_len])
