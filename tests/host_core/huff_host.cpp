@@ -88,6 +88,70 @@ struct StagedSink {
 
 extern "C" void huff_set_write_mode(int mode) { g_write_mode = mode; }
 
+// k_huff_scan's arithmetic, lane by lane: `warps` warps of 32 lanes, each warp scanning `per` stripes of 32
+// consecutive counts with a running carry, the warps' totals combined once per sweep, a carry from sweep to sweep
+// (the kernel: 32 warps, 16 stripes).  Bit 31 of a count starts a restart interval.
+static void scan_striped(const std::vector<uint32_t> &nslots, std::vector<uint32_t> &slots, int warps, int per) {
+  const uint32_t n = (uint32_t)nslots.size();
+  uint32_t s_carry = 0;
+  for (uint32_t base = 0; base < n; base += (uint32_t)(warps * 32 * per)) {
+    std::vector<uint32_t> w_val(warps), w_flag(warps);
+    std::vector<std::vector<uint32_t>> incl(warps, std::vector<uint32_t>(32 * per)), own(incl), seen(incl);
+    for (int w = 0; w < warps; w++) {
+      uint32_t c_val = 0, c_flag = 0;
+      for (int k = 0; k < per; k++) {
+        uint32_t val[32], flag[32];
+        for (int l = 0; l < 32; l++) {
+          const uint32_t i = base + (uint32_t)(w * 32 * per + 32 * k + l);
+          const uint32_t raw = i < n ? nslots[i] : 0u;
+          own[w][32 * k + l] = raw;
+          val[l] = raw & 0x7fffffffu;
+          flag[l] = raw >> 31;
+        }
+        for (int d = 1; d < 32; d <<= 1) {   // the shuffle steps: every lane reads the values of the step before
+          uint32_t v2[32], f2[32];
+          for (int l = 0; l < 32; l++) {
+            v2[l] = l >= d ? val[l - d] : 0;
+            f2[l] = l >= d ? flag[l - d] : 0;
+          }
+          for (int l = d; l < 32; l++) {
+            if (!flag[l]) val[l] += v2[l];
+            flag[l] |= f2[l];
+          }
+        }
+        for (int l = 0; l < 32; l++) {
+          if (!flag[l]) val[l] += c_val;
+          flag[l] |= c_flag;
+          incl[w][32 * k + l] = val[l];
+          seen[w][32 * k + l] = flag[l];
+        }
+        c_val = val[31];
+        c_flag = flag[31];
+      }
+      w_val[w] = c_val;
+      w_flag[w] = c_flag;
+    }
+    for (int w = 1; w < warps; w++) {   // inclusive over the warps (the kernel: one warp, shuffles)
+      if (!w_flag[w]) w_val[w] += w_val[w - 1];
+      w_flag[w] |= w_flag[w - 1];
+    }
+    for (int w = 0; w < warps; w++) {
+      uint32_t pre = 0, pre_flag = 0;
+      if (w > 0) {
+        pre = w_val[w - 1];
+        pre_flag = w_flag[w - 1];
+      }
+      if (!pre_flag) pre += s_carry;
+      for (int e = 0; e < 32 * per; e++) {
+        const uint32_t i = base + (uint32_t)(w * 32 * per + e);
+        const uint32_t v = incl[w][e] + (seen[w][e] ? 0u : pre);
+        if (i < n) slots[i] = (own[w][e] >> 31) ? 0u : v - (own[w][e] & 0x7fffffffu);
+      }
+    }
+    s_carry = w_flag[warps - 1] ? w_val[warps - 1] : w_val[warps - 1] + s_carry;
+  }
+}
+
 // Decodes one JPEG file's scan into QUANT planes (reference layout) the way the kernels do.
 //   subseq_words, cta   the kernel's constants (32, 256), shrinkable so that small files still
 //                       exercise hand-overs between subsequences, CTAs and launches
@@ -232,6 +296,16 @@ extern "C" long long huff_emulate(const unsigned char *jpeg, int size, short *co
       if (nslots[i] >> 31) acc = 0;
       slots[i] = acc;
       acc += nslots[i] & 0x7fffffffu;
+    }
+    // the kernel's striped arithmetic must give the same, in its own geometry and in one that makes small files
+    // cross warps and sweeps
+    const int geometries[2][2] = {{32, 16}, {2, 2}};
+    for (const auto &gm : geometries) {
+      std::vector<uint32_t> in(nslots.begin(), nslots.begin() + n), out(n, 0xdeadbeefu);
+      scan_striped(in, out, gm[0], gm[1]);
+      for (int i = 0; i < n; i++) {
+        if (out[i] != slots[i]) st_flags |= 0x80000000u;   // not a kernel status: fails every test that checks status == 0
+      }
     }
   }
   // ---- k_huff_write ----
