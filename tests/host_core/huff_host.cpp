@@ -88,6 +88,12 @@ struct StagedSink {
 
 extern "C" void huff_set_write_mode(int mode) { g_write_mode = mode; }
 
+// JGPU_HUFF_ENTRY and its fields, for the test of the invariants the decoding loop rests on
+extern "C" unsigned huff_entry(unsigned len, unsigned sym, int ac) { return JGPU_HUFF_ENTRY(len, sym, ac); }
+extern "C" unsigned huff_entry_field(unsigned e, int which) {
+  return which == 0 ? JGPU_HUFF_ENTRY_T(e) : which == 1 ? JGPU_HUFF_ENTRY_S(e) : JGPU_HUFF_ENTRY_A(e);
+}
+
 // k_huff_scan's arithmetic, lane by lane: `warps` warps of 32 lanes, each warp scanning `per` stripes of 32
 // consecutive counts with a running carry, the warps' totals combined once per sweep, a carry from sweep to sweep
 // (the kernel: 32 warps, 16 stripes).  Bit 31 of a count starts a restart interval.

@@ -71,6 +71,30 @@ def test_decoder_tables_agree_with_the_canonical_procedure(emu):
     assert emu.huff_table_selfcheck(bytes([3] + [0] * 15), bytes(range(3))) == -1   # over-subscribed
 
 
+def test_look_up_entries_carry_what_the_loop_assumes(emu):
+    """JGPU_HUFF_ENTRY: T = code length + extra bits (at most 31, so one 32-bit window holds a symbol), s = extra
+    bits, A = advance of the zig-zag index.  The loop ends a block when index + A >= 64 and stores a coefficient only
+    when index + A <= 64; for that to be the reader's behaviour an end-of-block must land beyond every run
+    (index + A > 63 + 16 for every index an AC symbol can meet) and a run past coefficient 63 must stay below it."""
+    emu.huff_entry.restype = emu.huff_entry_field.restype = C.c_uint
+    T, S, A = (lambda e: emu.huff_entry_field(e, 0)), (lambda e: emu.huff_entry_field(e, 1)), (lambda e: emu.huff_entry_field(e, 2))
+    for length in range(1, 17):
+        for sym in range(256):
+            for ac in (0, 1):
+                e = emu.huff_entry(length, sym, ac)
+                assert 0 < e < 65536, "fits the 16-bit table, and 0 stays free for 'no entry'"
+                assert T(e) == length + (sym & 15) <= 31 and S(e) == sym & 15
+                if not ac:
+                    assert A(e) == 1                      # DC: index 0 -> 1 whatever the high nibble says
+                elif sym == 0:
+                    assert A(e) == 96                     # end of block
+                else:
+                    assert A(e) == (sym >> 4) + 1         # run, then the coefficient (0xF0: sixteen zeros)
+    eob, longest_run = 96, 16
+    assert all(z + eob > 63 + longest_run for z in range(1, 64)), "an end of block is never taken for a run"
+    assert all(z + a < 1 + eob for z in range(1, 64) for a in range(1, longest_run + 1)), "nor a run for an end of block"
+
+
 @pytest.mark.parametrize("name", NAMES)
 def test_golden_files_match_the_reference_readers_planes(emu, name):
     """Kernel geometry shrunk (1-word subsequences, 4-thread CTAs) so that these small files
